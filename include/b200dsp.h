@@ -1,0 +1,237 @@
+/*
+ * include/b200dsp.h -- C ABI of libb200dsp.so: SDR++'s per-block streaming DSP hot path
+ * (windowed FFT -> dB line; multi-VFO xlate -> decimate -> resample -> FIR -> demodulate)
+ * as hand-written sm_100a CUDA kernels.
+ *
+ * The reference has no binary boundary at block level: dsp blocks are header-only C++
+ * templates whose contract is `int process(int count, const I* in, O* out)` / `run()` /
+ * `dsp::stream<T>` (core/src/dsp/processor.h:7-73, core/src/dsp/stream.h:25-141).  This
+ * library sits UNDER that contract: the adapter headers in sdrplusplus_b200/host/dsp/ keep
+ * the reference's class names and signatures and forward process() to the entry points
+ * below (INTEGRATION.md shows the binding a maintainer adds to core/CMakeLists.txt).
+ * Each entry point cites the reference interface it replaces.
+ *
+ * Conventions: plain pointers and sizes only; complex samples are interleaved (re, im)
+ * float pairs == dsp::complex_t, audio is (l, r) == dsp::stereo_t (core/src/dsp/types.h).
+ * Every function returns >= 0 on success and a negative B200_E* code on failure, never
+ * throws, and records a message retrievable with b200_last_error().  There is NO CPU
+ * fallback: without a usable CUDA device every compute call fails with B200_ENODEV.
+ * Handles are thread-confined (one worker thread per block, like the reference,
+ * core/src/dsp/block.h:71-73); setters may be called from another thread and take effect
+ * at the next chunk boundary (the reference applies them under ctrlMtx between run()
+ * iterations, core/src/dsp/channel/rx_vfo.h:72-77).
+ */
+#ifndef B200DSP_H
+#define B200DSP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_VERSION 100
+
+/* error codes */
+#define B200_OK        0
+#define B200_EINVAL   (-1)   /* bad argument */
+#define B200_ENODEV   (-2)   /* no CUDA device / driver: the product path refuses to run */
+#define B200_ECUDA    (-3)   /* CUDA runtime error (message in b200_last_error) */
+#define B200_ENOMEM   (-4)
+#define B200_ECAP     (-5)   /* caller buffer too small / chunk larger than configured maximum */
+#define B200_ENOPLAN  (-6)   /* decimation plan table not loaded / ratio unsupported */
+#define B200_ESTATE   (-7)   /* call sequence error (e.g. wait without submit) */
+
+/* sample formats of the IQ input */
+#define B200_FMT_CF32  0     /* dsp::complex_t, 8 B/sample */
+#define B200_FMT_CS16  1     /* int16 I,Q; x/32768 (file_source, source_modules/file_source/src/main.cpp:158-162) */
+#define B200_FMT_CS8   2     /* int8 I,Q; x/128 (dsp/compression/sample_stream_decompressor.h PCM_TYPE_I8) */
+
+/* where a caller buffer lives */
+#define B200_MEM_HOST   0
+#define B200_MEM_DEVICE 1
+
+/* FFT windows: IQFrontEnd::FFTWindow (core/src/signal_path/iq_frontend.h:13-17) */
+#define B200_WIN_RECTANGULAR 0
+#define B200_WIN_BLACKMAN    1
+#define B200_WIN_NUTTALL     2
+
+/* demodulators: decoder_modules/radio/src/demodulators/{raw,wfm,nfm,am,usb,lsb,dsb}.h */
+#define B200_DEMOD_RAW  0    /* VFO output itself (complex_t)            -- channel::RxVFO          */
+#define B200_DEMOD_WFM  1    /* demod::BroadcastFM (mono branch)         -- broadcast_fm.h:192-212  */
+#define B200_DEMOD_NFM  2    /* demod::FM<stereo_t>                      -- fm.h:79-96              */
+#define B200_DEMOD_AM   3    /* demod::AM<stereo_t>                      -- am.h:101-133            */
+#define B200_DEMOD_USB  4    /* demod::SSB<stereo_t> Mode::USB           -- ssb.h:77-92             */
+#define B200_DEMOD_LSB  5
+#define B200_DEMOD_DSB  6
+
+#define B200_AGC_CARRIER 0   /* demod::AM::AGCMode (am.h:14-17) */
+#define B200_AGC_AUDIO   1
+
+#define B200_MAX_VFOS 64
+
+/* ------------------------------------------------------------------------------------------
+ * Library / device
+ * ------------------------------------------------------------------------------------------ */
+
+/* Select the CUDA device for the calling thread's handles.  B200_ENODEV when no device. */
+int b200_init(int device);
+int b200_device_count(void);
+const char* b200_last_error(void);
+int b200_version(void);
+
+/* Power-of-two pre-decimation plans (stage decimations + FIR coefficient tables).  The
+ * reference keeps them in dsp::multirate::decim::plans (core/src/dsp/multirate/decim/plans.h:124-139);
+ * an adapter built against the reference headers registers them verbatim with
+ * b200_register_decim_plan(); standalone users load the flat table shipped in
+ * sdrplusplus_b200/data/decim_plans.bin (default location resolved next to the library,
+ * or $B200_DECIM_PLANS) -- done lazily on first use. */
+int b200_register_decim_plan(int ratio, int nstages, const int* decimations, const int* tapcounts,
+                             const float* const* taps);
+int b200_load_decim_plans(const char* path /* NULL = default */);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-side design helpers (fp64 -> fp32, identical formulas to the reference; exposed so that
+ * the parity tests can compare them bit-for-bit and so that adapters need not duplicate them)
+ * ------------------------------------------------------------------------------------------ */
+/* dsp::taps::lowPass (core/src/dsp/taps/low_pass.h:7-11): returns tap count, writes min(count,cap) */
+int b200_taps_lowpass(double cutoff, double transWidth, double samplerate, int oddTapCount, float* out, int cap);
+/* IQFrontEnd::updateFFTPath window (core/src/signal_path/iq_frontend.cpp:281-291): w(i,nz)*(-1)^i */
+int b200_window(int window, int nz, float* out);
+/* IQFrontEnd::genReshapeParams (core/src/signal_path/iq_frontend.h:59-63) */
+int b200_fft_frame_params(double samplerate, int fftSize, double fftRate, int* nz, int* skip);
+
+typedef struct {
+    int mode;            /* 0 BOTH, 1 DECIM_ONLY, 2 RESAMP_ONLY, 3 NONE (rational_resampler.h:112-117) */
+    int predec_ratio;    /* 1 when the power decimator is bypassed */
+    int nstages;         /* pre-decimation stages */
+    int stage_decim[8];
+    int stage_taps[8];
+    int interp, decim;   /* polyphase L / M */
+    int ntaps;           /* prototype taps */
+    int taps_per_phase;
+} b200_resamp_plan;
+/* dsp::multirate::RationalResampler::reconfigure (rational_resampler.h:120-165) */
+int b200_resamp_plan_get(double inSamplerate, double outSamplerate, b200_resamp_plan* plan);
+
+/* ------------------------------------------------------------------------------------------
+ * Front end: one IQ stream -> { FFT/waterfall branch, N x (RxVFO + demodulator) }
+ * Replaces IQFrontEnd's Splitter fan-out + Reshaper/handler FFT branch + per-VFO RxVFO blocks
+ * (core/src/signal_path/iq_frontend.h:23-49, iq_frontend.cpp:248-309) and the radio module's
+ * demodulator block behind each VFO (decoder_modules/radio/src/radio_module.h:80-125).
+ * One b200_fe_process() call == one IQ chunk == what the reference moves with one
+ * stream<complex_t>::swap(count); the raw IQ is read from HBM once for all consumers.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b200_fe b200_fe;
+
+typedef struct {
+    double offset;            /* Hz, VFO centre relative to the stream centre (RxVFO::init offset)       */
+    double out_samplerate;    /* RxVFO output rate == demodulator IF rate (e.g. WFM 250000)              */
+    double bandwidth;         /* channel filter bandwidth (RxVFO::init bandwidth)                        */
+    int    demod;             /* B200_DEMOD_*                                                            */
+    /* demodulator parameters (unused ones ignored) */
+    double deviation;         /* WFM: Hz (wfm.h:78 passes bandwidth/2); NFM uses bandwidth/2 (fm.h:28)  */
+    int    low_pass;          /* WFM/NFM post-demod audio low-pass enabled (wfm.h:364, nfm.h)            */
+    int    agc_mode;          /* AM: B200_AGC_*                                                          */
+    double agc_attack;        /* AM/SSB: per-sample coefficient (radio passes attack/IFrate)             */
+    double agc_decay;
+    double dc_block_rate;     /* AM: per-sample rate (radio passes 100/IFrate, demodulators/am.h:34)     */
+} b200_vfo_cfg;
+
+typedef struct {
+    /* per VFO: caller buffer for this chunk's output (stereo_t pairs, or complex_t for RAW) */
+    void* vfo_out[B200_MAX_VFOS];
+    int   vfo_cap[B200_MAX_VFOS];     /* capacity in output samples                               */
+    int   vfo_count[B200_MAX_VFOS];   /* OUT: samples produced this chunk                         */
+    /* FFT branch: dB lines completed during this chunk, fft_size floats each                     */
+    float* fft_out;
+    int   fft_cap_lines;
+    int   fft_lines;                  /* OUT                                                       */
+    int   out_mem;                    /* B200_MEM_HOST (pinned preferred) or B200_MEM_DEVICE       */
+} b200_outputs;
+
+/* samplerate: effective IQ rate; max_chunk: largest count ever passed to process (the reference caps a
+ * chunk at STREAM_BUFFER_SIZE = 1e6 samples, core/src/dsp/stream.h:9; stream<T>::setBufferSize raises it) */
+b200_fe* b200_fe_create(double samplerate, int max_chunk);
+void     b200_fe_destroy(b200_fe* fe);
+/* run on the caller's CUDA stream (cudaStream_t passed as void*), e.g. torch's current stream; NULL = own */
+int b200_fe_set_stream(b200_fe* fe, void* cuda_stream);
+
+/* IQFrontEnd::setFFTSize/Rate/Window (iq_frontend.h:37-39); size 0 disables the branch. size must be a
+ * power of two in [8, 4194304]. */
+int b200_fe_set_fft(b200_fe* fe, int size, double rate, int window);
+/* IQFrontEnd::addVFO / removeVFO (iq_frontend.h:32-33) + radio demodulator selection: returns vfo id */
+int b200_fe_add_vfo(b200_fe* fe, const b200_vfo_cfg* cfg);
+int b200_fe_remove_vfo(b200_fe* fe, int id);
+/* RxVFO::setOffset / setBandwidth (core/src/dsp/channel/rx_vfo.h:60-77): phase-continuous, next chunk */
+int b200_fe_set_vfo_offset(b200_fe* fe, int id, double offset);
+int b200_fe_set_vfo_bandwidth(b200_fe* fe, int id, double bandwidth);
+int b200_fe_vfo_count(b200_fe* fe);
+/* upper bound of output samples one chunk of `count` input samples can produce for VFO id */
+int b200_fe_vfo_max_out(b200_fe* fe, int id, int count);
+int b200_fe_fft_max_lines(b200_fe* fe, int count);
+/* clears every delay line / phase / counter (block::reset semantics) */
+int b200_fe_reset(b200_fe* fe);
+
+/* Synchronous chunk: returns when all outputs are in the caller's buffers (process() semantics of the
+ * reference: data available on return).  in_fmt: B200_FMT_*, in_mem: B200_MEM_* */
+int b200_fe_process(b200_fe* fe, const void* iq, int count, int in_fmt, int in_mem, b200_outputs* out);
+/* Pipelined pair: submit() enqueues chunk k (H2D on a side stream + kernels + D2H) and returns
+ * immediately; wait() blocks until the OLDEST submitted chunk's outputs are complete and fills its
+ * counts.  Up to 2 chunks in flight.  Values are identical to b200_fe_process; only timing changes. */
+int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt, int in_mem, b200_outputs* out);
+int b200_fe_wait(b200_fe* fe);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+long long b200_fe_launch_count(b200_fe* fe);
+/* selects kernel variants for A/B parity runs: key "s1" (0 plain, 1 register-blocked f32x2) etc. */
+int b200_fe_set_option(b200_fe* fe, const char* key, int value);
+
+/* waterfall zoom (max-decimate) + peak hold on the device line, bit-exact with
+ * doZoom / pushFFT hold loop (core/src/gui/widgets/waterfall.cpp:65-90, 935-939).
+ * line: fft_size dB values (mem), out/hold: out_size floats (same mem). hold may be NULL. */
+int b200_fft_zoom_hold(const float* line, int fft_size, int offset, int width, int out_size,
+                       float* out, float* hold, float hold_speed, int mem);
+
+/* ------------------------------------------------------------------------------------------
+ * Stand-alone blocks (un-fused graphs keep working): each mirrors one reference block's
+ * init(...) / process(count, in, out) -> out count.  Host buffers in, host buffers out,
+ * synchronous, state carried across calls exactly like the reference block.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b200_block b200_block;
+
+b200_block* b200_xlator_create(double offsetHz, double samplerate);             /* channel::FrequencyXlator (frequency_xlator.h:15-50) */
+int         b200_xlator_set_offset(b200_block* b, double offsetHz, double samplerate);
+b200_block* b200_decim_create(int ratio);                                       /* multirate::PowerDecimator<complex_t> (power_decimator.h:51-67) */
+b200_block* b200_resamp_create(double inSamplerate, double outSamplerate);      /* multirate::RationalResampler<complex_t|stereo_t> (rational_resampler.h:82-96) */
+b200_block* b200_fir_cr_create(const float* taps, int ntaps, int decimation);   /* filter::FIR / DecimatingFIR<complex_t,float> (fir.h:62-83, decimating_fir.h:45-68) */
+b200_block* b200_fir_rr_create(const float* taps, int ntaps);                   /* filter::FIR<float,float> */
+b200_block* b200_rxvfo_create(double inSamplerate, double outSamplerate, double bandwidth, double offset); /* channel::RxVFO (rx_vfo.h:89-100) */
+int         b200_rxvfo_set_offset(b200_block* b, double offset);
+int         b200_rxvfo_set_bandwidth(b200_block* b, double bandwidth);
+b200_block* b200_quad_create(double deviationHz, double samplerate);            /* demod::Quadrature (quadrature.h:39-46): complex -> float */
+b200_block* b200_wfm_create(double deviationHz, double samplerate, int stereo, int lowPass); /* demod::BroadcastFM: complex -> stereo */
+b200_block* b200_nfm_create(double samplerate, double bandwidth, int lowPass);  /* demod::FM<stereo_t> */
+b200_block* b200_am_create(int agcMode, double bandwidth, double agcAttack, double agcDecay, double dcBlockRate, double samplerate); /* demod::AM<stereo_t> */
+b200_block* b200_ssb_create(int mode /*0 USB,1 LSB,2 DSB*/, double bandwidth, double samplerate, double agcAttack, double agcDecay); /* demod::SSB<stereo_t> */
+/* returns the output sample count; in/out are host pointers of the block's sample types */
+int  b200_block_process(b200_block* b, int count, const void* in, void* out);
+int  b200_block_max_out(b200_block* b, int count);
+int  b200_block_reset(b200_block* b);
+void b200_block_destroy(b200_block* b);
+
+/* Stand-alone spectrum handler == IQFrontEnd::handler on one already-framed block of nz samples:
+ * window*(-1)^n -> FFT -> 10log10(|X/N|^2)  (iq_frontend.cpp:248-267).  Host in, host out. */
+typedef struct b200_fft b200_fft;
+b200_fft* b200_fft_create(int size, int nz, int window);
+int       b200_fft_frame(b200_fft* f, const float* iq_nz, float* out_db);
+int       b200_fft_raw(b200_fft* f, const float* iq_nz, float* out_complex);    /* test hook: complex spectrum */
+void      b200_fft_destroy(b200_fft* f);
+
+/* pinned host memory for stream buffers (replaces buffer::alloc/volk_malloc, core/src/dsp/buffer/buffer.h:7-18) */
+void* b200_host_alloc(uint64_t bytes);
+void  b200_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,766 @@
+// sdrplusplus_b200/csrc/api.cpp -- C ABI of libb200dsp.so (include/b200dsp.h) over engine.h.
+#include "../../include/b200dsp.h"
+#include "engine.h"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+
+using namespace b200;
+
+// ------------------------------------------------------------------ device
+static int g_device = -1;
+
+static int ensure_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        set_error("no usable CUDA device (%s): libb200dsp has no CPU fallback", e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return B200_ENODEV;
+    }
+    if (g_device < 0) { g_device = 0; }
+    B200_CK(cudaSetDevice(g_device));
+    return 0;
+}
+
+extern "C" int b200_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        set_error("no usable CUDA device (%s): libb200dsp has no CPU fallback", e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return B200_ENODEV;
+    }
+    if (device < 0 || device >= n) { set_error("device %d out of range (0..%d)", device, n - 1); return B200_EINVAL; }
+    g_device = device;
+    B200_CK(cudaSetDevice(device));
+    B200_CK(cudaFree(0));
+    return 0;
+}
+extern "C" int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" const char* b200_last_error(void) { return last_error(); }
+extern "C" int b200_version(void) { return B200_VERSION; }
+
+extern "C" int b200_register_decim_plan(int ratio, int nstages, const int* d, const int* t, const float* const* taps) {
+    if (!d || !t || !taps) { set_error("null argument"); return B200_EINVAL; }
+    if (register_decim_plan(ratio, nstages, d, t, taps)) { set_error("invalid decimation plan for ratio %d", ratio); return B200_EINVAL; }
+    return 0;
+}
+extern "C" int b200_load_decim_plans(const char* path) {
+    if (load_decim_plans(path)) { set_error("cannot load decimation plans from %s", path ? path : "(default location)"); return B200_ENOPLAN; }
+    return 0;
+}
+
+// ------------------------------------------------------------------ design helpers
+extern "C" int b200_taps_lowpass(double cutoff, double tw, double sr, int odd, float* out, int cap) {
+    std::vector<float> t = lowpass_taps(cutoff, tw, sr, odd != 0);
+    if (out) { memcpy(out, t.data(), sizeof(float) * (size_t)std::min<int>((int)t.size(), cap)); }
+    return (int)t.size();
+}
+extern "C" int b200_window(int window, int nz, float* out) {
+    if (nz < 0 || !out) { set_error("bad window args"); return B200_EINVAL; }
+    std::vector<float> w = fft_window(window, nz);
+    memcpy(out, w.data(), sizeof(float) * (size_t)nz);
+    return nz;
+}
+extern "C" int b200_fft_frame_params(double sr, int size, double rate, int* nz, int* skip) {
+    if (!nz || !skip || rate <= 0) { set_error("bad args"); return B200_EINVAL; }
+    fft_frame_params(sr, size, rate, *nz, *skip);
+    return 0;
+}
+extern "C" int b200_resamp_plan_get(double inSR, double outSR, b200_resamp_plan* out) {
+    if (!out) { set_error("null plan"); return B200_EINVAL; }
+    ResampPlan pl = make_resamp_plan(inSR, outSR);
+    memset(out, 0, sizeof(*out));
+    out->mode = pl.mode;
+    out->predec_ratio = pl.predec_ratio;
+    out->interp = pl.interp;
+    out->decim = pl.decim;
+    out->ntaps = (int)pl.rtaps.size();
+    out->taps_per_phase = pl.taps_per_phase;
+    if (pl.use_decim) {
+        const DecimPlan* dp = find_decim_plan(pl.predec_ratio);
+        if (!dp) { set_error("no decimation plan for ratio %d", pl.predec_ratio); return B200_ENOPLAN; }
+        out->nstages = (int)dp->stages.size();
+        for (int i = 0; i < out->nstages && i < 8; i++) {
+            out->stage_decim[i] = dp->stages[i].decim;
+            out->stage_taps[i] = (int)dp->stages[i].taps.size();
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ FFT plan
+static int bytes_per_sample(int fmt) { return fmt == B200_FMT_CF32 ? 8 : (fmt == B200_FMT_CS16 ? 4 : 2); }
+static int ilog2(int n) { int l = 0; while ((1 << l) < n) { l++; } return l; }
+
+struct FftCore {
+    FftPlanDev plan;
+    DevBuf tw, win, work;
+    int size = 0, nz = 0, window = 0;
+    int create(int size_, int nz_, int window_) {
+        if (size_ < 8 || size_ > (1 << 22) || (size_ & (size_ - 1))) { set_error("FFT size %d must be a power of two in [8, 4194304]", size_); return B200_EINVAL; }
+        if (nz_ < 1 || nz_ > size_) { set_error("bad nz %d", nz_); return B200_EINVAL; }
+        size = size_; nz = nz_; window = window_;
+        memset(&plan, 0, sizeof(plan));
+        plan.N = size; plan.logN = ilog2(size);
+        if (size <= 8192) { plan.N1 = size; plan.logN1 = plan.logN; plan.N2 = 1; plan.logN2 = 0; }
+        else {
+            plan.logN1 = (plan.logN + 1) / 2; plan.N1 = 1 << plan.logN1;
+            plan.logN2 = plan.logN - plan.logN1; plan.N2 = 1 << plan.logN2;
+        }
+        plan.TW = std::max(plan.N1, plan.N2); plan.logTW = ilog2(plan.TW);
+        std::vector<float2> t((size_t)plan.TW);
+        for (int k = 0; k < plan.TW; k++) {
+            double a = -2.0 * 3.14159265358979323846 * (double)k / (double)plan.TW;
+            t[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+        int rc;
+        if ((rc = tw.alloc(t.size() * sizeof(float2)))) { return rc; }
+        B200_CK(cudaMemcpy(tw.p, t.data(), t.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        std::vector<float> w = fft_window(window, nz);
+        if ((rc = win.alloc((size_t)nz * sizeof(float)))) { return rc; }
+        B200_CK(cudaMemcpy(win.p, w.data(), (size_t)nz * sizeof(float), cudaMemcpyHostToDevice));
+        if ((rc = work.alloc((size_t)size * sizeof(float2)))) { return rc; }
+        plan.tw = tw.as<float2>(); plan.window = win.as<float>(); plan.nz = nz;
+        return 0;
+    }
+};
+
+// ------------------------------------------------------------------ front end
+struct VfoSlot {
+    bool used = false;
+    b200_vfo_cfg cfg;
+    Chain chain;
+    bool pend_offset = false, pend_bw = false;
+    double new_offset = 0, new_bw = 0;
+};
+
+struct b200_fe {
+    double fs = 0;
+    int max_chunk = 0;
+    Scheduler sch;
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+    std::vector<std::unique_ptr<VfoSlot>> vfos;
+    std::mutex mtx;
+    DevBuf in_dev[2];
+    // FFT branch
+    bool fft_on = false;
+    FftCore fft;
+    double fft_rate = 0;
+    int skip = 0;
+    DevBuf frame, lines;
+    int max_lines = 0;
+    unsigned long long pos = 0, fstart = 0;
+    // pipelining
+    cudaEvent_t ev_h2d[2] = { nullptr, nullptr }, ev_compute[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
+    bool slot_used[2] = { false, false };
+    unsigned long long nsub = 0, nwait = 0;
+};
+
+static int fe_alloc_fft(b200_fe* fe) {
+    int rc;
+    if ((rc = fe->frame.alloc((size_t)fe->fft.nz * sizeof(float2)))) { return rc; }
+    long long interval = (long long)fe->fft.nz + fe->skip;
+    fe->max_lines = (int)(fe->max_chunk / interval) + 2;
+    return fe->lines.alloc((size_t)fe->max_lines * fe->fft.size * sizeof(float));
+}
+
+extern "C" b200_fe* b200_fe_create(double samplerate, int max_chunk) {
+    if (ensure_device()) { return nullptr; }
+    if (samplerate <= 0 || max_chunk < 1) { set_error("bad samplerate/max_chunk"); return nullptr; }
+    b200_fe* fe = new b200_fe;
+    fe->fs = samplerate;
+    fe->max_chunk = max_chunk;
+    bool ok = cudaStreamCreateWithFlags(&fe->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&fe->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; i++) {
+        ok = cudaEventCreateWithFlags(&fe->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&fe->ev_compute[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&fe->ev_out[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok || fe->sch.init_raw()) {
+        if (ok) {} else { cuda_fail(cudaGetLastError(), "stream/event creation"); }
+        b200_fe_destroy(fe);
+        return nullptr;
+    }
+    fe->sch.stream = fe->own_stream;
+    return fe;
+}
+
+extern "C" void b200_fe_destroy(b200_fe* fe) {
+    if (!fe) { return; }
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; i++) {
+        if (fe->ev_h2d[i]) { cudaEventDestroy(fe->ev_h2d[i]); }
+        if (fe->ev_compute[i]) { cudaEventDestroy(fe->ev_compute[i]); }
+        if (fe->ev_out[i]) { cudaEventDestroy(fe->ev_out[i]); }
+    }
+    if (fe->own_stream) { cudaStreamDestroy(fe->own_stream); }
+    if (fe->copy_stream) { cudaStreamDestroy(fe->copy_stream); }
+    delete fe;
+}
+
+extern "C" int b200_fe_set_stream(b200_fe* fe, void* s) {
+    if (!fe) { set_error("null fe"); return B200_EINVAL; }
+    fe->sch.stream = s ? (cudaStream_t)s : fe->own_stream;
+    return 0;
+}
+
+extern "C" int b200_fe_set_fft(b200_fe* fe, int size, double rate, int window) {
+    if (!fe) { set_error("null fe"); return B200_EINVAL; }
+    std::lock_guard<std::mutex> lck(fe->mtx);
+    B200_CK(cudaStreamSynchronize(fe->sch.stream));
+    if (size == 0) { fe->fft_on = false; return 0; }
+    if (rate <= 0) { set_error("bad fft rate"); return B200_EINVAL; }
+    int nz, skip;
+    fft_frame_params(fe->fs, size, rate, nz, skip);
+    int rc = fe->fft.create(size, nz, window);
+    if (rc) { return rc; }
+    fe->skip = skip;
+    fe->fft_rate = rate;
+    if ((rc = fe_alloc_fft(fe))) { return rc; }
+    // Reshaper restart (iq_frontend.cpp:269-279): framing restarts at the current stream position
+    fe->fstart = fe->pos;
+    fe->fft_on = true;
+    return 0;
+}
+
+static int build_vfo_chain(b200_fe* fe, VfoSlot* v) {
+    const b200_vfo_cfg& c = v->cfg;
+    int rc = v->chain.add_rxvfo(fe->fs, c.out_samplerate, c.bandwidth, c.offset);
+    if (rc) { return rc; }
+    switch (c.demod) {
+    case B200_DEMOD_RAW: break;
+    case B200_DEMOD_WFM: rc = v->chain.add_wfm(c.deviation, c.out_samplerate, c.low_pass != 0); break;
+    case B200_DEMOD_NFM: rc = v->chain.add_nfm(c.out_samplerate, c.bandwidth, c.low_pass != 0); break;
+    case B200_DEMOD_AM: rc = v->chain.add_am(c.agc_mode, c.bandwidth, c.agc_attack, c.agc_decay, c.dc_block_rate, c.out_samplerate); break;
+    case B200_DEMOD_USB: rc = v->chain.add_ssb(0, c.bandwidth, c.out_samplerate, c.agc_attack, c.agc_decay); break;
+    case B200_DEMOD_LSB: rc = v->chain.add_ssb(1, c.bandwidth, c.out_samplerate, c.agc_attack, c.agc_decay); break;
+    case B200_DEMOD_DSB: rc = v->chain.add_ssb(2, c.bandwidth, c.out_samplerate, c.agc_attack, c.agc_decay); break;
+    default: set_error("unknown demodulator %d", c.demod); return B200_EINVAL;
+    }
+    if (rc) { return rc; }
+    return v->chain.finalize(fe->max_chunk);
+}
+
+extern "C" int b200_fe_add_vfo(b200_fe* fe, const b200_vfo_cfg* cfg) {
+    if (!fe || !cfg) { set_error("null argument"); return B200_EINVAL; }
+    if (cfg->out_samplerate <= 0 || cfg->bandwidth <= 0) { set_error("bad VFO rates"); return B200_EINVAL; }
+    if (cfg->demod == B200_DEMOD_AM && cfg->agc_mode != B200_AGC_CARRIER && cfg->agc_mode != B200_AGC_AUDIO) {
+        set_error("bad AM agc_mode"); return B200_EINVAL;
+    }
+    std::lock_guard<std::mutex> lck(fe->mtx);
+    int id = -1;
+    for (size_t i = 0; i < fe->vfos.size(); i++) {
+        if (!fe->vfos[i]->used) { id = (int)i; break; }
+    }
+    if (id < 0) {
+        if (fe->vfos.size() >= B200_MAX_VFOS) { set_error("too many VFOs"); return B200_ECAP; }
+        fe->vfos.push_back(std::make_unique<VfoSlot>());
+        id = (int)fe->vfos.size() - 1;
+    }
+    else { fe->vfos[id] = std::make_unique<VfoSlot>(); }
+    VfoSlot* v = fe->vfos[id].get();
+    v->cfg = *cfg;
+    int rc = build_vfo_chain(fe, v);
+    if (rc) { fe->vfos[id] = std::make_unique<VfoSlot>(); return rc; }
+    v->used = true;
+    return id;
+}
+
+static VfoSlot* get_vfo(b200_fe* fe, int id) {
+    if (!fe || id < 0 || id >= (int)fe->vfos.size() || !fe->vfos[id]->used) { set_error("bad VFO id %d", id); return nullptr; }
+    return fe->vfos[id].get();
+}
+
+extern "C" int b200_fe_remove_vfo(b200_fe* fe, int id) {
+    if (!fe) { set_error("null fe"); return B200_EINVAL; }
+    std::lock_guard<std::mutex> lck(fe->mtx);
+    if (!get_vfo(fe, id)) { return B200_EINVAL; }
+    B200_CK(cudaStreamSynchronize(fe->sch.stream));
+    fe->vfos[id] = std::make_unique<VfoSlot>();
+    return 0;
+}
+extern "C" int b200_fe_set_vfo_offset(b200_fe* fe, int id, double offset) {
+    if (!fe) { set_error("null fe"); return B200_EINVAL; }
+    std::lock_guard<std::mutex> lck(fe->mtx);
+    VfoSlot* v = get_vfo(fe, id);
+    if (!v) { return B200_EINVAL; }
+    v->pend_offset = true;
+    v->new_offset = offset;
+    return 0;
+}
+extern "C" int b200_fe_set_vfo_bandwidth(b200_fe* fe, int id, double bw) {
+    if (!fe) { set_error("null fe"); return B200_EINVAL; }
+    std::lock_guard<std::mutex> lck(fe->mtx);
+    VfoSlot* v = get_vfo(fe, id);
+    if (!v || bw <= 0) { set_error("bad bandwidth"); return B200_EINVAL; }
+    v->pend_bw = true;
+    v->new_bw = bw;
+    return 0;
+}
+extern "C" int b200_fe_vfo_count(b200_fe* fe) {
+    if (!fe) { return 0; }
+    int n = 0;
+    for (auto& v : fe->vfos) { n += v->used ? 1 : 0; }
+    return n;
+}
+extern "C" int b200_fe_vfo_max_out(b200_fe* fe, int id, int count) {
+    VfoSlot* v = get_vfo(fe, id);
+    if (!v) { return B200_EINVAL; }
+    return v->chain.max_out(count);
+}
+extern "C" int b200_fe_fft_max_lines(b200_fe* fe, int count) {
+    if (!fe || !fe->fft_on) { return 0; }
+    return (int)(count / ((long long)fe->fft.nz + fe->skip)) + 2;
+}
+extern "C" long long b200_fe_launch_count(b200_fe* fe) { return fe ? fe->sch.launches : 0; }
+extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
+    if (!fe || !key) { set_error("null argument"); return B200_EINVAL; }
+    if (!strcmp(key, "s1")) { fe->sch.s1_variant = value; return 0; }
+    set_error("unknown option %s", key);
+    return B200_EINVAL;
+}
+
+extern "C" int b200_fe_reset(b200_fe* fe) {
+    if (!fe) { set_error("null fe"); return B200_EINVAL; }
+    std::lock_guard<std::mutex> lck(fe->mtx);
+    B200_CK(cudaStreamSynchronize(fe->sch.stream));
+    for (auto& v : fe->vfos) {
+        if (v->used) { v->chain.reset_state(); }
+    }
+    int rc = fe->sch.reset_raw();
+    fe->pos = 0;
+    fe->fstart = 0;
+    return rc;
+}
+
+// apply RxVFO::setOffset / setBandwidth at the chunk boundary (rx_vfo.h:60-77)
+static void apply_pending(b200_fe* fe) {
+    for (auto& up : fe->vfos) {
+        VfoSlot* v = up.get();
+        if (!v->used) { continue; }
+        if (v->pend_offset) {
+            v->cfg.offset = v->new_offset;
+            ((XdStage*)v->chain.st[0].get())->set_offset_rad(hz_to_rads(-v->cfg.offset, fe->fs));
+            v->pend_offset = false;
+        }
+        if (v->pend_bw) {
+            // only the channel filter follows the bandwidth (rx_vfo.h:60-70); it exists iff bw != outSR at creation
+            bool had_filter = (v->cfg.bandwidth != v->cfg.out_samplerate);
+            if (had_filter && v->new_bw != v->cfg.out_samplerate) {
+                // locate the channel FIR: the last FirC stage with decim == 1 before the demodulator stages
+                FirCStage* f = nullptr;
+                for (auto& s : v->chain.st) {
+                    if (s->kind == K_FIRC && ((FirCStage*)s.get())->decim == 1) { f = (FirCStage*)s.get(); }
+                }
+                if (f) {
+                    double fw = v->new_bw / 2.0;
+                    f->pending = lowpass_taps(fw, fw * 0.1, v->cfg.out_samplerate);
+                    v->cfg.bandwidth = v->new_bw;
+                }
+            }
+            v->pend_bw = false;
+        }
+    }
+}
+
+static int fe_fft_chunk(b200_fe* fe, const void* dptr, int fmt, int count, int* nlines) {
+    *nlines = 0;
+    if (!fe->fft_on) { fe->pos += (unsigned long long)count; return 0; }
+    const unsigned long long pos = fe->pos, end = pos + (unsigned long long)count;
+    const unsigned long long nz = (unsigned long long)fe->fft.nz, interval = nz + (unsigned long long)fe->skip;
+    const int bps = bytes_per_sample(fmt);
+    cudaStream_t s = fe->sch.stream;
+    while (fe->fstart < end) {
+        const unsigned long long fend = fe->fstart + nz;
+        if (*nlines >= fe->max_lines) { set_error("FFT line buffer overflow"); return B200_ECAP; }
+        float* line = fe->lines.as<float>() + (size_t)(*nlines) * fe->fft.size;
+        if (fe->fstart >= pos && fend <= end) {
+            const char* src = (const char*)dptr + (size_t)(fe->fstart - pos) * bps;
+            int nl = 0;
+            cudaError_t e = launch_fft_frame(fe->fft.plan, src, fmt, fe->fft.work.as<float2>(), line, nullptr, s, &nl);
+            if (e != cudaSuccess) { return cuda_fail(e, "launch_fft_frame"); }
+            fe->sch.launches += nl;
+            (*nlines)++;
+            fe->fstart += interval;
+            continue;
+        }
+        const unsigned long long lo = std::max(fe->fstart, pos), hi = std::min(fend, end);
+        if (hi > lo) {
+            const char* src = (const char*)dptr + (size_t)(lo - pos) * bps;
+            cudaError_t e = launch_convert_cf32(src, fmt, fe->frame.as<float2>() + (size_t)(lo - fe->fstart), (int)(hi - lo), s);
+            if (e != cudaSuccess) { return cuda_fail(e, "launch_convert_cf32"); }
+            fe->sch.launches++;
+        }
+        if (fend <= end) {
+            int nl = 0;
+            cudaError_t e = launch_fft_frame(fe->fft.plan, fe->frame.p, FMT_CF32, fe->fft.work.as<float2>(), line, nullptr, s, &nl);
+            if (e != cudaSuccess) { return cuda_fail(e, "launch_fft_frame"); }
+            fe->sch.launches += nl;
+            (*nlines)++;
+            fe->fstart += interval;
+        }
+        else { break; }
+    }
+    fe->pos = end;
+    return 0;
+}
+
+extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt, int in_mem, b200_outputs* out) {
+    if (!fe || !out || (count > 0 && !iq)) { set_error("null argument"); return B200_EINVAL; }
+    if (count < 0 || count > fe->max_chunk) { set_error("count %d exceeds max_chunk %d", count, fe->max_chunk); return B200_ECAP; }
+    if (in_fmt < 0 || in_fmt > 2) { set_error("bad input format"); return B200_EINVAL; }
+    if (fe->nsub - fe->nwait >= 2) { set_error("two chunks already in flight: call b200_fe_wait"); return B200_ESTATE; }
+    std::lock_guard<std::mutex> lck(fe->mtx);
+    apply_pending(fe);
+    const int slot = (int)(fe->nsub & 1);
+    cudaStream_t s = fe->sch.stream;
+    const size_t in_bytes = (size_t)count * bytes_per_sample(in_fmt);
+    const void* dptr = iq;
+    if (in_mem == B200_MEM_HOST && count > 0) {
+        if (fe->in_dev[slot].bytes < in_bytes) {
+            B200_CK(cudaStreamSynchronize(s));
+            int rc = fe->in_dev[slot].alloc(std::max(in_bytes, (size_t)fe->max_chunk * bytes_per_sample(in_fmt)), false);
+            if (rc) { return rc; }
+        }
+        if (fe->slot_used[slot]) { B200_CK(cudaStreamWaitEvent(fe->copy_stream, fe->ev_compute[slot], 0)); }
+        B200_CK(cudaMemcpyAsync(fe->in_dev[slot].p, iq, in_bytes, cudaMemcpyHostToDevice, fe->copy_stream));
+        B200_CK(cudaEventRecord(fe->ev_h2d[slot], fe->copy_stream));
+        B200_CK(cudaStreamWaitEvent(s, fe->ev_h2d[slot], 0));
+        dptr = fe->in_dev[slot].p;
+    }
+    // ---- capacity checks against the exact counts, before any state moves ----
+    std::vector<Chain*> chains;
+    std::vector<int> ids;
+    for (size_t i = 0; i < fe->vfos.size(); i++) {
+        if (fe->vfos[i]->used) { chains.push_back(&fe->vfos[i]->chain); ids.push_back((int)i); }
+    }
+    for (size_t k = 0; k < chains.size(); k++) {
+        int bound = chains[k]->max_out(count);
+        if (out->vfo_out[ids[k]] == nullptr || out->vfo_cap[ids[k]] < bound) {
+            set_error("VFO %d output buffer too small: need room for %d samples (b200_fe_vfo_max_out)", ids[k], bound);
+            return B200_ECAP;
+        }
+    }
+    if (fe->fft_on) {
+        int bound = b200_fe_fft_max_lines(fe, count);
+        if (out->fft_out == nullptr || out->fft_cap_lines < std::min(bound, fe->max_lines)) {
+            // exact count of lines this chunk completes
+            unsigned long long end = fe->pos + (unsigned long long)count, f = fe->fstart;
+            unsigned long long nz = (unsigned long long)fe->fft.nz, iv = nz + (unsigned long long)fe->skip;
+            int need = 0;
+            while (f + nz <= end) { need++; f += iv; }
+            if (need > 0 && (out->fft_out == nullptr || out->fft_cap_lines < need)) {
+                set_error("FFT output buffer too small: %d lines complete in this chunk", need);
+                return B200_ECAP;
+            }
+        }
+    }
+    for (Chain* c : chains) { c->plan(count); }
+    int rc = fe->sch.run(chains, dptr, in_fmt, count, true);
+    if (rc) { return rc; }
+    int nlines = 0;
+    if ((rc = fe_fft_chunk(fe, dptr, in_fmt, count, &nlines))) { return rc; }
+    B200_CK(cudaEventRecord(fe->ev_compute[slot], s));
+    fe->slot_used[slot] = true;
+    // ---- outputs ----
+    const cudaMemcpyKind kind = (out->out_mem == B200_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    for (size_t k = 0; k < chains.size(); k++) {
+        Chain* c = chains[k];
+        out->vfo_count[ids[k]] = c->n_out;
+        if (c->n_out > 0) {
+            B200_CK(cudaMemcpyAsync(out->vfo_out[ids[k]], c->out.p, (size_t)c->n_out * c->out_es * sizeof(float), kind, s));
+        }
+    }
+    out->fft_lines = nlines;
+    if (nlines > 0) {
+        B200_CK(cudaMemcpyAsync(out->fft_out, fe->lines.p, (size_t)nlines * fe->fft.size * sizeof(float), kind, s));
+    }
+    B200_CK(cudaEventRecord(fe->ev_out[slot], s));
+    fe->nsub++;
+    return 0;
+}
+
+extern "C" int b200_fe_wait(b200_fe* fe) {
+    if (!fe) { set_error("null fe"); return B200_EINVAL; }
+    if (fe->nwait >= fe->nsub) { set_error("nothing in flight"); return B200_ESTATE; }
+    const int slot = (int)(fe->nwait & 1);
+    B200_CK(cudaEventSynchronize(fe->ev_out[slot]));
+    fe->nwait++;
+    return 0;
+}
+
+extern "C" int b200_fe_process(b200_fe* fe, const void* iq, int count, int in_fmt, int in_mem, b200_outputs* out) {
+    if (fe && fe->nsub != fe->nwait) { set_error("chunks in flight: drain with b200_fe_wait first"); return B200_ESTATE; }
+    int rc = b200_fe_submit(fe, iq, count, in_fmt, in_mem, out);
+    if (rc) { return rc; }
+    return b200_fe_wait(fe);
+}
+
+// ------------------------------------------------------------------ zoom / hold
+extern "C" int b200_fft_zoom_hold(const float* line, int fft_size, int offset, int width, int out_size, float* out,
+                                  float* hold, float hold_speed, int mem) {
+    if (ensure_device()) { return B200_ENODEV; }
+    if (!line || !out || fft_size < 1 || out_size < 1) { set_error("bad zoom args"); return B200_EINVAL; }
+    // index loop of doZoom (waterfall.cpp:65-90), fp32 accumulator and all
+    std::vector<int> start(out_size), len(out_size);
+    if (offset < 0) { offset = 0; }
+    if (width > 524288) { width = 524288; }
+    float factor = (float)width / (float)out_size;
+    float sFactor = ceilf(factor);
+    float id = (float)offset;
+    for (int i = 0; i < out_size; i++) {
+        int sId = (int)id;
+        float uFactor = (sId + sFactor > fft_size) ? sFactor - ((sId + sFactor) - fft_size) : sFactor;
+        int l = 0;
+        for (int j = 0; j < uFactor; j++) { l++; }
+        start[i] = sId;
+        len[i] = l;
+        if (l > 0 && (sId < 0 || sId + l > fft_size)) { set_error("zoom window outside the line"); return B200_EINVAL; }
+        id += factor;
+    }
+    DevBuf tbl, dline, dout, dhold;
+    int rc;
+    if ((rc = tbl.alloc((size_t)out_size * 2 * sizeof(int), false))) { return rc; }
+    B200_CK(cudaMemcpy(tbl.p, start.data(), (size_t)out_size * sizeof(int), cudaMemcpyHostToDevice));
+    B200_CK(cudaMemcpy(tbl.as<int>() + out_size, len.data(), (size_t)out_size * sizeof(int), cudaMemcpyHostToDevice));
+    const float* l = line;
+    float* o = out;
+    float* h = hold;
+    if (mem == B200_MEM_HOST) {
+        if ((rc = dline.alloc((size_t)fft_size * sizeof(float), false))) { return rc; }
+        if ((rc = dout.alloc((size_t)out_size * sizeof(float), false))) { return rc; }
+        B200_CK(cudaMemcpy(dline.p, line, (size_t)fft_size * sizeof(float), cudaMemcpyHostToDevice));
+        l = dline.as<float>();
+        o = dout.as<float>();
+        if (hold) {
+            if ((rc = dhold.alloc((size_t)out_size * sizeof(float), false))) { return rc; }
+            B200_CK(cudaMemcpy(dhold.p, hold, (size_t)out_size * sizeof(float), cudaMemcpyHostToDevice));
+            h = dhold.as<float>();
+        }
+    }
+    cudaError_t e = launch_zoom_hold_tbl(l, tbl.as<int>(), tbl.as<int>() + out_size, out_size, o, h, hold_speed, 0);
+    if (e != cudaSuccess) { return cuda_fail(e, "launch_zoom_hold_tbl"); }
+    if (mem == B200_MEM_HOST) {
+        B200_CK(cudaMemcpy(out, o, (size_t)out_size * sizeof(float), cudaMemcpyDeviceToHost));
+        if (hold) { B200_CK(cudaMemcpy(hold, h, (size_t)out_size * sizeof(float), cudaMemcpyDeviceToHost)); }
+    }
+    else { B200_CK(cudaDeviceSynchronize()); }
+    return 0;
+}
+
+// ------------------------------------------------------------------ stand-alone blocks
+struct b200_block {
+    Chain chain;
+    Scheduler sch;
+    cudaStream_t stream = nullptr;
+    DevBuf in_dev;        // raw chains: the chunk as uploaded
+    int in_es = 2;
+    int max_chunk = 1000000;   // STREAM_BUFFER_SIZE (core/src/dsp/stream.h:9)
+    // rxvfo bookkeeping for the setters
+    double inSR = 0, outSR = 0, bw = 0;
+    bool is_rxvfo = false, is_xlator = false;
+};
+
+static b200_block* block_new() {
+    if (ensure_device()) { return nullptr; }
+    b200_block* b = new b200_block;
+    if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cuda_fail(cudaGetLastError(), "cudaStreamCreate");
+        delete b;
+        return nullptr;
+    }
+    b->sch.stream = b->stream;
+    return b;
+}
+static b200_block* block_finish(b200_block* b, int rc) {
+    if (!rc) {
+        b->in_es = b->chain.st[0]->in_es;
+        rc = b->chain.finalize(b->max_chunk);
+    }
+    if (!rc && b->chain.raw_input()) {
+        rc = b->sch.init_raw();
+        if (!rc) { rc = b->in_dev.alloc((size_t)b->max_chunk * sizeof(float2), false); }
+    }
+    if (rc) { b200_block_destroy(b); return nullptr; }
+    return b;
+}
+
+extern "C" void b200_block_destroy(b200_block* b) {
+    if (!b) { return; }
+    if (b->stream) { cudaStreamSynchronize(b->stream); cudaStreamDestroy(b->stream); }
+    delete b;
+}
+
+extern "C" b200_block* b200_xlator_create(double offsetHz, double sr) {
+    b200_block* b = block_new();
+    if (!b) { return nullptr; }
+    b->is_xlator = true;
+    return block_finish(b, b->chain.add_xlator(offsetHz, sr));
+}
+extern "C" int b200_xlator_set_offset(b200_block* b, double offsetHz, double sr) {
+    if (!b || !b->is_xlator) { set_error("not an xlator block"); return B200_EINVAL; }
+    ((XdStage*)b->chain.st[0].get())->set_offset_rad(hz_to_rads(offsetHz, sr));
+    return 0;
+}
+extern "C" b200_block* b200_decim_create(int ratio) {
+    if (ratio < 1 || (ratio & (ratio - 1)) || ratio > 8192) { set_error("ratio must be a power of two <= 8192"); return nullptr; }
+    b200_block* b = block_new();
+    if (!b) { return nullptr; }
+    return block_finish(b, b->chain.add_power_decim(ratio));
+}
+extern "C" b200_block* b200_resamp_create(double inSR, double outSR) {
+    if (inSR <= 0 || outSR <= 0) { set_error("bad rates"); return nullptr; }
+    b200_block* b = block_new();
+    if (!b) { return nullptr; }
+    return block_finish(b, b->chain.add_resampler(inSR, outSR));
+}
+extern "C" b200_block* b200_fir_cr_create(const float* taps, int n, int decim) {
+    if (!taps || n < 1 || decim < 1) { set_error("bad taps"); return nullptr; }
+    b200_block* b = block_new();
+    if (!b) { return nullptr; }
+    return block_finish(b, b->chain.add_fir_c(std::vector<float>(taps, taps + n), decim));
+}
+extern "C" b200_block* b200_fir_rr_create(const float* taps, int n) {
+    if (!taps || n < 1) { set_error("bad taps"); return nullptr; }
+    b200_block* b = block_new();
+    if (!b) { return nullptr; }
+    return block_finish(b, b->chain.add_fir_r(std::vector<float>(taps, taps + n), false));
+}
+extern "C" b200_block* b200_rxvfo_create(double inSR, double outSR, double bw, double offset) {
+    if (inSR <= 0 || outSR <= 0 || bw <= 0) { set_error("bad rates"); return nullptr; }
+    b200_block* b = block_new();
+    if (!b) { return nullptr; }
+    b->is_rxvfo = true; b->inSR = inSR; b->outSR = outSR; b->bw = bw;
+    return block_finish(b, b->chain.add_rxvfo(inSR, outSR, bw, offset));
+}
+extern "C" int b200_rxvfo_set_offset(b200_block* b, double offset) {
+    if (!b || !b->is_rxvfo) { set_error("not an RxVFO block"); return B200_EINVAL; }
+    ((XdStage*)b->chain.st[0].get())->set_offset_rad(hz_to_rads(-offset, b->inSR));
+    return 0;
+}
+extern "C" int b200_rxvfo_set_bandwidth(b200_block* b, double bw) {
+    if (!b || !b->is_rxvfo || bw <= 0) { set_error("not an RxVFO block / bad bandwidth"); return B200_EINVAL; }
+    if (b->bw == b->outSR || bw == b->outSR) { set_error("channel filter presence cannot change after creation"); return B200_EINVAL; }
+    FirCStage* f = nullptr;
+    for (auto& s : b->chain.st) {
+        if (s->kind == K_FIRC && ((FirCStage*)s.get())->decim == 1) { f = (FirCStage*)s.get(); }
+    }
+    if (!f) { set_error("no channel filter"); return B200_EINVAL; }
+    double fw = bw / 2.0;
+    f->pending = lowpass_taps(fw, fw * 0.1, b->outSR);
+    b->bw = bw;
+    return 0;
+}
+extern "C" b200_block* b200_quad_create(double dev, double sr) {
+    b200_block* b = block_new();
+    if (!b) { return nullptr; }
+    return block_finish(b, b->chain.add_quad(dev, sr));
+}
+extern "C" b200_block* b200_wfm_create(double dev, double sr, int stereo, int lowPass) {
+    if (stereo) { set_error("stereo/RDS branch of BroadcastFM is not built yet (SURVEY 8f rank 3)"); return nullptr; }
+    b200_block* b = block_new();
+    if (!b) { return nullptr; }
+    return block_finish(b, b->chain.add_wfm(dev, sr, lowPass != 0));
+}
+extern "C" b200_block* b200_nfm_create(double sr, double bw, int lowPass) {
+    b200_block* b = block_new();
+    if (!b) { return nullptr; }
+    return block_finish(b, b->chain.add_nfm(sr, bw, lowPass != 0));
+}
+extern "C" b200_block* b200_am_create(int agcMode, double bw, double att, double dec, double dcr, double sr) {
+    if (agcMode != 0 && agcMode != 1) { set_error("bad agcMode"); return nullptr; }
+    b200_block* b = block_new();
+    if (!b) { return nullptr; }
+    return block_finish(b, b->chain.add_am(agcMode, bw, att, dec, dcr, sr));
+}
+extern "C" b200_block* b200_ssb_create(int mode, double bw, double sr, double att, double dec) {
+    if (mode < 0 || mode > 2) { set_error("bad SSB mode"); return nullptr; }
+    b200_block* b = block_new();
+    if (!b) { return nullptr; }
+    return block_finish(b, b->chain.add_ssb(mode, bw, sr, att, dec));
+}
+
+extern "C" int b200_block_max_out(b200_block* b, int count) {
+    if (!b) { set_error("null block"); return B200_EINVAL; }
+    return b->chain.max_out(count);
+}
+
+extern "C" int b200_block_process(b200_block* b, int count, const void* in, void* out) {
+    if (!b || (count > 0 && (!in || !out))) { set_error("null argument"); return B200_EINVAL; }
+    if (count < 0 || count > b->max_chunk) { set_error("count %d exceeds the block's chunk limit %d", count, b->max_chunk); return B200_ECAP; }
+    cudaStream_t s = b->stream;
+    const bool raw = b->chain.raw_input();
+    const size_t in_bytes = (size_t)count * b->in_es * sizeof(float);
+    if (count > 0) {
+        void* dst = raw ? b->in_dev.p : (void*)b->chain.st[0]->in_data();
+        B200_CK(cudaMemcpyAsync(dst, in, in_bytes, cudaMemcpyHostToDevice, s));
+    }
+    b->chain.plan(count);
+    std::vector<Chain*> chains{ &b->chain };
+    int rc = b->sch.run(chains, raw ? b->in_dev.p : nullptr, FMT_CF32, count, raw);
+    if (rc) { return rc; }
+    if (b->chain.n_out > 0) {
+        B200_CK(cudaMemcpyAsync(out, b->chain.out.p, (size_t)b->chain.n_out * b->chain.out_es * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    B200_CK(cudaStreamSynchronize(s));
+    return b->chain.n_out;
+}
+
+extern "C" int b200_block_reset(b200_block* b) {
+    if (!b) { set_error("null block"); return B200_EINVAL; }
+    B200_CK(cudaStreamSynchronize(b->stream));
+    b->chain.reset_state();
+    return b->sch.reset_raw();
+}
+
+// ------------------------------------------------------------------ stand-alone spectrum handler
+struct b200_fft {
+    FftCore core;
+    DevBuf in, db, raw;
+};
+extern "C" b200_fft* b200_fft_create(int size, int nz, int window) {
+    if (ensure_device()) { return nullptr; }
+    b200_fft* f = new b200_fft;
+    int rc = f->core.create(size, nz, window);
+    if (!rc) { rc = f->in.alloc((size_t)nz * sizeof(float2), false); }
+    if (!rc) { rc = f->db.alloc((size_t)size * sizeof(float), false); }
+    if (!rc) { rc = f->raw.alloc((size_t)size * sizeof(float2), false); }
+    if (rc) { delete f; return nullptr; }
+    return f;
+}
+static int fft_run(b200_fft* f, const float* iq, float* out_db, float* out_c) {
+    if (!f || !iq) { set_error("null argument"); return B200_EINVAL; }
+    B200_CK(cudaMemcpy(f->in.p, iq, (size_t)f->core.nz * sizeof(float2), cudaMemcpyHostToDevice));
+    cudaError_t e = launch_fft_frame(f->core.plan, f->in.p, FMT_CF32, f->core.work.as<float2>(), f->db.as<float>(),
+                                     f->raw.as<float2>(), 0, nullptr);
+    if (e != cudaSuccess) { return cuda_fail(e, "launch_fft_frame"); }
+    if (out_db) { B200_CK(cudaMemcpy(out_db, f->db.p, (size_t)f->core.size * sizeof(float), cudaMemcpyDeviceToHost)); }
+    if (out_c) { B200_CK(cudaMemcpy(out_c, f->raw.p, (size_t)f->core.size * sizeof(float2), cudaMemcpyDeviceToHost)); }
+    B200_CK(cudaDeviceSynchronize());
+    return f->core.size;
+}
+extern "C" int b200_fft_frame(b200_fft* f, const float* iq, float* out_db) { return fft_run(f, iq, out_db, nullptr); }
+extern "C" int b200_fft_raw(b200_fft* f, const float* iq, float* out_c) { return fft_run(f, iq, nullptr, out_c); }
+extern "C" void b200_fft_destroy(b200_fft* f) {
+    if (f) { cudaDeviceSynchronize(); delete f; }
+}
+
+// ------------------------------------------------------------------ pinned host memory
+extern "C" void* b200_host_alloc(uint64_t bytes) {
+    if (ensure_device()) { return nullptr; }
+    void* p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 16);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaMallocHost"); return nullptr; }
+    return p;
+}
+extern "C" void b200_host_free(void* p) {
+    if (p) { cudaFreeHost(p); }
+}

@@ -1,0 +1,623 @@
+// sdrplusplus_b200/csrc/engine.cpp -- see engine.h
+#include "engine.h"
+#include "../../include/b200dsp.h"
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <map>
+
+namespace b200 {
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) { return B200_ENODEV; }
+    return B200_ECUDA;
+}
+
+// ------------------------------------------------------------------ DevBuf
+int DevBuf::alloc(size_t n, bool zero) {
+    release();
+    if (n == 0) { n = 16; }
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaMalloc"); }
+    bytes = n;
+    if (zero) {
+        e = cudaMemset(p, 0, n);
+        if (e != cudaSuccess) { return cuda_fail(e, "cudaMemset"); }
+    }
+    return 0;
+}
+void DevBuf::release() {
+    if (p) { cudaFree(p); }
+    p = nullptr;
+    bytes = 0;
+}
+
+int Stage::alloc_in(int cap) {
+    cap_in = cap;
+    return inbuf.alloc(((size_t)hist + (size_t)cap + 8) * in_es * sizeof(float));
+}
+
+// ------------------------------------------------------------------ XdStage
+void XdStage::configure(int D_, const std::vector<float>& taps) {
+    D = D_;
+    h = taps;
+    T = (int)taps.size();
+    QP = (T + D - 1 + D - 1) / D;                 // blocks of D covering the taps shifted by up to D-1
+    gpad_len = (D - 1) + (QP + 8) * D;            // room for the launcher's QC in {4,6,8} round-up
+    hist = T - 1;
+    taps_dirty = true;
+}
+
+static const long double kTwoPiL = 6.283185307179586476925286766559L;
+
+// The reference rotates by phaseDelta = ((float)cos(w), (float)sin(w)) (frequency_xlator.h:17,28): the
+// angle actually applied per sample is the angle of that fp32-rounded phasor, not w itself.
+static long double effective_omega(double rad) {
+    float dre = (float)std::cos(rad), dim = (float)std::sin(rad);
+    return atan2l((long double)dim, (long double)dre);
+}
+
+void XdStage::set_offset_rad(double rad) {
+    if (gpad.p && !retuned) { w_prev = w; retuned = true; }   // a retune of a running stage
+    offset_rad = rad;
+    long double turns = effective_omega(rad) / kTwoPiL;           // (-0.5, 0.5]
+    long double scaled = turns * 18446744073709551616.0L;         // * 2^64
+    if (scaled >= 9223372036854775807.0L) { scaled = 9223372036854775807.0L; }
+    if (scaled <= -9223372036854775807.0L) { scaled = -9223372036854775807.0L; }
+    w = (unsigned long long)(long long)llroundl(scaled);
+    taps_dirty = true;
+}
+
+int XdStage::upload_taps(cudaStream_t s) {
+    if (!gpad.p || gpad.bytes < (size_t)gpad_len * sizeof(float2)) {
+        int rc = gpad.alloc((size_t)gpad_len * sizeof(float2));
+        if (rc) { return rc; }
+    }
+    std::vector<float2> g((size_t)gpad_len, make_float2(0.0f, 0.0f));
+    const long double om = effective_omega(offset_rad);
+    for (int k = 0; k < T; k++) {
+        long double a = om * (long double)k;
+        g[(size_t)(D - 1) + k] = make_float2((float)((long double)h[k] * cosl(a)), (float)((long double)h[k] * sinl(a)));
+    }
+    B200_CK(cudaMemcpyAsync(gpad.p, g.data(), g.size() * sizeof(float2), cudaMemcpyHostToDevice, s));
+    if (!hdev.p) {
+        int rc = hdev.alloc((size_t)T * sizeof(float));
+        if (rc) { return rc; }
+        B200_CK(cudaMemcpyAsync(hdev.p, h.data(), (size_t)T * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    taps_dirty = false;
+    return 0;
+}
+
+int XdStage::plan(int n) {
+    n_in = n;
+    chunk_offset = offset;
+    chunk_phase0 = phase;
+    chunk_retuned = retuned && n > 0;
+    chunk_w_prev = w_prev;
+    if (n > 0) { retuned = false; }
+    n_out = (offset < n) ? (n - offset + D - 1) / D : 0;
+    offset = offset + n_out * D - n;
+    phase += w * (unsigned long long)(long long)n;
+    return n_out;
+}
+
+// ------------------------------------------------------------------ FirCStage
+int FirCStage::configure(const std::vector<float>& t, int decim_) {
+    ntaps = (int)t.size();
+    decim = decim_;
+    hist = ntaps - 1;
+    int rc = taps.alloc((size_t)ntaps * sizeof(float));
+    if (rc) { return rc; }
+    B200_CK(cudaMemcpy(taps.p, t.data(), (size_t)ntaps * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+int FirCStage::plan(int n) {
+    n_in = n;
+    chunk_offset = offset;
+    n_out = (offset < n) ? (n - offset + decim - 1) / decim : 0;
+    offset = offset + n_out * decim - n;
+    return n_out;
+}
+
+// ------------------------------------------------------------------ PolyStage
+int PolyStage::configure(int interp_, int decim_, const std::vector<float>& t) {
+    interp = interp_;
+    decim = decim_;
+    std::vector<float> b = build_polyphase_bank(interp, t, tpp);
+    hist = tpp - 1;
+    int rc = bank.alloc(b.size() * sizeof(float));
+    if (rc) { return rc; }
+    B200_CK(cudaMemcpy(bank.p, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+int PolyStage::plan(int n) {
+    n_in = n;
+    chunk_phase = phase;
+    chunk_offset = offset;
+    long long avail = ((long long)n - offset) * interp - phase;
+    long long no = avail > 0 ? (avail + decim - 1) / decim : 0;
+    n_out = (int)no;
+    long long tend = (long long)phase + no * decim;
+    offset = (int)((long long)offset + tend / interp - n);
+    phase = (int)(tend % interp);
+    return n_out;
+}
+
+// ------------------------------------------------------------------ QuadStage
+int QuadStage::configure(double deviationHz, double samplerate) {
+    inv_dev = (float)(1.0 / hz_to_rads(deviationHz, samplerate));    // quadrature.h:19-26
+    return state.alloc(2 * sizeof(float));
+}
+int QuadStage::plan(int n) {
+    n_in = n;
+    n_out = n;
+    chunk_flip = flip;
+    if (n > 0) { flip ^= 1; }
+    return n;
+}
+
+// ------------------------------------------------------------------ FirRStage
+int FirRStage::configure(const std::vector<float>& t, bool stereo_) {
+    ntaps = (int)t.size();
+    stereo = stereo_ ? 1 : 0;
+    out_es = stereo ? 2 : 1;
+    hist = ntaps - 1;
+    int rc = taps.alloc((size_t)ntaps * sizeof(float));
+    if (rc) { return rc; }
+    B200_CK(cudaMemcpy(taps.p, t.data(), (size_t)ntaps * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// ------------------------------------------------------------------ SeqStage
+static void agc_coefs(SeqJob& j, double setPoint, double attack, double decay, double maxGain, double maxOut) {
+    // loop::AGC::init (agc.h:13-24): doubles narrowed to float members
+    j.set_point = (float)setPoint;
+    j.attack = (float)attack;
+    j.inv_attack = 1.0f - j.attack;
+    j.decay = (float)decay;
+    j.inv_decay = 1.0f - j.decay;
+    j.max_gain = (float)maxGain;
+    j.max_out = (float)maxOut;
+}
+int SeqStage::configure_am(int agcMode, double attack, double decay, double dcRate) {
+    memset(&proto, 0, sizeof(proto));
+    proto.kind = 0;
+    proto.agc_mode = agcMode;
+    agc_coefs(proto, 1.0, attack, decay, 10e6, 10.0);            // am.h:33-34
+    proto.dc_rate = (float)dcRate;
+    memset(init_state, 0, sizeof(init_state));
+    // amp = setPoint / initGain with initGain = INFINITY -> 0  (agc.h:22, am.h:33)
+    init_state[0] = 0.0f;
+    init_state[1] = 0.0f;
+    int rc = state.alloc(sizeof(init_state));
+    if (rc) { return rc; }
+    B200_CK(cudaMemcpy(state.p, init_state, sizeof(init_state), cudaMemcpyHostToDevice));
+    return 0;
+}
+int SeqStage::configure_ssb(int mode, double bandwidth, double samplerate, double attack, double decay) {
+    memset(&proto, 0, sizeof(proto));
+    proto.kind = 1;
+    agc_coefs(proto, 1.0, attack, decay, 10e6, 10.0);            // ssb.h:29
+    double tr = (mode == 0) ? bandwidth / 2.0 : ((mode == 1) ? -bandwidth / 2.0 : 0.0);   // ssb.h:106-116
+    double rad = hz_to_rads(tr, samplerate);
+    proto.delta_re = (float)std::cos(rad);
+    proto.delta_im = (float)std::sin(rad);
+    memset(init_state, 0, sizeof(init_state));
+    init_state[3] = 1.0f;                                          // rotator phase (1, 0)
+    int rc = state.alloc(sizeof(init_state));
+    if (rc) { return rc; }
+    B200_CK(cudaMemcpy(state.p, init_state, sizeof(init_state), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// ------------------------------------------------------------------ Chain
+int Chain::finalize(int max_in) {
+    if (st.empty()) { set_error("empty chain"); return B200_EINVAL; }
+    int cap = max_in;
+    for (auto& s : st) {
+        if (s->kind != K_XD) {
+            int rc = s->alloc_in(cap);
+            if (rc) { return rc; }
+        }
+        else { s->cap_in = cap; }
+        cap = s->max_out(cap);
+    }
+    out_es = st.back()->out_es;
+    out_cap = cap;
+    return out.alloc(((size_t)cap + 8) * out_es * sizeof(float));
+}
+int Chain::plan(int n) {
+    for (auto& s : st) { n = s->plan(n); }
+    n_out = n;
+    return n;
+}
+int Chain::max_out(int n) const {
+    for (auto& s : st) { n = s->max_out(n); }
+    return n;
+}
+void Chain::reset_state() {
+    for (auto& s : st) {
+        s->reset_state();
+        if (s->inbuf.p && s->hist > 0) { cudaMemset(s->inbuf.p, 0, (size_t)s->hist * s->in_es * sizeof(float)); }
+        if (s->kind == K_QUAD) {
+            QuadStage* q = (QuadStage*)s.get();
+            cudaMemset(q->state.p, 0, 2 * sizeof(float));
+            q->flip = 0;
+        }
+        if (s->kind == K_SEQ) {
+            SeqStage* q = (SeqStage*)s.get();
+            // AM::reset / AGC::reset (am.h:90-98, agc.h:64-68); the SSB demodulator has no reset
+            cudaMemcpy(q->state.p, q->init_state, sizeof(q->init_state), cudaMemcpyHostToDevice);
+        }
+    }
+}
+
+int Chain::add_xlator(double offsetHz, double samplerate) {
+    auto x = std::make_unique<XdStage>();
+    x->configure(1, std::vector<float>{ 1.0f });
+    x->set_offset_rad(hz_to_rads(offsetHz, samplerate));
+    st.push_back(std::move(x));
+    return 0;
+}
+
+int Chain::add_power_decim(int ratio) {
+    if (ratio == 1) { return add_fir_c(std::vector<float>{ 1.0f }, 1); }   // memcpy path (power_decimator.h:53-56)
+    const DecimPlan* p = find_decim_plan(ratio);
+    if (!p) { set_error("no decimation plan for ratio %d (decim_plans.bin not found?)", ratio); return B200_ENOPLAN; }
+    for (auto& s : p->stages) {
+        int rc = add_fir_c(s.taps, s.decim);
+        if (rc) { return rc; }
+    }
+    return 0;
+}
+
+int Chain::add_fir_c(const std::vector<float>& taps, int decim) {
+    auto f = std::make_unique<FirCStage>();
+    int rc = f->configure(taps, decim);
+    if (rc) { return rc; }
+    st.push_back(std::move(f));
+    return 0;
+}
+int Chain::add_fir_r(const std::vector<float>& taps, bool stereo) {
+    auto f = std::make_unique<FirRStage>();
+    int rc = f->configure(taps, stereo);
+    if (rc) { return rc; }
+    st.push_back(std::move(f));
+    return 0;
+}
+
+int Chain::add_resampler(double inSR, double outSR) {
+    ResampPlan pl = make_resamp_plan(inSR, outSR);
+    if (pl.use_decim) {
+        int rc = add_power_decim(pl.predec_ratio);
+        if (rc) { return rc; }
+    }
+    if (!pl.rtaps.empty()) {
+        auto r = std::make_unique<PolyStage>();
+        int rc = r->configure(pl.interp, pl.decim, pl.rtaps);
+        if (rc) { return rc; }
+        st.push_back(std::move(r));
+    }
+    if (!pl.use_decim && pl.rtaps.empty()) { return add_fir_c(std::vector<float>{ 1.0f }, 1); }  // Mode::NONE memcpy
+    return 0;
+}
+
+// channel::RxVFO::init (rx_vfo.h:17-31): xlator(-offset) -> RationalResampler -> [FIR lowPass(bw/2, 0.1*bw/2, outSR)]
+int Chain::add_rxvfo(double inSR, double outSR, double bw, double offset) {
+    ResampPlan pl = make_resamp_plan(inSR, outSR);
+    auto x = std::make_unique<XdStage>();
+    size_t first_other = 0;
+    const DecimPlan* dp = nullptr;
+    if (pl.use_decim) {
+        dp = find_decim_plan(pl.predec_ratio);
+        if (!dp) { set_error("no decimation plan for ratio %d (decim_plans.bin not found?)", pl.predec_ratio); return B200_ENOPLAN; }
+        x->configure(dp->stages[0].decim, dp->stages[0].taps);     // xlator fused with the first DecimatingFIR
+        first_other = 1;
+    }
+    else {
+        x->configure(1, std::vector<float>{ 1.0f });
+    }
+    x->set_offset_rad(hz_to_rads(-offset, inSR));
+    st.push_back(std::move(x));
+    if (dp) {
+        for (size_t i = first_other; i < dp->stages.size(); i++) {
+            int rc = add_fir_c(dp->stages[i].taps, dp->stages[i].decim);
+            if (rc) { return rc; }
+        }
+    }
+    if (!pl.rtaps.empty()) {
+        auto r = std::make_unique<PolyStage>();
+        int rc = r->configure(pl.interp, pl.decim, pl.rtaps);
+        if (rc) { return rc; }
+        st.push_back(std::move(r));
+    }
+    if (bw != outSR) {
+        double fw = bw / 2.0;
+        int rc = add_fir_c(lowpass_taps(fw, fw * 0.1, outSR), 1);
+        if (rc) { return rc; }
+    }
+    return 0;
+}
+
+int Chain::add_quad(double deviationHz, double samplerate) {
+    auto q = std::make_unique<QuadStage>();
+    int rc = q->configure(deviationHz, samplerate);
+    if (rc) { return rc; }
+    st.push_back(std::move(q));
+    return 0;
+}
+int Chain::add_wfm(double deviationHz, double samplerate, bool lowPass) {
+    int rc = add_quad(deviationHz, samplerate);
+    if (rc) { return rc; }
+    if (lowPass) { return add_fir_r(lowpass_taps(15000.0, 4000.0, samplerate), true); }   // broadcast_fm.h:45
+    st.push_back(std::make_unique<M2SStage>());
+    return 0;
+}
+int Chain::add_nfm(double samplerate, double bandwidth, bool lowPass) {
+    int rc = add_quad(bandwidth / 2.0, samplerate);                                         // fm.h:28
+    if (rc) { return rc; }
+    if (lowPass) { return add_fir_r(lowpass_taps(bandwidth / 2.0, (bandwidth / 2.0) * 0.1, samplerate), true); } // fm.h:123
+    st.push_back(std::make_unique<M2SStage>());
+    return 0;
+}
+int Chain::add_am(int agcMode, double bandwidth, double attack, double decay, double dcRate, double samplerate) {
+    auto s = std::make_unique<SeqStage>();
+    int rc = s->configure_am(agcMode, attack, decay, dcRate);
+    if (rc) { return rc; }
+    st.push_back(std::move(s));
+    return add_fir_r(lowpass_taps(bandwidth / 2.0, (bandwidth / 2.0) * 0.1, samplerate), true);   // am.h:36-37
+}
+int Chain::add_ssb(int mode, double bandwidth, double samplerate, double attack, double decay) {
+    auto s = std::make_unique<SeqStage>();
+    int rc = s->configure_ssb(mode, bandwidth, samplerate, attack, decay);
+    if (rc) { return rc; }
+    st.push_back(std::move(s));
+    st.push_back(std::make_unique<M2SStage>());
+    return 0;
+}
+
+// ------------------------------------------------------------------ Scheduler
+int Scheduler::init_raw() {
+    if (raw_hist.p) { return 0; }
+    return raw_hist.alloc((size_t)RAW_HIST * sizeof(float2));
+}
+int Scheduler::reset_raw() {
+    if (raw_hist.p) { B200_CK(cudaMemset(raw_hist.p, 0, raw_hist.bytes)); }
+    return 0;
+}
+
+// FIR::setTaps (fir.h:31-52): new taps, keep the most recent history
+static int apply_pending_taps(FirCStage* f, cudaStream_t s) {
+    if (f->pending.empty()) { return 0; }
+    B200_CK(cudaStreamSynchronize(s));
+    const int newT = (int)f->pending.size(), oldT = f->ntaps;
+    const int newH = newT - 1, oldH = oldT - 1;
+    DevBuf nb;
+    int rc = nb.alloc(((size_t)newH + f->cap_in + 8) * f->in_es * sizeof(float));
+    if (rc) { return rc; }
+    int keep = std::min(newH, oldH);
+    if (keep > 0) {
+        B200_CK(cudaMemcpy(nb.as<float>() + (size_t)(newH - keep) * f->in_es, f->inbuf.as<float>() + (size_t)(oldH - keep) * f->in_es,
+                           (size_t)keep * f->in_es * sizeof(float), cudaMemcpyDeviceToDevice));
+    }
+    std::swap(f->inbuf.p, nb.p);
+    std::swap(f->inbuf.bytes, nb.bytes);
+    rc = f->taps.alloc((size_t)newT * sizeof(float));
+    if (rc) { return rc; }
+    B200_CK(cudaMemcpy(f->taps.p, f->pending.data(), (size_t)newT * sizeof(float), cudaMemcpyHostToDevice));
+    f->ntaps = newT;
+    f->hist = newH;
+    if (f->decim != 1) { f->offset = 0; }          // DecimatingFIR::setTaps (decimating_fir.h:18-25)
+    f->pending.clear();
+    return 0;
+}
+
+template <class P, class L>
+static int flush_batch(P& p, L launch, cudaStream_t s, long long& launches) {
+    if (p.njobs == 0) { return 0; }
+    cudaError_t e = launch(p, s);
+    if (e != cudaSuccess) { return cuda_fail(e, "kernel launch"); }
+    launches++;
+    p.njobs = 0;
+    return 0;
+}
+
+int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int count, bool carry_raw) {
+    // ---- wiring + deferred parameter changes ----
+    size_t depth = 0;
+    for (Chain* c : chains) {
+        for (auto& sp : c->st) {
+            if (sp->kind == K_FIRC) {
+                int rc = apply_pending_taps((FirCStage*)sp.get(), stream);
+                if (rc) { return rc; }
+            }
+        }
+    }
+    for (Chain* c : chains) {
+        depth = std::max(depth, c->st.size());
+        for (size_t i = 0; i < c->st.size(); i++) {
+            Stage* s = c->st[i].get();
+            s->out_ptr = (i + 1 < c->st.size()) ? c->st[i + 1]->in_data() : c->out.as<float>();
+            if (s->kind == K_XD) {
+                XdStage* x = (XdStage*)s;
+                if (x->taps_dirty) {
+                    int rc = x->upload_taps(stream);
+                    if (rc) { return rc; }
+                }
+            }
+        }
+    }
+    // ---- stage 1: every raw-input chain, grouped by first-stage decimation so they share the IQ tile ----
+    std::map<int, std::vector<XdStage*>> groups;
+    for (Chain* c : chains) {
+        if (c->raw_input()) {
+            XdStage* x = (XdStage*)c->st[0].get();
+            groups[x->D].push_back(x);
+        }
+    }
+    for (auto& kv : groups) {
+        std::vector<XdStage*>& g = kv.second;
+        for (size_t b = 0; b < g.size(); b += B200_BATCH) {
+            XdParams p;
+            memset(&p, 0, sizeof(p));
+            p.in = raw;
+            p.hist = raw_hist.as<float2>();
+            p.hist_len = RAW_HIST;
+            p.count = count;
+            p.D = kv.first;
+            p.QP = 1;
+            p.njobs = (int)std::min<size_t>(B200_BATCH, g.size() - b);
+            for (int v = 0; v < p.njobs; v++) {
+                XdStage* x = g[b + v];
+                p.job[v].out = (float2*)x->out_ptr;
+                p.job[v].gpad = x->gpad.as<float2>();
+                p.job[v].phase0 = x->chunk_phase0;
+                p.job[v].w = x->w;
+                p.job[v].offset = x->chunk_offset;
+                p.job[v].n_out = x->n_out;
+                p.job[v].T = x->T;
+                p.job[v].h = x->hdev.as<float>();
+                p.job[v].w_prev = x->chunk_w_prev;
+                p.job[v].retuned = x->chunk_retuned ? 1 : 0;
+                p.QP = std::max(p.QP, x->QP);
+            }
+            // the tiled kernel pads every job to the group's QP: all jobs of a batch must have room for it
+            int variant = s1_variant;
+            for (int v = 0; v < p.njobs; v++) {
+                if (g[b + v]->gpad_len < (p.D - 1) + (p.QP + 8) * p.D) { variant = 0; }
+            }
+            int nl = 0;
+            cudaError_t e = launch_xlate_decim(p, fmt, variant, stream, &nl);
+            if (e != cudaSuccess) { return cuda_fail(e, "launch_xlate_decim"); }
+            e = launch_xd_edge(p, fmt, stream, &nl);
+            if (e != cudaSuccess) { return cuda_fail(e, "launch_xd_edge"); }
+            launches += nl;
+        }
+    }
+    // ---- remaining stages level by level: one launch per stage kind per level (batches of 16 VFOs) ----
+    for (size_t lvl = 0; lvl < depth; lvl++) {
+        FirParams fp; fp.njobs = 0; fp.max_out = 0;
+        PolyParams pp; pp.njobs = 0; pp.max_out = 0;
+        QuadParams qp; qp.njobs = 0; qp.max_n = 0;
+        FirRParams rp; rp.njobs = 0; rp.max_out = 0;
+        SeqParams sp; sp.njobs = 0;
+        M2SParams mp; mp.njobs = 0; mp.max_n = 0;
+        for (Chain* c : chains) {
+            if (lvl >= c->st.size()) { continue; }
+            Stage* s = c->st[lvl].get();
+            int rc = 0;
+            switch (s->kind) {
+            case K_XD: break;
+            case K_FIRC: {
+                FirCStage* f = (FirCStage*)s;
+                if (f->n_out <= 0) { break; }
+                FirJob& j = fp.job[fp.njobs++];
+                j.in = f->inbuf.as<float2>(); j.out = (float2*)f->out_ptr; j.taps = f->taps.as<float>();
+                j.ntaps = f->ntaps; j.decim = f->decim; j.offset = f->chunk_offset; j.n_out = f->n_out;
+                fp.max_out = std::max(fp.max_out, f->n_out);
+                if (fp.njobs == B200_BATCH) { rc = flush_batch(fp, launch_fir_c, stream, launches); fp.max_out = 0; }
+                break;
+            }
+            case K_POLY: {
+                PolyStage* f = (PolyStage*)s;
+                if (f->n_out <= 0) { break; }
+                PolyJob& j = pp.job[pp.njobs++];
+                j.in = f->inbuf.as<float2>(); j.out = (float2*)f->out_ptr; j.bank = f->bank.as<float>();
+                j.tpp = f->tpp; j.interp = f->interp; j.decim = f->decim; j.phase0 = f->chunk_phase; j.offset0 = f->chunk_offset;
+                j.n_out = f->n_out;
+                pp.max_out = std::max(pp.max_out, f->n_out);
+                if (pp.njobs == B200_BATCH) { rc = flush_batch(pp, launch_poly, stream, launches); pp.max_out = 0; }
+                break;
+            }
+            case K_QUAD: {
+                QuadStage* f = (QuadStage*)s;
+                if (f->n_out <= 0) { break; }
+                QuadJob& j = qp.job[qp.njobs++];
+                j.in = (const float2*)f->in_data(); j.out = f->out_ptr;
+                j.state_in = f->state.as<float>() + f->chunk_flip; j.state_out = f->state.as<float>() + (f->chunk_flip ^ 1);
+                j.inv_dev = f->inv_dev; j.n = f->n_out;
+                qp.max_n = std::max(qp.max_n, f->n_out);
+                if (qp.njobs == B200_BATCH) { rc = flush_batch(qp, launch_quad, stream, launches); qp.max_n = 0; }
+                break;
+            }
+            case K_FIRR: {
+                FirRStage* f = (FirRStage*)s;
+                if (f->n_out <= 0) { break; }
+                FirRJob& j = rp.job[rp.njobs++];
+                j.in = f->inbuf.as<float>(); j.out = f->out_ptr; j.taps = f->taps.as<float>();
+                j.ntaps = f->ntaps; j.n_out = f->n_out; j.stereo = f->stereo;
+                rp.max_out = std::max(rp.max_out, f->n_out);
+                if (rp.njobs == B200_BATCH) { rc = flush_batch(rp, launch_fir_r, stream, launches); rp.max_out = 0; }
+                break;
+            }
+            case K_SEQ: {
+                SeqStage* f = (SeqStage*)s;
+                if (f->n_out <= 0) { break; }
+                SeqJob& j = sp.job[sp.njobs++];
+                j = f->proto;
+                j.in = (const float2*)f->in_data(); j.out = f->out_ptr; j.state = f->state.as<float>(); j.n = f->n_out;
+                if (sp.njobs == B200_BATCH) { rc = flush_batch(sp, launch_seq, stream, launches); }
+                break;
+            }
+            case K_M2S: {
+                if (s->n_out <= 0) { break; }
+                M2SJob& j = mp.job[mp.njobs++];
+                j.in = s->in_data(); j.out = s->out_ptr; j.n = s->n_out;
+                mp.max_n = std::max(mp.max_n, s->n_out);
+                if (mp.njobs == B200_BATCH) { rc = flush_batch(mp, launch_m2s, stream, launches); mp.max_n = 0; }
+                break;
+            }
+            }
+            if (rc) { return rc; }
+        }
+        int rc;
+        if ((rc = flush_batch(fp, launch_fir_c, stream, launches))) { return rc; }
+        if ((rc = flush_batch(pp, launch_poly, stream, launches))) { return rc; }
+        if ((rc = flush_batch(qp, launch_quad, stream, launches))) { return rc; }
+        if ((rc = flush_batch(rp, launch_fir_r, stream, launches))) { return rc; }
+        if ((rc = flush_batch(sp, launch_seq, stream, launches))) { return rc; }
+        if ((rc = flush_batch(mp, launch_m2s, stream, launches))) { return rc; }
+    }
+    // ---- history carry (the memmove at the end of every reference process()) ----
+    CarryParams cp;
+    cp.njobs = 0;
+    auto push = [&](const CarryJob& j) -> int {
+        cp.job[cp.njobs++] = j;
+        if (cp.njobs == CARRY_BATCH) { return flush_batch(cp, launch_carry, stream, launches); }
+        return 0;
+    };
+    if (carry_raw && count > 0) {
+        CarryJob j;
+        j.dst = raw_hist.as<float>(); j.a = raw_hist.as<float>(); j.b = raw;
+        j.h = RAW_HIST; j.la = RAW_HIST; j.lb = count; j.esize = 2; j.bfmt = fmt;
+        int rc = push(j);
+        if (rc) { return rc; }
+    }
+    for (Chain* c : chains) {
+        for (auto& sp : c->st) {
+            Stage* s = sp.get();
+            if (s->kind == K_XD || s->hist <= 0 || s->n_in <= 0) { continue; }
+            CarryJob j;
+            j.dst = s->inbuf.as<float>(); j.a = s->inbuf.as<float>(); j.b = s->in_data();
+            j.h = s->hist; j.la = s->hist; j.lb = s->n_in; j.esize = s->in_es; j.bfmt = -1;
+            int rc = push(j);
+            if (rc) { return rc; }
+        }
+    }
+    return flush_batch(cp, launch_carry, stream, launches);
+}
+
+}

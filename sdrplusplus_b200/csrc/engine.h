@@ -1,0 +1,176 @@
+// sdrplusplus_b200/csrc/engine.h -- host runtime of libb200dsp: stages with carried state, chains,
+// the per-chunk scheduler that batches the same stage of every VFO into one launch, and the FFT framer.
+// The integer state (decimation offsets, polyphase phase, frame cursor) is mirrored on the host so every
+// per-chunk output count is known without a device round trip.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "kernels.cuh"
+#include "design.h"
+
+namespace b200 {
+
+void set_error(const char* fmt, ...);
+const char* last_error();
+int cuda_fail(cudaError_t e, const char* what);   // records message, returns B200_ECUDA
+#define B200_CK(call)                                                     \
+    do {                                                                  \
+        cudaError_t _e = (call);                                          \
+        if (_e != cudaSuccess) { return b200::cuda_fail(_e, #call); }     \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    int alloc(size_t n, bool zero = true);
+    void release();
+    template <class T> T* as() const { return (T*)p; }
+};
+
+enum StageKind { K_XD, K_FIRC, K_POLY, K_QUAD, K_FIRR, K_SEQ, K_M2S };
+
+struct Stage {
+    StageKind kind;
+    int in_es = 2, out_es = 2;   // floats per input / output sample
+    int hist = 0;                // history samples kept in front of the data in inbuf
+    int cap_in = 0;              // max input samples per chunk
+    DevBuf inbuf;                // [hist | data]; unused by K_XD (reads the shared raw IQ)
+    int n_in = 0, n_out = 0;     // this chunk
+    float* out_ptr = nullptr;    // where this chunk's output goes (set by the scheduler)
+    virtual ~Stage() {}
+    virtual int plan(int n) = 0;             // host: output count for n inputs, advances the mirrored state
+    virtual int max_out(int n) const = 0;    // upper bound
+    virtual void reset_state() {}
+    float* in_data() const { return inbuf.as<float>() + (size_t)hist * in_es; }
+    int alloc_in(int cap);
+};
+
+struct XdStage : Stage {
+    int D = 1, T = 1;
+    std::vector<float> h;        // real taps of the first decimation stage ({1} for a pure translate)
+    double offset_rad = 0.0;     // hzToRads(-vfoOffset, fs) as the reference passes it to the xlator
+    unsigned long long phase = 0, w = 0, w_prev = 0;
+    bool retuned = false, chunk_retuned = false; unsigned long long chunk_w_prev = 0;
+    DevBuf hdev;                 // real taps on the device (retune edge kernel)
+    int offset = 0;              // DecimatingFIR::offset
+    DevBuf gpad;                 // complex taps, padded
+    int gpad_len = 0;
+    int QP = 1;
+    bool taps_dirty = true;
+    XdStage() { kind = K_XD; }
+    void configure(int D_, const std::vector<float>& taps);
+    void set_offset_rad(double rad);       // FrequencyXlator::setOffset: phase-continuous
+    int upload_taps(cudaStream_t s);
+    int plan(int n) override;
+    int max_out(int n) const override { return (n + D - 1) / D + 1; }
+    void reset_state() override { phase = 0; offset = 0; retuned = false; }
+    unsigned long long chunk_phase0 = 0; int chunk_offset = 0;   // snapshot used by this chunk's launch
+};
+
+struct FirCStage : Stage {
+    int ntaps = 1, decim = 1, offset = 0, chunk_offset = 0;
+    DevBuf taps;
+    std::vector<float> pending;  // FIR::setTaps applied at the next chunk boundary
+    FirCStage() { kind = K_FIRC; }
+    int configure(const std::vector<float>& t, int decim_);
+    int plan(int n) override;
+    int max_out(int n) const override { return (n + decim - 1) / decim + 1; }
+    void reset_state() override { offset = 0; }
+};
+
+struct PolyStage : Stage {
+    int interp = 1, decim = 1, tpp = 1, phase = 0, offset = 0, chunk_phase = 0, chunk_offset = 0;
+    DevBuf bank;
+    PolyStage() { kind = K_POLY; }
+    int configure(int interp_, int decim_, const std::vector<float>& taps);
+    int plan(int n) override;
+    int max_out(int n) const override { return (int)(((long long)n * interp + decim - 1) / decim) + 2; }
+    void reset_state() override { phase = 0; offset = 0; }
+};
+
+struct QuadStage : Stage {
+    float inv_dev = 1.0f;
+    DevBuf state;                // 2 floats, ping-pong
+    int flip = 0, chunk_flip = 0;
+    QuadStage() { kind = K_QUAD; out_es = 1; }
+    int configure(double deviationHz, double samplerate);
+    int plan(int n) override;
+    int max_out(int n) const override { return n; }
+};
+
+struct FirRStage : Stage {
+    int ntaps = 1, stereo = 0;
+    DevBuf taps;
+    FirRStage() { kind = K_FIRR; in_es = 1; out_es = 1; }
+    int configure(const std::vector<float>& t, bool stereo_);
+    int plan(int n) override { n_in = n; n_out = n; return n; }
+    int max_out(int n) const override { return n; }
+};
+
+struct SeqStage : Stage {
+    SeqJob proto;                // coefficients; pointers filled per chunk
+    DevBuf state;
+    float init_state[SEQ_STATE_FLOATS];
+    SeqStage() { kind = K_SEQ; out_es = 1; }
+    int configure_am(int agcMode, double attack, double decay, double dcRate);
+    int configure_ssb(int mode, double bandwidth, double samplerate, double attack, double decay);
+    int plan(int n) override { n_in = n; n_out = n; return n; }
+    int max_out(int n) const override { return n; }
+};
+
+struct M2SStage : Stage {
+    M2SStage() { kind = K_M2S; in_es = 1; out_es = 2; }
+    int plan(int n) override { n_in = n; n_out = n; return n; }
+    int max_out(int n) const override { return n; }
+};
+
+// A chain = one VFO (+ demodulator) or one stand-alone block.
+struct Chain {
+    std::vector<std::unique_ptr<Stage>> st;
+    DevBuf out;                  // final output of the chain
+    int out_es = 2;
+    int out_cap = 0;
+    int n_out = 0;               // this chunk
+    bool raw_input() const { return !st.empty() && st[0]->kind == K_XD; }
+    int finalize(int max_in);    // allocates stage buffers for chunks of up to max_in samples
+    int plan(int n);             // all stages; returns final count
+    int max_out(int n) const;
+    void reset_state();
+    // builders (reference block -> stage list)
+    int add_rxvfo(double inSR, double outSR, double bw, double offset);     // rx_vfo.h:17-31
+    int add_xlator(double offsetHz, double samplerate);
+    int add_power_decim(int ratio);                                         // power_decimator.h:92-110
+    int add_resampler(double inSR, double outSR);                           // rational_resampler.h:120-165
+    int add_fir_c(const std::vector<float>& taps, int decim);
+    int add_fir_r(const std::vector<float>& taps, bool stereo);
+    int add_quad(double deviationHz, double samplerate);
+    int add_wfm(double deviationHz, double samplerate, bool lowPass);       // broadcast_fm.h:36-52 (mono)
+    int add_nfm(double samplerate, double bandwidth, bool lowPass);         // fm.h:24-40
+    int add_am(int agcMode, double bandwidth, double attack, double decay, double dcRate, double samplerate); // am.h:28-45
+    int add_ssb(int mode, double bandwidth, double samplerate, double attack, double decay); // ssb.h:22-35
+};
+
+// Runs a set of chains over one chunk: stage-1 launches grouped by decimation, then level by level one
+// launch per stage kind, then the history carry.
+struct Scheduler {
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    int s1_variant = 1;
+    DevBuf raw_hist;             // last RAW_HIST samples of the raw IQ stream (cf32)
+    static const int RAW_HIST = 1024;
+    int init_raw();
+    // raw: device pointer to the chunk (format fmt) for chains with raw_input(); typed chains were fed by
+    // copying into st[0]->in_data() beforehand.  counts were planned already (Chain::plan).
+    int run(std::vector<Chain*>& chains, const void* raw, int fmt, int count, bool carry_raw);
+    int reset_raw();
+};
+
+}

@@ -1,0 +1,905 @@
+// sdrplusplus_b200/csrc/kernels.cu -- hand-written sm_100a kernels of the SDR++ streaming DSP hot path.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (see __graft_entry__.build()).
+// No cuFFT / cuBLAS / Thrust on any path; tensor cores are not used (no dense contraction here).
+//
+// Kernel inventory (reference call site each one replaces):
+//   k_xd_tile / k_xd_simple   FrequencyXlator::process + first DecimatingFIR, all VFOs share one IQ tile
+//                             (frequency_xlator.h:43-50, decimating_fir.h:45-68, splitter.h:46-61)
+//   k_fir_c                   DecimatingFIR / FIR<complex_t,float>::process (decimating_fir.h:45-68, fir.h:62-83)
+//   k_poly                    PolyphaseResampler::process (polyphase_resampler.h:69-99)
+//   k_quad                    Quadrature::process (quadrature.h:39-46)
+//   k_fir_r                   FIR<float,float>::process + LRToStereo/MonoToStereo (fir.h:69, l_r_to_stereo.h:21)
+//   k_seq                     AM: AGC/magnitude/DCBlocker (am.h:101-133, agc.h:70-110, dc_blocker.h:54-60)
+//                             SSB: second FrequencyXlator + ComplexToReal + AGC (ssb.h:77-92)
+//   k_carry                   delay-line memmove at the end of process() (fir.h:80, decimating_fir.h:65)
+//   k_fft_single / k_fft_p1 / k_fft_p2
+//                             IQFrontEnd::handler: window multiply, forward FFT, 10log10(|X/N|^2)
+//                             (iq_frontend.cpp:248-267)
+//   k_zoom_hold               doZoom + peak hold (waterfall.cpp:65-90, 935-939)
+#include "kernels.cuh"
+#include <math.h>
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+template <int FMT>
+__device__ __forceinline__ float2 load_iq(const void* __restrict__ p, long long i) {
+    if (FMT == FMT_CF32) {
+        return __ldg(reinterpret_cast<const float2*>(p) + i);
+    }
+    else if (FMT == FMT_CS16) {
+        short2 v = __ldg(reinterpret_cast<const short2*>(p) + i);
+        // volk_16i_s32f_convert_32f(.., 32768.0f): (float)x * (1/32768)  (file_source main.cpp:162)
+        return make_float2((float)v.x * (1.0f / 32768.0f), (float)v.y * (1.0f / 32768.0f));
+    }
+    else {
+        char2 v = __ldg(reinterpret_cast<const char2*>(p) + i);
+        return make_float2((float)v.x * (1.0f / 128.0f), (float)v.y * (1.0f / 128.0f));
+    }
+}
+
+// sample at chunk-relative index i: history for i < 0, zero outside [-hist_len, count)
+template <int FMT>
+__device__ __forceinline__ float2 load_x(const XdParams& p, long long i) {
+    if (i >= 0) {
+        if (i < p.count) { return load_iq<FMT>(p.in, i); }
+        return make_float2(0.0f, 0.0f);
+    }
+    long long h = (long long)p.hist_len + i;
+    if (h >= 0) { return __ldg(p.hist + h); }
+    return make_float2(0.0f, 0.0f);
+}
+
+// e^{j*2*pi*phase/2^64}: phase is exact u64 "turns"; top 32 bits -> float in [-1,1) half-turns -> sincospi
+__device__ __forceinline__ float2 phasor_u64(unsigned long long phase) {
+    int hi = (int)(phase >> 32);
+    float t = (float)hi * (1.0f / 2147483648.0f);
+    float s, c;
+    sincospif(t, &s, &c);
+    return make_float2(c, s);
+}
+
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// packed fp32x2 FMA (sm_100+): d = a*b + c on both halves.  ptxas folds a {s,s} operand into the
+// scalar-broadcast form  FFMA2 Rd, Rx.F32x2, Rs.F32, Rc.F32x2 .
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+    unsigned long long rc = *reinterpret_cast<unsigned long long*>(&c);
+    unsigned long long rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 1, plain variant: one thread per (output, VFO); reads IQ through L1/L2.  Kept as the in-library
+// cross-check of the tiled kernel (option "s1" = 0) and as the fallback for shapes the tile does not cover.
+// ------------------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(128) k_xd_simple(const __grid_constant__ XdParams p) {
+    const XdJob& J = p.job[blockIdx.y];
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= J.n_out) { return; }
+    const int T = J.T;
+    const long long i0 = (long long)J.offset + (long long)m * p.D - (T - 1);
+    const float2* __restrict__ g = J.gpad + (p.D - 1);
+    float ar = 0.0f, ai = 0.0f;
+    for (int k = 0; k < T; k++) {
+        float2 x = load_x<FMT>(p, i0 + k);
+        float2 t = __ldg(g + k);
+        ar += x.x * t.x - x.y * t.y;
+        ai += x.x * t.y + x.y * t.x;
+    }
+    float2 ph = phasor_u64(J.phase0 + J.w * (unsigned long long)i0);
+    J.out[m] = cmulf(make_float2(ar, ai), ph);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 1, tiled variant.  One CTA stages MT*D raw IQ samples ONCE in shared memory, de-interleaved by
+// decimation phase (X[r][j] = x(j*D + r)), and every VFO of the group convolves that tile with its own
+// complex taps: the IQ stream is read from HBM once for all VFOs.  Per lane: RM outputs (RM/2 aligned
+// pairs) x VR VFOs are register-blocked; the inner product uses packed f32x2 FMAs with the tap as the
+// scalar-broadcast operand:  A += g.re * x,  B += g.im * x,  y = (A.x - B.y, A.y + B.x).
+// ------------------------------------------------------------------------------------------------
+#define XD_VR 4
+template <int FMT, int RM, int QC>
+__global__ void __launch_bounds__(256) k_xd_tile(const __grid_constant__ XdParams p, int MT, int JP, int QPC, int jmin) {
+    extern __shared__ __align__(16) float2 smem[];
+    float2* X = smem;                         // [D][JP]
+    float2* G = smem + (size_t)p.D * JP;      // [njobs][QPC*D]
+    const int D = p.D;
+    const int tid = threadIdx.x;
+    const int nthr = blockDim.x;
+    const long long J0 = (long long)jmin + (long long)blockIdx.x * MT;
+
+    // ---- stage taps: G[v][k'] = gpad_v[(D-1-s_v) + k'] ----
+    const int gl = QPC * D;
+    for (int idx = tid; idx < p.njobs * gl; idx += nthr) {
+        int v = idx / gl, k = idx - v * gl;
+        const XdJob& Jv = p.job[v];
+        int a = Jv.offset - (Jv.T - 1);
+        int s = ((a % D) + D) % D;
+        G[idx] = __ldg(Jv.gpad + (D - 1 - s) + k);
+    }
+    // ---- stage the IQ tile, de-interleaved ----
+    const int ntile = D * (MT + QPC);
+    const long long ibase = J0 * D;
+    for (int idx = tid; idx < ntile; idx += nthr) {
+        int j = idx / D, r = idx - j * D;
+        X[r * JP + j] = load_x<FMT>(p, ibase + idx);
+    }
+    __syncthreads();
+
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    constexpr int NP = RM / 2;                // aligned output pairs per lane
+    const int nstrips = MT / (32 * RM);
+    const int ngroups = (p.njobs + XD_VR - 1) / XD_VR;
+    constexpr int WN = QC + 2;                // window samples per pair (even)
+
+    for (int task = warp; task < nstrips * ngroups; task += nwarps) {
+        const int strip = task % nstrips, grp = task / nstrips;
+        const int v0 = grp * XD_VR;
+        float2 A[NP][2][XD_VR], B[NP][2][XD_VR];
+#pragma unroll
+        for (int pi = 0; pi < NP; pi++)
+#pragma unroll
+            for (int o = 0; o < 2; o++)
+#pragma unroll
+                for (int v = 0; v < XD_VR; v++) { A[pi][o][v] = make_float2(0.f, 0.f); B[pi][o][v] = make_float2(0.f, 0.f); }
+
+        const int jl0 = strip * 32 * RM + 2 * lane;      // local j' of pair 0 (even); pair pi adds 64*pi
+        for (int r = 0; r < D; r++) {
+            const float2* row = X + r * JP;
+            for (int qc = 0; qc < QPC; qc += QC) {
+                float2 xs[NP][WN];
+#pragma unroll
+                for (int pi = 0; pi < NP; pi++) {
+                    const float4* src = reinterpret_cast<const float4*>(row + jl0 + 64 * pi + qc);
+#pragma unroll
+                    for (int u = 0; u < WN / 2; u++) {
+                        float4 t = src[u];
+                        xs[pi][2 * u] = make_float2(t.x, t.y);
+                        xs[pi][2 * u + 1] = make_float2(t.z, t.w);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < QC; q++) {
+#pragma unroll
+                    for (int v = 0; v < XD_VR; v++) {
+                        // taps of VFOs beyond njobs read the zero-filled tail of G? no: clamp to a valid job
+                        int vv = (v0 + v < p.njobs) ? (v0 + v) : (p.njobs - 1);
+                        float2 g = G[vv * gl + (qc + q) * D + r];
+#pragma unroll
+                        for (int pi = 0; pi < NP; pi++)
+#pragma unroll
+                            for (int o = 0; o < 2; o++) {
+                                A[pi][o][v] = ffma2(make_float2(g.x, g.x), xs[pi][q + o], A[pi][o][v]);
+                                B[pi][o][v] = ffma2(make_float2(g.y, g.y), xs[pi][q + o], B[pi][o][v]);
+                            }
+                    }
+                }
+            }
+        }
+        // ---- epilogue: rotate by the closed-form phase at the window start and store ----
+#pragma unroll
+        for (int v = 0; v < XD_VR; v++) {
+            if (v0 + v >= p.njobs) { break; }
+            const XdJob& Jv = p.job[v0 + v];
+            const int a = Jv.offset - (Jv.T - 1);
+            const int s = ((a % D) + D) % D;
+            const int c = (a - s) / D;
+#pragma unroll
+            for (int pi = 0; pi < NP; pi++)
+#pragma unroll
+                for (int o = 0; o < 2; o++) {
+                    long long jj = J0 + jl0 + 64 * pi + o;
+                    long long m = jj - c;
+                    if (m >= 0 && m < Jv.n_out) {
+                        long long im = (long long)a + m * D;
+                        float2 acc = make_float2(A[pi][o][v].x - B[pi][o][v].y, A[pi][o][v].y + B[pi][o][v].x);
+                        float2 ph = phasor_u64(Jv.phase0 + Jv.w * (unsigned long long)im);
+                        Jv.out[m] = cmulf(acc, ph);
+                    }
+                }
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// retune edge: outputs whose tap window straddles the chunk start when the VFO offset changed at this
+// boundary.  Explicit per-sample rotation (old increment for history, new one for this chunk), real taps.
+// ------------------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(128) k_xd_edge(const __grid_constant__ XdParams p) {
+    const XdJob& J = p.job[blockIdx.y];
+    if (!J.retuned) { return; }
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= J.n_out) { return; }
+    const int T = J.T;
+    const long long i0 = (long long)J.offset + (long long)m * p.D - (T - 1);
+    if (i0 >= 0) { return; }
+    float ar = 0.0f, ai = 0.0f;
+    for (int k = 0; k < T; k++) {
+        long long i = i0 + k;
+        float2 x = load_x<FMT>(p, i);
+        unsigned long long ph = J.phase0 + ((i < 0) ? J.w_prev : J.w) * (unsigned long long)i;
+        float2 z = cmulf(x, phasor_u64(ph));
+        float t = __ldg(J.h + k);
+        ar = fmaf(z.x, t, ar);
+        ai = fmaf(z.y, t, ai);
+    }
+    J.out[m] = make_float2(ar, ai);
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic decimating FIR, complex data x real taps
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fir_c(const __grid_constant__ FirParams p) {
+    const FirJob& J = p.job[blockIdx.y];
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= J.n_out) { return; }
+    const float2* __restrict__ x = J.in + (size_t)J.offset + (size_t)m * J.decim;
+    const float* __restrict__ h = J.taps;
+    float ar = 0.0f, ai = 0.0f;
+    for (int k = 0; k < J.ntaps; k++) {
+        float2 v = __ldg(x + k);
+        float t = __ldg(h + k);
+        ar = fmaf(v.x, t, ar);
+        ai = fmaf(v.y, t, ai);
+    }
+    J.out[m] = make_float2(ar, ai);
+}
+
+// ------------------------------------------------------------------------------------------------
+// polyphase rational resampler
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_poly(const __grid_constant__ PolyParams p) {
+    const PolyJob& J = p.job[blockIdx.y];
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= J.n_out) { return; }
+    long long t = (long long)J.phase0 + (long long)m * J.decim;
+    long long off = (long long)J.offset0 + t / J.interp;
+    int ph = (int)(t % J.interp);
+    const float2* __restrict__ x = J.in + off;
+    const float* __restrict__ h = J.bank + (size_t)ph * J.tpp;
+    float ar = 0.0f, ai = 0.0f;
+    for (int k = 0; k < J.tpp; k++) {
+        float2 v = __ldg(x + k);
+        float c = __ldg(h + k);
+        ar = fmaf(v.x, c, ar);
+        ai = fmaf(v.y, c, ai);
+    }
+    J.out[m] = make_float2(ar, ai);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FM discriminator: out[i] = wrap(atan2f(x[i]) - atan2f(x[i-1])) * invDeviation
+// wrap rule and the constant 3.1415926535f follow math::normalizePhase (normalize_phase.h:6-10)
+// ------------------------------------------------------------------------------------------------
+#define FL_M_PI_REF 3.1415926535f
+__global__ void __launch_bounds__(256) k_quad(const __grid_constant__ QuadParams p) {
+    const QuadJob& J = p.job[blockIdx.y];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= J.n) { return; }
+    float2 c = __ldg(J.in + i);
+    float cur = atan2f(c.y, c.x);
+    float prev;
+    if (i == 0) { prev = *J.state_in; }
+    else {
+        float2 q = __ldg(J.in + i - 1);
+        prev = atan2f(q.y, q.x);
+    }
+    float diff = __fsub_rn(cur, prev);
+    if (diff > FL_M_PI_REF) { diff = __fsub_rn(diff, 2.0f * FL_M_PI_REF); }
+    else if (diff <= -FL_M_PI_REF) { diff = __fadd_rn(diff, 2.0f * FL_M_PI_REF); }
+    J.out[i] = __fmul_rn(diff, J.inv_dev);
+    if (i == J.n - 1) { *J.state_out = cur; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// real FIR with optional stereo duplication
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fir_r(const __grid_constant__ FirRParams p) {
+    const FirRJob& J = p.job[blockIdx.y];
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= J.n_out) { return; }
+    const float* __restrict__ x = J.in + m;
+    const float* __restrict__ h = J.taps;
+    float acc = 0.0f;
+    for (int k = 0; k < J.ntaps; k++) { acc = fmaf(__ldg(x + k), __ldg(h + k), acc); }
+    if (J.stereo) { reinterpret_cast<float2*>(J.out)[m] = make_float2(acc, acc); }
+    else { J.out[m] = acc; }
+}
+
+__global__ void __launch_bounds__(256) k_m2s(const __grid_constant__ M2SParams p) {
+    const M2SJob& J = p.job[blockIdx.y];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= J.n) { return; }
+    float v = __ldg(J.in + i);
+    reinterpret_cast<float2*>(J.out)[i] = make_float2(v, v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sequential audio-rate tails: one thread per VFO.  Arithmetic is written with explicit _rn intrinsics
+// (no FMA contraction) because the AGC is branchy: the decisions must follow the reference's rounding.
+// ------------------------------------------------------------------------------------------------
+struct AgcCoef { float set_point, attack, inv_attack, decay, inv_decay, max_gain, max_out; };
+
+__device__ __forceinline__ float agc_step(const AgcCoef& c, float& amp, float inAmp) {
+    float gain;
+    if (inAmp != 0.0f) {
+        amp = (inAmp > amp) ? __fadd_rn(__fmul_rn(amp, c.inv_attack), __fmul_rn(inAmp, c.attack))
+                            : __fadd_rn(__fmul_rn(amp, c.inv_decay), __fmul_rn(inAmp, c.decay));
+        gain = fminf(__fdiv_rn(c.set_point, amp), c.max_gain);
+    }
+    else { gain = 1.0f; }
+    return gain;
+}
+__device__ __forceinline__ float camp(float2 x) {
+    return __fsqrt_rn(__fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y)));
+}
+
+__global__ void k_seq(const __grid_constant__ SeqParams p) {
+    if (threadIdx.x != 0) { return; }
+    const SeqJob& J = p.job[blockIdx.x];
+    const int n = J.n;
+    AgcCoef c = { J.set_point, J.attack, J.inv_attack, J.decay, J.inv_decay, J.max_gain, J.max_out };
+    float* st = J.state;
+    if (J.kind == 0) {
+        // ---- AM: [carrier AGC] -> magnitude -> DC block -> [audio AGC]   (am.h:101-133) ----
+        float camp_state = st[0], aamp = st[1], dc = st[2];
+        for (int i = 0; i < n; i++) {
+            float2 x = J.in[i];
+            if (J.agc_mode == 0) {
+                float inAmp = camp(x);
+                float gain = agc_step(c, camp_state, inAmp);
+                if (__fmul_rn(inAmp, gain) > c.max_out) {
+                    float maxAmp = 0.0f;
+                    for (int j = i; j < n; j++) {
+                        float a = camp(J.in[j]);
+                        if (a > maxAmp) { maxAmp = a; }
+                    }
+                    camp_state = maxAmp;
+                    gain = fminf(__fdiv_rn(c.set_point, camp_state), c.max_gain);
+                }
+                x = make_float2(__fmul_rn(x.x, gain), __fmul_rn(x.y, gain));
+            }
+            float mag = camp(x);                       // volk_32fc_magnitude_32f
+            float y = __fsub_rn(mag, dc);              // DCBlocker (dc_blocker.h:54-60)
+            dc = __fadd_rn(dc, __fmul_rn(y, J.dc_rate));
+            J.out[i] = y;
+        }
+        if (J.agc_mode == 1) {
+            for (int i = 0; i < n; i++) {
+                float v = J.out[i];
+                float inAmp = fabsf(v);
+                float gain = agc_step(c, aamp, inAmp);
+                if (__fmul_rn(inAmp, gain) > c.max_out) {
+                    float maxAmp = 0.0f;
+                    for (int j = i; j < n; j++) {
+                        float a = fabsf(J.out[j]);
+                        if (a > maxAmp) { maxAmp = a; }
+                    }
+                    aamp = maxAmp;
+                    gain = fminf(__fdiv_rn(c.set_point, aamp), c.max_gain);
+                }
+                J.out[i] = __fmul_rn(v, gain);
+            }
+        }
+        st[0] = camp_state; st[1] = aamp; st[2] = dc;
+    }
+    else {
+        // ---- SSB: rotate by +-bw/2 (faithful fp32 recurrence, renormalised every 512 samples and at the
+        //      end of the call: the VOLK rotator2 semantics) -> real part -> AGC   (ssb.h:77-92) ----
+        float aamp = st[1];
+        float pr = st[3], pi = st[4];
+        const float dr = J.delta_re, di = J.delta_im;
+        int since = 0;
+        for (int i = 0; i < n; i++) {
+            float2 x = J.in[i];
+            float re = __fsub_rn(__fmul_rn(x.x, pr), __fmul_rn(x.y, pi));
+            float nr = __fsub_rn(__fmul_rn(pr, dr), __fmul_rn(pi, di));
+            float ni = __fadd_rn(__fmul_rn(pr, di), __fmul_rn(pi, dr));
+            pr = nr; pi = ni;
+            if (++since == 512) {
+                float h = hypotf(pr, pi);
+                pr = __fdiv_rn(pr, h); pi = __fdiv_rn(pi, h);
+                since = 0;
+            }
+            J.out[i] = re;
+        }
+        if (since) {
+            float h = hypotf(pr, pi);
+            pr = __fdiv_rn(pr, h); pi = __fdiv_rn(pi, h);
+        }
+        for (int i = 0; i < n; i++) {
+            float v = J.out[i];
+            float inAmp = fabsf(v);
+            float gain = agc_step(c, aamp, inAmp);
+            if (__fmul_rn(inAmp, gain) > c.max_out) {
+                float maxAmp = 0.0f;
+                for (int j = i; j < n; j++) {
+                    float a = fabsf(J.out[j]);
+                    if (a > maxAmp) { maxAmp = a; }
+                }
+                aamp = maxAmp;
+                gain = fminf(__fdiv_rn(c.set_point, aamp), c.max_gain);
+            }
+            J.out[i] = __fmul_rn(v, gain);
+        }
+        st[1] = aamp; st[3] = pr; st[4] = pi;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// end-of-chunk history carry (one CTA per delay line)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float carry_elem(const CarryJob& J, long long s, int comp) {
+    if (s < J.la) { return J.a[s * J.esize + comp]; }
+    long long b = s - J.la;
+    if (J.bfmt < 0) { return reinterpret_cast<const float*>(J.b)[b * J.esize + comp]; }
+    float2 v;
+    if (J.bfmt == FMT_CF32) { v = load_iq<FMT_CF32>(J.b, b); }
+    else if (J.bfmt == FMT_CS16) { v = load_iq<FMT_CS16>(J.b, b); }
+    else { v = load_iq<FMT_CS8>(J.b, b); }
+    return comp ? v.y : v.x;
+}
+__global__ void __launch_bounds__(256) k_carry(const __grid_constant__ CarryParams p) {
+    const CarryJob& J = p.job[blockIdx.x];
+    const long long L = (long long)J.la + J.lb;
+    const int hf = J.h * J.esize;                 // floats to produce
+    for (int base = 0; base < hf; base += blockDim.x) {
+        int f = base + threadIdx.x;
+        float v = 0.0f;
+        if (f < hf) {
+            int e = f / J.esize, comp = f - e * J.esize;
+            long long s = L - J.h + e;
+            v = (s >= 0) ? carry_elem(J, s, comp) : 0.0f;
+        }
+        __syncthreads();
+        if (f < hf) { J.dst[f] = v; }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FFT branch: radix-2 DIF stages fused three at a time (radix-8 butterflies in registers) on a shared
+// memory tile; output of the in-place DIF is bit-reversed, undone when the result is read back.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mul_mj(float2 a) { return make_float2(a.y, -a.x); }   // a * (-j)
+#define RSQRT2 0.70710678118654752440f
+__device__ __forceinline__ float2 mul_w8_1(float2 a) { return make_float2((a.x + a.y) * RSQRT2, (a.y - a.x) * RSQRT2); }  // *(1-j)/sqrt2
+__device__ __forceinline__ float2 mul_w8_3(float2 a) { return make_float2((a.y - a.x) * RSQRT2, -(a.x + a.y) * RSQRT2); } // *(-1-j)/sqrt2
+
+// address of element r of transform c
+template <bool BATCH_INNER>
+__device__ __forceinline__ int fft_addr(int r, int c, int C, int pitch) { return BATCH_INNER ? (r * C + c) : (c * pitch + r); }
+
+// In-place forward DIF FFT of C transforms of length n = 2^logn living in shared memory.
+template <bool BATCH_INNER>
+__device__ void fft_dif_smem(float2* s, int logn, int C, int pitch, const float2* __restrict__ tw, int logTW) {
+    const int n = 1 << logn;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    int lognb = logn;
+    while (lognb >= 3) {
+        const int nb = 1 << lognb, e = nb >> 3;     // e = butterflies per sub-block
+        const int per = n >> 3;                      // butterflies per transform
+        const int twsh = logTW - lognb;              // W_nb^j = tw[j << twsh]
+        for (int t = tid; t < per * C; t += nthr) {
+            int c, bi;
+            if (BATCH_INNER) { c = t % C; bi = t / C; }
+            else { bi = t % per; c = t / per; }
+            const int blk = bi / e, j = bi - blk * e;
+            const int base = blk * nb + j;
+            float2 a[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) { a[i] = s[fft_addr<BATCH_INNER>(base + i * e, c, C, pitch)]; }
+            const float2 w1 = __ldg(tw + ((size_t)j << twsh));
+            const float2 w2 = __ldg(tw + ((size_t)(2 * j) << twsh));
+            const float2 w4 = __ldg(tw + ((size_t)(4 * j) << twsh));
+            // stage A: pairs (i, i+4), twiddle W_nb^(j + i*e) = w1 * W8^i
+            float2 t0 = csub(a[0], a[4]); a[0] = cadd(a[0], a[4]);
+            float2 t1 = csub(a[1], a[5]); a[1] = cadd(a[1], a[5]);
+            float2 t2 = csub(a[2], a[6]); a[2] = cadd(a[2], a[6]);
+            float2 t3 = csub(a[3], a[7]); a[3] = cadd(a[3], a[7]);
+            a[4] = cmulf(t0, w1);
+            a[5] = cmulf(mul_w8_1(t1), w1);
+            a[6] = cmulf(mul_mj(t2), w1);
+            a[7] = cmulf(mul_w8_3(t3), w1);
+            // stage B: within each half, pairs (i, i+2), twiddle W_(nb/2)^(j + i*e) = w2 * W4^i
+#pragma unroll
+            for (int h = 0; h < 8; h += 4) {
+                float2 u0 = csub(a[h + 0], a[h + 2]); a[h + 0] = cadd(a[h + 0], a[h + 2]);
+                float2 u1 = csub(a[h + 1], a[h + 3]); a[h + 1] = cadd(a[h + 1], a[h + 3]);
+                a[h + 2] = cmulf(u0, w2);
+                a[h + 3] = cmulf(mul_mj(u1), w2);
+            }
+            // stage C: pairs (i, i+1), twiddle W_(nb/4)^j = w4
+#pragma unroll
+            for (int h = 0; h < 8; h += 2) {
+                float2 u = csub(a[h], a[h + 1]); a[h] = cadd(a[h], a[h + 1]);
+                a[h + 1] = cmulf(u, w4);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) { s[fft_addr<BATCH_INNER>(base + i * e, c, C, pitch)] = a[i]; }
+        }
+        __syncthreads();
+        lognb -= 3;
+    }
+    if (lognb == 2) {
+        // radix-4: sub-blocks of 4, twiddles trivial (nb = 4: W_4^0 = 1, W_4^1 = -j; last stage W_2^0 = 1)
+        const int per = n >> 2;
+        for (int t = tid; t < per * C; t += nthr) {
+            int c, bi;
+            if (BATCH_INNER) { c = t % C; bi = t / C; }
+            else { bi = t % per; c = t / per; }
+            const int base = bi * 4;
+            float2 a0 = s[fft_addr<BATCH_INNER>(base + 0, c, C, pitch)];
+            float2 a1 = s[fft_addr<BATCH_INNER>(base + 1, c, C, pitch)];
+            float2 a2 = s[fft_addr<BATCH_INNER>(base + 2, c, C, pitch)];
+            float2 a3 = s[fft_addr<BATCH_INNER>(base + 3, c, C, pitch)];
+            float2 u0 = cadd(a0, a2), u1 = cadd(a1, a3);
+            float2 v0 = csub(a0, a2), v1 = mul_mj(csub(a1, a3));
+            s[fft_addr<BATCH_INNER>(base + 0, c, C, pitch)] = cadd(u0, u1);
+            s[fft_addr<BATCH_INNER>(base + 1, c, C, pitch)] = csub(u0, u1);
+            s[fft_addr<BATCH_INNER>(base + 2, c, C, pitch)] = cadd(v0, v1);
+            s[fft_addr<BATCH_INNER>(base + 3, c, C, pitch)] = csub(v0, v1);
+        }
+        __syncthreads();
+    }
+    else if (lognb == 1) {
+        const int per = n >> 1;
+        for (int t = tid; t < per * C; t += nthr) {
+            int c, bi;
+            if (BATCH_INNER) { c = t % C; bi = t / C; }
+            else { bi = t % per; c = t / per; }
+            const int base = bi * 2;
+            float2 a0 = s[fft_addr<BATCH_INNER>(base + 0, c, C, pitch)];
+            float2 a1 = s[fft_addr<BATCH_INNER>(base + 1, c, C, pitch)];
+            s[fft_addr<BATCH_INNER>(base + 0, c, C, pitch)] = cadd(a0, a1);
+            s[fft_addr<BATCH_INNER>(base + 1, c, C, pitch)] = csub(a0, a1);
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ int bitrev(int k, int bits) { return (int)(__brev((unsigned)k) >> (32 - bits)); }
+
+// 10*log10(|X/N|^2) in VOLK's log2 formulation (volk_32fc_s32f_power_spectrum_32f, iq_frontend.cpp:262)
+__device__ __forceinline__ float power_db(float2 X, float normFactSq) {
+    float m2 = (X.x * X.x + X.y * X.y) * normFactSq;
+    float l = log2f(m2);
+    if (isinf(l)) { l = copysignf(127.0f, l); }
+    return l * 3.01029995663981209120f;
+}
+
+template <int FMT>
+__device__ __forceinline__ float2 load_windowed(const FftPlanDev& pl, const void* __restrict__ src, int n) {
+    if (n >= pl.nz) { return make_float2(0.0f, 0.0f); }    // zero padding [nz, N)  (iq_frontend.cpp:301)
+    float2 x = load_iq<FMT>(src, n);
+    float w = __ldg(pl.window + n);
+    return make_float2(x.x * w, x.y * w);
+}
+
+// single-pass: the whole transform fits one CTA's shared memory
+template <int FMT>
+__global__ void __launch_bounds__(512) k_fft_single(const __grid_constant__ FftPlanDev pl, const void* __restrict__ src,
+                                                      float* __restrict__ out_db, float2* __restrict__ out_raw) {
+    extern __shared__ __align__(16) float2 smem[];
+    const int N = pl.N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { smem[i] = load_windowed<FMT>(pl, src, i); }
+    __syncthreads();
+    fft_dif_smem<false>(smem, pl.logN, 1, N, pl.tw, pl.logTW);
+    const float nf = 1.0f / ((float)N * (float)N);
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        float2 X = smem[bitrev(k, pl.logN)];
+        out_db[k] = power_db(X, nf);
+        if (out_raw) { out_raw[k] = X; }
+    }
+}
+
+// pass 1 of the two-pass (four-step) transform: n = n1*N2 + n2, k = k1 + N1*k2.
+// CTA = C adjacent columns n2, all rows n1: A[k1][n2] = W_N^(k1*n2) * sum_n1 x[n1*N2+n2] W_N1^(n1*k1)
+template <int FMT>
+__global__ void __launch_bounds__(512) k_fft_p1(const __grid_constant__ FftPlanDev pl, const void* __restrict__ src,
+                                                  float2* __restrict__ work, int C) {
+    extern __shared__ __align__(16) float2 smem[];
+    const int N1 = pl.N1, N2 = pl.N2;
+    const int c0 = blockIdx.x * C;
+    for (int t = threadIdx.x; t < N1 * C; t += blockDim.x) {
+        int n1 = t / C, c = t - n1 * C;
+        smem[t] = load_windowed<FMT>(pl, src, n1 * N2 + c0 + c);
+    }
+    __syncthreads();
+    fft_dif_smem<true>(smem, pl.logN1, C, 0, pl.tw, pl.logTW);
+    const float scale = -2.0f / (float)pl.N;
+    for (int t = threadIdx.x; t < N1 * C; t += blockDim.x) {
+        int k1 = t / C, c = t - k1 * C;
+        float2 a = smem[bitrev(k1, pl.logN1) * C + c];
+        int n2 = c0 + c;
+        float sn, cs;
+        sincospif((float)(k1 * n2) * scale, &sn, &cs);   // k1*n2 < N <= 2^22: exact in fp32
+        work[(size_t)k1 * N2 + n2] = cmulf(a, make_float2(cs, sn));
+    }
+}
+
+// pass 2: CTA = R adjacent rows k1; X[k1 + N1*k2] = sum_n2 A[k1][n2] W_N2^(n2*k2); fused dB epilogue
+__global__ void __launch_bounds__(512) k_fft_p2(const __grid_constant__ FftPlanDev pl, const float2* __restrict__ work,
+                                                  float* __restrict__ out_db, float2* __restrict__ out_raw, int R) {
+    extern __shared__ __align__(16) float2 smem[];
+    const int N1 = pl.N1, N2 = pl.N2;
+    const int pitch = N2 + 1;
+    const int r0 = blockIdx.x * R;
+    for (int t = threadIdx.x; t < R * N2; t += blockDim.x) {
+        int rl = t / N2, n2 = t - rl * N2;
+        smem[rl * pitch + n2] = __ldg(work + (size_t)(r0 + rl) * N2 + n2);
+    }
+    __syncthreads();
+    fft_dif_smem<false>(smem, pl.logN2, R, pitch, pl.tw, pl.logTW);
+    const float nf = 1.0f / ((float)pl.N * (float)pl.N);
+    for (int t = threadIdx.x; t < R * N2; t += blockDim.x) {
+        int k2 = t / R, rl = t - k2 * R;
+        float2 X = smem[rl * pitch + bitrev(k2, pl.logN2)];
+        size_t k = (size_t)(r0 + rl) + (size_t)N1 * k2;
+        out_db[k] = power_db(X, nf);
+        if (out_raw) { out_raw[k] = X; }
+    }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256) k_convert(const void* __restrict__ src, float2* __restrict__ dst, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { dst[i] = load_iq<FMT>(src, i); }
+}
+
+// doZoom + hold; start/len come from the host, which runs the reference's fp32 index loop verbatim so the
+// bin selection is bit-exact (waterfall.cpp:65-90); the max-reduce and the hold update are exact in fp32.
+__global__ void __launch_bounds__(256) k_zoom_hold(const float* __restrict__ line, const int* __restrict__ start,
+                                                     const int* __restrict__ len, int out_size, float* __restrict__ out,
+                                                     float* hold, float hold_speed) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= out_size) { return; }
+    float maxVal = -INFINITY;
+    const int s = start[i], l = len[i];
+    for (int j = 0; j < l; j++) {
+        float v = __ldg(line + s + j);
+        if (v > maxVal) { maxVal = v; }
+    }
+    out[i] = maxVal;
+    if (hold && i >= 1) {
+        float d = __fsub_rn(hold[i], hold_speed);
+        hold[i] = (maxVal < d) ? d : maxVal;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch wrappers
+// ------------------------------------------------------------------------------------------------
+static int g_smem_optin = -1;
+int kernels_max_smem_optin() {
+    if (g_smem_optin < 0) {
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        g_smem_optin = v;
+    }
+    return g_smem_optin;
+}
+
+template <typename K>
+static cudaError_t set_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+template <int FMT, int RM, int QC>
+static cudaError_t launch_xd_tile_t(const XdParams& p, int MT, int JP, int QPC, int jmin, int ntiles, size_t smem,
+                                    cudaStream_t s) {
+    cudaError_t e = set_smem(k_xd_tile<FMT, RM, QC>, smem);
+    if (e != cudaSuccess) { return e; }
+    int ntasks = (MT / (32 * RM)) * ((p.njobs + XD_VR - 1) / XD_VR);
+    int nthr = 32 * (ntasks < 2 ? 2 : (ntasks > 8 ? 8 : ntasks));
+    k_xd_tile<FMT, RM, QC><<<ntiles, nthr, smem, s>>>(p, MT, JP, QPC, jmin);
+    return cudaGetLastError();
+}
+
+template <int FMT>
+static cudaError_t launch_xd_fmt(const XdParams& p, int variant, cudaStream_t s, int* nlaunch) {
+    int max_out = 0;
+    for (int v = 0; v < p.njobs; v++) { max_out = p.job[v].n_out > max_out ? p.job[v].n_out : max_out; }
+    if (max_out <= 0) { return cudaSuccess; }
+    const int D = p.D;
+    // ---- tiled variant: needs padded taps of QPC*D entries; the host sized gpad for QC in {4,6,8} ----
+    if (variant >= 1 && D >= 2) {
+        int QP = p.QP;
+        // pick the unroll chunk that wastes the least padding (ties: larger chunk)
+        int best_qc = 6, best_pad = 1 << 30;
+        const int qcs[3] = { 8, 6, 4 };
+        for (int i = 0; i < 3; i++) {
+            int pad = ((QP + qcs[i] - 1) / qcs[i]) * qcs[i] - QP;
+            if (pad < best_pad) { best_pad = pad; best_qc = qcs[i]; }
+        }
+        const int QC = best_qc;
+        const int QPC = ((QP + QC - 1) / QC) * QC;
+        const int RM = (variant == 2) ? 2 : 4;
+        // tile range in block-index space
+        long long jmin = (1LL << 60), jmax = -(1LL << 60);
+        for (int v = 0; v < p.njobs; v++) {
+            if (p.job[v].n_out <= 0) { continue; }
+            int a = p.job[v].offset - (p.job[v].T - 1);
+            int sft = ((a % D) + D) % D;
+            long long c = (a - sft) / D;
+            if (c < jmin) { jmin = c; }
+            if (c + p.job[v].n_out > jmax) { jmax = c + p.job[v].n_out; }
+        }
+        if (jmin & 1) { jmin -= 1; }   // keep J0 even: LDS.128 alignment of the window loads
+        const int limit = kernels_max_smem_optin();
+        int MT = 0, JP = 0;
+        size_t smem = 0;
+        const int mts[4] = { 256, 128, 64, 32 * RM };
+        for (int i = 0; i < 4; i++) {
+            int mt = mts[i];
+            if (mt % (32 * RM)) { continue; }
+            int jp = mt + QPC + 2;
+            jp += (jp & 1);            // even pitch: rows stay 16-byte aligned (LDS.128 window loads)
+            if ((jp & 3) == 0) { jp += 2; }   // pitch = 2*odd: de-interleaving stores are at worst 2-way conflicted
+            size_t need = ((size_t)D * jp + (size_t)p.njobs * QPC * D) * sizeof(float2);
+            // aim for two CTAs per SM when possible
+            if (need * 2 <= (size_t)limit || (i == 3 && need <= (size_t)limit) || (need <= (size_t)limit && mt <= 64)) {
+                MT = mt; JP = jp; smem = need;
+                break;
+            }
+        }
+        if (MT) {
+            int ntiles = cdiv(jmax - jmin, MT);
+            cudaError_t e;
+#define XD_CASE(rm, qc) e = launch_xd_tile_t<FMT, rm, qc>(p, MT, JP, QPC, (int)jmin, ntiles, smem, s)
+            if (RM == 4) {
+                if (QC == 8) { XD_CASE(4, 8); } else if (QC == 6) { XD_CASE(4, 6); } else { XD_CASE(4, 4); }
+            }
+            else {
+                if (QC == 8) { XD_CASE(2, 8); } else if (QC == 6) { XD_CASE(2, 6); } else { XD_CASE(2, 4); }
+            }
+#undef XD_CASE
+            if (nlaunch) { (*nlaunch)++; }
+            return e;
+        }
+    }
+    dim3 grid(cdiv(max_out, 128), p.njobs);
+    k_xd_simple<FMT><<<grid, 128, 0, s>>>(p);
+    if (nlaunch) { (*nlaunch)++; }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_xlate_decim(const XdParams& p, int fmt, int variant, cudaStream_t s, int* nlaunch) {
+    if (fmt == FMT_CF32) { return launch_xd_fmt<FMT_CF32>(p, variant, s, nlaunch); }
+    if (fmt == FMT_CS16) { return launch_xd_fmt<FMT_CS16>(p, variant, s, nlaunch); }
+    return launch_xd_fmt<FMT_CS8>(p, variant, s, nlaunch);
+}
+
+
+cudaError_t launch_xd_edge(const XdParams& p, int fmt, cudaStream_t s, int* nlaunch) {
+    int medge = 0;
+    bool any = false;
+    for (int v = 0; v < p.njobs; v++) {
+        if (!p.job[v].retuned || p.job[v].n_out <= 0) { continue; }
+        any = true;
+        int need = p.job[v].T - 1 - p.job[v].offset;          // outputs with i_m < 0
+        int me = need > 0 ? (need + p.D - 1) / p.D : 0;
+        if (me > p.job[v].n_out) { me = p.job[v].n_out; }
+        if (me > medge) { medge = me; }
+    }
+    if (!any || medge <= 0) { return cudaSuccess; }
+    dim3 grid(cdiv(medge, 128), p.njobs);
+    if (fmt == FMT_CF32) { k_xd_edge<FMT_CF32><<<grid, 128, 0, s>>>(p); }
+    else if (fmt == FMT_CS16) { k_xd_edge<FMT_CS16><<<grid, 128, 0, s>>>(p); }
+    else { k_xd_edge<FMT_CS8><<<grid, 128, 0, s>>>(p); }
+    if (nlaunch) { (*nlaunch)++; }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fir_c(const FirParams& p, cudaStream_t s) {
+    if (p.max_out <= 0 || p.njobs <= 0) { return cudaSuccess; }
+    dim3 grid(cdiv(p.max_out, 256), p.njobs);
+    k_fir_c<<<grid, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_poly(const PolyParams& p, cudaStream_t s) {
+    if (p.max_out <= 0 || p.njobs <= 0) { return cudaSuccess; }
+    dim3 grid(cdiv(p.max_out, 256), p.njobs);
+    k_poly<<<grid, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_quad(const QuadParams& p, cudaStream_t s) {
+    if (p.max_n <= 0 || p.njobs <= 0) { return cudaSuccess; }
+    dim3 grid(cdiv(p.max_n, 256), p.njobs);
+    k_quad<<<grid, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_fir_r(const FirRParams& p, cudaStream_t s) {
+    if (p.max_out <= 0 || p.njobs <= 0) { return cudaSuccess; }
+    dim3 grid(cdiv(p.max_out, 256), p.njobs);
+    k_fir_r<<<grid, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_seq(const SeqParams& p, cudaStream_t s) {
+    if (p.njobs <= 0) { return cudaSuccess; }
+    k_seq<<<p.njobs, 32, 0, s>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_m2s(const M2SParams& p, cudaStream_t s) {
+    if (p.max_n <= 0 || p.njobs <= 0) { return cudaSuccess; }
+    dim3 grid(cdiv(p.max_n, 256), p.njobs);
+    k_m2s<<<grid, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_carry(const CarryParams& p, cudaStream_t s) {
+    if (p.njobs <= 0) { return cudaSuccess; }
+    k_carry<<<p.njobs, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <int FMT>
+static cudaError_t launch_fft_fmt(const FftPlanDev& pl, const void* src, float2* work, float* out_db, float2* out_raw,
+                                  cudaStream_t s, int* nlaunch) {
+    cudaError_t e;
+    if (pl.N1 == pl.N) {
+        size_t smem = (size_t)pl.N * sizeof(float2);
+        e = set_smem(k_fft_single<FMT>, smem);
+        if (e != cudaSuccess) { return e; }
+        int thr = pl.N / 8 < 32 ? 32 : (pl.N / 8 > 512 ? 512 : pl.N / 8);
+        k_fft_single<FMT><<<1, thr, smem, s>>>(pl, src, out_db, out_raw);
+        if (nlaunch) { (*nlaunch)++; }
+        return cudaGetLastError();
+    }
+    // two passes
+    int C = 16;
+    while ((size_t)pl.N1 * C * sizeof(float2) > 196608 && C > 1) { C >>= 1; }
+    if (C > pl.N2) { C = pl.N2; }
+    int R = 16;
+    while ((size_t)R * (pl.N2 + 1) * sizeof(float2) > 196608 && R > 1) { R >>= 1; }
+    if (R > pl.N1) { R = pl.N1; }
+    size_t smem1 = (size_t)pl.N1 * C * sizeof(float2);
+    size_t smem2 = (size_t)R * (pl.N2 + 1) * sizeof(float2);
+    e = set_smem(k_fft_p1<FMT>, smem1);
+    if (e != cudaSuccess) { return e; }
+    e = set_smem(k_fft_p2, smem2);
+    if (e != cudaSuccess) { return e; }
+    k_fft_p1<FMT><<<pl.N2 / C, 512, smem1, s>>>(pl, src, work, C);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { return e; }
+    k_fft_p2<<<pl.N1 / R, 512, smem2, s>>>(pl, work, out_db, out_raw, R);
+    if (nlaunch) { (*nlaunch) += 2; }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fft_frame(const FftPlanDev& pl, const void* src, int fmt, float2* work, float* out_db,
+                             float2* out_raw, cudaStream_t s, int* nlaunch) {
+    if (fmt == FMT_CF32) { return launch_fft_fmt<FMT_CF32>(pl, src, work, out_db, out_raw, s, nlaunch); }
+    if (fmt == FMT_CS16) { return launch_fft_fmt<FMT_CS16>(pl, src, work, out_db, out_raw, s, nlaunch); }
+    return launch_fft_fmt<FMT_CS8>(pl, src, work, out_db, out_raw, s, nlaunch);
+}
+
+cudaError_t launch_convert_cf32(const void* src, int fmt, float2* dst, int n, cudaStream_t s) {
+    if (n <= 0) { return cudaSuccess; }
+    int grid = cdiv(n, 256);
+    if (fmt == FMT_CF32) { k_convert<FMT_CF32><<<grid, 256, 0, s>>>(src, dst, n); }
+    else if (fmt == FMT_CS16) { k_convert<FMT_CS16><<<grid, 256, 0, s>>>(src, dst, n); }
+    else { k_convert<FMT_CS8><<<grid, 256, 0, s>>>(src, dst, n); }
+    return cudaGetLastError();
+}
+
+// start/len device arrays are supplied by the caller through `out`-adjacent scratch: see api.cpp
+cudaError_t launch_zoom_hold_tbl(const float* line, const int* start, const int* len, int out_size, float* out,
+                                 float* hold, float hold_speed, cudaStream_t s) {
+    if (out_size <= 0) { return cudaSuccess; }
+    k_zoom_hold<<<cdiv(out_size, 256), 256, 0, s>>>(line, start, len, out_size, out, hold, hold_speed);
+    return cudaGetLastError();
+}

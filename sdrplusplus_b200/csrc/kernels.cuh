@@ -1,0 +1,144 @@
+// sdrplusplus_b200/csrc/kernels.cuh -- job descriptors and launch wrappers of the sm_100a kernels.
+// Plain structs passed BY VALUE as kernel parameters (one launch covers up to B200_BATCH jobs, i.e.
+// the same stage of up to 16 VFOs); pointers are device pointers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define B200_BATCH 16
+
+// ---- sample formats (must match include/b200dsp.h) ----
+enum { FMT_CF32 = 0, FMT_CS16 = 1, FMT_CS8 = 2 };
+
+// ---- stage 1: frequency translate + first decimating FIR, all VFOs of a group share the IQ tile ----
+// y_v[m] = e^{j phi_v(i_m)} * sum_k x(i_m + k) * g_v[k],  i_m = offset_v + m*D - (T-1)  (chunk-relative),
+// g_v[k] = h[k] e^{j w_v k} (host, fp64 -> fp32), phi_v(i) = 2*pi*(phase0_v + W_v*i)/2^64 (exact u64 turns).
+// Replaces FrequencyXlator::process (frequency_xlator.h:43-50) + the first DecimatingFIR of
+// PowerDecimator::process (power_decimator.h:58-65, decimating_fir.h:45-68) for every VFO at once.
+struct XdJob {
+    float2* out;            // stage output (data region of the next stage's [hist|data] buffer)
+    const float2* gpad;     // complex taps, zero padded: (D-1) zeros | T taps | zeros up to (QP+1)*D total
+    unsigned long long phase0;  // phase (turns * 2^64) at chunk-relative index 0
+    unsigned long long w;       // phase increment per input sample (turns * 2^64)
+    int offset;             // DecimatingFIR::offset for this chunk (decimating_fir.h:50), 0 <= offset
+    int n_out;              // outputs this chunk
+    int T;                  // tap count
+    // retune at this chunk boundary (FrequencyXlator::setOffset keeps `phase`, frequency_xlator.h:25-29):
+    // history samples (index < 0) were rotated with w_prev, new samples with w.  The edge kernel recomputes
+    // the few outputs whose window straddles index 0 with the real taps h.
+    const float* h;         // real taps (T)
+    unsigned long long w_prev;
+    int retuned;
+};
+struct XdParams {
+    const void* in;         // chunk data (format FMT), chunk-relative index 0
+    const float2* hist;     // last `hist_len` samples before the chunk (cf32), hist[hist_len + i] for i < 0
+    int hist_len;
+    int count;              // samples in this chunk
+    int D;                  // decimation of the first stage (1 = pure translate)
+    int QP;                 // taps are padded to QP*D entries after the (D-1) leading zeros (see gpad)
+    int njobs;
+    XdJob job[B200_BATCH];
+};
+
+// ---- generic decimating FIR, complex data x real taps (DecimatingFIR / FIR<complex_t,float>) ----
+// out[m] = sum_k in[offset + m*decim + k] * taps[k];  `in` points at the oldest history sample.
+struct FirJob {
+    const float2* in;
+    float2* out;
+    const float* taps;
+    int ntaps, decim, offset, n_out;
+};
+struct FirParams { int njobs; int max_out; FirJob job[B200_BATCH]; };
+
+// ---- polyphase rational resampler (PolyphaseResampler::process, polyphase_resampler.h:69-99) ----
+// output m: t = phase0 + m*decim; off = offset0 + t/interp; ph = t%interp;
+// out[m] = sum_k in[off + k] * bank[ph*tpp + k]
+struct PolyJob {
+    const float2* in;
+    float2* out;
+    const float* bank;      // [interp][tpp]
+    int tpp, interp, decim, phase0, offset0, n_out;
+};
+struct PolyParams { int njobs; int max_out; PolyJob job[B200_BATCH]; };
+
+// ---- FM discriminator (Quadrature::process, quadrature.h:39-46) ----
+struct QuadJob {
+    const float2* in;       // n samples (no history)
+    float* out;
+    const float* state_in;  // previous chunk's last phase
+    float* state_out;       // this chunk's last phase (ping-pong: != state_in)
+    float inv_dev;
+    int n;
+};
+struct QuadParams { int njobs; int max_n; QuadJob job[B200_BATCH]; };
+
+// ---- real FIR (FIR<float,float>, fir.h:69) with optional mono->stereo duplication on store ----
+struct FirRJob {
+    const float* in;        // oldest history sample
+    float* out;             // n floats, or n (l,r) pairs when stereo
+    const float* taps;
+    int ntaps, n_out, stereo;
+};
+struct FirRParams { int njobs; int max_out; FirRJob job[B200_BATCH]; };
+
+// ---- sequential audio-rate tails (one thread per job): AM envelope + DC block + AGC, SSB rotate + AGC ----
+struct AgcState { float amp; };
+struct SeqJob {
+    const float2* in;       // n complex samples
+    float* out;             // n mono floats
+    float* state;           // device state block (see kernels.cu: SEQ_STATE_*)
+    int n;
+    int kind;               // 0 AM, 1 SSB
+    int agc_mode;           // AM: 0 carrier, 1 audio
+    float set_point, attack, inv_attack, decay, inv_decay, max_gain, max_out; // loop::AGC (agc.h:13-24)
+    float dc_rate;          // AM
+    float delta_re, delta_im; // SSB second rotator phaseDelta (ssb.h:29, frequency_xlator.h:17)
+};
+struct SeqParams { int njobs; SeqJob job[B200_BATCH]; };
+#define SEQ_STATE_FLOATS 8   // [0] carrier amp [1] audio amp [2] dc offset [3] rot re [4] rot im
+
+// ---- mono -> stereo copy (convert::MonoToStereo) ----
+struct M2SJob { const float* in; float* out; int n; };
+struct M2SParams { int njobs; int max_n; M2SJob job[B200_BATCH]; };
+
+// ---- end-of-chunk history carry: dst[0..h) = last h elements of concat(a[0..la), b[0..lb)) ----
+// dst may alias a (memmove semantics of fir.h:80 / decimating_fir.h:65 / polyphase_resampler.h:96).
+struct CarryJob {
+    float* dst; const float* a; const void* b;
+    int h, la, lb;          // element counts
+    int esize;              // floats per element (1 or 2)
+    int bfmt;               // format of b: -1 = float elements of esize, else FMT_* (IQ input -> cf32)
+};
+#define CARRY_BATCH 64
+struct CarryParams { int njobs; CarryJob job[CARRY_BATCH]; };
+
+// ---- FFT branch ----
+struct FftPlanDev {
+    int N, logN;            // transform size
+    int N1, logN1;          // pass 1 (column) length; N1 == N -> single pass
+    int N2, logN2;          // pass 2 (row) length
+    const float2* tw;       // twiddle table exp(-2 pi i k / TW), k < TW
+    int TW, logTW;
+    const float* window;    // nz floats: window(i,nz) * (-1)^i
+    int nz;
+};
+
+// launch wrappers (return cudaGetLastError())
+cudaError_t launch_xlate_decim(const XdParams& p, int fmt, int variant, cudaStream_t s, int* nlaunch);
+cudaError_t launch_xd_edge(const XdParams& p, int fmt, cudaStream_t s, int* nlaunch);
+cudaError_t launch_fir_c(const FirParams& p, cudaStream_t s);
+cudaError_t launch_poly(const PolyParams& p, cudaStream_t s);
+cudaError_t launch_quad(const QuadParams& p, cudaStream_t s);
+cudaError_t launch_fir_r(const FirRParams& p, cudaStream_t s);
+cudaError_t launch_seq(const SeqParams& p, cudaStream_t s);
+cudaError_t launch_m2s(const M2SParams& p, cudaStream_t s);
+cudaError_t launch_carry(const CarryParams& p, cudaStream_t s);
+// src: nz samples of format fmt (chunk data), read directly; out_db: N floats; work: N float2 scratch
+cudaError_t launch_fft_frame(const FftPlanDev& pl, const void* src, int fmt, float2* work, float* out_db,
+                             float2* out_raw, cudaStream_t s, int* nlaunch);
+cudaError_t launch_convert_cf32(const void* src, int fmt, float2* dst, int n, cudaStream_t s);
+// start/len: per-pixel bin ranges built on the host with the reference's fp32 index loop
+cudaError_t launch_zoom_hold_tbl(const float* line, const int* start, const int* len, int out_size, float* out,
+                                 float* hold, float hold_speed, cudaStream_t s);
+int kernels_max_smem_optin();

@@ -1,0 +1,347 @@
+"""Host-side mirrors of the reference interfaces on top of the C ABI.
+
+FrontEnd          <-> IQFrontEnd (core/src/signal_path/iq_frontend.h:23-49) + the radio module's demodulator
+                      behind each VFO (decoder_modules/radio/src/radio_module.h:80-125)
+Block             <-> one dsp block: init(...) / process(count, in, out) -> out count (core/src/dsp/processor.h)
+SpectrumHandler   <-> IQFrontEnd::handler on one framed block (iq_frontend.cpp:248-267)
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import lib as L
+
+
+@dataclass
+class VfoConfig:
+    offset: float
+    out_samplerate: float
+    bandwidth: float
+    demod: int = L.DEMOD_WFM
+    deviation: float = 75000.0
+    low_pass: bool = True
+    agc_mode: int = L.AGC_AUDIO
+    agc_attack: float = 0.0
+    agc_decay: float = 0.0
+    dc_block_rate: float = 0.0
+
+    @staticmethod
+    def wfm(offset, bandwidth=150000.0):
+        # decoder_modules/radio/src/demodulators/wfm.h:78,268-270: IF 250 kS/s, deviation = bandwidth/2
+        return VfoConfig(offset, 250000.0, bandwidth, L.DEMOD_WFM, deviation=bandwidth / 2.0, low_pass=True)
+
+    @staticmethod
+    def nfm(offset, bandwidth=12500.0):
+        return VfoConfig(offset, 50000.0, bandwidth, L.DEMOD_NFM, low_pass=True)          # nfm.h:29,56-58
+
+    @staticmethod
+    def am(offset, bandwidth=10000.0, agc_mode=L.AGC_AUDIO, attack=50.0, decay=5.0):
+        sr = 15000.0                                                                       # am.h:34,76-78
+        return VfoConfig(offset, sr, bandwidth, L.DEMOD_AM, agc_mode=agc_mode, agc_attack=attack / sr,
+                         agc_decay=decay / sr, dc_block_rate=100.0 / sr)
+
+    @staticmethod
+    def ssb(offset, mode=L.DEMOD_USB, bandwidth=2800.0, attack=50.0, decay=5.0):
+        sr = 24000.0                                                                       # usb.h:34,70-72
+        return VfoConfig(offset, sr, bandwidth, mode, agc_attack=attack / sr, agc_decay=decay / sr)
+
+    @staticmethod
+    def raw(offset, out_samplerate, bandwidth):
+        return VfoConfig(offset, out_samplerate, bandwidth, L.DEMOD_RAW)
+
+    def to_c(self):
+        return L.VfoCfg(self.offset, self.out_samplerate, self.bandwidth, self.demod, self.deviation, int(self.low_pass),
+                        self.agc_mode, self.agc_attack, self.agc_decay, self.dc_block_rate)
+
+
+_NP_FMT = {L.FMT_CF32: (np.complex64, 1), L.FMT_CS16: (np.int16, 2), L.FMT_CS8: (np.int8, 2)}
+
+
+def _as_input(iq, fmt):
+    dt, per = _NP_FMT[fmt]
+    a = np.ascontiguousarray(iq, dtype=dt).reshape(-1)
+    return a, a.size // per
+
+
+class FrontEnd:
+    """One IQ stream -> FFT/waterfall lines + N VFO/demodulator outputs, one chunk per process()."""
+
+    def __init__(self, samplerate, max_chunk=1000000, device=None):
+        self._l = L.load()
+        if device is not None:
+            L.check(self._l.b200_init(device))
+        self._h = L.check_ptr(self._l.b200_fe_create(float(samplerate), int(max_chunk)))
+        self.samplerate = float(samplerate)
+        self.max_chunk = int(max_chunk)
+        self.fft_size = 0
+        self.vfos = {}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._l.b200_fe_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # IQFrontEnd::setFFTSize / setFFTRate / setFFTWindow
+    def set_fft(self, size, rate, window=L.WIN_NUTTALL):
+        L.check(self._l.b200_fe_set_fft(self._h, int(size), float(rate), int(window)))
+        self.fft_size = int(size)
+
+    def set_stream(self, cuda_stream):
+        L.check(self._l.b200_fe_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def add_vfo(self, cfg):
+        c = cfg.to_c()
+        vid = L.check(self._l.b200_fe_add_vfo(self._h, C.byref(c)))
+        self.vfos[vid] = cfg
+        return vid
+
+    def remove_vfo(self, vid):
+        L.check(self._l.b200_fe_remove_vfo(self._h, vid))
+        self.vfos.pop(vid, None)
+
+    def set_vfo_offset(self, vid, offset):
+        L.check(self._l.b200_fe_set_vfo_offset(self._h, vid, float(offset)))
+
+    def set_vfo_bandwidth(self, vid, bw):
+        L.check(self._l.b200_fe_set_vfo_bandwidth(self._h, vid, float(bw)))
+
+    def set_option(self, key, value):
+        L.check(self._l.b200_fe_set_option(self._h, key.encode(), int(value)))
+
+    def reset(self):
+        L.check(self._l.b200_fe_reset(self._h))
+
+    def launch_count(self):
+        return self._l.b200_fe_launch_count(self._h)
+
+    def vfo_max_out(self, vid, count):
+        return L.check(self._l.b200_fe_vfo_max_out(self._h, vid, count))
+
+    def fft_max_lines(self, count):
+        return self._l.b200_fe_fft_max_lines(self._h, count)
+
+    def _alloc_outputs(self, count):
+        o = L.Outputs()
+        bufs = {}
+        for vid, cfg in self.vfos.items():
+            cap = self.vfo_max_out(vid, count)
+            b = np.empty(cap * 2, np.float32)
+            bufs[vid] = b
+            o.vfo_out[vid] = b.ctypes.data
+            o.vfo_cap[vid] = cap
+        fft = None
+        if self.fft_size:
+            nl = self.fft_max_lines(count)
+            fft = np.empty((nl, self.fft_size), np.float32)
+            o.fft_out = fft.ctypes.data
+            o.fft_cap_lines = nl
+        o.out_mem = L.MEM_HOST
+        return o, bufs, fft
+
+    def process(self, iq, fmt=L.FMT_CF32):
+        """Host numpy in, host numpy out.  Returns ({vfo_id: array}, fft_lines[n, N])."""
+        a, count = _as_input(iq, fmt)
+        o, bufs, fft = self._alloc_outputs(count)
+        L.check(self._l.b200_fe_process(self._h, a.ctypes.data, count, fmt, L.MEM_HOST, C.byref(o)))
+        outs = {}
+        for vid, cfg in self.vfos.items():
+            n = o.vfo_count[vid]
+            y = bufs[vid][: 2 * n].copy()
+            outs[vid] = y.view(np.complex64) if cfg.demod == L.DEMOD_RAW else y.reshape(-1, 2)
+        lines = fft[: o.fft_lines].copy() if fft is not None else np.empty((0, 0), np.float32)
+        return outs, lines
+
+    def process_chunks(self, iq, chunk, fmt=L.FMT_CF32):
+        a, count = _as_input(iq, fmt)
+        per = _NP_FMT[fmt][1]
+        acc = {vid: [] for vid in self.vfos}
+        lines = []
+        for i in range(0, count, chunk):
+            outs, ln = self.process(a[i * per:(i + chunk) * per], fmt)
+            for vid, y in outs.items():
+                acc[vid].append(y)
+            if ln.size:
+                lines.append(ln)
+        res = {vid: (np.concatenate(v) if v else np.empty(0, np.float32)) for vid, v in acc.items()}
+        return res, (np.concatenate(lines) if lines else np.empty((0, self.fft_size), np.float32))
+
+    # raw-pointer variants used by bench.py (device-resident or pinned buffers, no numpy copies)
+    def submit_ptr(self, ptr, count, fmt, mem, outputs):
+        L.check(self._l.b200_fe_submit(self._h, C.c_void_p(ptr), count, fmt, mem, C.byref(outputs)))
+
+    def process_ptr(self, ptr, count, fmt, mem, outputs):
+        L.check(self._l.b200_fe_process(self._h, C.c_void_p(ptr), count, fmt, mem, C.byref(outputs)))
+
+    def wait(self):
+        L.check(self._l.b200_fe_wait(self._h))
+
+
+class Block:
+    """Stand-alone block with the reference's process(count, in, out) contract; state carried across calls."""
+
+    def __init__(self, handle, in_floats, out_floats):
+        self._l = L.load()
+        self._h = L.check_ptr(handle)
+        self._in_f, self._out_f = in_floats, out_floats
+
+    @staticmethod
+    def xlator(offset_hz, sr):
+        return Block(L.load().b200_xlator_create(offset_hz, sr), 2, 2)
+
+    @staticmethod
+    def decim(ratio):
+        return Block(L.load().b200_decim_create(ratio), 2, 2)
+
+    @staticmethod
+    def resamp(in_sr, out_sr):
+        return Block(L.load().b200_resamp_create(in_sr, out_sr), 2, 2)
+
+    @staticmethod
+    def fir_cr(taps, decim=1):
+        t = np.ascontiguousarray(taps, np.float32)
+        return Block(L.load().b200_fir_cr_create(t.ctypes.data, t.size, decim), 2, 2)
+
+    @staticmethod
+    def fir_rr(taps):
+        t = np.ascontiguousarray(taps, np.float32)
+        return Block(L.load().b200_fir_rr_create(t.ctypes.data, t.size), 1, 1)
+
+    @staticmethod
+    def rxvfo(in_sr, out_sr, bw, offset):
+        return Block(L.load().b200_rxvfo_create(in_sr, out_sr, bw, offset), 2, 2)
+
+    @staticmethod
+    def quad(dev, sr):
+        return Block(L.load().b200_quad_create(dev, sr), 2, 1)
+
+    @staticmethod
+    def wfm(dev, sr, stereo=False, lowpass=True):
+        return Block(L.load().b200_wfm_create(dev, sr, int(stereo), int(lowpass)), 2, 2)
+
+    @staticmethod
+    def nfm(sr, bw, lowpass=True):
+        return Block(L.load().b200_nfm_create(sr, bw, int(lowpass)), 2, 2)
+
+    @staticmethod
+    def am(agc_mode, bw, attack, decay, dcrate, sr):
+        return Block(L.load().b200_am_create(agc_mode, bw, attack, decay, dcrate, sr), 2, 2)
+
+    @staticmethod
+    def ssb(mode, bw, sr, attack, decay):
+        return Block(L.load().b200_ssb_create(mode, bw, sr, attack, decay), 2, 2)
+
+    def set_offset(self, *a):
+        if len(a) == 2:
+            L.check(self._l.b200_xlator_set_offset(self._h, a[0], a[1]))
+        else:
+            L.check(self._l.b200_rxvfo_set_offset(self._h, a[0]))
+
+    def set_bandwidth(self, bw):
+        L.check(self._l.b200_rxvfo_set_bandwidth(self._h, bw))
+
+    def process(self, x):
+        x = np.ascontiguousarray(x, np.float32).reshape(-1)
+        count = x.size // self._in_f
+        cap = L.check(self._l.b200_block_max_out(self._h, count))
+        out = np.empty(max(cap, 1) * self._out_f, np.float32)
+        n = L.check(self._l.b200_block_process(self._h, count, x.ctypes.data, out.ctypes.data))
+        return out[: n * self._out_f].copy()
+
+    def process_chunks(self, x, chunk):
+        x = np.ascontiguousarray(x, np.float32).reshape(-1)
+        step = chunk * self._in_f
+        outs = [self.process(x[i:i + step]) for i in range(0, x.size, step)]
+        return np.concatenate(outs) if outs else np.empty(0, np.float32)
+
+    def reset(self):
+        L.check(self._l.b200_block_reset(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._l.b200_block_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SpectrumHandler:
+    def __init__(self, size, nz, window=L.WIN_NUTTALL):
+        self._l = L.load()
+        self._h = L.check_ptr(self._l.b200_fft_create(size, nz, window))
+        self.size, self.nz = size, nz
+
+    def frame(self, iq):
+        iq = np.ascontiguousarray(iq, np.complex64)
+        assert iq.size == self.nz
+        out = np.empty(self.size, np.float32)
+        L.check(self._l.b200_fft_frame(self._h, iq.ctypes.data, out.ctypes.data))
+        return out
+
+    def raw(self, iq):
+        iq = np.ascontiguousarray(iq, np.complex64)
+        out = np.empty(self.size, np.complex64)
+        L.check(self._l.b200_fft_raw(self._h, iq.ctypes.data, out.ctypes.data))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._l.b200_fft_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def zoom_hold(line, offset, width, out_size, hold=None, hold_speed=0.0):
+    """doZoom + peak hold on the GPU (waterfall.cpp:65-90,935-939); returns (out, hold)."""
+    l = L.load()
+    line = np.ascontiguousarray(line, np.float32)
+    out = np.empty(out_size, np.float32)
+    h = None if hold is None else np.ascontiguousarray(hold, np.float32).copy()
+    L.check(l.b200_fft_zoom_hold(line.ctypes.data, line.size, offset, width, out_size, out.ctypes.data,
+                                 None if h is None else h.ctypes.data, hold_speed, L.MEM_HOST))
+    return out, h
+
+
+def taps_lowpass(cutoff, tw, sr, odd=False):
+    l = L.load()
+    n = l.b200_taps_lowpass(cutoff, tw, sr, int(odd), None, 0)
+    out = np.empty(n, np.float32)
+    l.b200_taps_lowpass(cutoff, tw, sr, int(odd), out.ctypes.data, n)
+    return out
+
+
+def window(win, nz):
+    l = L.load()
+    out = np.empty(nz, np.float32)
+    L.check(l.b200_window(win, nz, out.ctypes.data))
+    return out
+
+
+def resamp_plan(in_sr, out_sr):
+    l = L.load()
+    p = L.ResampPlan()
+    L.check(l.b200_resamp_plan_get(in_sr, out_sr, C.byref(p)))
+    return {"mode": p.mode, "predec_ratio": p.predec_ratio, "stages": [(p.stage_decim[i], p.stage_taps[i]) for i in range(p.nstages)],
+            "interp": p.interp, "decim": p.decim, "ntaps": p.ntaps, "taps_per_phase": p.taps_per_phase}
+
+
+def fft_frame_params(sr, size, rate):
+    l = L.load()
+    nz, skip = C.c_int(), C.c_int()
+    L.check(l.b200_fft_frame_params(sr, size, rate, C.byref(nz), C.byref(skip)))
+    return nz.value, skip.value

@@ -1,0 +1,77 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/b200dsp.h declares, refuses to compute without a device, and its host-side design helpers are
+bit-identical to the reference's formulas (checked through the oracle)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from sdrplusplus_b200 import lib, frontend
+
+
+def test_library_exports_every_declared_symbol():
+    L = lib.load()
+    declared = lib.header_symbols()
+    assert len(declared) >= 50
+    for name in declared:
+        assert hasattr(L, name), "libb200dsp.so does not export %s" % name
+        assert name in lib.SIGNATURES, "python binding lacks %s" % name
+    assert L.b200_version() == 100
+
+
+def test_no_device_fails_loudly():
+    L = lib.load()
+    if L.b200_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    assert L.b200_init(0) == -2
+    assert b"no CPU fallback" in L.b200_last_error()
+    assert not L.b200_fe_create(2.4e6, 1000)
+    assert not L.b200_rxvfo_create(2.4e6, 250e3, 150e3, 0.0)
+    assert not L.b200_fft_create(1024, 1024, 2)
+    with pytest.raises(lib.B200Error):
+        frontend.FrontEnd(2.4e6)
+
+
+def test_bad_arguments_return_error_codes():
+    L = lib.load()
+    assert L.b200_register_decim_plan(3, 1, None, None, None) == -1
+    assert L.b200_resamp_plan_get(1e6, 1e5, None) == -1
+    assert L.b200_fft_frame_params(1e6, 1024, 0.0, None, None) == -1
+
+
+@pytest.mark.parametrize("args", [(15000.0, 4000.0, 250000.0, False), (75000.0, 7500.0, 250000.0, False),
+                                  (6250.0, 625.0, 50000.0, False), (1400.0, 140.0, 24000.0, True),
+                                  (125000.0, 12500.0, 6250000.0, False)])
+def test_lowpass_taps_bit_exact(oracle, args):
+    a = frontend.taps_lowpass(*args)
+    b = oracle.lowpass(*args)
+    assert a.size == b.size
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("win,nz", [(0, 1000), (1, 4097), (2, 65536), (2, 12000)])
+def test_window_bit_exact(oracle, win, nz):
+    assert np.array_equal(frontend.window(win, nz).view(np.uint32), oracle.window_buf(win, nz).view(np.uint32))
+
+
+@pytest.mark.parametrize("rates", [(2.4e6, 250e3), (100e6, 250e3), (1.024e9, 250e3), (2.4e6, 50e3), (2.4e6, 15e3),
+                                   (2.4e6, 24e3), (250e3, 48e3), (48e3, 250e3), (1e6, 1e6), (100e6, 50e3), (1.024e9, 24e3)])
+def test_resampler_plan_matches(oracle, rates):
+    p = frontend.resamp_plan(*rates)
+    q = oracle.resamp_plan(*rates)
+    for k in ("mode", "predec_ratio", "interp", "decim", "ntaps", "taps_per_phase"):
+        assert p[k] == q[k], (k, p, q)
+    if p["predec_ratio"] > 1:
+        assert p["stages"] == oracle.decim_plan(p["predec_ratio"])
+
+
+@pytest.mark.parametrize("cfg", [(2.4e6, 65536, 20.0), (100e6, 1 << 20, 20.0), (8e6, 1024, 20.0), (1e6, 65536, 60.0)])
+def test_frame_params_match(oracle, cfg):
+    nz, skip = frontend.fft_frame_params(*cfg)
+    assert (skip, nz) == oracle.fft_params(*cfg)
+
+
+def test_decim_plan_table_loads():
+    L = lib.load()
+    assert L.b200_load_decim_plans(None) == 0
+    assert L.b200_load_decim_plans(b"/nonexistent/file") == -6
