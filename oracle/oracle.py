@@ -87,6 +87,7 @@ class Oracle:
         ip = C.POINTER(C.c_int)
         sig = {
             "orc_impl": (C.c_char_p, []),
+            "orc_set_rotator_mode": (None, [i]),
             "orc_estimate_tap_count": (i, [d, d]),
             "orc_lowpass": (i, [d, d, d, i, vp, i]),
             "orc_bandpass_c": (i, [d, d, d, d, i, vp, i]),
@@ -133,6 +134,10 @@ class Oracle:
 
     def impl(self):
         return self.lib.orc_impl().decode()
+
+    def set_rotator_mode(self, mode):
+        """0 = faithful fp32 recurrence (declared oracle), 1 = exact-phase rotator (restatement only)."""
+        self.lib.orc_set_rotator_mode(int(mode))
 
     # ---- design ----
     def estimate_tap_count(self, tw, sr):

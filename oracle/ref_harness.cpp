@@ -193,6 +193,7 @@ namespace {
 extern "C" {
 
 const char* orc_impl(void) { return "reference-headers"; }
+void orc_set_rotator_mode(int) {}   // the reference is always its own faithful recurrence
 
 int orc_estimate_tap_count(double tw, double sr) { return taps::estimateTapCount(tw, sr); }
 

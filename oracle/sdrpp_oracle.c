@@ -284,19 +284,41 @@ struct node {
     void (*destroy)(node*);
 };
 
-/* ---- channel::FrequencyXlator  (core/src/dsp/channel/frequency_xlator.h:15-50) ---- */
-typedef struct { cf32 phase, delta; } xlator_t;
+/* ---- channel::FrequencyXlator  (core/src/dsp/channel/frequency_xlator.h:15-50) ----
+ * Rotator mode 0 (default, the declared oracle): the faithful fp32 recurrence phase *= phaseDelta of VOLK's
+ * rotator2.  Mode 1 ("exact phase"): same phaseDelta, but the phase is carried as an fp64 angle
+ * n*angle(phaseDelta) and rounded to fp32 per sample, i.e. the recurrence WITHOUT its fp32 rounding walk.
+ * SSB/DSB audio Re{x e^{j theta}} is first-order sensitive to that walk, so those outputs
+ * are gated against mode 1 and the mode-0-vs-mode-1 gap is reported as the reference's own numerical floor.
+ * Mode 1 exists only in this restatement (the reference-header build is always mode 0). */
+static int g_rotator_mode = 0;
+void orc_set_rotator_mode(int mode) { g_rotator_mode = mode; }
+typedef struct { cf32 phase, delta; double angle; } xlator_t;
 static void xl_init(xlator_t* x, double offsetRad) {
     x->phase.re = 1.0f; x->phase.im = 0.0f;
     x->delta.re = (float)cos(offsetRad);
     x->delta.im = (float)sin(offsetRad);
+    x->angle = 0.0;
 }
 static void xl_set(xlator_t* x, double offsetRad) {
     x->delta.re = (float)cos(offsetRad);
     x->delta.im = (float)sin(offsetRad);
 }
 static int xl_process(xlator_t* x, int count, const cf32* in, cf32* out) {
-    ovk_rotator2(out, in, &x->delta, &x->phase, (unsigned)count);
+    if (g_rotator_mode == 0) {
+        ovk_rotator2(out, in, &x->delta, &x->phase, (unsigned)count);
+        return count;
+    }
+    const double w = atan2((double)x->delta.im, (double)x->delta.re);
+    for (int i = 0; i < count; i++) {
+        double a = x->angle + w * (double)i;
+        float pr = (float)cos(a), pi = (float)sin(a);
+        cf32 v = in[i], y;
+        y.re = v.re * pr - v.im * pi;
+        y.im = v.re * pi + v.im * pr;
+        out[i] = y;
+    }
+    x->angle = fmod(x->angle + w * (double)count, 2.0 * DB_M_PI);
     return count;
 }
 
@@ -616,7 +638,7 @@ static int dcblock_c(float rate, cf32* offset, int count, const cf32* in, cf32* 
 
 typedef struct { node base; xlator_t x; } n_xl;
 static int n_xl_proc(node* b, int c, const void* i, void* o) { return xl_process(&((n_xl*)b)->x, c, (const cf32*)i, (cf32*)o); }
-static void n_xl_reset(node* b) { ((n_xl*)b)->x.phase.re = 1.0f; ((n_xl*)b)->x.phase.im = 0.0f; }
+static void n_xl_reset(node* b) { ((n_xl*)b)->x.phase.re = 1.0f; ((n_xl*)b)->x.phase.im = 0.0f; ((n_xl*)b)->x.angle = 0.0; }
 static void n_plain_destroy(node* b) { free(b); }
 void* orc_xlator_create(double offsetHz, double sr) {
     NODE_ALLOC(n_xl);
@@ -683,7 +705,7 @@ typedef struct { node base; rxvfo_t v; } n_vfo;
 static int n_vfo_proc(node* b, int c, const void* i, void* o) { return vfo_process(&((n_vfo*)b)->v, c, (const cf32*)i, (cf32*)o); }
 static void n_vfo_reset(node* b) {
     rxvfo_t* v = &((n_vfo*)b)->v;
-    v->xl.phase.re = 1.0f; v->xl.phase.im = 0.0f;
+    v->xl.phase.re = 1.0f; v->xl.phase.im = 0.0f; v->xl.angle = 0.0;
     rr_reset(&v->rs);
     fir_reset(&v->filt);
 }

@@ -29,6 +29,8 @@ extern "C" {
 
 /* which implementation is this: "restatement" or "reference-headers" */
 const char* orc_impl(void);
+/* restatement only: 0 = faithful fp32 rotator recurrence (default), 1 = exact-phase rotator (see sdrpp_oracle.c) */
+void orc_set_rotator_mode(int mode);
 
 /* ---- host-side design (taps, windows, plans) ---- */
 int orc_estimate_tap_count(double transWidth, double samplerate);
