@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- complex IQ MSamples/s through the FFT-waterfall + 8-VFO WFM chain (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one chunk of synthetic IQ (BASELINE config 2: 100 MS/s stream,
+1,048,576-point Nuttall FFT @ 20 fps, 8 WFM VFOs at +-5/15/25/35 MHz -> 250 kS/s stereo audio each).
+
+  value     whole-job throughput with the chunks already resident in HBM (cf32), timed with CUDA events on the
+            stream the kernels run on, max over ranks
+  e2e       the same metric through the reference-facing C-ABI call with HOST (pinned) buffers: every step
+            copies its IQ chunk host->device and its audio / FFT lines device->host inside the timed region.
+            Reported for int16 IQ (file_source's native format, 4 B/sample) as the headline and for cf32.
+  roofline  dominant kernel (stage 1: translate + first decimation of all VFOs, IQ read once): algorithmic bytes
+            per launch / its device time measured live with CUDA events (b200_fe_s1_stats)
+  cpu_baseline  the reference's own blocks (oracle/_ref/ref_pipeline: reference headers + restated VOLK/FFT leaf
+            kernels, one thread per block, SpeedTester method) timed on this box's host cores
+
+N > 1 (torchrun): N independent IQ streams, one full front end per GPU, no collective on the data path
+(BASELINE config 5 style replicas) -> weak scaling, value = sum over ranks / max time.
+`--impl reference` times the reference CPU path only (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS = 100e6
+OFFSETS = [5e6, -5e6, 15e6, -15e6, 25e6, -25e6, 35e6, -35e6]
+FFT_SIZE, FFT_RATE = 1 << 20, 20.0
+WORKLOAD = "C2: 100 MS/s complex IQ, 1048576-pt Nuttall FFT @20 fps + 8 VFO WFM (250 kS/s, 150 kHz, mono+LPF)"
+# algorithmic bytes per input sample: read IQ once + 8 stereo outputs + dB lines
+ALGO_BYTES_PER_SAMPLE = 8.0 + 8 * 8 * (250e3 / FS) + 4.0 * FFT_SIZE * FFT_RATE / FS     # = 9.0
+# fp32 work per input sample in stage 1 as executed (complex taps): 8 VFOs * ceil-padded taps / D * 4 FMA
+METRIC = "complex IQ MSamples/s through FFT + 8-VFO WFM chain"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_run(duration_ms, nvfo=8):
+    """Times the reference's own blocks on the host cores.  Returns (samples_per_s, threads, kind, what)."""
+    # -march=native build first (AVX-512 where the container had it); the x86-64-v3 build if that one cannot run here
+    for name, flags in (("ref_pipeline", "-O3 -march=native of the build container"), ("ref_pipeline_v3", "-O3 -march=x86-64-v3")):
+        exe = os.path.join(ROOT, "oracle", "_ref", name)
+        if not os.path.exists(exe):
+            continue
+        out = subprocess.run([exe, str(FS), "500000", str(FFT_SIZE), str(FFT_RATE), str(nvfo), str(int(duration_ms)), "wfm"],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=duration_ms / 1000.0 * 3 + 120)
+        rows = [l for l in out.stdout.strip().splitlines() if l and not l.startswith("[")]
+        if out.returncode != 0 or not rows:
+            continue
+        last = rows[-1].split()
+        return float(last[0]), int(last[1]), "reference", ("reference dsp headers + restated VOLK-generic/FFT leaf kernels (%s), one thread per block, "
+                                                           "SpeedTester method, chunk 500000, %d ms" % (flags, duration_ms))
+    # port: the plain-C restatement, single thread, bounded sample
+    import numpy as np
+    from oracle.oracle import Oracle, available
+    o = Oracle("restatement_fast" if available("restatement_fast") else "restatement")
+    n = 2000000
+    rng = np.random.default_rng(0x5D12)
+    x = rng.uniform(-1, 1, 2 * n).astype(np.float32)
+    blocks = [(o.rxvfo(FS, 250e3, 150e3, off), o.wfm(75e3, 250e3, False, True)) for off in OFFSETS[:nvfo]]
+    t0 = time.perf_counter()
+    for i in range(0, n, 500000):
+        seg = x[2 * i: 2 * (i + 500000)]
+        for v, d in blocks:
+            d.process(v.process(seg))
+    o.fft_frame(FFT_SIZE, FFT_SIZE, 2, x[: 2 * FFT_SIZE].view(np.complex64))
+    dt = time.perf_counter() - t0
+    return n / dt, 1, "port", "plain-C restatement (oracle/liboracle), single thread, %d samples" % n
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    total = args.steps + args.warmup
+    step_ms = max(500, min(3000, int(150000 / max(total, 1))))
+    vals = []
+    threads = kind = what = None
+    for i in range(total):
+        v, threads, kind, what = cpu_reference_run(step_ms)
+        if i >= args.warmup:
+            vals.append(v)
+    v = sum(vals) / len(vals) / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "chunk_samples": 500000, "note": "reference chunk cap STREAM_BUFFER_SIZE=1e6"},
+            "cpu_baseline": {"value": v, "unit": "MS/s", "cores": threads, "host_cpus": os.cpu_count(), "kind": kind, "sample": what},
+            "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import sdrplusplus_b200 as sb
+    from sdrplusplus_b200 import lib
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- libb200dsp has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = lib.load()
+    lib.check(L.b200_init(local))
+
+    chunk = args.chunk
+    nbuf = 3
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        fe = sb.FrontEnd(FS, chunk)
+        fe.set_stream(stream.cuda_stream)
+        fe.set_option("s1", args.s1)
+        fe.set_fft(FFT_SIZE, FFT_RATE, lib.WIN_NUTTALL)
+        ids = [fe.add_vfo(sb.VfoConfig.wfm(o)) for o in OFFSETS]
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(0x5D12 + rank)
+        # synthetic inputs, SpeedTester distribution: i.i.d. uniform[-1,1) re/im; distinct per buffer and per rank
+        dev_in = [(torch.rand(2 * chunk, device="cuda", generator=gen, dtype=torch.float32) * 2.0 - 1.0) for _ in range(nbuf)]
+        cap = {v: fe.vfo_max_out(v, chunk) for v in ids}
+        nl = fe.fft_max_lines(chunk)
+
+        def make_outputs(pinned):
+            o = lib.Outputs()
+            keep = []
+            for v in ids:
+                t = torch.empty(2 * cap[v], dtype=torch.float32, pin_memory=True) if pinned else torch.empty(2 * cap[v], device="cuda", dtype=torch.float32)
+                keep.append(t)
+                o.vfo_out[v] = t.data_ptr()
+                o.vfo_cap[v] = cap[v]
+            t = torch.empty(nl * FFT_SIZE, dtype=torch.float32, pin_memory=True) if pinned else torch.empty(nl * FFT_SIZE, device="cuda", dtype=torch.float32)
+            keep.append(t)
+            o.fft_out = t.data_ptr()
+            o.fft_cap_lines = nl
+            o.out_mem = lib.MEM_HOST if pinned else lib.MEM_DEVICE
+            return o, keep
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def timed_loop(ptrs, fmt, mem, outs, steps, warm):
+            """pipelined submit/wait (two chunks in flight); returns (ms by CUDA events on `stream`, wall ms, d2h bytes)."""
+            inflight = 0
+            for i in range(warm):
+                fe.submit_ptr(ptrs[i % len(ptrs)], chunk, fmt, mem, outs[i % 2][0])
+                inflight += 1
+                if inflight == 2:
+                    fe.wait()
+                    inflight -= 1
+            while inflight:
+                fe.wait()
+                inflight -= 1
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record(stream)
+            d2h = 0
+            for i in range(steps):
+                o = outs[i % 2][0]
+                fe.submit_ptr(ptrs[i % len(ptrs)], chunk, fmt, mem, o)
+                d2h = sum(o.vfo_count[v] for v in ids) * 8 + o.fft_lines * FFT_SIZE * 4
+                inflight += 1
+                if inflight == 2:
+                    fe.wait()
+                    inflight -= 1
+            while inflight:
+                fe.wait()
+                inflight -= 1
+            e1.record(stream)
+            torch.cuda.synchronize()
+            wall = (time.perf_counter() - t0) * 1e3
+            ms = e0.elapsed_time(e1)
+            barrier()
+            if world > 1:
+                t = torch.tensor([ms, wall], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms, wall = float(t[0]), float(t[1])
+            return ms, wall, d2h
+
+        clocks = ClockSampler(local)
+        # ---------------- device-resident leg ----------------
+        outs_dev = [make_outputs(False), make_outputs(False)]
+        ptrs = [t.data_ptr() for t in dev_in]
+        fe.set_option("time_s1", 0)
+        l0 = fe.launch_count()
+        timed_loop(ptrs, lib.FMT_CF32, lib.MEM_DEVICE, outs_dev, 0, args.warmup)       # warm-up only
+        fe.set_option("time_s1", 1)
+        clocks.start()
+        l0 = fe.launch_count()
+        ms, wall, _ = timed_loop(ptrs, lib.FMT_CF32, lib.MEM_DEVICE, outs_dev, args.steps, 0)
+        launches = fe.launch_count() - l0
+        s1_ms, s1_n = fe.s1_stats()
+        fe.set_option("time_s1", 0)
+        value = world * chunk * args.steps / (ms * 1e-3) / 1e6
+
+        # ---------------- end-to-end legs (host pinned in, host pinned out) ----------------
+        outs_host = [make_outputs(True), make_outputs(True)]
+        e2e = {}
+        for name, fmt, bps in (("cs16", lib.FMT_CS16, 4), ("cf32", lib.FMT_CF32, 8)):
+            if name == "cs16":
+                host_in = [torch.empty(2 * chunk, dtype=torch.int16, pin_memory=True) for _ in range(2)]
+                for k, t in enumerate(host_in):
+                    t.copy_((dev_in[k] * 32767.0).to(torch.int16).cpu())
+            else:
+                host_in = [torch.empty(2 * chunk, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+                for k, t in enumerate(host_in):
+                    t.copy_(dev_in[k].cpu())
+            hp = [t.data_ptr() for t in host_in]
+            steps = max(4, args.steps // 2)
+            ems, ewall, d2h = timed_loop(hp, fmt, lib.MEM_HOST, outs_host, steps, 3)
+            e2e[name] = {"value": world * chunk * steps / (ewall * 1e-3) / 1e6, "unit": "MS/s", "h2d_bytes_per_step": chunk * bps,
+                         "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step_wall": ewall / steps, "ms_per_step_events": ems / steps}
+            del host_in
+        clk = clocks.stop()
+        fe.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    peak, peak_src = measured_peak_hbm()
+    algo_bytes = ALGO_BYTES_PER_SAMPLE * chunk
+    s1_avg = s1_ms / max(s1_n, 1)
+    achieved = algo_bytes / (s1_avg * 1e-3) / 1e9 if s1_n else None
+    line = {
+        "metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "chunk_samples": chunk, "samplerate": FS, "parallelism": "replicas x%d (one IQ stream per GPU, no collective)" % world,
+                   "l2": "inputs larger than L2: %d MiB cf32 chunk, %d rotating device buffers" % (chunk * 8 >> 20, nbuf),
+                   "value_input": "cf32 resident in HBM, outputs to HBM", "e2e_input": "int16 IQ in pinned host memory (file_source format); cf32 also reported",
+                   "pipelining": "b200_fe_submit/wait, 2 chunks in flight", "s1_variant": args.s1},
+        "e2e": dict(e2e["cs16"], format="cs16", cf32=e2e["cf32"]),
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": {"bound": "hbm", "kernel": "k_xd_tile (stage 1: translate + first decimating FIR of all VFOs, IQ read once)",
+                     "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": s1_avg, "launches_timed": s1_n,
+                     "share_of_step": (s1_ms / ms) if ms else None,
+                     "step_level": {"achieved": algo_bytes * args.steps / (ms * 1e-3) / 1e9, "frac": algo_bytes * args.steps / (ms * 1e-3) / 1e9 / peak},
+                     "note": "fp32-FMA bound, not HBM bound: 8 VFOs x 143 complex taps / 32 = 143 FMA per input sample vs 9 B (see DESIGN.md)"},
+    }
+    if world == 1 and not args.no_cpu:
+        try:
+            v, threads, kind, what = cpu_reference_run(args.cpu_ms)
+            line["cpu_baseline"] = {"value": v / 1e6, "unit": "MS/s", "cores": threads, "host_cpus": os.cpu_count(), "kind": kind, "sample": what}
+        except Exception as ex:          # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": "MS/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (ex,)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chunk", type=int, default=1 << 24, help="IQ samples per step (default 16 Mi = 128 MiB cf32 > L2)")
+    ap.add_argument("--s1", type=int, default=1, help="stage-1 kernel variant")
+    ap.add_argument("--cpu-ms", type=int, default=12000, help="duration of the CPU reference sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

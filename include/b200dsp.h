@@ -183,8 +183,12 @@ int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt, int in_me
 int b200_fe_wait(b200_fe* fe);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 long long b200_fe_launch_count(b200_fe* fe);
-/* selects kernel variants for A/B parity runs: key "s1" (0 plain, 1 register-blocked f32x2) etc. */
+/* "s1": stage-1 kernel variant for A/B parity runs (0 plain per-output kernel, 1 tiled 4 outputs/lane,
+ * 2 tiled 2 outputs/lane); "time_s1": 1 = bracket every stage-1 launch with CUDA events on the handle's stream */
 int b200_fe_set_option(b200_fe* fe, const char* key, int value);
+/* device time spent in the stage-1 (translate + first decimation) launches since the last call, and their count;
+ * synchronises on the recorded events ("time_s1" must be on).  bench.py's roofline leg reads this. */
+int b200_fe_s1_stats(b200_fe* fe, double* ms_total, int* launches);
 
 /* waterfall zoom (max-decimate) + peak hold on the device line, bit-exact with
  * doZoom / pushFFT hold loop (core/src/gui/widgets/waterfall.cpp:65-90, 935-939).

@@ -324,8 +324,14 @@ extern "C" long long b200_fe_launch_count(b200_fe* fe) { return fe ? fe->sch.lau
 extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
     if (!fe || !key) { set_error("null argument"); return B200_EINVAL; }
     if (!strcmp(key, "s1")) { fe->sch.s1_variant = value; return 0; }
+    if (!strcmp(key, "time_s1")) { fe->sch.time_s1 = value != 0; fe->sch.ev_used = 0; return 0; }
     set_error("unknown option %s", key);
     return B200_EINVAL;
+}
+
+extern "C" int b200_fe_s1_stats(b200_fe* fe, double* ms_total, int* launches) {
+    if (!fe || !ms_total || !launches) { set_error("null argument"); return B200_EINVAL; }
+    return fe->sch.s1_stats(ms_total, launches);
 }
 
 extern "C" int b200_fe_reset(b200_fe* fe) {

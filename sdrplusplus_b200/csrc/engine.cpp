@@ -394,6 +394,22 @@ int Scheduler::init_raw() {
     if (raw_hist.p) { return 0; }
     return raw_hist.alloc((size_t)RAW_HIST * sizeof(float2));
 }
+Scheduler::~Scheduler() {
+    for (cudaEvent_t e : ev_s1) { cudaEventDestroy(e); }
+}
+int Scheduler::s1_stats(double* ms_total, int* n) {
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < ev_used; i += 2) {
+        B200_CK(cudaEventSynchronize(ev_s1[i + 1]));
+        float ms = 0.0f;
+        B200_CK(cudaEventElapsedTime(&ms, ev_s1[i], ev_s1[i + 1]));
+        tot += ms;
+    }
+    *ms_total = tot;
+    *n = (int)(ev_used / 2);
+    ev_used = 0;
+    return 0;
+}
 int Scheduler::reset_raw() {
     if (raw_hist.p) { B200_CK(cudaMemset(raw_hist.p, 0, raw_hist.bytes)); }
     return 0;
@@ -500,8 +516,22 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
                 if (g[b + v]->gpad_len < (p.D - 1) + (p.QP + 8) * p.D) { variant = 0; }
             }
             int nl = 0;
+            cudaEvent_t t0 = nullptr, t1 = nullptr;
+            if (time_s1) {
+                if (ev_used + 2 > ev_s1.size()) {
+                    cudaEvent_t a, b;
+                    B200_CK(cudaEventCreate(&a));
+                    B200_CK(cudaEventCreate(&b));
+                    ev_s1.push_back(a);
+                    ev_s1.push_back(b);
+                }
+                t0 = ev_s1[ev_used]; t1 = ev_s1[ev_used + 1];
+                ev_used += 2;
+                B200_CK(cudaEventRecord(t0, stream));
+            }
             cudaError_t e = launch_xlate_decim(p, fmt, variant, stream, &nl);
             if (e != cudaSuccess) { return cuda_fail(e, "launch_xlate_decim"); }
+            if (t1) { B200_CK(cudaEventRecord(t1, stream)); }
             e = launch_xd_edge(p, fmt, stream, &nl);
             if (e != cudaSuccess) { return cuda_fail(e, "launch_xd_edge"); }
             launches += nl;

@@ -164,6 +164,12 @@ struct Scheduler {
     cudaStream_t stream = nullptr;
     long long launches = 0;
     int s1_variant = 1;
+    // optional device-side timing of the stage-1 launches (bench.py's roofline leg): CUDA events on `stream`
+    bool time_s1 = false;
+    std::vector<cudaEvent_t> ev_s1;     // pairs (start, stop)
+    size_t ev_used = 0;
+    int s1_stats(double* ms_total, int* launches);   // synchronises the recorded events, then clears them
+    ~Scheduler();
     DevBuf raw_hist;             // last RAW_HIST samples of the raw IQ stream (cf32)
     static const int RAW_HIST = 1024;
     int init_raw();

@@ -118,6 +118,11 @@ class FrontEnd:
     def reset(self):
         L.check(self._l.b200_fe_reset(self._h))
 
+    def s1_stats(self):
+        ms, n = C.c_double(), C.c_int()
+        L.check(self._l.b200_fe_s1_stats(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def launch_count(self):
         return self._l.b200_fe_launch_count(self._h)
 

@@ -69,6 +69,7 @@ SIGNATURES = {
     "b200_fe_wait": (_i, [_vp]),
     "b200_fe_launch_count": (_ll, [_vp]),
     "b200_fe_set_option": (_i, [_vp, C.c_char_p, _i]),
+    "b200_fe_s1_stats": (_i, [_vp, C.POINTER(C.c_double), _ip]),
     "b200_fft_zoom_hold": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, C.c_float, _i]),
     "b200_xlator_create": (_vp, [_d, _d]),
     "b200_xlator_set_offset": (_i, [_vp, _d, _d]),
