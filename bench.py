@@ -96,6 +96,47 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa(local):
+    """Run this process (and first-touch its pinned buffers) on the CPUs of the GPU's own NUMA node."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%s -> cpus %s" % (bdf, txt)
+    except Exception as ex:       # noqa: BLE001
+        return "unbound (%r)" % (ex,)
+    return "unbound"
+
+
+def pcie_probe(torch, nbytes=256 << 20):
+    """Plain pinned<->device copy bandwidth of this box: the ceiling of the end-to-end legs."""
+    h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    res = {}
+    for name, (dst, src) in (("h2d_gbs", (d, h)), ("d2h_gbs", (h, d))):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4):
+            dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = 4 * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    return res
+
+
 def measured_peak_hbm():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -171,6 +212,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- libb200dsp has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = lib.load()
@@ -183,6 +225,7 @@ def run_b200(args):
         fe = sb.FrontEnd(FS, chunk)
         fe.set_stream(stream.cuda_stream)
         fe.set_option("s1", args.s1)
+        fe.set_option("tails", args.tails)
         fe.set_fft(FFT_SIZE, FFT_RATE, lib.WIN_NUTTALL)
         ids = [fe.add_vfo(sb.VfoConfig.wfm(o)) for o in OFFSETS]
         gen = torch.Generator(device="cuda")
@@ -251,6 +294,7 @@ def run_b200(args):
                 ms, wall = float(t[0]), float(t[1])
             return ms, wall, d2h
 
+        probe = pcie_probe(torch)
         clocks = ClockSampler(local)
         # ---------------- device-resident leg ----------------
         outs_dev = [make_outputs(False), make_outputs(False)]
@@ -303,11 +347,11 @@ def run_b200(args):
         "config": {"workload": WORKLOAD, "chunk_samples": chunk, "samplerate": FS, "parallelism": "replicas x%d (one IQ stream per GPU, no collective)" % world,
                    "l2": "inputs larger than L2: %d MiB cf32 chunk, %d rotating device buffers" % (chunk * 8 >> 20, nbuf),
                    "value_input": "cf32 resident in HBM, outputs to HBM", "e2e_input": "int16 IQ in pinned host memory (file_source format); cf32 also reported",
-                   "pipelining": "b200_fe_submit/wait, 2 chunks in flight", "s1_variant": args.s1},
-        "e2e": dict(e2e["cs16"], format="cs16", cf32=e2e["cf32"]),
+                   "pipelining": "b200_fe_submit/wait, 2 chunks in flight", "s1_variant": args.s1, "tails_variant": args.tails},
+        "e2e": dict(e2e["cs16"], format="cs16", cf32=e2e["cf32"], pcie_probe=probe, numa=numa),
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": "k_xd_tile (stage 1: translate + first decimating FIR of all VFOs, IQ read once)",
+        "roofline": {"bound": "hbm", "kernel": "k_xd_pipe (stage 1: translate + first decimating FIR of all VFOs, IQ read once)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": None,
                      "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": s1_avg, "launches_timed": s1_n,
@@ -334,7 +378,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunk", type=int, default=1 << 24, help="IQ samples per step (default 16 Mi = 128 MiB cf32 > L2)")
-    ap.add_argument("--s1", type=int, default=1, help="stage-1 kernel variant")
+    ap.add_argument("--s1", type=int, default=3, help="stage-1 kernel variant (3 = pipelined, default)")
+    ap.add_argument("--tails", type=int, default=1, help="tail kernel variant (1 = shared-memory tiled, default)")
     ap.add_argument("--cpu-ms", type=int, default=12000, help="duration of the CPU reference sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -324,6 +324,7 @@ extern "C" long long b200_fe_launch_count(b200_fe* fe) { return fe ? fe->sch.lau
 extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
     if (!fe || !key) { set_error("null argument"); return B200_EINVAL; }
     if (!strcmp(key, "s1")) { fe->sch.s1_variant = value; return 0; }
+    if (!strcmp(key, "tails")) { kernels_set_tail_variant(value); return 0; }
     if (!strcmp(key, "time_s1")) { fe->sch.time_s1 = value != 0; fe->sch.ev_used = 0; return 0; }
     set_error("unknown option %s", key);
     return B200_EINVAL;

@@ -163,7 +163,7 @@ struct Chain {
 struct Scheduler {
     cudaStream_t stream = nullptr;
     long long launches = 0;
-    int s1_variant = 1;
+    int s1_variant = 3;
     // optional device-side timing of the stage-1 launches (bench.py's roofline leg): CUDA events on `stream`
     bool time_s1 = false;
     std::vector<cudaEvent_t> ev_s1;     // pairs (start, stop)

@@ -209,6 +209,9 @@ __global__ void __launch_bounds__(256) k_xd_tile(const __grid_constant__ XdParam
 }
 
 
+#include "xd_pipe.cuh"
+#include "tails.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // retune edge: outputs whose tap window straddles the chunk start when the VFO offset changed at this
 // boundary.  Explicit per-sample rotation (old increment for history, new one for this chunk), real taps.
@@ -710,12 +713,115 @@ static cudaError_t launch_xd_tile_t(const XdParams& p, int MT, int JP, int QPC, 
     return cudaGetLastError();
 }
 
+
+static int g_num_sms = -1;
+static int num_sms() {
+    if (g_num_sms < 0) {
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        g_num_sms = v > 0 ? v : 148;
+    }
+    return g_num_sms;
+}
+
+template <int FMT, int QC>
+static cudaError_t launch_xd_pipe_t(const XdParams& p, const XpGeom& g, size_t smem, cudaStream_t s) {
+    cudaError_t e = set_smem(k_xd_pipe<FMT, QC>, smem);
+    if (e != cudaSuccess) { return e; }
+    int grid = g.ntiles < num_sms() ? g.ntiles : num_sms();
+    k_xd_pipe<FMT, QC><<<grid, 256, smem, s>>>(p, g);
+    return cudaGetLastError();
+}
+
+// returns true when the pipelined kernel was launched
+template <int FMT>
+static bool try_xd_pipe(const XdParams& p, cudaStream_t s, cudaError_t* err) {
+    const int D = p.D;
+    if (D < 2 || (D & (D - 1))) { return false; }
+    int logD = 0;
+    while ((1 << logD) < D) { logD++; }
+    // origin of the block grid: align it with job 0's window start so that the common case needs no tap shift
+    int first = -1;
+    for (int v = 0; v < p.njobs; v++) { if (p.job[v].n_out > 0) { first = v; break; } }
+    if (first < 0) { return false; }
+    const int a_first = p.job[first].offset - (p.job[first].T - 1);
+    const int org = ((a_first % D) + D) % D;
+    int QP = 1;
+    long long jmin = (1LL << 60), jmax = -(1LL << 60);
+    for (int v = 0; v < p.njobs; v++) {
+        const int a = p.job[v].offset - (p.job[v].T - 1) - org;
+        const int sft = ((a % D) + D) % D;
+        const int qp = (p.job[v].T + sft + D - 1) / D;
+        if (qp > QP) { QP = qp; }
+        if (p.job[v].n_out <= 0) { continue; }
+        const long long c = (a - sft) / D;
+        if (c < jmin) { jmin = c; }
+        if (c + p.job[v].n_out > jmax) { jmax = c + p.job[v].n_out; }
+    }
+    if (QP > p.QP) { return false; }              // the host sized gpad for p.QP blocks (+8 slack)
+    int QC;
+    if (QP <= 4) { QC = 4; }
+    else if (QP <= 8) { QC = QP; }                // single chunk, odd sizes allowed
+    else {
+        QC = 6;
+        int best = 1 << 30;
+        const int qcs[3] = { 8, 6, 4 };           // several chunks: even sizes keep the LDS.128 window aligned
+        for (int i = 0; i < 3; i++) {
+            int pad = ((QP + qcs[i] - 1) / qcs[i]) * qcs[i] - QP;
+            if (pad < best) { best = pad; QC = qcs[i]; }
+        }
+    }
+    const int QPC = ((QP + QC - 1) / QC) * QC;
+    if (jmin & 1) { jmin -= 1; }
+    const int ngroups = (p.njobs + XP_VR - 1) / XP_VR;
+    const int limit = kernels_max_smem_optin();
+    // tile: about 8K raw samples, a multiple of 128 outputs
+    int MT = (8192 / D) / 128 * 128;
+    if (MT < 128) { MT = 128; }
+    if (MT > 1024) { MT = 1024; }
+    XpGeom g;
+    size_t smem = 0;
+    for (;; MT -= 128) {
+        if (MT < 128) { return false; }
+        int jp = MT + QPC + 2;
+        jp += (jp & 1);
+        if ((jp & 3) == 0) { jp += 2; }
+        smem = ((size_t)2 * D * jp + (size_t)ngroups * QPC * D * XP_VR + (size_t)8 * 16 * 32) * sizeof(float2);
+        if (smem <= (size_t)limit) { g.JP = jp; break; }
+    }
+    const int nstrips = MT / 128;
+    int RS = 8 / (nstrips * ngroups);
+    if (RS < 1) { RS = 1; }
+    while (RS > 1 && (D % RS || (RS & (RS - 1)))) { RS--; }
+    g.MT = MT; g.QPC = QPC; g.org = org; g.RS = RS; g.logD = logD; g.jmin = jmin;
+    g.ntiles = cdiv(jmax - jmin, MT);
+    cudaError_t e;
+    switch (QC) {
+    case 4: e = launch_xd_pipe_t<FMT, 4>(p, g, smem, s); break;
+    case 5: e = launch_xd_pipe_t<FMT, 5>(p, g, smem, s); break;
+    case 6: e = launch_xd_pipe_t<FMT, 6>(p, g, smem, s); break;
+    case 7: e = launch_xd_pipe_t<FMT, 7>(p, g, smem, s); break;
+    default: e = launch_xd_pipe_t<FMT, 8>(p, g, smem, s); break;
+    }
+    *err = e;
+    return true;
+}
+
 template <int FMT>
 static cudaError_t launch_xd_fmt(const XdParams& p, int variant, cudaStream_t s, int* nlaunch) {
     int max_out = 0;
     for (int v = 0; v < p.njobs; v++) { max_out = p.job[v].n_out > max_out ? p.job[v].n_out : max_out; }
     if (max_out <= 0) { return cudaSuccess; }
     const int D = p.D;
+    if (variant >= 3) {
+        cudaError_t e = cudaSuccess;
+        if (try_xd_pipe<FMT>(p, s, &e)) {
+            if (nlaunch) { (*nlaunch)++; }
+            return e;
+        }
+        variant = 1;     // shapes the pipelined kernel does not cover
+    }
     // ---- tiled variant: needs padded taps of QPC*D entries; the host sized gpad for QC in {4,6,8} ----
     if (variant >= 1 && D >= 2) {
         int QP = p.QP;
@@ -805,14 +911,68 @@ cudaError_t launch_xd_edge(const XdParams& p, int fmt, cudaStream_t s, int* nlau
     return cudaGetLastError();
 }
 
+int g_tail_variant = 1;     // 0 = v0 kernels (operands through L1), 1 = shared-memory tiled kernels
+void kernels_set_tail_variant(int v) { g_tail_variant = v; }
+
 cudaError_t launch_fir_c(const FirParams& p, cudaStream_t s) {
     if (p.max_out <= 0 || p.njobs <= 0) { return cudaSuccess; }
+    if (g_tail_variant >= 1) {
+        // all jobs of a batch share one kernel shape: pick by the first job, require the others to agree
+        bool all_d1 = true, same_d = true;
+        int maxT = 0, D0 = p.job[0].decim;
+        for (int v = 0; v < p.njobs; v++) {
+            all_d1 = all_d1 && p.job[v].decim == 1 && p.job[v].offset == 0;
+            same_d = same_d && p.job[v].decim == D0;
+            maxT = p.job[v].ntaps > maxT ? p.job[v].ntaps : maxT;
+        }
+        if (all_d1 && maxT <= TAIL_MAX_TAPS) {
+            const int OB = FC2_THREADS * FC2_R;
+            const int span = OB + maxT + FC2_R;
+            size_t smem = ((size_t)((maxT + 1) >> 1) + (size_t)(span + (span >> 3) + 2)) * sizeof(float2);
+            cudaError_t e = set_smem(k_fir_c2, smem);
+            if (e != cudaSuccess) { return e; }
+            dim3 grid(cdiv(p.max_out, OB), p.njobs);
+            k_fir_c2<<<grid, FC2_THREADS, smem, s>>>(p);
+            return cudaGetLastError();
+        }
+        if (same_d && D0 > 1 && D0 <= 64 && maxT <= TAIL_MAX_TAPS) {
+            int lg = 30;
+            if ((D0 & (D0 - 1)) == 0) { lg = 0; while ((1 << lg) < D0) { lg++; } }
+            const int span = (FCD_THREADS - 1) * D0 + maxT;
+            size_t smem = ((size_t)((maxT + 1) >> 1) + (size_t)(span + (lg < 30 ? (span >> lg) : 0) + 2)) * sizeof(float2);
+            if (smem <= (size_t)kernels_max_smem_optin()) {
+                cudaError_t e = set_smem(k_fir_cd, smem);
+                if (e != cudaSuccess) { return e; }
+                dim3 grid(cdiv(p.max_out, FCD_THREADS), p.njobs);
+                k_fir_cd<<<grid, FCD_THREADS, smem, s>>>(p, lg);
+                return cudaGetLastError();
+            }
+        }
+    }
     dim3 grid(cdiv(p.max_out, 256), p.njobs);
     k_fir_c<<<grid, 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 cudaError_t launch_poly(const PolyParams& p, cudaStream_t s) {
     if (p.max_out <= 0 || p.njobs <= 0) { return cudaSuccess; }
+    if (g_tail_variant >= 1) {
+        long long span_cap = 0, bank_floats = 0;
+        for (int v = 0; v < p.njobs; v++) {
+            long long sp = ((long long)PL2_THREADS * p.job[v].decim + p.job[v].interp - 1) / p.job[v].interp + p.job[v].tpp + 2;
+            span_cap = sp > span_cap ? sp : span_cap;
+            long long bf = (long long)p.job[v].interp * (p.job[v].tpp | 1);
+            bank_floats = bf > bank_floats ? bf : bank_floats;
+        }
+        if (span_cap <= 8192) {
+            const int in_smem = bank_floats <= 16384 ? 1 : 0;
+            size_t smem = (size_t)span_cap * sizeof(float2) + (in_smem ? (size_t)bank_floats * sizeof(float) : 0);
+            cudaError_t e = set_smem(k_poly2, smem);
+            if (e != cudaSuccess) { return e; }
+            dim3 grid(cdiv(p.max_out, PL2_THREADS), p.njobs);
+            k_poly2<<<grid, PL2_THREADS, smem, s>>>(p, (int)span_cap, in_smem);
+            return cudaGetLastError();
+        }
+    }
     dim3 grid(cdiv(p.max_out, 256), p.njobs);
     k_poly<<<grid, 256, 0, s>>>(p);
     return cudaGetLastError();
@@ -825,6 +985,20 @@ cudaError_t launch_quad(const QuadParams& p, cudaStream_t s) {
 }
 cudaError_t launch_fir_r(const FirRParams& p, cudaStream_t s) {
     if (p.max_out <= 0 || p.njobs <= 0) { return cudaSuccess; }
+    if (g_tail_variant >= 1) {
+        int maxT = 0;
+        for (int v = 0; v < p.njobs; v++) { maxT = p.job[v].ntaps > maxT ? p.job[v].ntaps : maxT; }
+        if (maxT <= TAIL_MAX_TAPS) {
+            const int OB = FR2_THREADS * FR2_R;
+            const int span = OB + maxT + FR2_R;
+            size_t smem = ((size_t)maxT + (size_t)(span + (span >> 3) + 2)) * sizeof(float);
+            cudaError_t e = set_smem(k_fir_r2, smem);
+            if (e != cudaSuccess) { return e; }
+            dim3 grid(cdiv(p.max_out, OB), p.njobs);
+            k_fir_r2<<<grid, FR2_THREADS, smem, s>>>(p);
+            return cudaGetLastError();
+        }
+    }
     dim3 grid(cdiv(p.max_out, 256), p.njobs);
     k_fir_r<<<grid, 256, 0, s>>>(p);
     return cudaGetLastError();
@@ -860,10 +1034,13 @@ static cudaError_t launch_fft_fmt(const FftPlanDev& pl, const void* src, float2*
         return cudaGetLastError();
     }
     // two passes
+    // columns / rows per CTA: enough CTAs to fill the chip about twice, at least 4 (32-byte segments)
     int C = 16;
+    while (C > 4 && pl.N2 / C < 2 * num_sms()) { C >>= 1; }
     while ((size_t)pl.N1 * C * sizeof(float2) > 196608 && C > 1) { C >>= 1; }
     if (C > pl.N2) { C = pl.N2; }
     int R = 16;
+    while (R > 4 && pl.N1 / R < 2 * num_sms()) { R >>= 1; }
     while ((size_t)R * (pl.N2 + 1) * sizeof(float2) > 196608 && R > 1) { R >>= 1; }
     if (R > pl.N1) { R = pl.N1; }
     size_t smem1 = (size_t)pl.N1 * C * sizeof(float2);
@@ -872,10 +1049,11 @@ static cudaError_t launch_fft_fmt(const FftPlanDev& pl, const void* src, float2*
     if (e != cudaSuccess) { return e; }
     e = set_smem(k_fft_p2, smem2);
     if (e != cudaSuccess) { return e; }
-    k_fft_p1<FMT><<<pl.N2 / C, 512, smem1, s>>>(pl, src, work, C);
+    const int thr1 = (pl.N1 / 8) * C >= 512 ? 512 : 256, thr2 = (pl.N2 / 8) * R >= 512 ? 512 : 256;
+    k_fft_p1<FMT><<<pl.N2 / C, thr1, smem1, s>>>(pl, src, work, C);
     e = cudaGetLastError();
     if (e != cudaSuccess) { return e; }
-    k_fft_p2<<<pl.N1 / R, 512, smem2, s>>>(pl, work, out_db, out_raw, R);
+    k_fft_p2<<<pl.N1 / R, thr2, smem2, s>>>(pl, work, out_db, out_raw, R);
     if (nlaunch) { (*nlaunch) += 2; }
     return cudaGetLastError();
 }

@@ -142,3 +142,4 @@ cudaError_t launch_convert_cf32(const void* src, int fmt, float2* dst, int n, cu
 cudaError_t launch_zoom_hold_tbl(const float* line, const int* start, const int* len, int out_size, float* out,
                                  float* hold, float hold_speed, cudaStream_t s);
 int kernels_max_smem_optin();
+void kernels_set_tail_variant(int v);

@@ -1,0 +1,214 @@
+// sdrplusplus_b200/csrc/xd_pipe.cuh -- stage 1 (frequency translate + first decimating FIR of every VFO),
+// persistent double-buffered variant ("s1" = 3, the default).  Included by kernels.cu.
+//
+// One CTA per SM walks over tiles of MT decimated output positions.  While the warps convolve tile t out of
+// shared-memory buffer b, the raw IQ of tile t+1 streams into buffer b^1 with cp.async (8-byte LDGSTS whose
+// shared-memory destination de-interleaves the samples by decimation phase: X[r][j] = x((J0+j)*D + r + org)),
+// so HBM latency is hidden behind the FMAs instead of stalling every warp of the CTA (the single-buffered
+// k_xd_tile spent most of its time in long-scoreboard stalls, profiles/r01_xd_tile_v1.txt).
+//
+// Work split per tile: (strip of 128 outputs) x (group of 4 VFOs) x (RS-way split of the D phases); every warp
+// owns one such task: 4 outputs x 4 VFOs per lane in registers, taps read as broadcast LDS.128 (two VFOs per
+// load), inner product as packed f32x2 FMAs with the tap as scalar-broadcast operand.  Partial sums of an RS
+// split are exchanged through shared memory.
+#pragma once
+
+#define XP_VR 4
+#define XP_RM 4
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+struct XpGeom {
+    int MT, JP, QPC, ntiles, org, RS, logD;
+    long long jmin;
+};
+
+template <int FMT, int QC>
+__global__ void __launch_bounds__(256, 1) k_xd_pipe(const __grid_constant__ XdParams p, const XpGeom g) {
+    extern __shared__ __align__(16) float2 smem[];
+    const int D = p.D, JP = g.JP, MT = g.MT, QPC = g.QPC;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    const int gl = QPC * D;
+    const int ngroups = (p.njobs + XP_VR - 1) / XP_VR;
+    float2* Xb0 = smem;
+    float2* Xb1 = smem + (size_t)D * JP;
+    float2* G = smem + (size_t)2 * D * JP;                    // [ngroups][gl][XP_VR]
+    float2* P = G + (size_t)ngroups * gl * XP_VR;             // [nwarps][16][32] partial sums (RS > 1)
+
+    // ---- taps: G[grp][k][vv] = gpad_v[(D-1-s_v) + k], zero for VFO slots beyond njobs ----
+    for (int idx = tid; idx < ngroups * gl * XP_VR; idx += nthr) {
+        int vv = idx % XP_VR, k = (idx / XP_VR) % gl, grp = idx / (XP_VR * gl);
+        int v = grp * XP_VR + vv;
+        float2 t = make_float2(0.0f, 0.0f);
+        if (v < p.njobs) {
+            const XdJob& Jv = p.job[v];
+            int a = Jv.offset - (Jv.T - 1) - g.org;
+            int s = ((a % D) + D) % D;
+            t = __ldg(Jv.gpad + (D - 1 - s) + k);
+        }
+        G[idx] = t;
+    }
+
+    const int ntile_samples = D * (MT + QPC);
+    const int dmask = D - 1;
+    auto issue = [&](int tile, float2* X) {
+        const long long ibase = (g.jmin + (long long)tile * MT) * D + g.org;
+        for (int idx = tid; idx < ntile_samples; idx += nthr) {
+            const int j = idx >> g.logD, r = idx & dmask;
+            const long long i = ibase + idx;
+            float2* dst = X + r * JP + j;
+            if (FMT == FMT_CF32 && i >= 0 && i < p.count) {
+                cp_async8(dst, reinterpret_cast<const float2*>(p.in) + i);
+            }
+            else {
+                *dst = load_x<FMT>(p, i);
+            }
+        }
+        cp_async_commit();
+    };
+
+    const int nstrips = MT / (32 * XP_RM);
+    const int RS = g.RS;
+    const int ntasks = nstrips * ngroups * RS;
+    const int rper = D / RS;
+    constexpr int NP = XP_RM / 2;
+    constexpr int WN = (QC + 2) & ~1;             // window samples per pair: QC+1 needed, loaded as LDS.128 pairs
+
+    int tile = blockIdx.x, buf = 0;
+    if (tile < g.ntiles) { issue(tile, Xb0); }
+    for (; tile < g.ntiles; tile += gridDim.x, buf ^= 1) {
+        const int next = tile + gridDim.x;
+        float2* X = buf ? Xb1 : Xb0;
+        if (next < g.ntiles) {
+            issue(next, buf ? Xb0 : Xb1);
+            cp_async_wait<1>();
+        }
+        else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const long long J0 = g.jmin + (long long)tile * MT;
+
+        for (int task0 = 0; task0 < ntasks; task0 += nwarps) {
+            const int task = task0 + warp;
+            const bool active = task < ntasks;
+            const int half = task % RS, sg = task / RS;
+            const int strip = sg % nstrips, grp = sg / nstrips;
+            float2 acc[NP][2][XP_VR];
+            const int jl0 = strip * 32 * XP_RM + 2 * lane;
+            if (active) {
+                float2 A[NP][2][XP_VR], B[NP][2][XP_VR];
+#pragma unroll
+                for (int pi = 0; pi < NP; pi++)
+#pragma unroll
+                    for (int o = 0; o < 2; o++)
+#pragma unroll
+                        for (int v = 0; v < XP_VR; v++) { A[pi][o][v] = make_float2(0.f, 0.f); B[pi][o][v] = make_float2(0.f, 0.f); }
+                const float2* Gg = G + (size_t)grp * gl * XP_VR;
+                for (int r = half * rper; r < (half + 1) * rper; r++) {
+                    const float2* row = X + r * JP;
+                    for (int qc = 0; qc < QPC; qc += QC) {
+                        float2 xs[NP][WN];
+#pragma unroll
+                        for (int pi = 0; pi < NP; pi++) {
+                            const float4* src = reinterpret_cast<const float4*>(row + jl0 + 64 * pi + qc);
+#pragma unroll
+                            for (int u = 0; u < WN / 2; u++) {
+                                float4 t = src[u];
+                                xs[pi][2 * u] = make_float2(t.x, t.y);
+                                xs[pi][2 * u + 1] = make_float2(t.z, t.w);
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < QC; q++) {
+                            const float4* tp = reinterpret_cast<const float4*>(Gg + (size_t)((qc + q) * D + r) * XP_VR);
+#pragma unroll
+                            for (int vp = 0; vp < XP_VR / 2; vp++) {
+                                const float4 t2 = tp[vp];            // taps of two VFOs, broadcast
+                                const float2 gA = make_float2(t2.x, t2.y), gB = make_float2(t2.z, t2.w);
+#pragma unroll
+                                for (int pi = 0; pi < NP; pi++)
+#pragma unroll
+                                    for (int o = 0; o < 2; o++) {
+                                        A[pi][o][2 * vp] = ffma2(make_float2(gA.x, gA.x), xs[pi][q + o], A[pi][o][2 * vp]);
+                                        B[pi][o][2 * vp] = ffma2(make_float2(gA.y, gA.y), xs[pi][q + o], B[pi][o][2 * vp]);
+                                        A[pi][o][2 * vp + 1] = ffma2(make_float2(gB.x, gB.x), xs[pi][q + o], A[pi][o][2 * vp + 1]);
+                                        B[pi][o][2 * vp + 1] = ffma2(make_float2(gB.y, gB.y), xs[pi][q + o], B[pi][o][2 * vp + 1]);
+                                    }
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int pi = 0; pi < NP; pi++)
+#pragma unroll
+                    for (int o = 0; o < 2; o++)
+#pragma unroll
+                        for (int v = 0; v < XP_VR; v++) {
+                            acc[pi][o][v] = make_float2(A[pi][o][v].x - B[pi][o][v].y, A[pi][o][v].y + B[pi][o][v].x);
+                        }
+            }
+            if (RS > 1) {
+                // exchange partial sums of the phase split: halves 1..RS-1 publish, half 0 reduces
+                if (active && half != 0) {
+                    float2* dst = P + (size_t)warp * 16 * 32 + lane;
+#pragma unroll
+                    for (int pi = 0; pi < NP; pi++)
+#pragma unroll
+                        for (int o = 0; o < 2; o++)
+#pragma unroll
+                            for (int v = 0; v < XP_VR; v++) { dst[((pi * 2 + o) * XP_VR + v) * 32] = acc[pi][o][v]; }
+                }
+                __syncthreads();
+                if (active && half == 0) {
+                    for (int h = 1; h < RS; h++) {
+                        const float2* src = P + (size_t)(warp + h) * 16 * 32 + lane;
+#pragma unroll
+                        for (int pi = 0; pi < NP; pi++)
+#pragma unroll
+                            for (int o = 0; o < 2; o++)
+#pragma unroll
+                                for (int v = 0; v < XP_VR; v++) {
+                                    float2 t = src[((pi * 2 + o) * XP_VR + v) * 32];
+                                    acc[pi][o][v].x += t.x;
+                                    acc[pi][o][v].y += t.y;
+                                }
+                    }
+                }
+            }
+            if (active && half == 0) {
+#pragma unroll
+                for (int v = 0; v < XP_VR; v++) {
+                    const int vj = grp * XP_VR + v;
+                    if (vj < p.njobs) {
+                        const XdJob& Jv = p.job[vj];
+                        const int a0 = Jv.offset - (Jv.T - 1);
+                        const int a = a0 - g.org;
+                        const int s = ((a % D) + D) % D;
+                        const int c = (a - s) / D;
+#pragma unroll
+                        for (int pi = 0; pi < NP; pi++)
+#pragma unroll
+                            for (int o = 0; o < 2; o++) {
+                                const long long m = J0 + jl0 + 64 * pi + o - c;
+                                if (m >= 0 && m < Jv.n_out) {
+                                    const long long im = (long long)a0 + m * D;
+                                    const float2 ph = phasor_u64(Jv.phase0 + Jv.w * (unsigned long long)im);
+                                    Jv.out[m] = cmulf(acc[pi][o][v], ph);
+                                }
+                            }
+                    }
+                }
+            }
+            if (RS > 1) { __syncthreads(); }
+        }
+        __syncthreads();       // everyone is done with X before the next iteration's prefetch overwrites it
+    }
+}

@@ -247,7 +247,7 @@ def _oracle_lines(oracle, x, fs, size, rate):
     return np.array(lines)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_frontend_c1_geometry(sb, oracle, report, variant):
     """BASELINE config 1: 2.4 MS/s, chunk 12000, 65536-pt FFT @ 20 fps, one WFM VFO at +300 kHz."""
     n = 600000
