@@ -103,7 +103,7 @@ struct FftCore {
     FftPlanDev plan;
     DevBuf tw, win, work;
     int size = 0, nz = 0, window = 0;
-    int create(int size_, int nz_, int window_) {
+    int create(int size_, int nz_, int window_, int max_batch = 1) {
         if (size_ < 8 || size_ > (1 << 22) || (size_ & (size_ - 1))) { set_error("FFT size %d must be a power of two in [8, 4194304]", size_); return B200_EINVAL; }
         if (nz_ < 1 || nz_ > size_) { set_error("bad nz %d", nz_); return B200_EINVAL; }
         size = size_; nz = nz_; window = window_;
@@ -126,7 +126,7 @@ struct FftCore {
         std::vector<float> w = fft_window(window, nz);
         if ((rc = win.alloc((size_t)nz * sizeof(float)))) { return rc; }
         B200_CK(cudaMemcpy(win.p, w.data(), (size_t)nz * sizeof(float), cudaMemcpyHostToDevice));
-        if ((rc = work.alloc((size_t)size * sizeof(float2)))) { return rc; }
+        if ((rc = work.alloc((size_t)size * sizeof(float2) * (size_t)(max_batch > 0 ? max_batch : 1)))) { return rc; }
         plan.tw = tw.as<float2>(); plan.window = win.as<float>(); plan.nz = nz;
         return 0;
     }
@@ -145,7 +145,10 @@ struct b200_fe {
     double fs = 0;
     int max_chunk = 0;
     Scheduler sch;
-    cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr, fft_stream = nullptr;
+    cudaEvent_t ev_fft_go = nullptr, ev_fft_done = nullptr;
+    bool fft_async = true;       // spectrum branch on its own stream, concurrent with the VFO branch
+    bool fft_join_pending = false;
     std::vector<std::unique_ptr<VfoSlot>> vfos;
     std::mutex mtx;
     DevBuf in_dev[2];
@@ -178,7 +181,10 @@ extern "C" b200_fe* b200_fe_create(double samplerate, int max_chunk) {
     fe->fs = samplerate;
     fe->max_chunk = max_chunk;
     bool ok = cudaStreamCreateWithFlags(&fe->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&fe->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+              cudaStreamCreateWithFlags(&fe->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&fe->fft_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&fe->ev_fft_go, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&fe->ev_fft_done, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2 && ok; i++) {
         ok = cudaEventCreateWithFlags(&fe->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&fe->ev_compute[i], cudaEventDisableTiming) == cudaSuccess &&
@@ -201,8 +207,11 @@ extern "C" void b200_fe_destroy(b200_fe* fe) {
         if (fe->ev_compute[i]) { cudaEventDestroy(fe->ev_compute[i]); }
         if (fe->ev_out[i]) { cudaEventDestroy(fe->ev_out[i]); }
     }
+    if (fe->ev_fft_go) { cudaEventDestroy(fe->ev_fft_go); }
+    if (fe->ev_fft_done) { cudaEventDestroy(fe->ev_fft_done); }
     if (fe->own_stream) { cudaStreamDestroy(fe->own_stream); }
     if (fe->copy_stream) { cudaStreamDestroy(fe->copy_stream); }
+    if (fe->fft_stream) { cudaStreamDestroy(fe->fft_stream); }
     delete fe;
 }
 
@@ -216,11 +225,12 @@ extern "C" int b200_fe_set_fft(b200_fe* fe, int size, double rate, int window) {
     if (!fe) { set_error("null fe"); return B200_EINVAL; }
     std::lock_guard<std::mutex> lck(fe->mtx);
     B200_CK(cudaStreamSynchronize(fe->sch.stream));
+    B200_CK(cudaStreamSynchronize(fe->fft_stream));
     if (size == 0) { fe->fft_on = false; return 0; }
     if (rate <= 0) { set_error("bad fft rate"); return B200_EINVAL; }
     int nz, skip;
     fft_frame_params(fe->fs, size, rate, nz, skip);
-    int rc = fe->fft.create(size, nz, window);
+    int rc = fe->fft.create(size, nz, window, (int)(fe->max_chunk / ((long long)nz + skip)) + 2);
     if (rc) { return rc; }
     fe->skip = skip;
     fe->fft_rate = rate;
@@ -324,6 +334,7 @@ extern "C" long long b200_fe_launch_count(b200_fe* fe) { return fe ? fe->sch.lau
 extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
     if (!fe || !key) { set_error("null argument"); return B200_EINVAL; }
     if (!strcmp(key, "s1")) { fe->sch.s1_variant = value; return 0; }
+    if (!strcmp(key, "fft_async")) { fe->fft_async = value != 0; return 0; }
     if (!strcmp(key, "tails")) { kernels_set_tail_variant(value); return 0; }
     if (!strcmp(key, "time_s1")) { fe->sch.time_s1 = value != 0; fe->sch.ev_used = 0; return 0; }
     set_error("unknown option %s", key);
@@ -384,37 +395,68 @@ static int fe_fft_chunk(b200_fe* fe, const void* dptr, int fmt, int count, int* 
     const unsigned long long pos = fe->pos, end = pos + (unsigned long long)count;
     const unsigned long long nz = (unsigned long long)fe->fft.nz, interval = nz + (unsigned long long)fe->skip;
     const int bps = bytes_per_sample(fmt);
-    cudaStream_t s = fe->sch.stream;
-    while (fe->fstart < end) {
-        const unsigned long long fend = fe->fstart + nz;
-        if (*nlines >= fe->max_lines) { set_error("FFT line buffer overflow"); return B200_ECAP; }
-        float* line = fe->lines.as<float>() + (size_t)(*nlines) * fe->fft.size;
-        if (fe->fstart >= pos && fend <= end) {
-            const char* src = (const char*)dptr + (size_t)(fe->fstart - pos) * bps;
-            int nl = 0;
-            cudaError_t e = launch_fft_frame(fe->fft.plan, src, fmt, fe->fft.work.as<float2>(), line, nullptr, s, &nl);
-            if (e != cudaSuccess) { return cuda_fail(e, "launch_fft_frame"); }
-            fe->sch.launches += nl;
-            (*nlines)++;
-            fe->fstart += interval;
-            continue;
+    cudaStream_t main_s = fe->sch.stream;
+    cudaStream_t s = fe->fft_async ? fe->fft_stream : main_s;
+    bool forked = false;
+    auto fork = [&]() -> int {
+        // the spectrum branch only reads the chunk: run it beside the VFO branch, join before the outputs
+        if (fe->fft_async && !forked) {
+            B200_CK(cudaEventRecord(fe->ev_fft_go, main_s));
+            B200_CK(cudaStreamWaitEvent(s, fe->ev_fft_go, 0));
+            forked = true;
         }
-        const unsigned long long lo = std::max(fe->fstart, pos), hi = std::min(fend, end);
+        return 0;
+    };
+    int rc = 0;
+    // 1) a frame that started in an earlier chunk: stage this chunk's part, transform it if it completes here
+    if (fe->fstart < pos) {
+        const unsigned long long fend = fe->fstart + nz;
+        const unsigned long long lo = pos, hi = std::min(fend, end);
         if (hi > lo) {
-            const char* src = (const char*)dptr + (size_t)(lo - pos) * bps;
-            cudaError_t e = launch_convert_cf32(src, fmt, fe->frame.as<float2>() + (size_t)(lo - fe->fstart), (int)(hi - lo), s);
+            if ((rc = fork())) { return rc; }
+            cudaError_t e = launch_convert_cf32(dptr, fmt, fe->frame.as<float2>() + (size_t)(lo - fe->fstart), (int)(hi - lo), s);
             if (e != cudaSuccess) { return cuda_fail(e, "launch_convert_cf32"); }
             fe->sch.launches++;
         }
         if (fend <= end) {
+            if ((rc = fork())) { return rc; }
             int nl = 0;
-            cudaError_t e = launch_fft_frame(fe->fft.plan, fe->frame.p, FMT_CF32, fe->fft.work.as<float2>(), line, nullptr, s, &nl);
+            cudaError_t e = launch_fft_frame(fe->fft.plan, fe->frame.p, FMT_CF32, fe->fft.work.as<float2>(), fe->lines.as<float>(), nullptr, s, &nl);
             if (e != cudaSuccess) { return cuda_fail(e, "launch_fft_frame"); }
             fe->sch.launches += nl;
             (*nlines)++;
             fe->fstart += interval;
         }
-        else { break; }
+    }
+    // 2) frames that lie completely inside this chunk: one batched launch pair, read straight from the chunk
+    if (fe->fstart >= pos && fe->fstart + nz <= end) {
+        int nb = (int)((end - fe->fstart - nz) / interval) + 1;
+        if (*nlines + nb > fe->max_lines) { set_error("FFT line buffer overflow"); return B200_ECAP; }
+        if ((rc = fork())) { return rc; }
+        const char* src = (const char*)dptr + (size_t)(fe->fstart - pos) * bps;
+        int nl = 0;
+        cudaError_t e = launch_fft_frames(fe->fft.plan, src, fmt, fe->fft.work.as<float2>(),
+                                          fe->lines.as<float>() + (size_t)(*nlines) * fe->fft.size, nullptr, s, &nl, nb,
+                                          (long long)interval * bps);
+        if (e != cudaSuccess) { return cuda_fail(e, "launch_fft_frames"); }
+        fe->sch.launches += nl;
+        *nlines += nb;
+        fe->fstart += interval * (unsigned long long)nb;
+    }
+    // 3) the head of a frame that continues into the next chunk
+    if (fe->fstart < end && fe->fstart >= pos) {
+        const unsigned long long lo = fe->fstart, hi = end;
+        if (hi > lo) {
+            if ((rc = fork())) { return rc; }
+            const char* src = (const char*)dptr + (size_t)(lo - pos) * bps;
+            cudaError_t e = launch_convert_cf32(src, fmt, fe->frame.as<float2>(), (int)(hi - lo), s);
+            if (e != cudaSuccess) { return cuda_fail(e, "launch_convert_cf32"); }
+            fe->sch.launches++;
+        }
+    }
+    if (forked) {
+        B200_CK(cudaEventRecord(fe->ev_fft_done, s));
+        fe->fft_join_pending = true;     // joined by the caller after the VFO branch has been enqueued
     }
     fe->pos = end;
     return 0;
@@ -471,10 +513,16 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
         }
     }
     for (Chain* c : chains) { c->plan(count); }
-    int rc = fe->sch.run(chains, dptr, in_fmt, count, true);
-    if (rc) { return rc; }
     int nlines = 0;
+    int rc;
+    // fork the spectrum branch first; its join (a wait on the main stream) comes after the VFO branch has been
+    // enqueued, so the two overlap on the device
     if ((rc = fe_fft_chunk(fe, dptr, in_fmt, count, &nlines))) { return rc; }
+    if ((rc = fe->sch.run(chains, dptr, in_fmt, count, true))) { return rc; }
+    if (fe->fft_join_pending) {
+        B200_CK(cudaStreamWaitEvent(s, fe->ev_fft_done, 0));
+        fe->fft_join_pending = false;
+    }
     B200_CK(cudaEventRecord(fe->ev_compute[slot], s));
     fe->slot_used[slot] = true;
     // ---- outputs ----

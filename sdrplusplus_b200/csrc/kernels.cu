@@ -592,10 +592,13 @@ __device__ __forceinline__ float2 load_windowed(const FftPlanDev& pl, const void
 
 // single-pass: the whole transform fits one CTA's shared memory
 template <int FMT>
-__global__ void __launch_bounds__(512) k_fft_single(const __grid_constant__ FftPlanDev pl, const void* __restrict__ src,
-                                                      float* __restrict__ out_db, float2* __restrict__ out_raw) {
+__global__ void __launch_bounds__(512) k_fft_single(const __grid_constant__ FftPlanDev pl, const void* __restrict__ src0,
+                                                      float* __restrict__ out_db0, float2* __restrict__ out_raw,
+                                                      long long src_stride_bytes) {
     extern __shared__ __align__(16) float2 smem[];
     const int N = pl.N;
+    const void* src = reinterpret_cast<const char*>(src0) + (size_t)blockIdx.y * src_stride_bytes;
+    float* out_db = out_db0 + (size_t)blockIdx.y * N;
     for (int i = threadIdx.x; i < N; i += blockDim.x) { smem[i] = load_windowed<FMT>(pl, src, i); }
     __syncthreads();
     fft_dif_smem<false>(smem, pl.logN, 1, N, pl.tw, pl.logTW);
@@ -610,10 +613,12 @@ __global__ void __launch_bounds__(512) k_fft_single(const __grid_constant__ FftP
 // pass 1 of the two-pass (four-step) transform: n = n1*N2 + n2, k = k1 + N1*k2.
 // CTA = C adjacent columns n2, all rows n1: A[k1][n2] = W_N^(k1*n2) * sum_n1 x[n1*N2+n2] W_N1^(n1*k1)
 template <int FMT>
-__global__ void __launch_bounds__(512) k_fft_p1(const __grid_constant__ FftPlanDev pl, const void* __restrict__ src,
-                                                  float2* __restrict__ work, int C) {
+__global__ void __launch_bounds__(512) k_fft_p1(const __grid_constant__ FftPlanDev pl, const void* __restrict__ src0,
+                                                  float2* __restrict__ work0, int C, long long src_stride_bytes) {
     extern __shared__ __align__(16) float2 smem[];
     const int N1 = pl.N1, N2 = pl.N2;
+    const void* src = reinterpret_cast<const char*>(src0) + (size_t)blockIdx.y * src_stride_bytes;
+    float2* work = work0 + (size_t)blockIdx.y * pl.N;
     const int c0 = blockIdx.x * C;
     for (int t = threadIdx.x; t < N1 * C; t += blockDim.x) {
         int n1 = t / C, c = t - n1 * C;
@@ -633,10 +638,12 @@ __global__ void __launch_bounds__(512) k_fft_p1(const __grid_constant__ FftPlanD
 }
 
 // pass 2: CTA = R adjacent rows k1; X[k1 + N1*k2] = sum_n2 A[k1][n2] W_N2^(n2*k2); fused dB epilogue
-__global__ void __launch_bounds__(512) k_fft_p2(const __grid_constant__ FftPlanDev pl, const float2* __restrict__ work,
-                                                  float* __restrict__ out_db, float2* __restrict__ out_raw, int R) {
+__global__ void __launch_bounds__(512) k_fft_p2(const __grid_constant__ FftPlanDev pl, const float2* __restrict__ work0,
+                                                  float* __restrict__ out_db0, float2* __restrict__ out_raw, int R) {
     extern __shared__ __align__(16) float2 smem[];
     const int N1 = pl.N1, N2 = pl.N2;
+    const float2* work = work0 + (size_t)blockIdx.y * pl.N;
+    float* out_db = out_db0 + (size_t)blockIdx.y * pl.N;
     const int pitch = N2 + 1;
     const int r0 = blockIdx.x * R;
     for (int t = threadIdx.x; t < R * N2; t += blockDim.x) {
@@ -725,18 +732,18 @@ static int num_sms() {
     return g_num_sms;
 }
 
-template <int FMT, int QC>
+template <int FMT, int QC, int NT>
 static cudaError_t launch_xd_pipe_t(const XdParams& p, const XpGeom& g, size_t smem, cudaStream_t s) {
-    cudaError_t e = set_smem(k_xd_pipe<FMT, QC>, smem);
+    cudaError_t e = set_smem(k_xd_pipe<FMT, QC, NT>, smem);
     if (e != cudaSuccess) { return e; }
     int grid = g.ntiles < num_sms() ? g.ntiles : num_sms();
-    k_xd_pipe<FMT, QC><<<grid, 256, smem, s>>>(p, g);
+    k_xd_pipe<FMT, QC, NT><<<grid, NT, smem, s>>>(p, g);
     return cudaGetLastError();
 }
 
 // returns true when the pipelined kernel was launched
 template <int FMT>
-static bool try_xd_pipe(const XdParams& p, cudaStream_t s, cudaError_t* err) {
+static bool try_xd_pipe(const XdParams& p, cudaStream_t s, cudaError_t* err, int nwarps) {
     const int D = p.D;
     if (D < 2 || (D & (D - 1))) { return false; }
     int logD = 0;
@@ -787,22 +794,33 @@ static bool try_xd_pipe(const XdParams& p, cudaStream_t s, cudaError_t* err) {
         int jp = MT + QPC + 2;
         jp += (jp & 1);
         if ((jp & 3) == 0) { jp += 2; }
-        smem = ((size_t)2 * D * jp + (size_t)ngroups * QPC * D * XP_VR + (size_t)8 * 16 * 32) * sizeof(float2);
+        smem = ((size_t)2 * D * jp + (size_t)ngroups * QPC * D * XP_VR + (size_t)nwarps * 16 * 32) * sizeof(float2);
         if (smem <= (size_t)limit) { g.JP = jp; break; }
     }
     const int nstrips = MT / 128;
-    int RS = 8 / (nstrips * ngroups);
+    int RS = nwarps / (nstrips * ngroups);
     if (RS < 1) { RS = 1; }
     while (RS > 1 && (D % RS || (RS & (RS - 1)))) { RS--; }
     g.MT = MT; g.QPC = QPC; g.org = org; g.RS = RS; g.logD = logD; g.jmin = jmin;
     g.ntiles = cdiv(jmax - jmin, MT);
     cudaError_t e;
-    switch (QC) {
-    case 4: e = launch_xd_pipe_t<FMT, 4>(p, g, smem, s); break;
-    case 5: e = launch_xd_pipe_t<FMT, 5>(p, g, smem, s); break;
-    case 6: e = launch_xd_pipe_t<FMT, 6>(p, g, smem, s); break;
-    case 7: e = launch_xd_pipe_t<FMT, 7>(p, g, smem, s); break;
-    default: e = launch_xd_pipe_t<FMT, 8>(p, g, smem, s); break;
+    if (nwarps == 16) {
+        switch (QC) {
+        case 4: e = launch_xd_pipe_t<FMT, 4, 512>(p, g, smem, s); break;
+        case 5: e = launch_xd_pipe_t<FMT, 5, 512>(p, g, smem, s); break;
+        case 6: e = launch_xd_pipe_t<FMT, 6, 512>(p, g, smem, s); break;
+        case 7: e = launch_xd_pipe_t<FMT, 7, 512>(p, g, smem, s); break;
+        default: e = launch_xd_pipe_t<FMT, 8, 512>(p, g, smem, s); break;
+        }
+    }
+    else {
+        switch (QC) {
+        case 4: e = launch_xd_pipe_t<FMT, 4, 256>(p, g, smem, s); break;
+        case 5: e = launch_xd_pipe_t<FMT, 5, 256>(p, g, smem, s); break;
+        case 6: e = launch_xd_pipe_t<FMT, 6, 256>(p, g, smem, s); break;
+        case 7: e = launch_xd_pipe_t<FMT, 7, 256>(p, g, smem, s); break;
+        default: e = launch_xd_pipe_t<FMT, 8, 256>(p, g, smem, s); break;
+        }
     }
     *err = e;
     return true;
@@ -816,7 +834,7 @@ static cudaError_t launch_xd_fmt(const XdParams& p, int variant, cudaStream_t s,
     const int D = p.D;
     if (variant >= 3) {
         cudaError_t e = cudaSuccess;
-        if (try_xd_pipe<FMT>(p, s, &e)) {
+        if (try_xd_pipe<FMT>(p, s, &e, variant >= 4 ? 16 : 8)) {
             if (nlaunch) { (*nlaunch)++; }
             return e;
         }
@@ -1022,25 +1040,25 @@ cudaError_t launch_carry(const CarryParams& p, cudaStream_t s) {
 
 template <int FMT>
 static cudaError_t launch_fft_fmt(const FftPlanDev& pl, const void* src, float2* work, float* out_db, float2* out_raw,
-                                  cudaStream_t s, int* nlaunch) {
+                                  cudaStream_t s, int* nlaunch, int nbatch, long long src_stride_bytes) {
     cudaError_t e;
     if (pl.N1 == pl.N) {
         size_t smem = (size_t)pl.N * sizeof(float2);
         e = set_smem(k_fft_single<FMT>, smem);
         if (e != cudaSuccess) { return e; }
         int thr = pl.N / 8 < 32 ? 32 : (pl.N / 8 > 512 ? 512 : pl.N / 8);
-        k_fft_single<FMT><<<1, thr, smem, s>>>(pl, src, out_db, out_raw);
+        k_fft_single<FMT><<<dim3(1, nbatch), thr, smem, s>>>(pl, src, out_db, out_raw, src_stride_bytes);
         if (nlaunch) { (*nlaunch)++; }
         return cudaGetLastError();
     }
     // two passes
     // columns / rows per CTA: enough CTAs to fill the chip about twice, at least 4 (32-byte segments)
     int C = 16;
-    while (C > 4 && pl.N2 / C < 2 * num_sms()) { C >>= 1; }
+    while (C > 4 && (pl.N2 / C) * nbatch < 2 * num_sms()) { C >>= 1; }
     while ((size_t)pl.N1 * C * sizeof(float2) > 196608 && C > 1) { C >>= 1; }
     if (C > pl.N2) { C = pl.N2; }
     int R = 16;
-    while (R > 4 && pl.N1 / R < 2 * num_sms()) { R >>= 1; }
+    while (R > 4 && (pl.N1 / R) * nbatch < 2 * num_sms()) { R >>= 1; }
     while ((size_t)R * (pl.N2 + 1) * sizeof(float2) > 196608 && R > 1) { R >>= 1; }
     if (R > pl.N1) { R = pl.N1; }
     size_t smem1 = (size_t)pl.N1 * C * sizeof(float2);
@@ -1050,19 +1068,24 @@ static cudaError_t launch_fft_fmt(const FftPlanDev& pl, const void* src, float2*
     e = set_smem(k_fft_p2, smem2);
     if (e != cudaSuccess) { return e; }
     const int thr1 = (pl.N1 / 8) * C >= 512 ? 512 : 256, thr2 = (pl.N2 / 8) * R >= 512 ? 512 : 256;
-    k_fft_p1<FMT><<<pl.N2 / C, thr1, smem1, s>>>(pl, src, work, C);
+    k_fft_p1<FMT><<<dim3(pl.N2 / C, nbatch), thr1, smem1, s>>>(pl, src, work, C, src_stride_bytes);
     e = cudaGetLastError();
     if (e != cudaSuccess) { return e; }
-    k_fft_p2<<<pl.N1 / R, thr2, smem2, s>>>(pl, work, out_db, out_raw, R);
+    k_fft_p2<<<dim3(pl.N1 / R, nbatch), thr2, smem2, s>>>(pl, work, out_db, out_raw, R);
     if (nlaunch) { (*nlaunch) += 2; }
     return cudaGetLastError();
 }
 
+cudaError_t launch_fft_frames(const FftPlanDev& pl, const void* src, int fmt, float2* work, float* out_db,
+                              float2* out_raw, cudaStream_t s, int* nlaunch, int nbatch, long long src_stride_bytes) {
+    if (nbatch <= 0) { return cudaSuccess; }
+    if (fmt == FMT_CF32) { return launch_fft_fmt<FMT_CF32>(pl, src, work, out_db, out_raw, s, nlaunch, nbatch, src_stride_bytes); }
+    if (fmt == FMT_CS16) { return launch_fft_fmt<FMT_CS16>(pl, src, work, out_db, out_raw, s, nlaunch, nbatch, src_stride_bytes); }
+    return launch_fft_fmt<FMT_CS8>(pl, src, work, out_db, out_raw, s, nlaunch, nbatch, src_stride_bytes);
+}
 cudaError_t launch_fft_frame(const FftPlanDev& pl, const void* src, int fmt, float2* work, float* out_db,
                              float2* out_raw, cudaStream_t s, int* nlaunch) {
-    if (fmt == FMT_CF32) { return launch_fft_fmt<FMT_CF32>(pl, src, work, out_db, out_raw, s, nlaunch); }
-    if (fmt == FMT_CS16) { return launch_fft_fmt<FMT_CS16>(pl, src, work, out_db, out_raw, s, nlaunch); }
-    return launch_fft_fmt<FMT_CS8>(pl, src, work, out_db, out_raw, s, nlaunch);
+    return launch_fft_frames(pl, src, fmt, work, out_db, out_raw, s, nlaunch, 1, 0);
 }
 
 cudaError_t launch_convert_cf32(const void* src, int fmt, float2* dst, int n, cudaStream_t s) {

@@ -137,6 +137,9 @@ cudaError_t launch_carry(const CarryParams& p, cudaStream_t s);
 // src: nz samples of format fmt (chunk data), read directly; out_db: N floats; work: N float2 scratch
 cudaError_t launch_fft_frame(const FftPlanDev& pl, const void* src, int fmt, float2* work, float* out_db,
                              float2* out_raw, cudaStream_t s, int* nlaunch);
+// nbatch equally spaced frames (src_stride_bytes apart) in one launch pair; work: nbatch*N float2, out_db: nbatch*N
+cudaError_t launch_fft_frames(const FftPlanDev& pl, const void* src, int fmt, float2* work, float* out_db,
+                              float2* out_raw, cudaStream_t s, int* nlaunch, int nbatch, long long src_stride_bytes);
 cudaError_t launch_convert_cf32(const void* src, int fmt, float2* dst, int n, cudaStream_t s);
 // start/len: per-pixel bin ranges built on the host with the reference's fp32 index loop
 cudaError_t launch_zoom_hold_tbl(const float* line, const int* start, const int* len, int out_size, float* out,

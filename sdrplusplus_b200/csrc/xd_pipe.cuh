@@ -29,8 +29,8 @@ struct XpGeom {
     long long jmin;
 };
 
-template <int FMT, int QC>
-__global__ void __launch_bounds__(256, 1) k_xd_pipe(const __grid_constant__ XdParams p, const XpGeom g) {
+template <int FMT, int QC, int NT>
+__global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdParams p, const XpGeom g) {
     extern __shared__ __align__(16) float2 smem[];
     const int D = p.D, JP = g.JP, MT = g.MT, QPC = g.QPC;
     const int tid = threadIdx.x, nthr = blockDim.x;

@@ -48,7 +48,9 @@ def test_fft_line_vs_oracle(sb, oracle, report, N, nz):
     report["fft_%d_%d" % (N, nz)] = {"raw_rel_rms": e_raw, "power_rel_max": e_pow}
     assert e_raw < 2e-6, e_raw
     assert e_pow < TOL, e_pow
-    assert int(np.argmax(line)) == int(np.argmax(ref)) == b
+    assert int(np.argmax(line)) == int(np.argmax(ref))
+    if N >= 64:
+        assert int(np.argmax(line)) == b          # the injected tone dominates the noise
     h.close()
 
 
@@ -247,7 +249,7 @@ def _oracle_lines(oracle, x, fs, size, rate):
     return np.array(lines)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_frontend_c1_geometry(sb, oracle, report, variant):
     """BASELINE config 1: 2.4 MS/s, chunk 12000, 65536-pt FFT @ 20 fps, one WFM VFO at +300 kHz."""
     n = 600000
@@ -396,6 +398,37 @@ def test_frontend_multi_vfo_100msps(sb, oracle, report):
         assert outs[vid].shape == ya.shape
         errs.append(rel_rms(outs[vid][1500:], ya[1500:]))
     report["frontend_c2_8vfo"] = {"wfm_audio_rel_rms": errs, "fft_power_rel_max": e_fft}
+    assert e_fft < TOL, e_fft
+    assert max(errs) < TOL, errs
+    fe.close()
+
+
+@pytest.mark.parametrize("variant,fft_async", [(4, 1), (3, 0), (1, 1)])
+def test_frontend_variants_100msps(sb, oracle, report, variant, fft_async):
+    """kernel-variant A/B on the config-2 geometry (short): 16-warp stage 1, synchronous spectrum branch."""
+    fs, chunk, nch = 100e6, 1000000, 3
+    n = chunk * nch
+    offs = [5e6, -5e6, 15e6, -25e6, 35e6]
+    x = noise_iq(n, 21, 0.01).copy()
+    for o in offs:
+        x += fm_carrier(n, fs, o)
+    fe = sb.FrontEnd(fs, chunk)
+    fe.set_option("s1", variant)
+    fe.set_option("fft_async", fft_async)
+    fe.set_fft(1 << 18, 200.0, 2)              # 500000-sample interval: frames inside chunks and across them
+    cfgs = [sb.VfoConfig.wfm(o) for o in offs]
+    ids = [fe.add_vfo(c) for c in cfgs]
+    outs, lines = fe.process_chunks(x, chunk)
+    la = _oracle_lines(oracle, x, fs, 1 << 18, 200.0)
+    assert lines.shape == la.shape and lines.shape[0] == 6
+    p, pr = 10.0 ** (lines.astype(np.float64) / 10), 10.0 ** (la.astype(np.float64) / 10)
+    e_fft = float(np.max(np.abs(p - pr)) / np.max(pr))
+    errs = []
+    for vid, c in zip(ids, cfgs):
+        ya = _oracle_chain(oracle, x, fs, chunk, c).reshape(-1, 2)
+        assert outs[vid].shape == ya.shape
+        errs.append(rel_rms(outs[vid][1500:], ya[1500:]))
+    report["frontend_variant%d_fftasync%d" % (variant, fft_async)] = {"wfm_audio_rel_rms": errs, "fft_power_rel_max": e_fft}
     assert e_fft < TOL, e_fft
     assert max(errs) < TOL, errs
     fe.close()
