@@ -1,0 +1,88 @@
+"""The golden cases: one function that drives an oracle implementation (reference-header build or plain-C
+restatement) over seeded inputs and returns {name: array}.  tools/make_golden.py runs it on the reference build
+and commits the result; tests/test_oracle.py runs it on the restatement and demands bit-identical arrays."""
+import numpy as np
+
+from util import noise_iq, fm_carrier, am_carrier, ssb_tone
+
+FS = 2.4e6
+
+
+def signal(n, seed):
+    x = noise_iq(n, seed, 0.02).copy()
+    x += fm_carrier(n, FS, 300e3)
+    x += fm_carrier(n, FS, -650e3, tones=((3000.0, 0.6),))
+    x += am_carrier(n, FS, -400e3)
+    x += ssb_tone(n, FS, 600e3, 1000.0)
+    return x
+
+
+def digest(a):
+    """order-sensitive checksum of a float32 array: [count, sum a[i]*(1 + i mod 251), sum |a|] in float64"""
+    a = np.asarray(a, np.float32).reshape(-1).astype(np.float64)
+    w = 1.0 + (np.arange(a.size) % 251)
+    return np.array([a.size, float(np.sum(a * w)), float(np.sum(np.abs(a)))])
+
+
+def run_cases(R):
+    g = {}
+    # ---- host-side design ----
+    g["lowpass_wfm_audio"] = R.lowpass(15000.0, 4000.0, 250000.0)
+    g["lowpass_vfo_150k"] = R.lowpass(75000.0, 7500.0, 250000.0)
+    g["lowpass_odd"] = R.lowpass(1400.0, 140.0, 24000.0, True)
+    g["window_nuttall_4096"] = R.window_buf(2, 4096)
+    g["window_blackman_1000"] = R.window_buf(1, 1000)
+    for rates in ((2.4e6, 250e3), (100e6, 250e3), (1.024e9, 250e3), (2.4e6, 15e3), (250e3, 48e3)):
+        p = R.resamp_plan(*rates)
+        g["plan_%g_%g" % rates] = np.array([p[k] for k in ("mode", "predec_ratio", "interp", "decim", "ntaps", "taps_per_phase")])
+    g["resamp_taps_2.4M_250k"] = R.resamp_taps(2.4e6, 250e3)
+    g["decim_plan_256"] = np.array(R.decim_plan(256)).reshape(-1)
+    g["decim_taps_256_0_digest"] = digest(R.decim_taps(256, 0))
+    g["fft_params"] = np.array([R.fft_params(2.4e6, 65536, 20.0), R.fft_params(100e6, 1 << 20, 20.0)]).reshape(-1)
+    # ---- streaming blocks on a seeded signal, chunked like file_source (fs/200) ----
+    n, chunk = 240000, 12000
+    x = signal(n, 0x5D12)
+    xf = x.view(np.float32)
+    g["seed"] = np.array([0x5D12, n, chunk])
+    y = R.xlator(-300e3, FS).process_chunks(xf, chunk)
+    g["xlator_head"] = y[:256]
+    g["xlator_digest"] = digest(y)
+    y = R.decim(8).process_chunks(xf, chunk)
+    g["decim8_head"] = y[:256]
+    g["decim8_digest"] = digest(y)
+    y = R.resamp(FS, 250e3).process_chunks(xf, chunk)
+    g["resamp_head"] = y[:256]
+    g["resamp_digest"] = digest(y)
+    vfo = R.rxvfo(FS, 250e3, 150e3, 300e3).process_chunks(xf, chunk)
+    g["rxvfo_tail"] = vfo[-512:]
+    g["rxvfo_digest"] = digest(vfo)
+    a = R.wfm(75e3, 250e3).process_chunks(vfo, 1250)
+    g["wfm_tail"] = a[-512:]
+    g["wfm_digest"] = digest(a)
+    g["quad_digest"] = digest(R.quad(75e3, 250e3).process_chunks(vfo, 1250))
+    v = R.rxvfo(FS, 50e3, 12500.0, 300e3).process_chunks(xf, chunk)
+    g["nfm_digest"] = digest(R.nfm(50e3, 12500.0, True).process_chunks(v, 250))
+    v = R.rxvfo(FS, 15e3, 10e3, -400e3).process_chunks(xf, chunk)
+    a = R.am(1, 10e3, 50 / 15e3, 5 / 15e3, 100 / 15e3, 15e3).process_chunks(v, 75)
+    g["am_audio_tail"] = a[-128:]
+    g["am_audio_digest"] = digest(a)
+    g["am_carrier_digest"] = digest(R.am(0, 10e3, 50 / 15e3, 5 / 15e3, 100 / 15e3, 15e3).process_chunks(v, 75))
+    v = R.rxvfo(FS, 24e3, 2800.0, 600e3).process_chunks(xf, chunk)
+    a = R.ssb(0, 2800.0, 24e3, 50 / 24e3, 5 / 24e3).process_chunks(v, 120)
+    g["usb_tail"] = a[-128:]
+    g["usb_digest"] = digest(a)
+    g["lsb_digest"] = digest(R.ssb(1, 2800.0, 24e3, 50 / 24e3, 5 / 24e3).process_chunks(v, 120))
+    g["deemph_digest"] = digest(R.deemph(50e-6, 48e3).process_chunks(a, 480))
+    # ---- spectrum branch ----
+    line = R.fft_frame(65536, 65536, 2, x[:65536])
+    g["fft_65536_stride"] = line[::64]
+    g["fft_65536_digest"] = digest(line)
+    g["fft_65536_argmax"] = np.array([int(np.argmax(line))])
+    g["fft_4096_3000"] = R.fft_frame(4096, 3000, 1, x[:3000])
+    g["zoom_1280"] = R.zoom(1000, 60000, 1280, line)
+    g["zoom_edge"] = R.zoom(60000, 8000, 777, line)
+    g["hold"] = R.hold(np.full(1280, -200.0, np.float32), g["zoom_1280"], 0.5)
+    i16 = np.random.default_rng(3).integers(-32768, 32767, 512).astype(np.int16)
+    g["i16_in"] = i16
+    g["i16_out"] = R.i16_to_f32(i16)
+    return g
