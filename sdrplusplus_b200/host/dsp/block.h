@@ -1,0 +1,83 @@
+// host/dsp/block.h -- worker-thread block base and the typed Processor<I,O> of the operator API
+// (start / stop / tempStart / tempStop / run, core/src/dsp/block.h:18-131, processor.h:42-73), for adapters whose
+// process() forwards to libb200dsp.  One worker thread per started block, `while (run() >= 0)`.
+#pragma once
+#include <algorithm>
+#include <cassert>
+#include <mutex>
+#include <thread>
+#include <vector>
+#include "stream.h"
+#include "types.h"
+
+namespace dsp {
+    class block {
+    public:
+        virtual ~block() { if (inited) { stop(); } }
+        virtual void start() {
+            std::lock_guard<std::recursive_mutex> lk(ctrlMtx);
+            if (running) { return; }
+            running = true;
+            launch();
+        }
+        virtual void stop() {
+            std::lock_guard<std::recursive_mutex> lk(ctrlMtx);
+            if (!running) { return; }
+            halt();
+            running = false;
+        }
+        void tempStop() {
+            if (depth++ == 0 && running && !paused) { halt(); paused = true; }
+        }
+        void tempStart() {
+            if (depth > 0 && --depth == 0 && paused) { launch(); paused = false; }
+        }
+        virtual int run() = 0;
+
+    protected:
+        void registerInput(untyped_stream* s) { ins.push_back(s); }
+        void unregisterInput(untyped_stream* s) { ins.erase(std::remove(ins.begin(), ins.end(), s), ins.end()); }
+        void registerOutput(untyped_stream* s) { outs.push_back(s); }
+        void unregisterOutput(untyped_stream* s) { outs.erase(std::remove(outs.begin(), outs.end(), s), outs.end()); }
+        bool inited = false;
+        bool& _block_init = inited;
+        std::recursive_mutex ctrlMtx;
+
+    private:
+        void launch() { worker = std::thread([this] { while (run() >= 0) {} }); }
+        void halt() {
+            for (auto* s : ins) { s->stopReader(); }
+            for (auto* s : outs) { s->stopWriter(); }
+            if (worker.joinable()) { worker.join(); }
+            for (auto* s : ins) { s->clearReadStop(); }
+            for (auto* s : outs) { s->clearWriteStop(); }
+        }
+        std::vector<untyped_stream*> ins, outs;
+        std::thread worker;
+        bool running = false, paused = false;
+        int depth = 0;
+    };
+
+    template <class I, class O>
+    class Processor : public block {
+    public:
+        void init(stream<I>* in) {
+            _in = in;
+            registerInput(_in);
+            registerOutput(&out);
+            inited = true;
+        }
+        virtual void setInput(stream<I>* in) {
+            std::lock_guard<std::recursive_mutex> lk(ctrlMtx);
+            tempStop();
+            unregisterInput(_in);
+            _in = in;
+            registerInput(_in);
+            tempStart();
+        }
+        stream<O> out;
+
+    protected:
+        stream<I>* _in = nullptr;
+    };
+}

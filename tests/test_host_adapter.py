@@ -1,0 +1,44 @@
+"""The C++ adapter headers (sdrplusplus_b200/host/dsp: reference class names and signatures over the C ABI) used the
+way a reference module uses the real blocks: worker-thread blocks joined by dsp::stream<T>.  The program is built by
+__graft_entry__.build(); here it runs on the GPU and its audio is compared with the oracle."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from util import rel_rms, noise_iq, fm_carrier
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "build", "test_adapter")
+
+
+def test_adapter_headers_compile():
+    """CPU-side: the adapter headers are self-contained C++17 and only need include/b200dsp.h."""
+    host = os.path.join(ROOT, "sdrplusplus_b200", "host")
+    for h in ("dsp/stream.h", "dsp/block.h", "dsp/channel/rx_vfo.h", "dsp/demod/broadcast_fm.h", "dsp/b200/frontend.h"):
+        r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", host, "-x", "c++", os.path.join(host, h)],
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["blocks", "fused"])
+def test_adapter_graph_matches_oracle(oracle, tmp_path, mode):
+    if not os.path.exists(EXE):
+        pytest.skip("build/test_adapter missing: run python __graft_entry__.py")
+    fs, n, chunk = 2.4e6, 240000, 12000
+    x = noise_iq(n, 31, 0.02).copy() + fm_carrier(n, fs, 300e3)
+    src, dst = tmp_path / "iq.f32", tmp_path / "audio.f32"
+    x.tofile(src)
+    args = [EXE, str(src), str(dst)] + (["fused"] if mode == "fused" else [])
+    r = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout
+    got = np.fromfile(dst, np.float32).reshape(-1, 2)
+    v, d = oracle.rxvfo(fs, 250e3, 150e3, 300e3), oracle.wfm(75e3, 250e3)
+    ref = np.concatenate([d.process(v.process(x.view(np.float32)[2 * i: 2 * (i + chunk)])) for i in range(0, n, chunk)]).reshape(-1, 2)
+    assert got.shape == ref.shape
+    assert rel_rms(got[4000:], ref[4000:]) < 1e-5
+    if mode == "fused":
+        assert int(r.stdout.split()[1]) == 2          # two 65536-pt lines completed in 240000 samples at 20 fps
