@@ -209,6 +209,10 @@ def run_b200(args):
     from sdrplusplus_b200 import lib
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    # libraries (NCCL's version banner) write to fd 1: keep stdout clean for the single JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- libb200dsp has no CPU fallback")
     torch.cuda.set_device(local)
@@ -222,12 +226,15 @@ def run_b200(args):
     nbuf = 3
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
+        offsets = OFFSETS if args.offsets == "sym" else [5e6, -7e6, 15e6, -17e6, 25e6, -27e6, 35e6, -37e6]
         fe = sb.FrontEnd(FS, chunk)
         fe.set_stream(stream.cuda_stream)
+        fe.set_option("overlap", args.overlap)
+        fe.set_option("pair", args.pair)
         fe.set_option("s1", args.s1)
         fe.set_option("tails", args.tails)
         fe.set_fft(FFT_SIZE, FFT_RATE, lib.WIN_NUTTALL)
-        ids = [fe.add_vfo(sb.VfoConfig.wfm(o)) for o in OFFSETS]
+        ids = [fe.add_vfo(sb.VfoConfig.wfm(o)) for o in offsets]
         gen = torch.Generator(device="cuda")
         gen.manual_seed(0x5D12 + rank)
         # synthetic inputs, SpeedTester distribution: i.i.d. uniform[-1,1) re/im; distinct per buffer and per rank
@@ -347,7 +354,9 @@ def run_b200(args):
         "config": {"workload": WORKLOAD, "chunk_samples": chunk, "samplerate": FS, "parallelism": "replicas x%d (one IQ stream per GPU, no collective)" % world,
                    "l2": "inputs larger than L2: %d MiB cf32 chunk, %d rotating device buffers" % (chunk * 8 >> 20, nbuf),
                    "value_input": "cf32 resident in HBM, outputs to HBM", "e2e_input": "int16 IQ in pinned host memory (file_source format); cf32 also reported",
-                   "pipelining": "b200_fe_submit/wait, 2 chunks in flight", "s1_variant": args.s1, "tails_variant": args.tails},
+                   "pipelining": "b200_fe_submit/wait, 2 chunks in flight", "s1_variant": args.s1, "tails_variant": args.tails,
+                   "vfo_offsets_hz": offsets, "conjugate_pair_sharing": bool(args.pair) and args.offsets == "sym",
+                   "tails_overlap_next_chunk": bool(args.overlap)},
         "e2e": dict(e2e["cs16"], format="cs16", cf32=e2e["cf32"], pcie_probe=probe, numa=numa),
         "gpu_launches": int(launches),
         "clocks": clk,
@@ -365,7 +374,10 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": v / 1e6, "unit": "MS/s", "cores": threads, "host_cpus": os.cpu_count(), "kind": kind, "sample": what}
         except Exception as ex:          # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "MS/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (ex,)}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -380,6 +392,10 @@ def main():
     ap.add_argument("--chunk", type=int, default=1 << 24, help="IQ samples per step (default 16 Mi = 128 MiB cf32 > L2)")
     ap.add_argument("--s1", type=int, default=3, help="stage-1 kernel variant (3 = pipelined, default)")
     ap.add_argument("--tails", type=int, default=1, help="tail kernel variant (1 = shared-memory tiled, default)")
+    ap.add_argument("--overlap", type=int, default=1, help="1 = tails of chunk k overlap stage 1 of chunk k+1 (default)")
+    ap.add_argument("--pair", type=int, default=1, help="1 = VFOs at +f/-f share their stage-1 multiply-accumulates (default)")
+    ap.add_argument("--offsets", default="sym", choices=["sym", "asym"],
+                    help="sym = BASELINE config 2 (+-5/15/25/35 MHz); asym = 8 offsets without conjugate pairs")
     ap.add_argument("--cpu-ms", type=int, default=12000, help="duration of the CPU reference sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -145,8 +145,10 @@ struct b200_fe {
     double fs = 0;
     int max_chunk = 0;
     Scheduler sch;
-    cudaStream_t own_stream = nullptr, copy_stream = nullptr, fft_stream = nullptr;
-    cudaEvent_t ev_fft_go = nullptr, ev_fft_done = nullptr;
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr, fft_stream = nullptr, tail_stream = nullptr;
+    cudaEvent_t ev_fft_go = nullptr, ev_fft_done = nullptr, ev_lines_free = nullptr;
+    bool overlap = true;         // tails of chunk k on their own stream, overlapping stage 1 of chunk k+1
+    bool lines_busy = false;
     bool fft_async = true;       // spectrum branch on its own stream, concurrent with the VFO branch
     bool fft_join_pending = false;
     std::vector<std::unique_ptr<VfoSlot>> vfos;
@@ -183,6 +185,8 @@ extern "C" b200_fe* b200_fe_create(double samplerate, int max_chunk) {
     bool ok = cudaStreamCreateWithFlags(&fe->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&fe->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&fe->fft_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&fe->tail_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&fe->ev_lines_free, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&fe->ev_fft_go, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&fe->ev_fft_done, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2 && ok; i++) {
@@ -196,6 +200,7 @@ extern "C" b200_fe* b200_fe_create(double samplerate, int max_chunk) {
         return nullptr;
     }
     fe->sch.stream = fe->own_stream;
+    if (fe->sch.enable_overlap(fe->tail_stream)) { b200_fe_destroy(fe); return nullptr; }
     return fe;
 }
 
@@ -206,6 +211,12 @@ extern "C" void b200_fe_destroy(b200_fe* fe) {
         if (fe->ev_h2d[i]) { cudaEventDestroy(fe->ev_h2d[i]); }
         if (fe->ev_compute[i]) { cudaEventDestroy(fe->ev_compute[i]); }
         if (fe->ev_out[i]) { cudaEventDestroy(fe->ev_out[i]); }
+    }
+    if (fe->ev_lines_free) { cudaEventDestroy(fe->ev_lines_free); }
+    if (fe->tail_stream) { cudaStreamDestroy(fe->tail_stream); }
+    for (int i = 0; i < 2; i++) {
+        if (fe->sch.ev_stage1[i]) { cudaEventDestroy(fe->sch.ev_stage1[i]); }
+        if (fe->sch.ev_tail[i]) { cudaEventDestroy(fe->sch.ev_tail[i]); }
     }
     if (fe->ev_fft_go) { cudaEventDestroy(fe->ev_fft_go); }
     if (fe->ev_fft_done) { cudaEventDestroy(fe->ev_fft_done); }
@@ -224,8 +235,7 @@ extern "C" int b200_fe_set_stream(b200_fe* fe, void* s) {
 extern "C" int b200_fe_set_fft(b200_fe* fe, int size, double rate, int window) {
     if (!fe) { set_error("null fe"); return B200_EINVAL; }
     std::lock_guard<std::mutex> lck(fe->mtx);
-    B200_CK(cudaStreamSynchronize(fe->sch.stream));
-    B200_CK(cudaStreamSynchronize(fe->fft_stream));
+    B200_CK(cudaDeviceSynchronize());
     if (size == 0) { fe->fft_on = false; return 0; }
     if (rate <= 0) { set_error("bad fft rate"); return B200_EINVAL; }
     int nz, skip;
@@ -256,7 +266,12 @@ static int build_vfo_chain(b200_fe* fe, VfoSlot* v) {
     default: set_error("unknown demodulator %d", c.demod); return B200_EINVAL;
     }
     if (rc) { return rc; }
-    return v->chain.finalize(fe->max_chunk);
+    const bool ov = fe->sch.tail_stream != nullptr;
+    if (ov && v->chain.st.size() == 1) {
+        // overlapped mode hands every chain's output to the tail stream: give a stage-1-only chain an exact copy stage
+        if ((rc = v->chain.add_fir_c(std::vector<float>{ 1.0f }, 1))) { return rc; }
+    }
+    return v->chain.finalize(fe->max_chunk, ov);
 }
 
 extern "C" int b200_fe_add_vfo(b200_fe* fe, const b200_vfo_cfg* cfg) {
@@ -293,7 +308,7 @@ extern "C" int b200_fe_remove_vfo(b200_fe* fe, int id) {
     if (!fe) { set_error("null fe"); return B200_EINVAL; }
     std::lock_guard<std::mutex> lck(fe->mtx);
     if (!get_vfo(fe, id)) { return B200_EINVAL; }
-    B200_CK(cudaStreamSynchronize(fe->sch.stream));
+    B200_CK(cudaDeviceSynchronize());
     fe->vfos[id] = std::make_unique<VfoSlot>();
     return 0;
 }
@@ -334,6 +349,13 @@ extern "C" long long b200_fe_launch_count(b200_fe* fe) { return fe ? fe->sch.lau
 extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
     if (!fe || !key) { set_error("null argument"); return B200_EINVAL; }
     if (!strcmp(key, "s1")) { fe->sch.s1_variant = value; return 0; }
+    if (!strcmp(key, "overlap")) {
+        if (b200_fe_vfo_count(fe) > 0) { set_error("'overlap' must be chosen before VFOs are added"); return B200_ESTATE; }
+        if (cudaDeviceSynchronize() != cudaSuccess) { return cuda_fail(cudaGetLastError(), "sync"); }
+        fe->sch.tail_stream = value ? fe->tail_stream : nullptr;
+        return 0;
+    }
+    if (!strcmp(key, "pair")) { fe->sch.pair_conjugates = value != 0; return 0; }
     if (!strcmp(key, "fft_async")) { fe->fft_async = value != 0; return 0; }
     if (!strcmp(key, "tails")) { kernels_set_tail_variant(value); return 0; }
     if (!strcmp(key, "time_s1")) { fe->sch.time_s1 = value != 0; fe->sch.ev_used = 0; return 0; }
@@ -349,7 +371,7 @@ extern "C" int b200_fe_s1_stats(b200_fe* fe, double* ms_total, int* launches) {
 extern "C" int b200_fe_reset(b200_fe* fe) {
     if (!fe) { set_error("null fe"); return B200_EINVAL; }
     std::lock_guard<std::mutex> lck(fe->mtx);
-    B200_CK(cudaStreamSynchronize(fe->sch.stream));
+    B200_CK(cudaDeviceSynchronize());
     for (auto& v : fe->vfos) {
         if (v->used) { v->chain.reset_state(); }
     }
@@ -396,13 +418,17 @@ static int fe_fft_chunk(b200_fe* fe, const void* dptr, int fmt, int count, int* 
     const unsigned long long nz = (unsigned long long)fe->fft.nz, interval = nz + (unsigned long long)fe->skip;
     const int bps = bytes_per_sample(fmt);
     cudaStream_t main_s = fe->sch.stream;
-    cudaStream_t s = fe->fft_async ? fe->fft_stream : main_s;
+    // with overlapped tails the spectrum branch must be on its own stream (its output leaves through the tail stream)
+    const bool async = fe->fft_async || fe->sch.tail_stream != nullptr;
+    cudaStream_t s = async ? fe->fft_stream : main_s;
     bool forked = false;
     auto fork = [&]() -> int {
         // the spectrum branch only reads the chunk: run it beside the VFO branch, join before the outputs
-        if (fe->fft_async && !forked) {
+        if (async && !forked) {
             B200_CK(cudaEventRecord(fe->ev_fft_go, main_s));
             B200_CK(cudaStreamWaitEvent(s, fe->ev_fft_go, 0));
+            // the line buffer of the previous chunk may still be on its way out (tail stream)
+            if (fe->lines_busy) { B200_CK(cudaStreamWaitEvent(s, fe->ev_lines_free, 0)); }
             forked = true;
         }
         return 0;
@@ -519,11 +545,14 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
     // enqueued, so the two overlap on the device
     if ((rc = fe_fft_chunk(fe, dptr, in_fmt, count, &nlines))) { return rc; }
     if ((rc = fe->sch.run(chains, dptr, in_fmt, count, true))) { return rc; }
+    cudaStream_t os = fe->sch.out_stream();       // tail stream in overlapped mode, else the main stream
     if (fe->fft_join_pending) {
-        B200_CK(cudaStreamWaitEvent(s, fe->ev_fft_done, 0));
+        B200_CK(cudaStreamWaitEvent(os, fe->ev_fft_done, 0));
         fe->fft_join_pending = false;
     }
-    B200_CK(cudaEventRecord(fe->ev_compute[slot], s));
+    // the input chunk is no longer needed once stage 1, the raw carry (both before ev_s1 on the main stream, which
+    // `os` already waits on) and the spectrum branch are done
+    B200_CK(cudaEventRecord(fe->ev_compute[slot], os));
     fe->slot_used[slot] = true;
     // ---- outputs ----
     const cudaMemcpyKind kind = (out->out_mem == B200_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
@@ -531,14 +560,16 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
         Chain* c = chains[k];
         out->vfo_count[ids[k]] = c->n_out;
         if (c->n_out > 0) {
-            B200_CK(cudaMemcpyAsync(out->vfo_out[ids[k]], c->out.p, (size_t)c->n_out * c->out_es * sizeof(float), kind, s));
+            B200_CK(cudaMemcpyAsync(out->vfo_out[ids[k]], c->out.p, (size_t)c->n_out * c->out_es * sizeof(float), kind, os));
         }
     }
     out->fft_lines = nlines;
     if (nlines > 0) {
-        B200_CK(cudaMemcpyAsync(out->fft_out, fe->lines.p, (size_t)nlines * fe->fft.size * sizeof(float), kind, s));
+        B200_CK(cudaMemcpyAsync(out->fft_out, fe->lines.p, (size_t)nlines * fe->fft.size * sizeof(float), kind, os));
+        B200_CK(cudaEventRecord(fe->ev_lines_free, os));
+        fe->lines_busy = true;
     }
-    B200_CK(cudaEventRecord(fe->ev_out[slot], s));
+    B200_CK(cudaEventRecord(fe->ev_out[slot], os));
     fe->nsub++;
     return 0;
 }

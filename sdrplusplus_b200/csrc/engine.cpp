@@ -46,7 +46,9 @@ void DevBuf::release() {
 
 int Stage::alloc_in(int cap) {
     cap_in = cap;
-    return inbuf.alloc(((size_t)hist + (size_t)cap + 8) * in_es * sizeof(float));
+    int rc = inbuf.alloc(((size_t)hist + (size_t)cap + 8) * in_es * sizeof(float));
+    if (!rc && dbl) { rc = inbuf_alt.alloc(((size_t)hist + (size_t)cap + 8) * in_es * sizeof(float)); }
+    return rc;
 }
 
 // ------------------------------------------------------------------ XdStage
@@ -224,9 +226,10 @@ int SeqStage::configure_ssb(int mode, double bandwidth, double samplerate, doubl
 }
 
 // ------------------------------------------------------------------ Chain
-int Chain::finalize(int max_in) {
+int Chain::finalize(int max_in, bool dbl_first) {
     if (st.empty()) { set_error("empty chain"); return B200_EINVAL; }
     int cap = max_in;
+    if (dbl_first && st.size() >= 2 && st[0]->kind == K_XD) { st[1]->dbl = true; }
     for (auto& s : st) {
         if (s->kind != K_XD) {
             int rc = s->alloc_in(cap);
@@ -252,6 +255,7 @@ void Chain::reset_state() {
     for (auto& s : st) {
         s->reset_state();
         if (s->inbuf.p && s->hist > 0) { cudaMemset(s->inbuf.p, 0, (size_t)s->hist * s->in_es * sizeof(float)); }
+        if (s->inbuf_alt.p && s->hist > 0) { cudaMemset(s->inbuf_alt.p, 0, (size_t)s->hist * s->in_es * sizeof(float)); }
         if (s->kind == K_QUAD) {
             QuadStage* q = (QuadStage*)s.get();
             cudaMemset(q->state.p, 0, 2 * sizeof(float));
@@ -418,19 +422,29 @@ int Scheduler::reset_raw() {
 // FIR::setTaps (fir.h:31-52): new taps, keep the most recent history
 static int apply_pending_taps(FirCStage* f, cudaStream_t s) {
     if (f->pending.empty()) { return 0; }
-    B200_CK(cudaStreamSynchronize(s));
+    (void)s;
+    B200_CK(cudaDeviceSynchronize());
     const int newT = (int)f->pending.size(), oldT = f->ntaps;
     const int newH = newT - 1, oldH = oldT - 1;
-    DevBuf nb;
-    int rc = nb.alloc(((size_t)newH + f->cap_in + 8) * f->in_es * sizeof(float));
+    const size_t bytes = ((size_t)newH + f->cap_in + 8) * f->in_es * sizeof(float);
+    DevBuf nb, nb2;
+    int rc = nb.alloc(bytes);
     if (rc) { return rc; }
+    if (f->dbl && (rc = nb2.alloc(bytes))) { return rc; }
     int keep = std::min(newH, oldH);
+    // the live history sits in the buffer the NEXT chunk will use (the carry wrote it there)
+    const float* live = f->dbl ? ((f->par ? f->inbuf.as<float>() : f->inbuf_alt.as<float>())) : f->inbuf.as<float>();
+    float* live_new = f->dbl ? ((f->par ? nb.as<float>() : nb2.as<float>())) : nb.as<float>();
     if (keep > 0) {
-        B200_CK(cudaMemcpy(nb.as<float>() + (size_t)(newH - keep) * f->in_es, f->inbuf.as<float>() + (size_t)(oldH - keep) * f->in_es,
+        B200_CK(cudaMemcpy(live_new + (size_t)(newH - keep) * f->in_es, live + (size_t)(oldH - keep) * f->in_es,
                            (size_t)keep * f->in_es * sizeof(float), cudaMemcpyDeviceToDevice));
     }
     std::swap(f->inbuf.p, nb.p);
     std::swap(f->inbuf.bytes, nb.bytes);
+    if (f->dbl) {
+        std::swap(f->inbuf_alt.p, nb2.p);
+        std::swap(f->inbuf_alt.bytes, nb2.bytes);
+    }
     rc = f->taps.alloc((size_t)newT * sizeof(float));
     if (rc) { return rc; }
     B200_CK(cudaMemcpy(f->taps.p, f->pending.data(), (size_t)newT * sizeof(float), cudaMemcpyHostToDevice));
@@ -451,8 +465,19 @@ static int flush_batch(P& p, L launch, cudaStream_t s, long long& launches) {
     return 0;
 }
 
+int Scheduler::enable_overlap(cudaStream_t tail) {
+    tail_stream = tail;
+    for (int i = 0; i < 2; i++) {
+        if (!ev_stage1[i]) { B200_CK(cudaEventCreateWithFlags(&ev_stage1[i], cudaEventDisableTiming)); }
+        if (!ev_tail[i]) { B200_CK(cudaEventCreateWithFlags(&ev_tail[i], cudaEventDisableTiming)); }
+    }
+    return 0;
+}
+
 int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int count, bool carry_raw) {
     // ---- wiring + deferred parameter changes ----
+    const int parity = (int)(chunk_idx & 1);
+    cudaStream_t ts = tail_stream ? tail_stream : stream;
     size_t depth = 0;
     for (Chain* c : chains) {
         for (auto& sp : c->st) {
@@ -461,6 +486,13 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
                 if (rc) { return rc; }
             }
         }
+    }
+    for (Chain* c : chains) {
+        for (auto& sp : c->st) { sp->par = parity; }
+    }
+    if (tail_stream && chunk_idx >= 2) {
+        // stage 1 of this chunk overwrites the stage-2 input buffers that the tails of chunk-2 were reading
+        B200_CK(cudaStreamWaitEvent(stream, ev_tail[parity], 0));
     }
     for (Chain* c : chains) {
         depth = std::max(depth, c->st.size());
@@ -510,6 +542,32 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
                 p.job[v].retuned = x->chunk_retuned ? 1 : 0;
                 p.QP = std::max(p.QP, x->QP);
             }
+            // slots: pair VFOs whose complex taps are exact conjugates (offsets +f / -f, same real prototype, same
+            // decimation phase): they share every multiply-accumulate of stage 1 (kernels.cuh: XdParams)
+            {
+                bool used[B200_BATCH] = { false };
+                p.nslots = 0;
+                for (int v = 0; v < p.njobs; v++) {
+                    if (used[v]) { continue; }
+                    used[v] = true;
+                    int partner = -1;
+                    XdStage* a = g[b + v];
+                    if (pair_conjugates && a->w != 0) {
+                        for (int u = v + 1; u < p.njobs; u++) {
+                            XdStage* c = g[b + u];
+                            if (!used[u] && c->w == (0ULL - a->w) && c->T == a->T && c->chunk_offset == a->chunk_offset &&
+                                c->n_out == a->n_out && c->h == a->h) {
+                                partner = u;
+                                used[u] = true;
+                                break;
+                            }
+                        }
+                    }
+                    p.slot_a[p.nslots] = (signed char)v;
+                    p.slot_b[p.nslots] = (signed char)partner;
+                    p.nslots++;
+                }
+            }
             // the tiled kernel pads every job to the group's QP: all jobs of a batch must have room for it
             int variant = s1_variant;
             for (int v = 0; v < p.njobs; v++) {
@@ -537,6 +595,21 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
             launches += nl;
         }
     }
+    // ---- raw-IQ history for the next chunk's stage 1 (same stream as stage 1) ----
+    if (carry_raw && count > 0) {
+        CarryParams rc1;
+        rc1.njobs = 1;
+        CarryJob& j = rc1.job[0];
+        j.dst = raw_hist.as<float>(); j.a = raw_hist.as<float>(); j.b = raw;
+        j.h = RAW_HIST; j.la = RAW_HIST; j.lb = count; j.esize = 2; j.bfmt = fmt;
+        cudaError_t e = launch_carry(rc1, stream);
+        if (e != cudaSuccess) { return cuda_fail(e, "launch_carry"); }
+        launches++;
+    }
+    if (tail_stream) {
+        B200_CK(cudaEventRecord(ev_stage1[parity], stream));
+        B200_CK(cudaStreamWaitEvent(ts, ev_stage1[parity], 0));
+    }
     // ---- remaining stages level by level: one launch per stage kind per level (batches of 16 VFOs) ----
     for (size_t lvl = 0; lvl < depth; lvl++) {
         FirParams fp; fp.njobs = 0; fp.max_out = 0;
@@ -555,21 +628,21 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
                 FirCStage* f = (FirCStage*)s;
                 if (f->n_out <= 0) { break; }
                 FirJob& j = fp.job[fp.njobs++];
-                j.in = f->inbuf.as<float2>(); j.out = (float2*)f->out_ptr; j.taps = f->taps.as<float>();
+                j.in = (const float2*)f->base(); j.out = (float2*)f->out_ptr; j.taps = f->taps.as<float>();
                 j.ntaps = f->ntaps; j.decim = f->decim; j.offset = f->chunk_offset; j.n_out = f->n_out;
                 fp.max_out = std::max(fp.max_out, f->n_out);
-                if (fp.njobs == B200_BATCH) { rc = flush_batch(fp, launch_fir_c, stream, launches); fp.max_out = 0; }
+                if (fp.njobs == B200_BATCH) { rc = flush_batch(fp, launch_fir_c, ts, launches); fp.max_out = 0; }
                 break;
             }
             case K_POLY: {
                 PolyStage* f = (PolyStage*)s;
                 if (f->n_out <= 0) { break; }
                 PolyJob& j = pp.job[pp.njobs++];
-                j.in = f->inbuf.as<float2>(); j.out = (float2*)f->out_ptr; j.bank = f->bank.as<float>();
+                j.in = (const float2*)f->base(); j.out = (float2*)f->out_ptr; j.bank = f->bank.as<float>();
                 j.tpp = f->tpp; j.interp = f->interp; j.decim = f->decim; j.phase0 = f->chunk_phase; j.offset0 = f->chunk_offset;
                 j.n_out = f->n_out;
                 pp.max_out = std::max(pp.max_out, f->n_out);
-                if (pp.njobs == B200_BATCH) { rc = flush_batch(pp, launch_poly, stream, launches); pp.max_out = 0; }
+                if (pp.njobs == B200_BATCH) { rc = flush_batch(pp, launch_poly, ts, launches); pp.max_out = 0; }
                 break;
             }
             case K_QUAD: {
@@ -580,17 +653,17 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
                 j.state_in = f->state.as<float>() + f->chunk_flip; j.state_out = f->state.as<float>() + (f->chunk_flip ^ 1);
                 j.inv_dev = f->inv_dev; j.n = f->n_out;
                 qp.max_n = std::max(qp.max_n, f->n_out);
-                if (qp.njobs == B200_BATCH) { rc = flush_batch(qp, launch_quad, stream, launches); qp.max_n = 0; }
+                if (qp.njobs == B200_BATCH) { rc = flush_batch(qp, launch_quad, ts, launches); qp.max_n = 0; }
                 break;
             }
             case K_FIRR: {
                 FirRStage* f = (FirRStage*)s;
                 if (f->n_out <= 0) { break; }
                 FirRJob& j = rp.job[rp.njobs++];
-                j.in = f->inbuf.as<float>(); j.out = f->out_ptr; j.taps = f->taps.as<float>();
+                j.in = f->base(); j.out = f->out_ptr; j.taps = f->taps.as<float>();
                 j.ntaps = f->ntaps; j.n_out = f->n_out; j.stereo = f->stereo;
                 rp.max_out = std::max(rp.max_out, f->n_out);
-                if (rp.njobs == B200_BATCH) { rc = flush_batch(rp, launch_fir_r, stream, launches); rp.max_out = 0; }
+                if (rp.njobs == B200_BATCH) { rc = flush_batch(rp, launch_fir_r, ts, launches); rp.max_out = 0; }
                 break;
             }
             case K_SEQ: {
@@ -599,7 +672,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
                 SeqJob& j = sp.job[sp.njobs++];
                 j = f->proto;
                 j.in = (const float2*)f->in_data(); j.out = f->out_ptr; j.state = f->state.as<float>(); j.n = f->n_out;
-                if (sp.njobs == B200_BATCH) { rc = flush_batch(sp, launch_seq, stream, launches); }
+                if (sp.njobs == B200_BATCH) { rc = flush_batch(sp, launch_seq, ts, launches); }
                 break;
             }
             case K_M2S: {
@@ -607,47 +680,45 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
                 M2SJob& j = mp.job[mp.njobs++];
                 j.in = s->in_data(); j.out = s->out_ptr; j.n = s->n_out;
                 mp.max_n = std::max(mp.max_n, s->n_out);
-                if (mp.njobs == B200_BATCH) { rc = flush_batch(mp, launch_m2s, stream, launches); mp.max_n = 0; }
+                if (mp.njobs == B200_BATCH) { rc = flush_batch(mp, launch_m2s, ts, launches); mp.max_n = 0; }
                 break;
             }
             }
             if (rc) { return rc; }
         }
         int rc;
-        if ((rc = flush_batch(fp, launch_fir_c, stream, launches))) { return rc; }
-        if ((rc = flush_batch(pp, launch_poly, stream, launches))) { return rc; }
-        if ((rc = flush_batch(qp, launch_quad, stream, launches))) { return rc; }
-        if ((rc = flush_batch(rp, launch_fir_r, stream, launches))) { return rc; }
-        if ((rc = flush_batch(sp, launch_seq, stream, launches))) { return rc; }
-        if ((rc = flush_batch(mp, launch_m2s, stream, launches))) { return rc; }
+        if ((rc = flush_batch(fp, launch_fir_c, ts, launches))) { return rc; }
+        if ((rc = flush_batch(pp, launch_poly, ts, launches))) { return rc; }
+        if ((rc = flush_batch(qp, launch_quad, ts, launches))) { return rc; }
+        if ((rc = flush_batch(rp, launch_fir_r, ts, launches))) { return rc; }
+        if ((rc = flush_batch(sp, launch_seq, ts, launches))) { return rc; }
+        if ((rc = flush_batch(mp, launch_m2s, ts, launches))) { return rc; }
     }
     // ---- history carry (the memmove at the end of every reference process()) ----
     CarryParams cp;
     cp.njobs = 0;
     auto push = [&](const CarryJob& j) -> int {
         cp.job[cp.njobs++] = j;
-        if (cp.njobs == CARRY_BATCH) { return flush_batch(cp, launch_carry, stream, launches); }
+        if (cp.njobs == CARRY_BATCH) { return flush_batch(cp, launch_carry, ts, launches); }
         return 0;
     };
-    if (carry_raw && count > 0) {
-        CarryJob j;
-        j.dst = raw_hist.as<float>(); j.a = raw_hist.as<float>(); j.b = raw;
-        j.h = RAW_HIST; j.la = RAW_HIST; j.lb = count; j.esize = 2; j.bfmt = fmt;
-        int rc = push(j);
-        if (rc) { return rc; }
-    }
     for (Chain* c : chains) {
         for (auto& sp : c->st) {
             Stage* s = sp.get();
-            if (s->kind == K_XD || s->hist <= 0 || s->n_in <= 0) { continue; }
+            if (s->kind == K_XD || s->hist <= 0) { continue; }
+            if (s->n_in <= 0 && !s->dbl) { continue; }      // a double-buffered stage always hands its history over
             CarryJob j;
-            j.dst = s->inbuf.as<float>(); j.a = s->inbuf.as<float>(); j.b = s->in_data();
+            j.dst = s->other_base(); j.a = s->base(); j.b = s->in_data();
             j.h = s->hist; j.la = s->hist; j.lb = s->n_in; j.esize = s->in_es; j.bfmt = -1;
             int rc = push(j);
             if (rc) { return rc; }
         }
     }
-    return flush_batch(cp, launch_carry, stream, launches);
+    int rcf = flush_batch(cp, launch_carry, ts, launches);
+    if (rcf) { return rcf; }
+    if (tail_stream) { B200_CK(cudaEventRecord(ev_tail[parity], ts)); }
+    chunk_idx++;
+    return 0;
 }
 
 }

@@ -43,13 +43,18 @@ struct Stage {
     int hist = 0;                // history samples kept in front of the data in inbuf
     int cap_in = 0;              // max input samples per chunk
     DevBuf inbuf;                // [hist | data]; unused by K_XD (reads the shared raw IQ)
+    DevBuf inbuf_alt;            // second buffer of the stage fed by stage 1 when tails overlap the next chunk
+    bool dbl = false;
+    int par = 0;                 // which buffer this chunk uses (dbl only)
     int n_in = 0, n_out = 0;     // this chunk
     float* out_ptr = nullptr;    // where this chunk's output goes (set by the scheduler)
     virtual ~Stage() {}
     virtual int plan(int n) = 0;             // host: output count for n inputs, advances the mirrored state
     virtual int max_out(int n) const = 0;    // upper bound
     virtual void reset_state() {}
-    float* in_data() const { return inbuf.as<float>() + (size_t)hist * in_es; }
+    float* base() const { return (dbl && par) ? inbuf_alt.as<float>() : inbuf.as<float>(); }
+    float* other_base() const { return (dbl && !par) ? inbuf_alt.as<float>() : inbuf.as<float>(); }
+    float* in_data() const { return base() + (size_t)hist * in_es; }
     int alloc_in(int cap);
 };
 
@@ -140,7 +145,7 @@ struct Chain {
     int out_cap = 0;
     int n_out = 0;               // this chunk
     bool raw_input() const { return !st.empty() && st[0]->kind == K_XD; }
-    int finalize(int max_in);    // allocates stage buffers for chunks of up to max_in samples
+    int finalize(int max_in, bool dbl_first = false);    // allocates stage buffers for chunks of up to max_in samples
     int plan(int n);             // all stages; returns final count
     int max_out(int n) const;
     void reset_state();
@@ -162,8 +167,16 @@ struct Chain {
 // launch per stage kind, then the history carry.
 struct Scheduler {
     cudaStream_t stream = nullptr;
+    // overlapped mode: stage 1 (+ raw history carry) runs on `stream`, every later stage on `tail_stream`, so the
+    // tails of chunk k overlap stage 1 of chunk k+1.  The stage fed by stage 1 is double-buffered (Stage::dbl).
+    cudaStream_t tail_stream = nullptr;
+    cudaEvent_t ev_stage1[2] = { nullptr, nullptr }, ev_tail[2] = { nullptr, nullptr };
+    unsigned long long chunk_idx = 0;
+    cudaStream_t out_stream() const { return tail_stream ? tail_stream : stream; }
+    int enable_overlap(cudaStream_t tail);
     long long launches = 0;
     int s1_variant = 3;
+    bool pair_conjugates = true;   // stage 1: VFOs at +f / -f share their multiply-accumulates (exact identity)
     // optional device-side timing of the stage-1 launches (bench.py's roofline leg): CUDA events on `stream`
     bool time_s1 = false;
     std::vector<cudaEvent_t> ev_s1;     // pairs (start, stop)

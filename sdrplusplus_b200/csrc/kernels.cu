@@ -781,7 +781,7 @@ static bool try_xd_pipe(const XdParams& p, cudaStream_t s, cudaError_t* err, int
     }
     const int QPC = ((QP + QC - 1) / QC) * QC;
     if (jmin & 1) { jmin -= 1; }
-    const int ngroups = (p.njobs + XP_VR - 1) / XP_VR;
+    const int ngroups = (p.nslots + XP_VR - 1) / XP_VR;
     const int limit = kernels_max_smem_optin();
     // tile: about 8K raw samples, a multiple of 128 outputs
     int MT = (8192 / D) / 128 * 128;
@@ -794,7 +794,7 @@ static bool try_xd_pipe(const XdParams& p, cudaStream_t s, cudaError_t* err, int
         int jp = MT + QPC + 2;
         jp += (jp & 1);
         if ((jp & 3) == 0) { jp += 2; }
-        smem = ((size_t)2 * D * jp + (size_t)ngroups * QPC * D * XP_VR + (size_t)nwarps * 16 * 32) * sizeof(float2);
+        smem = ((size_t)2 * D * jp + (size_t)ngroups * QPC * D * XP_VR + (size_t)nwarps * 32 * 32) * sizeof(float2);
         if (smem <= (size_t)limit) { g.JP = jp; break; }
     }
     const int nstrips = MT / 128;

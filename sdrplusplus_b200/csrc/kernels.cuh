@@ -38,6 +38,11 @@ struct XdParams {
     int D;                  // decimation of the first stage (1 = pure translate)
     int QP;                 // taps are padded to QP*D entries after the (D-1) leading zeros (see gpad)
     int njobs;
+    // "slots" of the pipelined kernel: a slot is one VFO, or two VFOs whose complex taps are exact conjugates
+    // (offsets +f and -f through the same real prototype): both share the accumulators A = sum Re(g) x and
+    // B = sum Im(g) x;  y(+f) = (A.x - B.y, A.y + B.x),  y(-f) = (A.x + B.y, A.y - B.x).  slot_b = -1: single.
+    int nslots;
+    signed char slot_a[B200_BATCH], slot_b[B200_BATCH];
     XdJob job[B200_BATCH];
 };
 

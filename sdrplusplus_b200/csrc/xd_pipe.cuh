@@ -36,19 +36,19 @@ __global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdPar
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     const int gl = QPC * D;
-    const int ngroups = (p.njobs + XP_VR - 1) / XP_VR;
+    const int ngroups = (p.nslots + XP_VR - 1) / XP_VR;
     float2* Xb0 = smem;
     float2* Xb1 = smem + (size_t)D * JP;
     float2* G = smem + (size_t)2 * D * JP;                    // [ngroups][gl][XP_VR]
-    float2* P = G + (size_t)ngroups * gl * XP_VR;             // [nwarps][16][32] partial sums (RS > 1)
+    float2* P = G + (size_t)ngroups * gl * XP_VR;             // [nwarps][32][32] partial sums A,B (RS > 1)
 
     // ---- taps: G[grp][k][vv] = gpad_v[(D-1-s_v) + k], zero for VFO slots beyond njobs ----
     for (int idx = tid; idx < ngroups * gl * XP_VR; idx += nthr) {
         int vv = idx % XP_VR, k = (idx / XP_VR) % gl, grp = idx / (XP_VR * gl);
-        int v = grp * XP_VR + vv;
+        int slot = grp * XP_VR + vv;
         float2 t = make_float2(0.0f, 0.0f);
-        if (v < p.njobs) {
-            const XdJob& Jv = p.job[v];
+        if (slot < p.nslots) {
+            const XdJob& Jv = p.job[p.slot_a[slot]];
             int a = Jv.offset - (Jv.T - 1) - g.org;
             int s = ((a % D) + D) % D;
             t = __ldg(Jv.gpad + (D - 1 - s) + k);
@@ -101,10 +101,9 @@ __global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdPar
             const bool active = task < ntasks;
             const int half = task % RS, sg = task / RS;
             const int strip = sg % nstrips, grp = sg / nstrips;
-            float2 acc[NP][2][XP_VR];
+            float2 A[NP][2][XP_VR], B[NP][2][XP_VR];
             const int jl0 = strip * 32 * XP_RM + 2 * lane;
             if (active) {
-                float2 A[NP][2][XP_VR], B[NP][2][XP_VR];
 #pragma unroll
                 for (int pi = 0; pi < NP; pi++)
 #pragma unroll
@@ -131,7 +130,7 @@ __global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdPar
                             const float4* tp = reinterpret_cast<const float4*>(Gg + (size_t)((qc + q) * D + r) * XP_VR);
 #pragma unroll
                             for (int vp = 0; vp < XP_VR / 2; vp++) {
-                                const float4 t2 = tp[vp];            // taps of two VFOs, broadcast
+                                const float4 t2 = tp[vp];            // taps of two slots, broadcast
                                 const float2 gA = make_float2(t2.x, t2.y), gB = make_float2(t2.z, t2.w);
 #pragma unroll
                                 for (int pi = 0; pi < NP; pi++)
@@ -146,39 +145,35 @@ __global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdPar
                         }
                     }
                 }
-#pragma unroll
-                for (int pi = 0; pi < NP; pi++)
-#pragma unroll
-                    for (int o = 0; o < 2; o++)
-#pragma unroll
-                        for (int v = 0; v < XP_VR; v++) {
-                            acc[pi][o][v] = make_float2(A[pi][o][v].x - B[pi][o][v].y, A[pi][o][v].y + B[pi][o][v].x);
-                        }
             }
             if (RS > 1) {
                 // exchange partial sums of the phase split: halves 1..RS-1 publish, half 0 reduces
                 if (active && half != 0) {
-                    float2* dst = P + (size_t)warp * 16 * 32 + lane;
+                    float2* dst = P + (size_t)warp * 32 * 32 + lane;
 #pragma unroll
                     for (int pi = 0; pi < NP; pi++)
 #pragma unroll
                         for (int o = 0; o < 2; o++)
 #pragma unroll
-                            for (int v = 0; v < XP_VR; v++) { dst[((pi * 2 + o) * XP_VR + v) * 32] = acc[pi][o][v]; }
+                            for (int v = 0; v < XP_VR; v++) {
+                                dst[(((pi * 2 + o) * XP_VR + v) * 2 + 0) * 32] = A[pi][o][v];
+                                dst[(((pi * 2 + o) * XP_VR + v) * 2 + 1) * 32] = B[pi][o][v];
+                            }
                 }
                 __syncthreads();
                 if (active && half == 0) {
                     for (int h = 1; h < RS; h++) {
-                        const float2* src = P + (size_t)(warp + h) * 16 * 32 + lane;
+                        const float2* src = P + (size_t)(warp + h) * 32 * 32 + lane;
 #pragma unroll
                         for (int pi = 0; pi < NP; pi++)
 #pragma unroll
                             for (int o = 0; o < 2; o++)
 #pragma unroll
                                 for (int v = 0; v < XP_VR; v++) {
-                                    float2 t = src[((pi * 2 + o) * XP_VR + v) * 32];
-                                    acc[pi][o][v].x += t.x;
-                                    acc[pi][o][v].y += t.y;
+                                    float2 ta = src[(((pi * 2 + o) * XP_VR + v) * 2 + 0) * 32];
+                                    float2 tb = src[(((pi * 2 + o) * XP_VR + v) * 2 + 1) * 32];
+                                    A[pi][o][v].x += ta.x; A[pi][o][v].y += ta.y;
+                                    B[pi][o][v].x += tb.x; B[pi][o][v].y += tb.y;
                                 }
                     }
                 }
@@ -186,24 +181,32 @@ __global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdPar
             if (active && half == 0) {
 #pragma unroll
                 for (int v = 0; v < XP_VR; v++) {
-                    const int vj = grp * XP_VR + v;
-                    if (vj < p.njobs) {
-                        const XdJob& Jv = p.job[vj];
-                        const int a0 = Jv.offset - (Jv.T - 1);
-                        const int a = a0 - g.org;
-                        const int s = ((a % D) + D) % D;
-                        const int c = (a - s) / D;
+                    const int slot = grp * XP_VR + v;
+                    if (slot < p.nslots) {
 #pragma unroll
-                        for (int pi = 0; pi < NP; pi++)
+                        for (int side = 0; side < 2; side++) {
+                            const int vj = side ? p.slot_b[slot] : p.slot_a[slot];
+                            if (vj < 0) { continue; }
+                            const XdJob& Jv = p.job[vj];
+                            const int a0 = Jv.offset - (Jv.T - 1);
+                            const int a = a0 - g.org;
+                            const int s = ((a % D) + D) % D;
+                            const int c = (a - s) / D;
 #pragma unroll
-                            for (int o = 0; o < 2; o++) {
-                                const long long m = J0 + jl0 + 64 * pi + o - c;
-                                if (m >= 0 && m < Jv.n_out) {
-                                    const long long im = (long long)a0 + m * D;
-                                    const float2 ph = phasor_u64(Jv.phase0 + Jv.w * (unsigned long long)im);
-                                    Jv.out[m] = cmulf(acc[pi][o][v], ph);
+                            for (int pi = 0; pi < NP; pi++)
+#pragma unroll
+                                for (int o = 0; o < 2; o++) {
+                                    const long long m = J0 + jl0 + 64 * pi + o - c;
+                                    if (m >= 0 && m < Jv.n_out) {
+                                        const long long im = (long long)a0 + m * D;
+                                        const float2 ph = phasor_u64(Jv.phase0 + Jv.w * (unsigned long long)im);
+                                        const float2 Av = A[pi][o][v], Bv = B[pi][o][v];
+                                        const float2 y = side ? make_float2(Av.x + Bv.y, Av.y - Bv.x)      // conjugate taps
+                                                              : make_float2(Av.x - Bv.y, Av.y + Bv.x);
+                                        Jv.out[m] = cmulf(y, ph);
+                                    }
                                 }
-                            }
+                        }
                     }
                 }
             }

@@ -403,24 +403,27 @@ def test_frontend_multi_vfo_100msps(sb, oracle, report):
     fe.close()
 
 
-@pytest.mark.parametrize("variant,fft_async", [(4, 1), (3, 0), (1, 1)])
-def test_frontend_variants_100msps(sb, oracle, report, variant, fft_async):
-    """kernel-variant A/B on the config-2 geometry (short): 16-warp stage 1, synchronous spectrum branch."""
-    fs, chunk, nch = 100e6, 1000000, 3
+@pytest.mark.parametrize("variant,fft_async,overlap,pair", [(4, 1, 1, 1), (3, 0, 0, 1), (1, 1, 0, 0), (3, 1, 1, 0), (3, 1, 0, 1)])
+def test_frontend_variants_100msps(sb, oracle, report, variant, fft_async, overlap, pair):
+    """kernel / scheduling A-B on the config-2 geometry (short): 16-warp stage 1, synchronous spectrum branch,
+    tails on the main stream, conjugate-pair sharing off."""
+    fs, chunk, nch = 100e6, 1000000, 4
     n = chunk * nch
-    offs = [5e6, -5e6, 15e6, -25e6, 35e6]
+    offs = [5e6, -5e6, 15e6, -25e6, 35e6, 25e6]
     x = noise_iq(n, 21, 0.01).copy()
     for o in offs:
         x += fm_carrier(n, fs, o)
     fe = sb.FrontEnd(fs, chunk)
+    fe.set_option("overlap", overlap)
     fe.set_option("s1", variant)
+    fe.set_option("pair", pair)
     fe.set_option("fft_async", fft_async)
     fe.set_fft(1 << 18, 200.0, 2)              # 500000-sample interval: frames inside chunks and across them
     cfgs = [sb.VfoConfig.wfm(o) for o in offs]
     ids = [fe.add_vfo(c) for c in cfgs]
     outs, lines = fe.process_chunks(x, chunk)
     la = _oracle_lines(oracle, x, fs, 1 << 18, 200.0)
-    assert lines.shape == la.shape and lines.shape[0] == 6
+    assert lines.shape == la.shape and lines.shape[0] == 8
     p, pr = 10.0 ** (lines.astype(np.float64) / 10), 10.0 ** (la.astype(np.float64) / 10)
     e_fft = float(np.max(np.abs(p - pr)) / np.max(pr))
     errs = []
@@ -428,7 +431,7 @@ def test_frontend_variants_100msps(sb, oracle, report, variant, fft_async):
         ya = _oracle_chain(oracle, x, fs, chunk, c).reshape(-1, 2)
         assert outs[vid].shape == ya.shape
         errs.append(rel_rms(outs[vid][1500:], ya[1500:]))
-    report["frontend_variant%d_fftasync%d" % (variant, fft_async)] = {"wfm_audio_rel_rms": errs, "fft_power_rel_max": e_fft}
+    report["frontend_s1v%d_fftasync%d_overlap%d_pair%d" % (variant, fft_async, overlap, pair)] = {"wfm_audio_rel_rms": errs, "fft_power_rel_max": e_fft}
     assert e_fft < TOL, e_fft
     assert max(errs) < TOL, errs
     fe.close()
@@ -451,6 +454,34 @@ def test_chunking_invariance_and_pipelining(sb, report):
         assert rel_rms(y[4000:], res[0][0][4000:]) < 2e-6
         assert np.max(np.abs(l - res[0][1])) < 1e-3
     report["chunking_invariance"] = [rel_rms(r[0][4000:], res[0][0][4000:]) for r in res[1:]]
+
+
+def test_ragged_and_empty_chunks(sb, oracle, report):
+    """Edge cases of the chunked API: empty chunks, chunks shorter than a filter history, odd sizes."""
+    n = 120000
+    x = _sig(n, 14)
+    sizes = [0, 1, 7, 300, 0, 12000, 1, 36000, 5, 11, 4099, 0, 20000]
+    sizes.append(n - sum(sizes))
+    fe = sb.FrontEnd(FS, 40000)
+    fe.set_fft(4096, 500.0, 2)                 # 4800-sample interval: many frames, some split over tiny chunks
+    cfg = sb.VfoConfig.wfm(300e3)
+    vid = fe.add_vfo(cfg)
+    v, d = oracle.rxvfo(FS, 250e3, 150e3, 300e3), oracle.wfm(75e3, 250e3)
+    pos, yg, ya, nl = 0, [], [], 0
+    for sz in sizes:
+        seg = x[pos:pos + sz]
+        outs, lines = fe.process(seg)
+        nl += lines.shape[0]
+        yg.append(outs[vid])
+        ya.append(d.process(v.process(seg.view(np.float32))).reshape(-1, 2))
+        pos += sz
+    yg, ya = np.concatenate(yg), np.concatenate(ya)
+    assert yg.shape == ya.shape
+    assert nl == len(_oracle_lines(oracle, x, FS, 4096, 500.0))
+    e = rel_rms(yg[4000:], ya[4000:])
+    report["ragged_chunks"] = e
+    assert e < TOL, e
+    fe.close()
 
 
 # ---------------------------------------------------------------------------------------------- full-size properties
