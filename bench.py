@@ -232,6 +232,7 @@ def run_b200(args):
         fe.set_option("overlap", args.overlap)
         fe.set_option("pair", args.pair)
         fe.set_option("s1", args.s1)
+        fe.set_option("s1_mt", args.s1_mt)
         fe.set_option("tails", args.tails)
         fe.set_fft(FFT_SIZE, FFT_RATE, lib.WIN_NUTTALL)
         ids = [fe.add_vfo(sb.VfoConfig.wfm(o)) for o in offsets]
@@ -392,6 +393,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=1 << 24, help="IQ samples per step (default 16 Mi = 128 MiB cf32 > L2)")
     ap.add_argument("--s1", type=int, default=3, help="stage-1 kernel variant (3 = pipelined, default)")
     ap.add_argument("--tails", type=int, default=1, help="tail kernel variant (1 = shared-memory tiled, default)")
+    ap.add_argument("--s1-mt", type=int, default=0, help="force the stage-1 tile size (outputs per tile), 0 = automatic")
     ap.add_argument("--overlap", type=int, default=1, help="1 = tails of chunk k overlap stage 1 of chunk k+1 (default)")
     ap.add_argument("--pair", type=int, default=1, help="1 = VFOs at +f/-f share their stage-1 multiply-accumulates (default)")
     ap.add_argument("--offsets", default="sym", choices=["sym", "asym"],

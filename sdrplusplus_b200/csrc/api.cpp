@@ -357,6 +357,7 @@ extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
     }
     if (!strcmp(key, "pair")) { fe->sch.pair_conjugates = value != 0; return 0; }
     if (!strcmp(key, "fft_async")) { fe->fft_async = value != 0; return 0; }
+    if (!strcmp(key, "s1_mt")) { kernels_set_xd_tile(value); return 0; }
     if (!strcmp(key, "tails")) { kernels_set_tail_variant(value); return 0; }
     if (!strcmp(key, "time_s1")) { fe->sch.time_s1 = value != 0; fe->sch.ev_used = 0; return 0; }
     set_error("unknown option %s", key);
@@ -429,6 +430,7 @@ static int fe_fft_chunk(b200_fe* fe, const void* dptr, int fmt, int count, int* 
             B200_CK(cudaStreamWaitEvent(s, fe->ev_fft_go, 0));
             // the line buffer of the previous chunk may still be on its way out (tail stream)
             if (fe->lines_busy) { B200_CK(cudaStreamWaitEvent(s, fe->ev_lines_free, 0)); }
+            trace_mark("fft start", s);
             forked = true;
         }
         return 0;
@@ -481,6 +483,7 @@ static int fe_fft_chunk(b200_fe* fe, const void* dptr, int fmt, int count, int* 
         }
     }
     if (forked) {
+        trace_mark("fft done", s);
         B200_CK(cudaEventRecord(fe->ev_fft_done, s));
         fe->fft_join_pending = true;     // joined by the caller after the VFO branch has been enqueued
     }
@@ -570,6 +573,7 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
         fe->lines_busy = true;
     }
     B200_CK(cudaEventRecord(fe->ev_out[slot], os));
+    trace_mark("outputs done", os);
     fe->nsub++;
     return 0;
 }
@@ -580,6 +584,7 @@ extern "C" int b200_fe_wait(b200_fe* fe) {
     const int slot = (int)(fe->nwait & 1);
     B200_CK(cudaEventSynchronize(fe->ev_out[slot]));
     fe->nwait++;
+    if (trace_on() && fe->nwait == fe->nsub && fe->nsub >= 8) { trace_dump("chunks in flight drained"); }
     return 0;
 }
 

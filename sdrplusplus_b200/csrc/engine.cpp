@@ -7,6 +7,7 @@
 #include <cstring>
 #include <algorithm>
 #include <map>
+#include <cstdlib>
 
 namespace b200 {
 
@@ -23,6 +24,34 @@ int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
     if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) { return B200_ENODEV; }
     return B200_ECUDA;
+}
+
+// ------------------------------------------------------------------ trace
+struct TraceRec { const char* label; cudaEvent_t ev; };
+static std::vector<TraceRec> g_trace;
+static int g_trace_on = -1;
+bool trace_on() {
+    if (g_trace_on < 0) { const char* e = getenv("B200_TRACE"); g_trace_on = (e && *e && *e != '0') ? 1 : 0; }
+    return g_trace_on == 1;
+}
+void trace_mark(const char* label, cudaStream_t s) {
+    if (!trace_on()) { return; }
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) { return; }
+    cudaEventRecord(e, s);
+    g_trace.push_back({ label, e });
+}
+void trace_dump(const char* title) {
+    if (!trace_on() || g_trace.empty()) { return; }
+    cudaDeviceSynchronize();
+    fprintf(stderr, "[b200 trace] %s\n", title);
+    for (size_t i = 0; i < g_trace.size(); i++) {
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, g_trace[0].ev, g_trace[i].ev);
+        fprintf(stderr, "[b200 trace]   %9.1f us  %s\n", ms * 1e3, g_trace[i].label);
+    }
+    for (auto& r : g_trace) { cudaEventDestroy(r.ev); }
+    g_trace.clear();
 }
 
 // ------------------------------------------------------------------ DevBuf
@@ -494,6 +523,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
         // stage 1 of this chunk overwrites the stage-2 input buffers that the tails of chunk-2 were reading
         B200_CK(cudaStreamWaitEvent(stream, ev_tail[parity], 0));
     }
+    trace_mark("stage1 start", stream);
     for (Chain* c : chains) {
         depth = std::max(depth, c->st.size());
         for (size_t i = 0; i < c->st.size(); i++) {
@@ -590,6 +620,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
             cudaError_t e = launch_xlate_decim(p, fmt, variant, stream, &nl);
             if (e != cudaSuccess) { return cuda_fail(e, "launch_xlate_decim"); }
             if (t1) { B200_CK(cudaEventRecord(t1, stream)); }
+            trace_mark("stage1 done", stream);
             e = launch_xd_edge(p, fmt, stream, &nl);
             if (e != cudaSuccess) { return cuda_fail(e, "launch_xd_edge"); }
             launches += nl;
@@ -610,6 +641,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
         B200_CK(cudaEventRecord(ev_stage1[parity], stream));
         B200_CK(cudaStreamWaitEvent(ts, ev_stage1[parity], 0));
     }
+    trace_mark("tails start", ts);
     // ---- remaining stages level by level: one launch per stage kind per level (batches of 16 VFOs) ----
     for (size_t lvl = 0; lvl < depth; lvl++) {
         FirParams fp; fp.njobs = 0; fp.max_out = 0;
@@ -716,6 +748,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
     }
     int rcf = flush_batch(cp, launch_carry, ts, launches);
     if (rcf) { return rcf; }
+    trace_mark("tails+carry done", ts);
     if (tail_stream) { B200_CK(cudaEventRecord(ev_tail[parity], ts)); }
     chunk_idx++;
     return 0;

@@ -14,6 +14,11 @@
 
 namespace b200 {
 
+// optional launch timeline (env B200_TRACE=1): an event after every launch group, dumped by trace_dump()
+void trace_mark(const char* label, cudaStream_t s);
+void trace_dump(const char* title);
+bool trace_on();
+
 void set_error(const char* fmt, ...);
 const char* last_error();
 int cuda_fail(cudaError_t e, const char* what);   // records message, returns B200_ECUDA

@@ -721,6 +721,8 @@ static cudaError_t launch_xd_tile_t(const XdParams& p, int MT, int JP, int QPC, 
 }
 
 
+int g_xd_mt_override = 0;
+void kernels_set_xd_tile(int mt) { g_xd_mt_override = mt; }
 static int g_num_sms = -1;
 static int num_sms() {
     if (g_num_sms < 0) {
@@ -736,7 +738,14 @@ template <int FMT, int QC, int NT>
 static cudaError_t launch_xd_pipe_t(const XdParams& p, const XpGeom& g, size_t smem, cudaStream_t s) {
     cudaError_t e = set_smem(k_xd_pipe<FMT, QC, NT>, smem);
     if (e != cudaSuccess) { return e; }
-    int grid = g.ntiles < num_sms() ? g.ntiles : num_sms();
+    // CTAs per SM by shared memory (1 KB reserved per CTA), threads and registers (<= 128/thread assumed above 1 CTA)
+    int per_sm = (int)((size_t)233472 / (smem + 1024));
+    if (per_sm > 2048 / NT) { per_sm = 2048 / NT; }
+    if (per_sm > 512 / NT && NT >= 256) { per_sm = 512 / NT > 0 ? 512 / NT : 1; }
+    if (NT == 128 && per_sm > 3) { per_sm = 3; }
+    if (per_sm < 1) { per_sm = 1; }
+    int grid = num_sms() * per_sm;
+    if (grid > g.ntiles) { grid = g.ntiles; }
     k_xd_pipe<FMT, QC, NT><<<grid, NT, smem, s>>>(p, g);
     return cudaGetLastError();
 }
@@ -783,8 +792,9 @@ static bool try_xd_pipe(const XdParams& p, cudaStream_t s, cudaError_t* err, int
     if (jmin & 1) { jmin -= 1; }
     const int ngroups = (p.nslots + XP_VR - 1) / XP_VR;
     const int limit = kernels_max_smem_optin();
-    // tile: about 8K raw samples, a multiple of 128 outputs
-    int MT = (8192 / D) / 128 * 128;
+    // tile: about 8K raw samples (4K for the 4-warp configuration), a multiple of 128 outputs
+    int MT = ((nwarps == 4 ? 4096 : 8192) / D) / 128 * 128;
+    if (g_xd_mt_override > 0) { MT = g_xd_mt_override / 128 * 128; }
     if (MT < 128) { MT = 128; }
     if (MT > 1024) { MT = 1024; }
     XpGeom g;
@@ -794,17 +804,30 @@ static bool try_xd_pipe(const XdParams& p, cudaStream_t s, cudaError_t* err, int
         int jp = MT + QPC + 2;
         jp += (jp & 1);
         if ((jp & 3) == 0) { jp += 2; }
-        smem = ((size_t)2 * D * jp + (size_t)ngroups * QPC * D * XP_VR + (size_t)nwarps * 32 * 32) * sizeof(float2);
-        if (smem <= (size_t)limit) { g.JP = jp; break; }
+        const int nstrips_t = MT / 128;
+        int rs = nwarps / (nstrips_t * ngroups);
+        if (rs < 1) { rs = 1; }
+        while (rs > 1 && (D % rs || (rs & (rs - 1)))) { rs--; }
+        const int ntasks = nstrips_t * ngroups * rs;
+        // the exchange buffer can live in the consumed tile buffer when all tasks run in one round
+        const bool alias = rs > 1 && ntasks <= nwarps && (size_t)D * jp >= (size_t)nwarps * 32 * 32;
+        smem = ((size_t)2 * D * jp + (size_t)ngroups * QPC * D * XP_VR + (size_t)p.njobs * MT + B200_BATCH +
+                ((rs > 1 && !alias) ? (size_t)nwarps * 32 * 32 : 0)) * sizeof(float2);
+        if (smem <= (size_t)limit) { g.JP = jp; g.RS = rs; g.p_alias = alias ? 1 : 0; break; }
     }
-    const int nstrips = MT / 128;
-    int RS = nwarps / (nstrips * ngroups);
-    if (RS < 1) { RS = 1; }
-    while (RS > 1 && (D % RS || (RS & (RS - 1)))) { RS--; }
-    g.MT = MT; g.QPC = QPC; g.org = org; g.RS = RS; g.logD = logD; g.jmin = jmin;
+    g.MT = MT; g.QPC = QPC; g.org = org; g.logD = logD; g.jmin = jmin;
     g.ntiles = cdiv(jmax - jmin, MT);
     cudaError_t e;
-    if (nwarps == 16) {
+    if (nwarps == 4) {
+        switch (QC) {
+        case 4: e = launch_xd_pipe_t<FMT, 4, 128>(p, g, smem, s); break;
+        case 5: e = launch_xd_pipe_t<FMT, 5, 128>(p, g, smem, s); break;
+        case 6: e = launch_xd_pipe_t<FMT, 6, 128>(p, g, smem, s); break;
+        case 7: e = launch_xd_pipe_t<FMT, 7, 128>(p, g, smem, s); break;
+        default: e = launch_xd_pipe_t<FMT, 8, 128>(p, g, smem, s); break;
+        }
+    }
+    else if (nwarps == 16) {
         switch (QC) {
         case 4: e = launch_xd_pipe_t<FMT, 4, 512>(p, g, smem, s); break;
         case 5: e = launch_xd_pipe_t<FMT, 5, 512>(p, g, smem, s); break;
@@ -834,7 +857,7 @@ static cudaError_t launch_xd_fmt(const XdParams& p, int variant, cudaStream_t s,
     const int D = p.D;
     if (variant >= 3) {
         cudaError_t e = cudaSuccess;
-        if (try_xd_pipe<FMT>(p, s, &e, variant >= 4 ? 16 : 8)) {
+        if (try_xd_pipe<FMT>(p, s, &e, variant == 4 ? 16 : (variant >= 5 ? 4 : 8))) {
             if (nlaunch) { (*nlaunch)++; }
             return e;
         }

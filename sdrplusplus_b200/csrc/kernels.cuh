@@ -151,3 +151,4 @@ cudaError_t launch_zoom_hold_tbl(const float* line, const int* start, const int*
                                  float* hold, float hold_speed, cudaStream_t s);
 int kernels_max_smem_optin();
 void kernels_set_tail_variant(int v);
+void kernels_set_xd_tile(int mt);     // 0 = automatic

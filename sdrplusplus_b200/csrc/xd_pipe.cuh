@@ -26,6 +26,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 struct XpGeom {
     int MT, JP, QPC, ntiles, org, RS, logD;
+    int p_alias;      // 1: the RS exchange buffer lives in the tile buffer just consumed (single task round only)
     long long jmin;
 };
 
@@ -40,7 +41,9 @@ __global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdPar
     float2* Xb0 = smem;
     float2* Xb1 = smem + (size_t)D * JP;
     float2* G = smem + (size_t)2 * D * JP;                    // [ngroups][gl][XP_VR]
-    float2* P = G + (size_t)ngroups * gl * XP_VR;             // [nwarps][32][32] partial sums A,B (RS > 1)
+    float2* TB = G + (size_t)ngroups * gl * XP_VR;            // [njobs][MT] phase ramp e^{j W_v D k} + [njobs] per-tile base
+    float2* BASE = TB + (size_t)p.njobs * MT;
+    float2* P = BASE + B200_BATCH;                             // [nwarps][32][32] partial sums A,B (RS > 1, no alias)
 
     // ---- taps: G[grp][k][vv] = gpad_v[(D-1-s_v) + k], zero for VFO slots beyond njobs ----
     for (int idx = tid; idx < ngroups * gl * XP_VR; idx += nthr) {
@@ -56,6 +59,11 @@ __global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdPar
         G[idx] = t;
     }
 
+    // phase ramp of every job over one tile: exact u64 phase, one sincospi per entry, once per CTA
+    for (int idx = tid; idx < p.njobs * MT; idx += nthr) {
+        const int v = idx / MT, k = idx - v * MT;
+        TB[idx] = phasor_u64(p.job[v].w * (unsigned long long)((long long)k * D));
+    }
     const int ntile_samples = D * (MT + QPC);
     const int dmask = D - 1;
     auto issue = [&](int tile, float2* X) {
@@ -93,8 +101,18 @@ __global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdPar
         else {
             cp_async_wait<0>();
         }
-        __syncthreads();
         const long long J0 = g.jmin + (long long)tile * MT;
+        if (tid < p.njobs) {
+            // phase of this job at the tile's first output position (m = J0 - c): base * ramp[k] gives output J0 + k
+            const XdJob& Jv = p.job[tid];
+            const int a0 = Jv.offset - (Jv.T - 1);
+            const int a = a0 - g.org;
+            const int s = ((a % D) + D) % D;
+            const long long c = (a - s) / D;
+            const long long im0 = (long long)a0 + (J0 - c) * D;
+            BASE[tid] = phasor_u64(Jv.phase0 + Jv.w * (unsigned long long)im0);
+        }
+        __syncthreads();
 
         for (int task0 = 0; task0 < ntasks; task0 += nwarps) {
             const int task = task0 + warp;
@@ -148,8 +166,10 @@ __global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdPar
             }
             if (RS > 1) {
                 // exchange partial sums of the phase split: halves 1..RS-1 publish, half 0 reduces
+                float2* Pb = g.p_alias ? X : P;
+                if (g.p_alias) { __syncthreads(); }         // every warp is done reading X before it is reused
                 if (active && half != 0) {
-                    float2* dst = P + (size_t)warp * 32 * 32 + lane;
+                    float2* dst = Pb + (size_t)warp * 32 * 32 + lane;
 #pragma unroll
                     for (int pi = 0; pi < NP; pi++)
 #pragma unroll
@@ -163,7 +183,7 @@ __global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdPar
                 __syncthreads();
                 if (active && half == 0) {
                     for (int h = 1; h < RS; h++) {
-                        const float2* src = P + (size_t)(warp + h) * 32 * 32 + lane;
+                        const float2* src = Pb + (size_t)(warp + h) * 32 * 32 + lane;
 #pragma unroll
                         for (int pi = 0; pi < NP; pi++)
 #pragma unroll
@@ -192,14 +212,16 @@ __global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdPar
                             const int a = a0 - g.org;
                             const int s = ((a % D) + D) % D;
                             const int c = (a - s) / D;
+                            const float2 base = BASE[vj];
+                            const float2* ramp = TB + (size_t)vj * MT;
 #pragma unroll
                             for (int pi = 0; pi < NP; pi++)
 #pragma unroll
                                 for (int o = 0; o < 2; o++) {
-                                    const long long m = J0 + jl0 + 64 * pi + o - c;
+                                    const int jl = jl0 + 64 * pi + o;
+                                    const long long m = J0 + jl - c;
                                     if (m >= 0 && m < Jv.n_out) {
-                                        const long long im = (long long)a0 + m * D;
-                                        const float2 ph = phasor_u64(Jv.phase0 + Jv.w * (unsigned long long)im);
+                                        const float2 ph = cmulf(base, ramp[jl]);
                                         const float2 Av = A[pi][o][v], Bv = B[pi][o][v];
                                         const float2 y = side ? make_float2(Av.x + Bv.y, Av.y - Bv.x)      // conjugate taps
                                                               : make_float2(Av.x - Bv.y, Av.y + Bv.x);

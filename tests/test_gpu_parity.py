@@ -249,7 +249,7 @@ def _oracle_lines(oracle, x, fs, size, rate):
     return np.array(lines)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 def test_frontend_c1_geometry(sb, oracle, report, variant):
     """BASELINE config 1: 2.4 MS/s, chunk 12000, 65536-pt FFT @ 20 fps, one WFM VFO at +300 kHz."""
     n = 600000
@@ -403,7 +403,7 @@ def test_frontend_multi_vfo_100msps(sb, oracle, report):
     fe.close()
 
 
-@pytest.mark.parametrize("variant,fft_async,overlap,pair", [(4, 1, 1, 1), (3, 0, 0, 1), (1, 1, 0, 0), (3, 1, 1, 0), (3, 1, 0, 1)])
+@pytest.mark.parametrize("variant,fft_async,overlap,pair", [(4, 1, 1, 1), (3, 0, 0, 1), (1, 1, 0, 0), (3, 1, 1, 0), (3, 1, 0, 1), (5, 1, 1, 1), (5, 1, 0, 0)])
 def test_frontend_variants_100msps(sb, oracle, report, variant, fft_async, overlap, pair):
     """kernel / scheduling A-B on the config-2 geometry (short): 16-warp stage 1, synchronous spectrum branch,
     tails on the main stream, conjugate-pair sharing off."""
@@ -460,8 +460,9 @@ def test_ragged_and_empty_chunks(sb, oracle, report):
     """Edge cases of the chunked API: empty chunks, chunks shorter than a filter history, odd sizes."""
     n = 120000
     x = _sig(n, 14)
-    sizes = [0, 1, 7, 300, 0, 12000, 1, 36000, 5, 11, 4099, 0, 20000]
+    sizes = [0, 1, 7, 300, 0, 12000, 1, 36000, 5, 11, 4099, 0, 20000, 39999]
     sizes.append(n - sum(sizes))
+    assert 0 <= sizes[-1] <= 40000
     fe = sb.FrontEnd(FS, 40000)
     fe.set_fft(4096, 500.0, 2)                 # 4800-sample interval: many frames, some split over tiny chunks
     cfg = sb.VfoConfig.wfm(300e3)
