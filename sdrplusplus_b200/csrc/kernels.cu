@@ -810,9 +810,9 @@ static bool try_xd_pipe(const XdParams& p, cudaStream_t s, cudaError_t* err, int
         while (rs > 1 && (D % rs || (rs & (rs - 1)))) { rs--; }
         const int ntasks = nstrips_t * ngroups * rs;
         // the exchange buffer can live in the consumed tile buffer when all tasks run in one round
-        const bool alias = rs > 1 && ntasks <= nwarps && (size_t)D * jp >= (size_t)nwarps * 32 * 32;
-        smem = ((size_t)2 * D * jp + (size_t)ngroups * QPC * D * XP_VR + (size_t)p.njobs * MT + B200_BATCH +
-                ((rs > 1 && !alias) ? (size_t)nwarps * 32 * 32 : 0)) * sizeof(float2);
+        const bool alias = ntasks <= nwarps && (size_t)D * jp >= (size_t)nwarps * 32 * 32;
+        smem = ((size_t)2 * D * jp + (size_t)ngroups * QPC * D * XP_VR + (size_t)p.njobs * MT + 3 * B200_BATCH +
+                (!alias ? (size_t)nwarps * 32 * 32 : 0)) * sizeof(float2);
         if (smem <= (size_t)limit) { g.JP = jp; g.RS = rs; g.p_alias = alias ? 1 : 0; break; }
     }
     g.MT = MT; g.QPC = QPC; g.org = org; g.logD = logD; g.jmin = jmin;

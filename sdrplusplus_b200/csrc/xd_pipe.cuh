@@ -43,7 +43,10 @@ __global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdPar
     float2* G = smem + (size_t)2 * D * JP;                    // [ngroups][gl][XP_VR]
     float2* TB = G + (size_t)ngroups * gl * XP_VR;            // [njobs][MT] phase ramp e^{j W_v D k} + [njobs] per-tile base
     float2* BASE = TB + (size_t)p.njobs * MT;
-    float2* P = BASE + B200_BATCH;                             // [nwarps][32][32] partial sums A,B (RS > 1, no alias)
+    int* CJ = reinterpret_cast<int*>(BASE + B200_BATCH);      // [B200_BATCH] block offset c of every job
+    int* JN = CJ + B200_BATCH;                                 // [B200_BATCH] n_out of every job
+    float2** JOUT = reinterpret_cast<float2**>(BASE + 2 * B200_BATCH);   // [B200_BATCH] output pointers
+    float2* P = BASE + 3 * B200_BATCH;                         // [nwarps][32][32] partial sums A,B (no alias)
 
     // ---- taps: G[grp][k][vv] = gpad_v[(D-1-s_v) + k], zero for VFO slots beyond njobs ----
     for (int idx = tid; idx < ngroups * gl * XP_VR; idx += nthr) {
@@ -59,6 +62,14 @@ __global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdPar
         G[idx] = t;
     }
 
+    if (tid < p.njobs) {
+        const XdJob& Jv = p.job[tid];
+        const int a = Jv.offset - (Jv.T - 1) - g.org;
+        const int sft = ((a % D) + D) % D;
+        CJ[tid] = (a - sft) / D;
+        JN[tid] = Jv.n_out;
+        JOUT[tid] = Jv.out;
+    }
     // phase ramp of every job over one tile: exact u64 phase, one sincospi per entry, once per CTA
     for (int idx = tid; idx < p.njobs * MT; idx += nthr) {
         const int v = idx / MT, k = idx - v * MT;
@@ -68,15 +79,30 @@ __global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdPar
     const int dmask = D - 1;
     auto issue = [&](int tile, float2* X) {
         const long long ibase = (g.jmin + (long long)tile * MT) * D + g.org;
-        for (int idx = tid; idx < ntile_samples; idx += nthr) {
-            const int j = idx >> g.logD, r = idx & dmask;
-            const long long i = ibase + idx;
-            float2* dst = X + r * JP + j;
-            if (FMT == FMT_CF32 && i >= 0 && i < p.count) {
-                cp_async8(dst, reinterpret_cast<const float2*>(p.in) + i);
+        if (FMT == FMT_CF32 && ibase >= 0 && ibase + ntile_samples <= (long long)p.count && (nthr & dmask) == 0) {
+            // interior tile: every sample comes straight from the chunk; the thread's decimation phase r is fixed,
+            // only the block index j advances -> one add per element
+            const int r = tid & dmask;
+            const int jstep = nthr >> g.logD;
+            float2* dst = X + r * JP + (tid >> g.logD);
+            const float2* src = reinterpret_cast<const float2*>(p.in) + ibase + tid;
+            for (int idx = tid; idx < ntile_samples; idx += nthr) {
+                cp_async8(dst, src);
+                dst += jstep;
+                src += nthr;
             }
-            else {
-                *dst = load_x<FMT>(p, i);
+        }
+        else {
+            for (int idx = tid; idx < ntile_samples; idx += nthr) {
+                const int j = idx >> g.logD, r = idx & dmask;
+                const long long i = ibase + idx;
+                float2* dst = X + r * JP + j;
+                if (FMT == FMT_CF32 && i >= 0 && i < p.count) {
+                    cp_async8(dst, reinterpret_cast<const float2*>(p.in) + i);
+                }
+                else {
+                    *dst = load_x<FMT>(p, i);
+                }
             }
         }
         cp_async_commit();
@@ -164,11 +190,13 @@ __global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdPar
                     }
                 }
             }
-            if (RS > 1) {
-                // exchange partial sums of the phase split: halves 1..RS-1 publish, half 0 reduces
-                float2* Pb = g.p_alias ? X : P;
+            float2* Pb = g.p_alias ? X : P;
+            {
+                // Every warp publishes its 16 (A,B) pairs; the 16 (output, slot) combinations of a task are then dealt
+                // round-robin to its RS warps, which sum the RS partials and do the epilogue (phase rotation + store).
+                // Going through shared memory keeps this loop small (runtime indices) and spreads it over all warps.
                 if (g.p_alias) { __syncthreads(); }         // every warp is done reading X before it is reused
-                if (active && half != 0) {
+                if (active) {
                     float2* dst = Pb + (size_t)warp * 32 * 32 + lane;
 #pragma unroll
                     for (int pi = 0; pi < NP; pi++)
@@ -181,58 +209,39 @@ __global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdPar
                             }
                 }
                 __syncthreads();
-                if (active && half == 0) {
-                    for (int h = 1; h < RS; h++) {
-                        const float2* src = Pb + (size_t)(warp + h) * 32 * 32 + lane;
-#pragma unroll
-                        for (int pi = 0; pi < NP; pi++)
-#pragma unroll
-                            for (int o = 0; o < 2; o++)
-#pragma unroll
-                                for (int v = 0; v < XP_VR; v++) {
-                                    float2 ta = src[(((pi * 2 + o) * XP_VR + v) * 2 + 0) * 32];
-                                    float2 tb = src[(((pi * 2 + o) * XP_VR + v) * 2 + 1) * 32];
-                                    A[pi][o][v].x += ta.x; A[pi][o][v].y += ta.y;
-                                    B[pi][o][v].x += tb.x; B[pi][o][v].y += tb.y;
-                                }
-                    }
-                }
             }
-            if (active && half == 0) {
-#pragma unroll
-                for (int v = 0; v < XP_VR; v++) {
+            if (active) {
+                const float2* grpP = Pb + (size_t)(warp - half) * 32 * 32 + lane;      // first warp of this task's group
+                for (int ci = half; ci < NP * 2 * XP_VR; ci += RS) {
+                    const int v = ci & (XP_VR - 1), o = (ci / XP_VR) & 1, pi = ci / (2 * XP_VR);
                     const int slot = grp * XP_VR + v;
-                    if (slot < p.nslots) {
-#pragma unroll
-                        for (int side = 0; side < 2; side++) {
-                            const int vj = side ? p.slot_b[slot] : p.slot_a[slot];
-                            if (vj < 0) { continue; }
-                            const XdJob& Jv = p.job[vj];
-                            const int a0 = Jv.offset - (Jv.T - 1);
-                            const int a = a0 - g.org;
-                            const int s = ((a % D) + D) % D;
-                            const int c = (a - s) / D;
-                            const float2 base = BASE[vj];
-                            const float2* ramp = TB + (size_t)vj * MT;
-#pragma unroll
-                            for (int pi = 0; pi < NP; pi++)
-#pragma unroll
-                                for (int o = 0; o < 2; o++) {
-                                    const int jl = jl0 + 64 * pi + o;
-                                    const long long m = J0 + jl - c;
-                                    if (m >= 0 && m < Jv.n_out) {
-                                        const float2 ph = cmulf(base, ramp[jl]);
-                                        const float2 Av = A[pi][o][v], Bv = B[pi][o][v];
-                                        const float2 y = side ? make_float2(Av.x + Bv.y, Av.y - Bv.x)      // conjugate taps
-                                                              : make_float2(Av.x - Bv.y, Av.y + Bv.x);
-                                        Jv.out[m] = cmulf(y, ph);
-                                    }
-                                }
+                    if (slot >= p.nslots) { continue; }
+                    float2 Av = make_float2(0.f, 0.f), Bv = make_float2(0.f, 0.f);
+                    for (int h = 0; h < RS; h++) {
+                        const float2 ta = grpP[(size_t)h * 32 * 32 + (ci * 2 + 0) * 32];
+                        const float2 tb = grpP[(size_t)h * 32 * 32 + (ci * 2 + 1) * 32];
+                        Av.x += ta.x; Av.y += ta.y;
+                        Bv.x += tb.x; Bv.y += tb.y;
+                    }
+                    const int jl = jl0 + 64 * pi + o;
+                    const int ja = p.slot_a[slot], jb = p.slot_b[slot];
+                    {
+                        const long long m = J0 + jl - (long long)CJ[ja];
+                        if (m >= 0 && m < JN[ja]) {
+                            const float2 ph = cmulf(BASE[ja], TB[(size_t)ja * MT + jl]);
+                            JOUT[ja][m] = cmulf(make_float2(Av.x - Bv.y, Av.y + Bv.x), ph);
+                        }
+                    }
+                    if (jb >= 0) {
+                        const long long m = J0 + jl - (long long)CJ[jb];
+                        if (m >= 0 && m < JN[jb]) {
+                            const float2 ph = cmulf(BASE[jb], TB[(size_t)jb * MT + jl]);
+                            JOUT[jb][m] = cmulf(make_float2(Av.x + Bv.y, Av.y - Bv.x), ph);     // conjugate taps
                         }
                     }
                 }
             }
-            if (RS > 1) { __syncthreads(); }
+            if (task0 + nwarps < ntasks) { __syncthreads(); }    // P is reused by the next round
         }
         __syncthreads();       // everyone is done with X before the next iteration's prefetch overwrites it
     }
