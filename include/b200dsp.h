@@ -96,6 +96,8 @@ int b200_load_decim_plans(const char* path /* NULL = default */);
  * ------------------------------------------------------------------------------------------ */
 /* dsp::taps::lowPass (core/src/dsp/taps/low_pass.h:7-11): returns tap count, writes min(count,cap) */
 int b200_taps_lowpass(double cutoff, double transWidth, double samplerate, int oddTapCount, float* out, int cap);
+/* dsp::taps::highPass (core/src/dsp/taps/high_pass.h:7-14) */
+int b200_taps_highpass(double cutoff, double transWidth, double samplerate, int oddTapCount, float* out, int cap);
 /* IQFrontEnd::updateFFTPath window (core/src/signal_path/iq_frontend.cpp:281-291): w(i,nz)*(-1)^i */
 int b200_window(int window, int nz, float* out);
 /* IQFrontEnd::genReshapeParams (core/src/signal_path/iq_frontend.h:59-63) */
@@ -136,6 +138,11 @@ typedef struct {
     double agc_attack;        /* AM/SSB: per-sample coefficient (radio passes attack/IFrate)             */
     double agc_decay;
     double dc_block_rate;     /* AM: per-sample rate (radio passes 100/IFrate, demodulators/am.h:34)     */
+    /* optional radio AF chain behind the demodulator (decoder_modules/radio/src/radio_module.h:99-110,546-553):
+     * RationalResampler<stereo_t> out_samplerate -> af_samplerate, 300 Hz high-pass FIR, Deemphasis.          */
+    double af_samplerate;     /* 0 = no AF chain (output at out_samplerate); e.g. 48000                      */
+    int    af_high_pass;      /* taps::highPass(300, 100, af_samplerate)                                     */
+    double af_deemph_tau;     /* seconds, 0 = off (50e-6 EU / 75e-6 US, radio_module.h deempTaus)            */
 } b200_vfo_cfg;
 
 typedef struct {
@@ -216,6 +223,7 @@ b200_block* b200_quad_create(double deviationHz, double samplerate);            
 b200_block* b200_wfm_create(double deviationHz, double samplerate, int stereo, int lowPass); /* demod::BroadcastFM: complex -> stereo */
 b200_block* b200_nfm_create(double samplerate, double bandwidth, int lowPass);  /* demod::FM<stereo_t> */
 b200_block* b200_am_create(int agcMode, double bandwidth, double agcAttack, double agcDecay, double dcBlockRate, double samplerate); /* demod::AM<stereo_t> */
+b200_block* b200_deemph_create(double tau, double samplerate);                       /* filter::Deemphasis<stereo_t> (deephasis.h:58-77): stereo -> stereo */
 b200_block* b200_ssb_create(int mode /*0 USB,1 LSB,2 DSB*/, double bandwidth, double samplerate, double agcAttack, double agcDecay); /* demod::SSB<stereo_t> */
 /* returns the output sample count; in/out are host pointers of the block's sample types */
 int  b200_block_process(b200_block* b, int count, const void* in, void* out);

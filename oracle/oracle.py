@@ -90,6 +90,7 @@ class Oracle:
             "orc_set_rotator_mode": (None, [i]),
             "orc_estimate_tap_count": (i, [d, d]),
             "orc_lowpass": (i, [d, d, d, i, vp, i]),
+            "orc_highpass": (i, [d, d, d, i, vp, i]),
             "orc_bandpass_c": (i, [d, d, d, d, i, vp, i]),
             "orc_window": (d, [i, d, d]),
             "orc_decim_plan": (i, [i, ip, ip, i]),
@@ -147,6 +148,12 @@ class Oracle:
         n = self.lib.orc_lowpass(cutoff, tw, sr, int(odd), None, 0)
         out = np.empty(n, np.float32)
         self.lib.orc_lowpass(cutoff, tw, sr, int(odd), out.ctypes.data_as(C.c_void_p), n)
+        return out
+
+    def highpass(self, cutoff, tw, sr, odd=False):
+        n = self.lib.orc_highpass(cutoff, tw, sr, int(odd), None, 0)
+        out = np.empty(n, np.float32)
+        self.lib.orc_highpass(cutoff, tw, sr, int(odd), out.ctypes.data_as(C.c_void_p), n)
         return out
 
     def bandpass_c(self, b0, b1, tw, sr, odd=False):

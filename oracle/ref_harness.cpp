@@ -34,6 +34,7 @@
 #include <dsp/correction/dc_blocker.h>
 #include <dsp/taps/low_pass.h>
 #include <dsp/taps/band_pass.h>
+#include <dsp/taps/high_pass.h>
 #include <dsp/taps/from_array.h>
 #include <dsp/window/nuttall.h>
 #include <dsp/window/blackman.h>
@@ -199,6 +200,13 @@ int orc_estimate_tap_count(double tw, double sr) { return taps::estimateTapCount
 
 int orc_lowpass(double cutoff, double tw, double sr, int odd, float* out, int cap) {
     tap<float> t = taps::lowPass(cutoff, tw, sr, odd != 0);
+    int n = copyTaps(t, out, cap);
+    taps::free(t);
+    return n;
+}
+
+int orc_highpass(double cutoff, double tw, double sr, int odd, float* out, int cap) {
+    tap<float> t = taps::highPass(cutoff, tw, sr, odd != 0);
     int n = copyTaps(t, out, cap);
     taps::free(t);
     return n;

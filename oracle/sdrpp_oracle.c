@@ -100,6 +100,23 @@ int orc_lowpass(double cutoff, double transWidth, double samplerate, int odd, fl
     return n;
 }
 
+/* taps::highPass  (core/src/dsp/taps/high_pass.h:7-14): windowedSinc at (fs/2 - cutoff) with the window
+ * nuttall(n,N) * ((int)round(n) % 2 ? -1.0f : 1.0f)  (double * float -> double) */
+int orc_highpass(double cutoff, double transWidth, double sampleRate, int odd, float* out, int cap) {
+    int count = orc_estimate_tap_count(transWidth, sampleRate);
+    if (odd && !(count % 2)) { count++; }
+    const double omega = hz_to_rads((sampleRate / 2.0) - cutoff, sampleRate);
+    const double half = (double)count / 2.0;
+    const double corr = 1.0 * omega / DB_M_PI;
+    for (int i = 0; i < count && i < cap; i++) {
+        double t = (double)i - half + 0.5;
+        double n = t - half;
+        double w = win_nuttall(n, count) * ((((int)round(n)) % 2) ? -1.0f : 1.0f);
+        if (out) { out[i] = (float)(sinc_d(t * omega) * w * corr); }
+    }
+    return count;
+}
+
 /* taps::bandPass<complex_t>  (core/src/dsp/taps/band_pass.h:11-26) with
  * windowedSinc<complex_t> (windowed_sinc.h:22-25): cplx{(float)sinc,0} * window(..) * corr, where the
  * window is a complex_t (phasor * double -> float multiply, types.h:12-14) and the final "* corr" is the

@@ -36,6 +36,8 @@ void orc_set_rotator_mode(int mode);
 int orc_estimate_tap_count(double transWidth, double samplerate);
 /* taps::lowPass -> returns tap count (writes min(count,cap) taps) */
 int orc_lowpass(double cutoff, double transWidth, double samplerate, int oddTapCount, float* out, int cap);
+/* taps::highPass (core/src/dsp/taps/high_pass.h:7-14) -> count */
+int orc_highpass(double cutoff, double transWidth, double samplerate, int oddTapCount, float* out, int cap);
 /* taps::bandPass<complex_t>(bandStart, bandStop, transWidth, sr, odd) -> count (complex taps, interleaved) */
 int orc_bandpass_c(double bandStart, double bandStop, double transWidth, double samplerate, int oddTapCount, float* out, int cap);
 /* window::{0 rectangular(=1), 1 blackman, 2 nuttall}(n, N) */

@@ -62,6 +62,11 @@ extern "C" int b200_taps_lowpass(double cutoff, double tw, double sr, int odd, f
     if (out) { memcpy(out, t.data(), sizeof(float) * (size_t)std::min<int>((int)t.size(), cap)); }
     return (int)t.size();
 }
+extern "C" int b200_taps_highpass(double cutoff, double tw, double sr, int odd, float* out, int cap) {
+    std::vector<float> t = highpass_taps(cutoff, tw, sr, odd != 0);
+    if (out) { memcpy(out, t.data(), sizeof(float) * (size_t)std::min<int>((int)t.size(), cap)); }
+    return (int)t.size();
+}
 extern "C" int b200_window(int window, int nz, float* out) {
     if (nz < 0 || !out) { set_error("bad window args"); return B200_EINVAL; }
     std::vector<float> w = fft_window(window, nz);
@@ -266,6 +271,9 @@ static int build_vfo_chain(b200_fe* fe, VfoSlot* v) {
     default: set_error("unknown demodulator %d", c.demod); return B200_EINVAL;
     }
     if (rc) { return rc; }
+    if (c.af_samplerate > 0 && c.demod != B200_DEMOD_RAW) {
+        if ((rc = v->chain.add_af_chain(c.out_samplerate, c.af_samplerate, c.af_high_pass != 0, c.af_deemph_tau))) { return rc; }
+    }
     const bool ov = fe->sch.tail_stream != nullptr;
     if (ov && v->chain.st.size() == 1) {
         // overlapped mode hands every chain's output to the tail stream: give a stage-1-only chain an exact copy stage
@@ -771,6 +779,12 @@ extern "C" b200_block* b200_am_create(int agcMode, double bw, double att, double
     b200_block* b = block_new();
     if (!b) { return nullptr; }
     return block_finish(b, b->chain.add_am(agcMode, bw, att, dec, dcr, sr));
+}
+extern "C" b200_block* b200_deemph_create(double tau, double sr) {
+    if (tau <= 0 || sr <= 0) { set_error("bad deemphasis parameters"); return nullptr; }
+    b200_block* b = block_new();
+    if (!b) { return nullptr; }
+    return block_finish(b, b->chain.add_deemph(tau, sr));
 }
 extern "C" b200_block* b200_ssb_create(int mode, double bw, double sr, double att, double dec) {
     if (mode < 0 || mode > 2) { set_error("bad SSB mode"); return nullptr; }

@@ -52,6 +52,23 @@ std::vector<float> lowpass_taps(double cutoff, double transWidth, double sampler
     return taps;
 }
 
+// taps::highPass (taps/high_pass.h:7-14): sinc at fs/2 - cutoff, window nuttall(n,N) * (-1)^round(n)
+std::vector<float> highpass_taps(double cutoff, double transWidth, double samplerate, bool odd) {
+    int count = estimate_tap_count(transWidth, samplerate);
+    if (odd && !(count % 2)) { count++; }
+    std::vector<float> taps(count > 0 ? count : 0);
+    const double omega = hz_to_rads((samplerate / 2.0) - cutoff, samplerate);
+    const double half = (double)count / 2.0;
+    const double corr = 1.0 * omega / kPi;
+    for (int i = 0; i < count; i++) {
+        double t = (double)i - half + 0.5;
+        double n = t - half;
+        double w = nuttall(n, count) * ((((int)std::round(n)) % 2) ? -1.0f : 1.0f);
+        taps[i] = (float)(sinc(t * omega) * w * corr);
+    }
+    return taps;
+}
+
 // iq_frontend.cpp:281-291
 std::vector<float> fft_window(int window, int nz) {
     std::vector<float> w(nz);

@@ -10,6 +10,7 @@ namespace b200 {
 double hz_to_rads(double freq, double samplerate);                       // math::hzToRads (hz_to_rads.h:6-8)
 int estimate_tap_count(double transWidth, double samplerate);             // taps::estimateTapCount
 std::vector<float> lowpass_taps(double cutoff, double transWidth, double samplerate, bool odd = false); // taps::lowPass
+std::vector<float> highpass_taps(double cutoff, double transWidth, double samplerate, bool odd = false);                 // taps::highPass
 std::vector<float> fft_window(int window, int nz);                       // IQFrontEnd::updateFFTPath window * (-1)^i
 void fft_frame_params(double samplerate, int size, double rate, int& nz, int& skip); // genReshapeParams
 

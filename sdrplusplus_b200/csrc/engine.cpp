@@ -254,6 +254,20 @@ int SeqStage::configure_ssb(int mode, double bandwidth, double samplerate, doubl
     return 0;
 }
 
+int SeqStage::configure_deemph(double tau, double samplerate) {
+    memset(&proto, 0, sizeof(proto));
+    proto.kind = 2;
+    float dt = 1.0f / samplerate;                       // deephasis.h:91-94: dt is a float
+    proto.alpha = dt / (tau + dt);
+    in_es = 2;
+    out_es = 2;
+    memset(init_state, 0, sizeof(init_state));
+    int rc = state.alloc(sizeof(init_state));
+    if (rc) { return rc; }
+    B200_CK(cudaMemcpy(state.p, init_state, sizeof(init_state), cudaMemcpyHostToDevice));
+    return 0;
+}
+
 // ------------------------------------------------------------------ Chain
 int Chain::finalize(int max_in, bool dbl_first) {
     if (st.empty()) { set_error("empty chain"); return B200_EINVAL; }
@@ -292,7 +306,7 @@ void Chain::reset_state() {
         }
         if (s->kind == K_SEQ) {
             SeqStage* q = (SeqStage*)s.get();
-            // AM::reset / AGC::reset (am.h:90-98, agc.h:64-68); the SSB demodulator has no reset
+            // AM::reset / AGC::reset (am.h:90-98, agc.h:64-68), Deemphasis::reset; the SSB demodulator has no reset
             cudaMemcpy(q->state.p, q->init_state, sizeof(q->init_state), cudaMemcpyHostToDevice);
         }
     }
@@ -419,6 +433,21 @@ int Chain::add_ssb(int mode, double bandwidth, double samplerate, double attack,
     if (rc) { return rc; }
     st.push_back(std::move(s));
     st.push_back(std::make_unique<M2SStage>());
+    return 0;
+}
+
+int Chain::add_deemph(double tau, double samplerate) {
+    auto s = std::make_unique<SeqStage>();
+    int rc = s->configure_deemph(tau, samplerate);
+    if (rc) { return rc; }
+    st.push_back(std::move(s));
+    return 0;
+}
+int Chain::add_af_chain(double afSR, double audioSR, bool highPass, double deemphTau) {
+    int rc = add_resampler(afSR, audioSR);                                   // stereo_t == two packed floats: same kernels
+    if (rc) { return rc; }
+    if (highPass && (rc = add_fir_c(highpass_taps(300.0, 100.0, audioSR), 1))) { return rc; }   // radio_module.h:597-598
+    if (deemphTau > 0.0 && (rc = add_deemph(deemphTau, audioSR))) { return rc; }
     return 0;
 }
 

@@ -132,6 +132,7 @@ struct SeqStage : Stage {
     SeqStage() { kind = K_SEQ; out_es = 1; }
     int configure_am(int agcMode, double attack, double decay, double dcRate);
     int configure_ssb(int mode, double bandwidth, double samplerate, double attack, double decay);
+    int configure_deemph(double tau, double samplerate);
     int plan(int n) override { n_in = n; n_out = n; return n; }
     int max_out(int n) const override { return n; }
 };
@@ -166,6 +167,9 @@ struct Chain {
     int add_nfm(double samplerate, double bandwidth, bool lowPass);         // fm.h:24-40
     int add_am(int agcMode, double bandwidth, double attack, double decay, double dcRate, double samplerate); // am.h:28-45
     int add_ssb(int mode, double bandwidth, double samplerate, double attack, double decay); // ssb.h:22-35
+    int add_deemph(double tau, double samplerate);                          // filter::Deemphasis<stereo_t> (deephasis.h:14-28)
+    // radio AF chain: RationalResampler<stereo_t> -> [300 Hz high-pass FIR] -> [Deemphasis]  (radio_module.h:99-110,546-553)
+    int add_af_chain(double afSamplerate, double audioSamplerate, bool highPass, double deemphTau);
 };
 
 // Runs a set of chains over one chunk: stage-1 launches grouped by decimation, then level by level one

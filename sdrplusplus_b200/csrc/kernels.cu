@@ -347,9 +347,23 @@ __device__ __forceinline__ float camp(float2 x) {
 }
 
 __global__ void k_seq(const __grid_constant__ SeqParams p) {
-    if (threadIdx.x != 0) { return; }
     const SeqJob& J = p.job[blockIdx.x];
     const int n = J.n;
+    if (J.kind == 2) {
+        // ---- Deemphasis<stereo_t>: y = alpha*x + (1-alpha)*y[-1] per channel  (deephasis.h:58-77) ----
+        if (threadIdx.x >= 2) { return; }
+        const int ch = threadIdx.x;
+        const float* x = reinterpret_cast<const float*>(J.in);
+        float y = J.state[5 + ch];
+        const float a = J.alpha, b = __fsub_rn(1.0f, J.alpha);
+        for (int i = 0; i < n; i++) {
+            y = __fadd_rn(__fmul_rn(a, x[2 * i + ch]), __fmul_rn(b, y));
+            J.out[2 * i + ch] = y;
+        }
+        J.state[5 + ch] = y;
+        return;
+    }
+    if (threadIdx.x != 0) { return; }
     AgcCoef c = { J.set_point, J.attack, J.inv_attack, J.decay, J.inv_decay, J.max_gain, J.max_out };
     float* st = J.state;
     if (J.kind == 0) {

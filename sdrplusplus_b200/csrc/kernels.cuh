@@ -94,14 +94,15 @@ struct SeqJob {
     float* out;             // n mono floats
     float* state;           // device state block (see kernels.cu: SEQ_STATE_*)
     int n;
-    int kind;               // 0 AM, 1 SSB
+    int kind;               // 0 AM, 1 SSB, 2 stereo deemphasis (in/out are (l,r) pairs; threads 0/1 take one channel each)
     int agc_mode;           // AM: 0 carrier, 1 audio
     float set_point, attack, inv_attack, decay, inv_decay, max_gain, max_out; // loop::AGC (agc.h:13-24)
     float dc_rate;          // AM
     float delta_re, delta_im; // SSB second rotator phaseDelta (ssb.h:29, frequency_xlator.h:17)
+    float alpha;            // deemphasis: dt / (tau + dt)  (deephasis.h:91-94)
 };
 struct SeqParams { int njobs; SeqJob job[B200_BATCH]; };
-#define SEQ_STATE_FLOATS 8   // [0] carrier amp [1] audio amp [2] dc offset [3] rot re [4] rot im
+#define SEQ_STATE_FLOATS 8   // [0] carrier amp [1] audio amp [2] dc offset [3] rot re [4] rot im [5] deemph last l [6] last r
 
 // ---- mono -> stereo copy (convert::MonoToStereo) ----
 struct M2SJob { const float* in; float* out; int n; };

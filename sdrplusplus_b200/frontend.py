@@ -25,6 +25,13 @@ class VfoConfig:
     agc_attack: float = 0.0
     agc_decay: float = 0.0
     dc_block_rate: float = 0.0
+    af_samplerate: float = 0.0       # radio AF chain: resample to this rate (0 = off) ...
+    af_high_pass: bool = False       # ... 300 Hz high-pass ...
+    af_deemph_tau: float = 0.0       # ... deemphasis time constant in seconds (0 = off)
+
+    def with_af(self, audio_sr=48000.0, high_pass=False, deemph_tau=50e-6):
+        self.af_samplerate, self.af_high_pass, self.af_deemph_tau = audio_sr, high_pass, deemph_tau
+        return self
 
     @staticmethod
     def wfm(offset, bandwidth=150000.0):
@@ -52,7 +59,8 @@ class VfoConfig:
 
     def to_c(self):
         return L.VfoCfg(self.offset, self.out_samplerate, self.bandwidth, self.demod, self.deviation, int(self.low_pass),
-                        self.agc_mode, self.agc_attack, self.agc_decay, self.dc_block_rate)
+                        self.agc_mode, self.agc_attack, self.agc_decay, self.dc_block_rate, self.af_samplerate,
+                        int(self.af_high_pass), self.af_deemph_tau)
 
 
 _NP_FMT = {L.FMT_CF32: (np.complex64, 1), L.FMT_CS16: (np.int16, 2), L.FMT_CS8: (np.int8, 2)}
@@ -242,6 +250,10 @@ class Block:
     def ssb(mode, bw, sr, attack, decay):
         return Block(L.load().b200_ssb_create(mode, bw, sr, attack, decay), 2, 2)
 
+    @staticmethod
+    def deemph(tau, sr):
+        return Block(L.load().b200_deemph_create(tau, sr), 2, 2)
+
     def set_offset(self, *a):
         if len(a) == 2:
             L.check(self._l.b200_xlator_set_offset(self._h, a[0], a[1]))
@@ -327,6 +339,14 @@ def taps_lowpass(cutoff, tw, sr, odd=False):
     n = l.b200_taps_lowpass(cutoff, tw, sr, int(odd), None, 0)
     out = np.empty(n, np.float32)
     l.b200_taps_lowpass(cutoff, tw, sr, int(odd), out.ctypes.data, n)
+    return out
+
+
+def taps_highpass(cutoff, tw, sr, odd=False):
+    l = L.load()
+    n = l.b200_taps_highpass(cutoff, tw, sr, int(odd), None, 0)
+    out = np.empty(n, np.float32)
+    l.b200_taps_highpass(cutoff, tw, sr, int(odd), out.ctypes.data, n)
     return out
 
 

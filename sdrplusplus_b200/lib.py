@@ -25,7 +25,8 @@ class B200Error(RuntimeError):
 class VfoCfg(C.Structure):
     _fields_ = [("offset", C.c_double), ("out_samplerate", C.c_double), ("bandwidth", C.c_double), ("demod", C.c_int),
                 ("deviation", C.c_double), ("low_pass", C.c_int), ("agc_mode", C.c_int), ("agc_attack", C.c_double),
-                ("agc_decay", C.c_double), ("dc_block_rate", C.c_double)]
+                ("agc_decay", C.c_double), ("dc_block_rate", C.c_double), ("af_samplerate", C.c_double),
+                ("af_high_pass", C.c_int), ("af_deemph_tau", C.c_double)]
 
 
 class Outputs(C.Structure):
@@ -49,6 +50,7 @@ SIGNATURES = {
     "b200_register_decim_plan": (_i, [_i, _i, _ip, _ip, C.POINTER(C.POINTER(C.c_float))]),
     "b200_load_decim_plans": (_i, [C.c_char_p]),
     "b200_taps_lowpass": (_i, [_d, _d, _d, _i, _vp, _i]),
+    "b200_taps_highpass": (_i, [_d, _d, _d, _i, _vp, _i]),
     "b200_window": (_i, [_i, _i, _vp]),
     "b200_fft_frame_params": (_i, [_d, _i, _d, _ip, _ip]),
     "b200_resamp_plan_get": (_i, [_d, _d, C.POINTER(ResampPlan)]),
@@ -85,6 +87,7 @@ SIGNATURES = {
     "b200_nfm_create": (_vp, [_d, _d, _i]),
     "b200_am_create": (_vp, [_i, _d, _d, _d, _d, _d]),
     "b200_ssb_create": (_vp, [_i, _d, _d, _d, _d]),
+    "b200_deemph_create": (_vp, [_d, _d]),
     "b200_block_process": (_i, [_vp, _i, _vp, _vp]),
     "b200_block_max_out": (_i, [_vp, _i]),
     "b200_block_reset": (_i, [_vp]),

@@ -30,6 +30,7 @@ def run_cases(R):
     g["lowpass_wfm_audio"] = R.lowpass(15000.0, 4000.0, 250000.0)
     g["lowpass_vfo_150k"] = R.lowpass(75000.0, 7500.0, 250000.0)
     g["lowpass_odd"] = R.lowpass(1400.0, 140.0, 24000.0, True)
+    g["highpass_300_48k"] = R.highpass(300.0, 100.0, 48000.0)
     g["window_nuttall_4096"] = R.window_buf(2, 4096)
     g["window_blackman_1000"] = R.window_buf(1, 1000)
     for rates in ((2.4e6, 250e3), (100e6, 250e3), (1.024e9, 250e3), (2.4e6, 15e3), (250e3, 48e3)):
@@ -73,6 +74,13 @@ def run_cases(R):
     g["usb_digest"] = digest(a)
     g["lsb_digest"] = digest(R.ssb(1, 2800.0, 24e3, 50 / 24e3, 5 / 24e3).process_chunks(v, 120))
     g["deemph_digest"] = digest(R.deemph(50e-6, 48e3).process_chunks(a, 480))
+    # radio AF chain behind WFM: 250 k -> 48 k stereo resampler, 300 Hz high-pass, 50 us deemphasis
+    w = R.wfm(75e3, 250e3).process_chunks(vfo, 1250)
+    af = R.resamp_stereo(250e3, 48e3).process_chunks(w, 1250)
+    af = R.fir_cr(R.highpass(300.0, 100.0, 48000.0)).process_chunks(af, 240)
+    af = R.deemph(50e-6, 48e3).process_chunks(af, 240)
+    g["af_chain_tail"] = af[-256:]
+    g["af_chain_digest"] = digest(af)
     # ---- spectrum branch ----
     line = R.fft_frame(65536, 65536, 2, x[:65536])
     g["fft_65536_stride"] = line[::64]

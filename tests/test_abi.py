@@ -49,6 +49,13 @@ def test_lowpass_taps_bit_exact(oracle, args):
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+def test_highpass_taps_bit_exact(oracle):
+    a = frontend.taps_highpass(300.0, 100.0, 48000.0)
+    b = oracle.highpass(300.0, 100.0, 48000.0)
+    assert a.size == b.size == 1824
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
 @pytest.mark.parametrize("win,nz", [(0, 1000), (1, 4097), (2, 65536), (2, 12000)])
 def test_window_bit_exact(oracle, win, nz):
     assert np.array_equal(frontend.window(win, nz).view(np.uint32), oracle.window_buf(win, nz).view(np.uint32))

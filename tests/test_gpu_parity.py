@@ -346,6 +346,43 @@ def test_frontend_mixed_modes(sb, oracle, report):
     fe.close()
 
 
+def test_deemphasis_block_bit_exact(sb, oracle):
+    n = 20000
+    x = noise_iq(n, 15, 0.5).view(np.float32)            # (l, r) pairs
+    y = sb.Block.deemph(50e-6, 48e3).process_chunks(x, 480)
+    yo = oracle.deemph(50e-6, 48e3).process_chunks(x, 480)
+    assert np.array_equal(y.view(np.uint32), yo.view(np.uint32))
+
+
+@pytest.mark.parametrize("high_pass", [False, True])
+def test_frontend_af_chain(sb, oracle, report, high_pass):
+    """the radio module's AF chain behind the demodulator, fused into the same chunk pass:
+    WFM (250 kS/s) -> RationalResampler<stereo_t> 48 kS/s -> [300 Hz high-pass] -> 50 us deemphasis."""
+    n = 480000
+    x = _sig(n, 16)
+    fe = sb.FrontEnd(FS, 12000)
+    cfg = sb.VfoConfig.wfm(300e3).with_af(48000.0, high_pass, 50e-6)
+    vid = fe.add_vfo(cfg)
+    outs, _ = fe.process_chunks(x, 12000)
+    v, d = oracle.rxvfo(FS, 250e3, 150e3, 300e3), oracle.wfm(75e3, 250e3)
+    r = oracle.resamp_stereo(250e3, 48e3)
+    h = oracle.fir_cr(oracle.highpass(300.0, 100.0, 48000.0)) if high_pass else None
+    de = oracle.deemph(50e-6, 48e3)
+    ya = []
+    xf = x.view(np.float32)
+    for i in range(0, n, 12000):
+        a = r.process(d.process(v.process(xf[2 * i: 2 * (i + 12000)])))
+        if h is not None:
+            a = h.process(a)
+        ya.append(de.process(a).reshape(-1, 2))
+    ya = np.concatenate(ya)
+    assert outs[vid].shape == ya.shape
+    e = rel_rms(outs[vid][3000:], ya[3000:])
+    report["frontend_af_chain_hp%d" % int(high_pass)] = e
+    assert e < TOL, e
+    fe.close()
+
+
 def test_frontend_retune_and_bandwidth(sb, oracle, report):
     """RxVFO::setOffset / setBandwidth mid-stream, applied at a chunk boundary like the reference's ctrlMtx."""
     n = 480000

@@ -43,6 +43,7 @@ def test_design_and_spectrum_bit_identical(oracle, ref_oracle):
     R, S = ref_oracle, oracle
     for a in ((15000.0, 4000.0, 250000.0, False), (5000.0, 500.0, 15000.0, False), (3125.0, 312.5, 50000.0, True)):
         assert _same(R.lowpass(*a), S.lowpass(*a))
+    assert _same(R.highpass(300.0, 100.0, 48000.0), S.highpass(300.0, 100.0, 48000.0))
     assert _same(R.bandpass_c(18750, 19250, 3000, 250000, True).view(np.float32), S.bandpass_c(18750, 19250, 3000, 250000, True).view(np.float32))
     for r in (2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192):
         assert R.decim_plan(r) == S.decim_plan(r)
