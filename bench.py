@@ -311,7 +311,8 @@ def run_b200(args):
         l0 = fe.launch_count()
         timed_loop(ptrs, lib.FMT_CF32, lib.MEM_DEVICE, outs_dev, 0, args.warmup)       # warm-up only
         fe.set_option("time_s1", 1)
-        clocks.start()
+        if not args.no_clocks:
+            clocks.start()
         l0 = fe.launch_count()
         ms, wall, _ = timed_loop(ptrs, lib.FMT_CF32, lib.MEM_DEVICE, outs_dev, args.steps, 0)
         launches = fe.launch_count() - l0
@@ -400,6 +401,7 @@ def main():
                     help="sym = BASELINE config 2 (+-5/15/25/35 MHz); asym = 8 offsets without conjugate pairs")
     ap.add_argument("--cpu-ms", type=int, default=12000, help="duration of the CPU reference sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region (diagnostic)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -154,6 +154,7 @@ struct b200_fe {
     cudaEvent_t ev_fft_go = nullptr, ev_fft_done = nullptr, ev_lines_free = nullptr;
     bool overlap = true;         // tails of chunk k on their own stream, overlapping stage 1 of chunk k+1
     bool lines_busy = false;
+    float* lines_override = nullptr;   // this chunk: dB lines go straight to the caller's device buffer
     bool fft_async = true;       // spectrum branch on its own stream, concurrent with the VFO branch
     bool fft_join_pending = false;
     std::vector<std::unique_ptr<VfoSlot>> vfos;
@@ -429,6 +430,7 @@ static int fe_fft_chunk(b200_fe* fe, const void* dptr, int fmt, int count, int* 
     cudaStream_t main_s = fe->sch.stream;
     // with overlapped tails the spectrum branch must be on its own stream (its output leaves through the tail stream)
     const bool async = fe->fft_async || fe->sch.tail_stream != nullptr;
+    float* const lines_base = fe->lines_override ? fe->lines_override : fe->lines.as<float>();
     cudaStream_t s = async ? fe->fft_stream : main_s;
     bool forked = false;
     auto fork = [&]() -> int {
@@ -457,7 +459,7 @@ static int fe_fft_chunk(b200_fe* fe, const void* dptr, int fmt, int count, int* 
         if (fend <= end) {
             if ((rc = fork())) { return rc; }
             int nl = 0;
-            cudaError_t e = launch_fft_frame(fe->fft.plan, fe->frame.p, FMT_CF32, fe->fft.work.as<float2>(), fe->lines.as<float>(), nullptr, s, &nl);
+            cudaError_t e = launch_fft_frame(fe->fft.plan, fe->frame.p, FMT_CF32, fe->fft.work.as<float2>(), lines_base, nullptr, s, &nl);
             if (e != cudaSuccess) { return cuda_fail(e, "launch_fft_frame"); }
             fe->sch.launches += nl;
             (*nlines)++;
@@ -472,7 +474,7 @@ static int fe_fft_chunk(b200_fe* fe, const void* dptr, int fmt, int count, int* 
         const char* src = (const char*)dptr + (size_t)(fe->fstart - pos) * bps;
         int nl = 0;
         cudaError_t e = launch_fft_frames(fe->fft.plan, src, fmt, fe->fft.work.as<float2>(),
-                                          fe->lines.as<float>() + (size_t)(*nlines) * fe->fft.size, nullptr, s, &nl, nb,
+                                          lines_base + (size_t)(*nlines) * fe->fft.size, nullptr, s, &nl, nb,
                                           (long long)interval * bps);
         if (e != cudaSuccess) { return cuda_fail(e, "launch_fft_frames"); }
         fe->sch.launches += nl;
@@ -550,6 +552,10 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
         }
     }
     for (Chain* c : chains) { c->plan(count); }
+    // device-resident outputs: the last stage of every chain (and the FFT epilogue) write straight into the caller's buffers
+    const bool direct = (out->out_mem == B200_MEM_DEVICE);
+    for (size_t k = 0; k < chains.size(); k++) { chains[k]->out_override = direct ? (float*)out->vfo_out[ids[k]] : nullptr; }
+    fe->lines_override = direct ? out->fft_out : nullptr;
     int nlines = 0;
     int rc;
     // fork the spectrum branch first; its join (a wait on the main stream) comes after the VFO branch has been
@@ -570,12 +576,12 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
     for (size_t k = 0; k < chains.size(); k++) {
         Chain* c = chains[k];
         out->vfo_count[ids[k]] = c->n_out;
-        if (c->n_out > 0) {
+        if (c->n_out > 0 && !direct) {
             B200_CK(cudaMemcpyAsync(out->vfo_out[ids[k]], c->out.p, (size_t)c->n_out * c->out_es * sizeof(float), kind, os));
         }
     }
     out->fft_lines = nlines;
-    if (nlines > 0) {
+    if (nlines > 0 && !direct) {
         B200_CK(cudaMemcpyAsync(out->fft_out, fe->lines.p, (size_t)nlines * fe->fft.size * sizeof(float), kind, os));
         B200_CK(cudaEventRecord(fe->ev_lines_free, os));
         fe->lines_busy = true;

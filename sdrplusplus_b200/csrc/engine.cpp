@@ -557,7 +557,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
         depth = std::max(depth, c->st.size());
         for (size_t i = 0; i < c->st.size(); i++) {
             Stage* s = c->st[i].get();
-            s->out_ptr = (i + 1 < c->st.size()) ? c->st[i + 1]->in_data() : c->out.as<float>();
+            s->out_ptr = (i + 1 < c->st.size()) ? c->st[i + 1]->in_data() : (c->out_override ? c->out_override : c->out.as<float>());
             if (s->kind == K_XD) {
                 XdStage* x = (XdStage*)s;
                 if (x->taps_dirty) {

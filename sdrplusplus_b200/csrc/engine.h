@@ -150,6 +150,7 @@ struct Chain {
     int out_es = 2;
     int out_cap = 0;
     int n_out = 0;               // this chunk
+    float* out_override = nullptr;   // this chunk: final stage writes straight into the caller's device buffer
     bool raw_input() const { return !st.empty() && st[0]->kind == K_XD; }
     int finalize(int max_in, bool dbl_first = false);    // allocates stage buffers for chunks of up to max_in samples
     int plan(int n);             // all stages; returns final count

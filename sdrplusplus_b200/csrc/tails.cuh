@@ -14,7 +14,7 @@ __device__ __forceinline__ int pad_idx(int n, int padq_log2) { return n + (n >> 
 // ---- complex data x real taps, decimation 1, R consecutive outputs per thread with a sliding register window
 //      (RxVFO channel filter: FIR<complex_t,float>, fir.h:62-83) ----
 #define FC2_R 8
-#define FC2_THREADS 128
+#define FC2_THREADS 64
 __global__ void __launch_bounds__(FC2_THREADS) k_fir_c2(const __grid_constant__ FirParams p) {
     extern __shared__ __align__(16) float2 smem[];
     const FirJob& J = p.job[blockIdx.y];
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(FCD_THREADS) k_fir_cd(const __grid_constant__ 
 // ---- real data x real taps, R consecutive outputs per thread, optional stereo duplication on store
 //      (audio low-pass: FIR<float,float> + LRToStereo, fir.h:69, l_r_to_stereo.h:21) ----
 #define FR2_R 8
-#define FR2_THREADS 128
+#define FR2_THREADS 64
 __global__ void __launch_bounds__(FR2_THREADS) k_fir_r2(const __grid_constant__ FirRParams p) {
     extern __shared__ __align__(16) float smemf[];
     const FirRJob& J = p.job[blockIdx.y];
