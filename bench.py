@@ -243,15 +243,40 @@ def run_b200(args):
         cap = {v: fe.vfo_max_out(v, chunk) for v in ids}
         nl = fe.fft_max_lines(chunk)
 
+        L.b200_host_alloc.restype = C.c_void_p
+
+        class Pinned:
+            """Pinned host buffer from the library's own allocator (b200_host_alloc == what dsp::stream<T> uses in the
+            adapters).  torch's pinned allocator handed out an occasional buffer that DMAs at 11 GB/s on this box
+            (tools/diag_pinned.py); cudaHostAlloc is consistent at 55 / 57 GB/s."""
+
+            def __init__(self, nbytes):
+                self.nbytes = nbytes
+                self.ptr = L.b200_host_alloc(nbytes)
+                if not self.ptr:
+                    raise MemoryError("b200_host_alloc(%d) failed" % nbytes)
+
+            def array(self, dtype):
+                n = self.nbytes // np.dtype(dtype).itemsize
+                return np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_uint8)), shape=(self.nbytes,)).view(dtype)[:n]
+
+            def data_ptr(self):
+                return self.ptr
+
+            def free(self):
+                if self.ptr:
+                    L.b200_host_free(C.c_void_p(self.ptr))
+                    self.ptr = None
+
         def make_outputs(pinned):
             o = lib.Outputs()
             keep = []
             for v in ids:
-                t = torch.empty(2 * cap[v], dtype=torch.float32, pin_memory=True) if pinned else torch.empty(2 * cap[v], device="cuda", dtype=torch.float32)
+                t = Pinned(8 * cap[v]) if pinned else torch.empty(2 * cap[v], device="cuda", dtype=torch.float32)
                 keep.append(t)
                 o.vfo_out[v] = t.data_ptr()
                 o.vfo_cap[v] = cap[v]
-            t = torch.empty(nl * FFT_SIZE, dtype=torch.float32, pin_memory=True) if pinned else torch.empty(nl * FFT_SIZE, device="cuda", dtype=torch.float32)
+            t = Pinned(4 * nl * FFT_SIZE) if pinned else torch.empty(nl * FFT_SIZE, device="cuda", dtype=torch.float32)
             keep.append(t)
             o.fft_out = t.data_ptr()
             o.fft_cap_lines = nl
@@ -323,21 +348,22 @@ def run_b200(args):
         # ---------------- end-to-end legs (host pinned in, host pinned out) ----------------
         outs_host = [make_outputs(True), make_outputs(True)]
         e2e = {}
-        for name, fmt, bps in (("cs16", lib.FMT_CS16, 4), ("cf32", lib.FMT_CF32, 8)):
-            if name == "cs16":
-                host_in = [torch.empty(2 * chunk, dtype=torch.int16, pin_memory=True) for _ in range(2)]
-                for k, t in enumerate(host_in):
-                    t.copy_((dev_in[k] * 32767.0).to(torch.int16).cpu())
-            else:
-                host_in = [torch.empty(2 * chunk, dtype=torch.float32, pin_memory=True) for _ in range(2)]
-                for k, t in enumerate(host_in):
-                    t.copy_(dev_in[k].cpu())
+        for name, fmt, bps in (("cs16", lib.FMT_CS16, 4), ("cf32", lib.FMT_CF32, 8), ("cs8", lib.FMT_CS8, 2)):
+            host_in = [Pinned(chunk * bps) for _ in range(2)]
+            for k, t in enumerate(host_in):
+                if name == "cs16":
+                    t.array(np.int16)[:] = (dev_in[k] * 32767.0).to(torch.int16).cpu().numpy()
+                elif name == "cs8":
+                    t.array(np.int8)[:] = (dev_in[k] * 127.0).to(torch.int8).cpu().numpy()
+                else:
+                    t.array(np.float32)[:] = dev_in[k].cpu().numpy()
             hp = [t.data_ptr() for t in host_in]
-            steps = max(4, args.steps // 2)
+            steps = max(8, args.steps)
             ems, ewall, d2h = timed_loop(hp, fmt, lib.MEM_HOST, outs_host, steps, 3)
             e2e[name] = {"value": world * chunk * steps / (ewall * 1e-3) / 1e6, "unit": "MS/s", "h2d_bytes_per_step": chunk * bps,
                          "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step_wall": ewall / steps, "ms_per_step_events": ems / steps}
-            del host_in
+            for t in host_in:
+                t.free()
         clk = clocks.stop()
         fe.close()
 
@@ -355,11 +381,12 @@ def run_b200(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "chunk_samples": chunk, "samplerate": FS, "parallelism": "replicas x%d (one IQ stream per GPU, no collective)" % world,
                    "l2": "inputs larger than L2: %d MiB cf32 chunk, %d rotating device buffers" % (chunk * 8 >> 20, nbuf),
-                   "value_input": "cf32 resident in HBM, outputs to HBM", "e2e_input": "int16 IQ in pinned host memory (file_source format); cf32 also reported",
+                   "value_input": "cf32 resident in HBM, outputs to HBM", "e2e_input": "int16 IQ in pinned host memory (file_source format); cf32 and int8 also reported",
                    "pipelining": "b200_fe_submit/wait, 2 chunks in flight", "s1_variant": args.s1, "tails_variant": args.tails,
                    "vfo_offsets_hz": offsets, "conjugate_pair_sharing": bool(args.pair) and args.offsets == "sym",
                    "tails_overlap_next_chunk": bool(args.overlap)},
-        "e2e": dict(e2e["cs16"], format="cs16", cf32=e2e["cf32"], pcie_probe=probe, numa=numa),
+        "e2e": dict(e2e["cs16"], format="cs16", cf32=e2e["cf32"], cs8=e2e["cs8"], pcie_probe=probe, numa=numa,
+                    host_buffers="b200_host_alloc (cudaHostAlloc)"),
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": "k_xd_pipe (stage 1: translate + first decimating FIR of all VFOs, IQ read once)",

@@ -519,7 +519,9 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
             if (rc) { return rc; }
         }
         if (fe->slot_used[slot]) { B200_CK(cudaStreamWaitEvent(fe->copy_stream, fe->ev_compute[slot], 0)); }
+        trace_mark("h2d start", fe->copy_stream);
         B200_CK(cudaMemcpyAsync(fe->in_dev[slot].p, iq, in_bytes, cudaMemcpyHostToDevice, fe->copy_stream));
+        trace_mark("h2d done", fe->copy_stream);
         B200_CK(cudaEventRecord(fe->ev_h2d[slot], fe->copy_stream));
         B200_CK(cudaStreamWaitEvent(s, fe->ev_h2d[slot], 0));
         dptr = fe->in_dev[slot].p;
