@@ -419,7 +419,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunk", type=int, default=1 << 24, help="IQ samples per step (default 16 Mi = 128 MiB cf32 > L2)")
-    ap.add_argument("--s1", type=int, default=3, help="stage-1 kernel variant (3 = pipelined, default)")
+    ap.add_argument("--s1", type=int, default=6, help="stage-1 kernel variant (6 = 4-warp CTAs, 3 per SM, cp.async tiles; default)")
     ap.add_argument("--tails", type=int, default=1, help="tail kernel variant (1 = shared-memory tiled, default)")
     ap.add_argument("--s1-mt", type=int, default=0, help="force the stage-1 tile size (outputs per tile), 0 = automatic")
     ap.add_argument("--overlap", type=int, default=1, help="1 = tails of chunk k overlap stage 1 of chunk k+1 (default)")

@@ -185,7 +185,7 @@ struct Scheduler {
     cudaStream_t out_stream() const { return tail_stream ? tail_stream : stream; }
     int enable_overlap(cudaStream_t tail);
     long long launches = 0;
-    int s1_variant = 3;
+    int s1_variant = 6;
     bool pair_conjugates = true;   // stage 1: VFOs at +f / -f share their multiply-accumulates (exact identity)
     // optional device-side timing of the stage-1 launches (bench.py's roofline leg): CUDA events on `stream`
     bool time_s1 = false;

@@ -495,23 +495,28 @@ __device__ __forceinline__ float2 mul_w8_1(float2 a) { return make_float2((a.x +
 __device__ __forceinline__ float2 mul_w8_3(float2 a) { return make_float2((a.y - a.x) * RSQRT2, -(a.x + a.y) * RSQRT2); } // *(-1-j)/sqrt2
 
 // address of element r of transform c
+// one pad slot every 16 elements: the late (small-stride) butterfly stages would otherwise hit a few banks only
+__device__ __forceinline__ int padf(int a) { return a + (a >> 4); }
 template <bool BATCH_INNER>
-__device__ __forceinline__ int fft_addr(int r, int c, int C, int pitch) { return BATCH_INNER ? (r * C + c) : (c * pitch + r); }
+__device__ __forceinline__ int fft_addr(int r, int c, int C, int pitch) { return padf(BATCH_INNER ? (r * C + c) : (c * pitch + r)); }
 
 // In-place forward DIF FFT of C transforms of length n = 2^logn living in shared memory.
 template <bool BATCH_INNER>
 __device__ void fft_dif_smem(float2* s, int logn, int C, int pitch, const float2* __restrict__ tw, int logTW) {
     const int n = 1 << logn;
     const int tid = threadIdx.x, nthr = blockDim.x;
+    int logC = 0;
+    while ((1 << logC) < C) { logC++; }
     int lognb = logn;
     while (lognb >= 3) {
         const int nb = 1 << lognb, e = nb >> 3;     // e = butterflies per sub-block
         const int per = n >> 3;                      // butterflies per transform
+        const int logper = logn - 3;
         const int twsh = logTW - lognb;              // W_nb^j = tw[j << twsh]
         for (int t = tid; t < per * C; t += nthr) {
             int c, bi;
-            if (BATCH_INNER) { c = t % C; bi = t / C; }
-            else { bi = t % per; c = t / per; }
+            if (BATCH_INNER) { c = t & (C - 1); bi = t >> logC; }
+            else { bi = t & (per - 1); c = t >> logper; }
             const int blk = bi / e, j = bi - blk * e;
             const int base = blk * nb + j;
             float2 a[8];
@@ -551,11 +556,11 @@ __device__ void fft_dif_smem(float2* s, int logn, int C, int pitch, const float2
     }
     if (lognb == 2) {
         // radix-4: sub-blocks of 4, twiddles trivial (nb = 4: W_4^0 = 1, W_4^1 = -j; last stage W_2^0 = 1)
-        const int per = n >> 2;
+        const int per = n >> 2, logper = logn - 2;
         for (int t = tid; t < per * C; t += nthr) {
             int c, bi;
-            if (BATCH_INNER) { c = t % C; bi = t / C; }
-            else { bi = t % per; c = t / per; }
+            if (BATCH_INNER) { c = t & (C - 1); bi = t >> logC; }
+            else { bi = t & (per - 1); c = t >> logper; }
             const int base = bi * 4;
             float2 a0 = s[fft_addr<BATCH_INNER>(base + 0, c, C, pitch)];
             float2 a1 = s[fft_addr<BATCH_INNER>(base + 1, c, C, pitch)];
@@ -571,11 +576,11 @@ __device__ void fft_dif_smem(float2* s, int logn, int C, int pitch, const float2
         __syncthreads();
     }
     else if (lognb == 1) {
-        const int per = n >> 1;
+        const int per = n >> 1, logper = logn - 1;
         for (int t = tid; t < per * C; t += nthr) {
             int c, bi;
-            if (BATCH_INNER) { c = t % C; bi = t / C; }
-            else { bi = t % per; c = t / per; }
+            if (BATCH_INNER) { c = t & (C - 1); bi = t >> logC; }
+            else { bi = t & (per - 1); c = t >> logper; }
             const int base = bi * 2;
             float2 a0 = s[fft_addr<BATCH_INNER>(base + 0, c, C, pitch)];
             float2 a1 = s[fft_addr<BATCH_INNER>(base + 1, c, C, pitch)];
@@ -613,12 +618,13 @@ __global__ void __launch_bounds__(512) k_fft_single(const __grid_constant__ FftP
     const int N = pl.N;
     const void* src = reinterpret_cast<const char*>(src0) + (size_t)blockIdx.y * src_stride_bytes;
     float* out_db = out_db0 + (size_t)blockIdx.y * N;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) { smem[i] = load_windowed<FMT>(pl, src, i); }
+#pragma unroll 4
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { smem[padf(i)] = load_windowed<FMT>(pl, src, i); }
     __syncthreads();
     fft_dif_smem<false>(smem, pl.logN, 1, N, pl.tw, pl.logTW);
     const float nf = 1.0f / ((float)N * (float)N);
     for (int k = threadIdx.x; k < N; k += blockDim.x) {
-        float2 X = smem[bitrev(k, pl.logN)];
+        float2 X = smem[padf(bitrev(k, pl.logN))];
         out_db[k] = power_db(X, nf);
         if (out_raw) { out_raw[k] = X; }
     }
@@ -634,16 +640,17 @@ __global__ void __launch_bounds__(512) k_fft_p1(const __grid_constant__ FftPlanD
     const void* src = reinterpret_cast<const char*>(src0) + (size_t)blockIdx.y * src_stride_bytes;
     float2* work = work0 + (size_t)blockIdx.y * pl.N;
     const int c0 = blockIdx.x * C;
+#pragma unroll 4
     for (int t = threadIdx.x; t < N1 * C; t += blockDim.x) {
         int n1 = t / C, c = t - n1 * C;
-        smem[t] = load_windowed<FMT>(pl, src, n1 * N2 + c0 + c);
+        smem[padf(t)] = load_windowed<FMT>(pl, src, n1 * N2 + c0 + c);
     }
     __syncthreads();
     fft_dif_smem<true>(smem, pl.logN1, C, 0, pl.tw, pl.logTW);
     const float scale = -2.0f / (float)pl.N;
     for (int t = threadIdx.x; t < N1 * C; t += blockDim.x) {
         int k1 = t / C, c = t - k1 * C;
-        float2 a = smem[bitrev(k1, pl.logN1) * C + c];
+        float2 a = smem[padf(bitrev(k1, pl.logN1) * C + c)];
         int n2 = c0 + c;
         float sn, cs;
         sincospif((float)(k1 * n2) * scale, &sn, &cs);   // k1*n2 < N <= 2^22: exact in fp32
@@ -660,16 +667,17 @@ __global__ void __launch_bounds__(512) k_fft_p2(const __grid_constant__ FftPlanD
     float* out_db = out_db0 + (size_t)blockIdx.y * pl.N;
     const int pitch = N2 + 1;
     const int r0 = blockIdx.x * R;
+#pragma unroll 4
     for (int t = threadIdx.x; t < R * N2; t += blockDim.x) {
         int rl = t / N2, n2 = t - rl * N2;
-        smem[rl * pitch + n2] = __ldg(work + (size_t)(r0 + rl) * N2 + n2);
+        smem[padf(rl * pitch + n2)] = __ldg(work + (size_t)(r0 + rl) * N2 + n2);
     }
     __syncthreads();
     fft_dif_smem<false>(smem, pl.logN2, R, pitch, pl.tw, pl.logTW);
     const float nf = 1.0f / ((float)pl.N * (float)pl.N);
     for (int t = threadIdx.x; t < R * N2; t += blockDim.x) {
         int k2 = t / R, rl = t - k2 * R;
-        float2 X = smem[rl * pitch + bitrev(k2, pl.logN2)];
+        float2 X = smem[padf(rl * pitch + bitrev(k2, pl.logN2))];
         size_t k = (size_t)(r0 + rl) + (size_t)N1 * k2;
         out_db[k] = power_db(X, nf);
         if (out_raw) { out_raw[k] = X; }
@@ -766,7 +774,7 @@ static cudaError_t launch_xd_pipe_t(const XdParams& p, const XpGeom& g, size_t s
 
 // returns true when the pipelined kernel was launched
 template <int FMT>
-static bool try_xd_pipe(const XdParams& p, cudaStream_t s, cudaError_t* err, int nwarps) {
+static bool try_xd_pipe(const XdParams& p, cudaStream_t s, cudaError_t* err, int nwarps, bool single = false) {
     const int D = p.D;
     if (D < 2 || (D & (D - 1))) { return false; }
     int logD = 0;
@@ -825,9 +833,9 @@ static bool try_xd_pipe(const XdParams& p, cudaStream_t s, cudaError_t* err, int
         const int ntasks = nstrips_t * ngroups * rs;
         // the exchange buffer can live in the consumed tile buffer when all tasks run in one round
         const bool alias = ntasks <= nwarps && (size_t)D * jp >= (size_t)nwarps * 32 * 32;
-        smem = ((size_t)2 * D * jp + (size_t)ngroups * QPC * D * XP_VR + (size_t)p.njobs * MT + 3 * B200_BATCH +
+        smem = ((size_t)(single ? 1 : 2) * D * jp + (size_t)ngroups * QPC * D * XP_VR + (size_t)p.njobs * MT + 3 * B200_BATCH +
                 (!alias ? (size_t)nwarps * 32 * 32 : 0)) * sizeof(float2);
-        if (smem <= (size_t)limit) { g.JP = jp; g.RS = rs; g.p_alias = alias ? 1 : 0; break; }
+        if (smem <= (size_t)limit) { g.JP = jp; g.RS = rs; g.p_alias = alias ? 1 : 0; g.single = single ? 1 : 0; break; }
     }
     g.MT = MT; g.QPC = QPC; g.org = org; g.logD = logD; g.jmin = jmin;
     g.ntiles = cdiv(jmax - jmin, MT);
@@ -871,7 +879,7 @@ static cudaError_t launch_xd_fmt(const XdParams& p, int variant, cudaStream_t s,
     const int D = p.D;
     if (variant >= 3) {
         cudaError_t e = cudaSuccess;
-        if (try_xd_pipe<FMT>(p, s, &e, variant == 4 ? 16 : (variant >= 5 ? 4 : 8))) {
+        if (try_xd_pipe<FMT>(p, s, &e, variant == 4 ? 16 : (variant >= 5 ? 4 : 8), variant == 6)) {
             if (nlaunch) { (*nlaunch)++; }
             return e;
         }
@@ -1080,7 +1088,7 @@ static cudaError_t launch_fft_fmt(const FftPlanDev& pl, const void* src, float2*
                                   cudaStream_t s, int* nlaunch, int nbatch, long long src_stride_bytes) {
     cudaError_t e;
     if (pl.N1 == pl.N) {
-        size_t smem = (size_t)pl.N * sizeof(float2);
+        size_t smem = ((size_t)pl.N + (pl.N >> 4) + 2) * sizeof(float2);
         e = set_smem(k_fft_single<FMT>, smem);
         if (e != cudaSuccess) { return e; }
         int thr = pl.N / 8 < 32 ? 32 : (pl.N / 8 > 512 ? 512 : pl.N / 8);
@@ -1098,8 +1106,8 @@ static cudaError_t launch_fft_fmt(const FftPlanDev& pl, const void* src, float2*
     while (R > 4 && (pl.N1 / R) * nbatch < 2 * num_sms()) { R >>= 1; }
     while ((size_t)R * (pl.N2 + 1) * sizeof(float2) > 196608 && R > 1) { R >>= 1; }
     if (R > pl.N1) { R = pl.N1; }
-    size_t smem1 = (size_t)pl.N1 * C * sizeof(float2);
-    size_t smem2 = (size_t)R * (pl.N2 + 1) * sizeof(float2);
+    size_t smem1 = ((size_t)pl.N1 * C + ((size_t)pl.N1 * C >> 4) + 2) * sizeof(float2);
+    size_t smem2 = ((size_t)R * (pl.N2 + 1) + ((size_t)R * (pl.N2 + 1) >> 4) + 2) * sizeof(float2);
     e = set_smem(k_fft_p1<FMT>, smem1);
     if (e != cudaSuccess) { return e; }
     e = set_smem(k_fft_p2, smem2);

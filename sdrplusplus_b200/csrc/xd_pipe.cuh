@@ -27,6 +27,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 struct XpGeom {
     int MT, JP, QPC, ntiles, org, RS, logD;
     int p_alias;      // 1: the RS exchange buffer lives in the tile buffer just consumed (single task round only)
+    int single;       // 1: one tile buffer per CTA (several CTAs per SM overlap each other instead)
     long long jmin;
 };
 
@@ -39,8 +40,8 @@ __global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdPar
     const int gl = QPC * D;
     const int ngroups = (p.nslots + XP_VR - 1) / XP_VR;
     float2* Xb0 = smem;
-    float2* Xb1 = smem + (size_t)D * JP;
-    float2* G = smem + (size_t)2 * D * JP;                    // [ngroups][gl][XP_VR]
+    float2* Xb1 = g.single ? smem : smem + (size_t)D * JP;
+    float2* G = smem + (size_t)(g.single ? 1 : 2) * D * JP;   // [ngroups][gl][XP_VR]
     float2* TB = G + (size_t)ngroups * gl * XP_VR;            // [njobs][MT] phase ramp e^{j W_v D k} + [njobs] per-tile base
     float2* BASE = TB + (size_t)p.njobs * MT;
     int* CJ = reinterpret_cast<int*>(BASE + B200_BATCH);      // [B200_BATCH] block offset c of every job
@@ -116,11 +117,15 @@ __global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdPar
     constexpr int WN = (QC + 2) & ~1;             // window samples per pair: QC+1 needed, loaded as LDS.128 pairs
 
     int tile = blockIdx.x, buf = 0;
-    if (tile < g.ntiles) { issue(tile, Xb0); }
+    if (tile < g.ntiles && !g.single) { issue(tile, Xb0); }
     for (; tile < g.ntiles; tile += gridDim.x, buf ^= 1) {
         const int next = tile + gridDim.x;
         float2* X = buf ? Xb1 : Xb0;
-        if (next < g.ntiles) {
+        if (g.single) {
+            issue(tile, X);
+            cp_async_wait<0>();
+        }
+        else if (next < g.ntiles) {
             issue(next, buf ? Xb0 : Xb1);
             cp_async_wait<1>();
         }

@@ -249,7 +249,7 @@ def _oracle_lines(oracle, x, fs, size, rate):
     return np.array(lines)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
 def test_frontend_c1_geometry(sb, oracle, report, variant):
     """BASELINE config 1: 2.4 MS/s, chunk 12000, 65536-pt FFT @ 20 fps, one WFM VFO at +300 kHz."""
     n = 600000
@@ -440,7 +440,7 @@ def test_frontend_multi_vfo_100msps(sb, oracle, report):
     fe.close()
 
 
-@pytest.mark.parametrize("variant,fft_async,overlap,pair", [(4, 1, 1, 1), (3, 0, 0, 1), (1, 1, 0, 0), (3, 1, 1, 0), (3, 1, 0, 1), (5, 1, 1, 1), (5, 1, 0, 0)])
+@pytest.mark.parametrize("variant,fft_async,overlap,pair", [(4, 1, 1, 1), (3, 0, 0, 1), (1, 1, 0, 0), (3, 1, 1, 0), (3, 1, 0, 1), (5, 1, 1, 1), (5, 1, 0, 0), (6, 1, 1, 1), (6, 1, 0, 0)])
 def test_frontend_variants_100msps(sb, oracle, report, variant, fft_async, overlap, pair):
     """kernel / scheduling A-B on the config-2 geometry (short): 16-warp stage 1, synchronous spectrum branch,
     tails on the main stream, conjugate-pair sharing off."""
