@@ -305,9 +305,12 @@ def run_b200(args):
             t0 = time.perf_counter()
             e0.record(stream)
             d2h = 0
+            host_submit = 0.0
             for i in range(steps):
                 o = outs[i % 2][0]
+                th = time.perf_counter()
                 fe.submit_ptr(ptrs[i % len(ptrs)], chunk, fmt, mem, o)
+                host_submit += time.perf_counter() - th
                 d2h = sum(o.vfo_count[v] for v in ids) * 8 + o.fft_lines * FFT_SIZE * 4
                 inflight += 1
                 if inflight == 2:
@@ -325,6 +328,7 @@ def run_b200(args):
                 t = torch.tensor([ms, wall], device="cuda", dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 ms, wall = float(t[0]), float(t[1])
+            timed_loop.host_submit_ms = host_submit * 1e3 / max(steps, 1)
             return ms, wall, d2h
 
         probe = pcie_probe(torch)
@@ -341,6 +345,7 @@ def run_b200(args):
         l0 = fe.launch_count()
         ms, wall, _ = timed_loop(ptrs, lib.FMT_CF32, lib.MEM_DEVICE, outs_dev, args.steps, 0)
         launches = fe.launch_count() - l0
+        host_submit_ms = timed_loop.host_submit_ms
         s1_ms, s1_n = fe.s1_stats()
         fe.set_option("time_s1", 0)
         value = world * chunk * args.steps / (ms * 1e-3) / 1e6
@@ -377,7 +382,7 @@ def run_b200(args):
     achieved = algo_bytes / (s1_avg * 1e-3) / 1e9 if s1_n else None
     line = {
         "metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms / args.steps, "ms_per_step_wall": wall / args.steps, "host_ms_per_submit": host_submit_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "chunk_samples": chunk, "samplerate": FS, "parallelism": "replicas x%d (one IQ stream per GPU, no collective)" % world,
                    "l2": "inputs larger than L2: %d MiB cf32 chunk, %d rotating device buffers" % (chunk * 8 >> 20, nbuf),
