@@ -396,7 +396,9 @@ def run_b200(args):
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": "k_xd_pipe (stage 1: translate + first decimating FIR of all VFOs, IQ read once)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "frac": (achieved / peak) if achieved else None,
+                     "traffic": 151213056 if (chunk == 1 << 24 and args.offsets == "sym") else None,
+                     "traffic_source": "ncu --set full: dram__bytes_read.sum 134.31 MB + dram__bytes_write.sum 16.91 MB per launch (profiles/r01_ncu_full_xd_pipe_paired.txt)",
                      "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": s1_avg, "launches_timed": s1_n,
                      "share_of_step": (s1_ms / ms) if ms else None,
                      "step_level": {"achieved": algo_bytes * args.steps / (ms * 1e-3) / 1e9, "frac": algo_bytes * args.steps / (ms * 1e-3) / 1e9 / peak},

@@ -346,6 +346,56 @@ def test_frontend_mixed_modes(sb, oracle, report):
     fe.close()
 
 
+def test_frontend_many_vfos_batching(sb, oracle, report):
+    """20 VFOs of four kinds on one stream: more than one 16-job launch batch per stage, three different first-stage
+    decimations (stage-1 groups), conjugate pairs mixed with singles."""
+    from sdrplusplus_b200 import lib as L
+    n = 240000
+    x = noise_iq(n, 17, 0.002).copy()
+    cfgs = []
+    for k in range(6):
+        off = (k - 2.5) * 300e3
+        x += fm_carrier(n, FS, off)
+        cfgs.append(sb.VfoConfig.wfm(off))                       # +-150k, +-450k, +-750k: three conjugate pairs
+    for k in range(6):
+        off = -1.0e6 + k * 333e3
+        x += fm_carrier(n, FS, off, dev=5000.0, tones=((1000.0, 0.7),), amp=0.03)
+        cfgs.append(sb.VfoConfig.nfm(off))
+    for k in range(4):
+        off = 120e3 + k * 210e3
+        x += am_carrier(n, FS, off, amp=0.03)
+        cfgs.append(sb.VfoConfig.am(off))
+    for k in range(4):
+        off = -900e3 + k * 410e3
+        x += fm_carrier(n, FS, off, amp=0.04)
+        cfgs.append(sb.VfoConfig.raw(off, 250e3, 150e3))
+    fe = sb.FrontEnd(FS, 12000)
+    ids = [fe.add_vfo(c) for c in cfgs]
+    assert len(ids) == 20
+    outs, _ = fe.process_chunks(x, 12000)
+    errs = []
+    for vid, c in zip(ids, cfgs):
+        ya = _oracle_chain(oracle, x, FS, 12000, c)
+        y = outs[vid]
+        if c.demod == L.DEMOD_RAW:
+            ya = ya.view(np.complex64)
+            d, do = np.angle(y[1:] * np.conj(y[:-1])), np.angle(ya[1:] * np.conj(ya[:-1]))
+            errs.append(rel_rms(d[2000:], do[2000:]))
+        else:
+            ya = ya.reshape(-1, 2)
+            assert y.shape == ya.shape
+            sk = y.shape[0] // 4
+            errs.append(rel_rms(y[sk:], ya[sk:]))
+    report["frontend_20_vfos"] = errs
+    assert max(errs) < TOL, errs
+    # remove / re-add keeps the others running
+    fe.remove_vfo(ids[3])
+    vid = fe.add_vfo(sb.VfoConfig.wfm(0.0))
+    outs, _ = fe.process(x[:12000])
+    assert vid in outs and len(outs) == 20 and outs[vid].shape[0] > 0
+    fe.close()
+
+
 def test_deemphasis_block_bit_exact(sb, oracle):
     n = 20000
     x = noise_iq(n, 15, 0.5).view(np.float32)            # (l, r) pairs
