@@ -234,6 +234,8 @@ def run_b200(args):
         fe.set_option("s1", args.s1)
         fe.set_option("s1_mt", args.s1_mt)
         fe.set_option("tails", args.tails)
+        for kv in [a for a in args.ft.split(",") if a]:
+            fe.set_option(kv.split("=")[0], int(kv.split("=")[1]))
         fe.set_fft(FFT_SIZE, FFT_RATE, lib.WIN_NUTTALL)
         ids = [fe.add_vfo(sb.VfoConfig.wfm(o)) for o in offsets]
         gen = torch.Generator(device="cuda")
@@ -427,7 +429,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunk", type=int, default=1 << 24, help="IQ samples per step (default 16 Mi = 128 MiB cf32 > L2)")
     ap.add_argument("--s1", type=int, default=6, help="stage-1 kernel variant (6 = 4-warp CTAs, 3 per SM, cp.async tiles; default)")
-    ap.add_argument("--tails", type=int, default=1, help="tail kernel variant (1 = shared-memory tiled, default)")
+    ap.add_argument("--tails", type=int, default=2, help="2 = one fused tail launch per <= 16 VFOs (default), 1 = shared-memory tiled kernel per stage, 0 = one thread per output")
+    ap.add_argument("--ft", default="", help="fused-tail tuning, e.g. ft_threads=256,ft_obmax=1024,ft_smem_kb=72")
     ap.add_argument("--s1-mt", type=int, default=0, help="force the stage-1 tile size (outputs per tile), 0 = automatic")
     ap.add_argument("--overlap", type=int, default=1, help="1 = tails of chunk k overlap stage 1 of chunk k+1 (default)")
     ap.add_argument("--pair", type=int, default=1, help="1 = VFOs at +f/-f share their stage-1 multiply-accumulates (default)")

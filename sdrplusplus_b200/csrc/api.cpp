@@ -206,6 +206,13 @@ extern "C" b200_fe* b200_fe_create(double samplerate, int max_chunk) {
         return nullptr;
     }
     fe->sch.stream = fe->own_stream;
+    fe->sch.fuse.on = true;
+    {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) {
+            fe->sch.sm_count = sms;
+        }
+    }
     if (fe->sch.enable_overlap(fe->tail_stream)) { b200_fe_destroy(fe); return nullptr; }
     return fe;
 }
@@ -280,7 +287,7 @@ static int build_vfo_chain(b200_fe* fe, VfoSlot* v) {
         // overlapped mode hands every chain's output to the tail stream: give a stage-1-only chain an exact copy stage
         if ((rc = v->chain.add_fir_c(std::vector<float>{ 1.0f }, 1))) { return rc; }
     }
-    return v->chain.finalize(fe->max_chunk, ov);
+    return v->chain.finalize(fe->max_chunk, ov, &fe->sch.fuse);
 }
 
 extern "C" int b200_fe_add_vfo(b200_fe* fe, const b200_vfo_cfg* cfg) {
@@ -367,7 +374,15 @@ extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
     if (!strcmp(key, "pair")) { fe->sch.pair_conjugates = value != 0; return 0; }
     if (!strcmp(key, "fft_async")) { fe->fft_async = value != 0; return 0; }
     if (!strcmp(key, "s1_mt")) { kernels_set_xd_tile(value); return 0; }
-    if (!strcmp(key, "tails")) { kernels_set_tail_variant(value); return 0; }
+    if (!strcmp(key, "tails") || !strncmp(key, "ft_", 3)) {
+        // 0: one thread per output; 1: shared-memory tiled kernels, one launch per stage; 2: one fused launch per <= 16 VFOs
+        if (b200_fe_vfo_count(fe) > 0) { set_error("'%s' must be chosen before VFOs are added", key); return B200_ESTATE; }
+        if (!strcmp(key, "tails")) { kernels_set_tail_variant(value >= 1 ? 1 : 0); fe->sch.fuse.on = value >= 2; return 0; }
+        if (!strcmp(key, "ft_ob")) { fe->sch.fuse.ob_force = value; return 0; }
+        if (!strcmp(key, "ft_obmax")) { fe->sch.fuse.ob_max = value; return 0; }
+        if (!strcmp(key, "ft_smem_kb")) { fe->sch.fuse.smem_limit = value * 1024; return 0; }
+        if (!strcmp(key, "ft_threads")) { fe->sch.fuse.threads = value; return 0; }
+    }
     if (!strcmp(key, "time_s1")) { fe->sch.time_s1 = value != 0; fe->sch.ev_used = 0; return 0; }
     set_error("unknown option %s", key);
     return B200_EINVAL;

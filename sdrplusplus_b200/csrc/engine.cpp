@@ -80,6 +80,21 @@ int Stage::alloc_in(int cap) {
     return rc;
 }
 
+// t = `sets` tap sets of equal length T laid end to end; each set becomes D rows of pitch ceil(T/D), row r = t[q*D + r]
+int Stage::upload_pm(const std::vector<float>& t, int D, int sets) {
+    const int T = (int)(t.size() / (size_t)sets);
+    const int qp = (T + D - 1) / D;
+    pm_floats = (sets * D * qp + 3) & ~3;
+    std::vector<float> pm((size_t)pm_floats, 0.0f);
+    for (int s = 0; s < sets; s++) {
+        for (int k = 0; k < T; k++) { pm[((size_t)s * D + (k % D)) * qp + k / D] = t[(size_t)s * T + k]; }
+    }
+    int rc = taps_pm.alloc(pm.size() * sizeof(float));
+    if (rc) { return rc; }
+    B200_CK(cudaMemcpy(taps_pm.p, pm.data(), pm.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
 // ------------------------------------------------------------------ XdStage
 void XdStage::configure(int D_, const std::vector<float>& taps) {
     D = D_;
@@ -153,7 +168,7 @@ int FirCStage::configure(const std::vector<float>& t, int decim_) {
     int rc = taps.alloc((size_t)ntaps * sizeof(float));
     if (rc) { return rc; }
     B200_CK(cudaMemcpy(taps.p, t.data(), (size_t)ntaps * sizeof(float), cudaMemcpyHostToDevice));
-    return 0;
+    return upload_pm(t, decim, 1);
 }
 int FirCStage::plan(int n) {
     n_in = n;
@@ -172,7 +187,7 @@ int PolyStage::configure(int interp_, int decim_, const std::vector<float>& t) {
     int rc = bank.alloc(b.size() * sizeof(float));
     if (rc) { return rc; }
     B200_CK(cudaMemcpy(bank.p, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
-    return 0;
+    return upload_pm(b, decim, interp);
 }
 int PolyStage::plan(int n) {
     n_in = n;
@@ -190,14 +205,7 @@ int PolyStage::plan(int n) {
 // ------------------------------------------------------------------ QuadStage
 int QuadStage::configure(double deviationHz, double samplerate) {
     inv_dev = (float)(1.0 / hz_to_rads(deviationHz, samplerate));    // quadrature.h:19-26
-    return state.alloc(2 * sizeof(float));
-}
-int QuadStage::plan(int n) {
-    n_in = n;
-    n_out = n;
-    chunk_flip = flip;
-    if (n > 0) { flip ^= 1; }
-    return n;
+    return 0;
 }
 
 // ------------------------------------------------------------------ FirRStage
@@ -209,7 +217,7 @@ int FirRStage::configure(const std::vector<float>& t, bool stereo_) {
     int rc = taps.alloc((size_t)ntaps * sizeof(float));
     if (rc) { return rc; }
     B200_CK(cudaMemcpy(taps.p, t.data(), (size_t)ntaps * sizeof(float), cudaMemcpyHostToDevice));
-    return 0;
+    return upload_pm(t, 1, 1);
 }
 
 // ------------------------------------------------------------------ SeqStage
@@ -269,7 +277,7 @@ int SeqStage::configure_deemph(double tau, double samplerate) {
 }
 
 // ------------------------------------------------------------------ Chain
-int Chain::finalize(int max_in, bool dbl_first) {
+int Chain::finalize(int max_in, bool dbl_first, const FuseCfg* fuse) {
     if (st.empty()) { set_error("empty chain"); return B200_EINVAL; }
     int cap = max_in;
     if (dbl_first && st.size() >= 2 && st[0]->kind == K_XD) { st[1]->dbl = true; }
@@ -283,7 +291,133 @@ int Chain::finalize(int max_in, bool dbl_first) {
     }
     out_es = st.back()->out_es;
     out_cap = cap;
-    return out.alloc(((size_t)cap + 8) * out_es * sizeof(float));
+    int rc = out.alloc(((size_t)cap + 8) * out_es * sizeof(float));
+    if (rc) { return rc; }
+    if (fuse) { fcfg = *fuse; }
+    return plan_fused();
+}
+
+// ---- fused tail: static plan ----
+static bool ft_fusable(const Stage* s) {
+    switch (s->kind) {
+    case K_FIRC: case K_POLY: return s->in_es == 2;
+    case K_QUAD: case K_FIRR: case K_M2S: return true;
+    default: return false;
+    }
+}
+// fills the static fields of an FtStage from a Stage (the per-chunk fields are set by the scheduler)
+static void ft_describe(const Stage* s, FtStage& d) {
+    memset(&d, 0, sizeof(d));
+    d.D = 1; d.L = 1; d.T = 1;
+    d.hist = s->hist;
+    d.es = s->in_es;
+    switch (s->kind) {
+    case K_FIRC: { const FirCStage* f = (const FirCStage*)s; d.kind = FT_FIRC; d.T = f->ntaps; d.D = f->decim; break; }
+    case K_POLY: { const PolyStage* f = (const PolyStage*)s; d.kind = FT_POLY; d.T = f->tpp; d.D = f->decim; d.L = f->interp; break; }
+    case K_QUAD: { const QuadStage* f = (const QuadStage*)s; d.kind = FT_QUAD; d.scale = f->inv_dev; break; }
+    case K_FIRR: { const FirRStage* f = (const FirRStage*)s; d.kind = FT_FIRR; d.T = f->ntaps; d.dup = f->stereo; break; }
+    default: d.kind = FT_M2S; d.dup = 1; break;
+    }
+    d.taps = s->taps_pm.as<float>();
+    d.ntap_f = s->pm_floats;
+}
+static long long ft_need_len(const FtStage& d, long long len) {
+    switch (d.kind) {
+    case FT_FIRC: case FT_FIRR: return (len - 1) * d.D + d.T;
+    case FT_POLY: return ((len - 1) * d.D + d.L - 1) / d.L + d.T + 1;
+    case FT_QUAD: return len + 1;
+    default: return len;
+    }
+}
+static int ft_slack(const FtStage& d) {
+    if (d.kind == FT_FIRC || d.kind == FT_FIRR) { return d.D; }
+    if (d.kind == FT_POLY) { return d.D / d.L + 2; }
+    return 0;
+}
+static int round4(int x) { return (x + 3) & ~3; }
+
+int Chain::plan_fused() {
+    fp.active = false;
+    for (auto& s : st) { s->fmid = false; }
+    if (!fcfg.on || st.size() < 3 || st[0]->kind != K_XD) { return 0; }
+    int end = 1;
+    while (end < (int)st.size() && end - 1 < FT_MAXST && ft_fusable(st[end].get())) { end++; }
+    const int nst = end - 1;
+    if (nst < 2) { return 0; }
+    FtStage d[FT_MAXST];
+    for (int i = 0; i < nst; i++) { ft_describe(st[1 + i].get(), d[i]); }
+    // taps region
+    int toff = 0;
+    for (int i = 0; i < nst; i++) {
+        fp.tap_off[i] = toff;
+        fp.qpitch[i] = 0;
+        if (d[i].kind == FT_FIRC || d[i].kind == FT_FIRR || d[i].kind == FT_POLY) {
+            fp.qpitch[i] = (d[i].T + d[i].D - 1) / d[i].D;
+            toff += d[i].ntap_f;
+        }
+    }
+    const int limit_f = fcfg.smem_limit / 4;
+    int ob = fcfg.ob_force > 0 ? fcfg.ob_force : fcfg.ob_max;
+    for (; ob >= 4 * FT_R; ob = (ob * 3 / 4) / FT_R * FT_R) {
+        // bounds on the per-slab input range of every stage (fused tail)
+        long long lb[FT_MAXST + 1];
+        lb[nst] = ob;
+        for (int i = nst - 1; i >= 0; i--) {
+            long long need = ft_need_len(d[i], lb[i + 1]) + ft_slack(d[i]);
+            lb[i] = std::max<long long>(need, d[i].hist);
+        }
+        int region[2] = { 0, 0 };
+        bool ok = true;
+        for (int i = 1; i < nst; i++) {
+            const int rows = ft_rows(d[i]);
+            const long long cols = (lb[i] + rows + rows - 1) / rows + FT_R + 2;
+            if (cols * rows * d[i].es > limit_f) { ok = false; break; }
+            fp.pitch[i] = (int)cols;
+            region[i & 1] = std::max(region[i & 1], round4((int)(cols * rows * d[i].es)));
+        }
+        if (!ok) { continue; }
+        const int fixed = toff + region[1];
+        // stage 0 streams through what is left of the budget, at most what one pass over the slab needs
+        const int rows0 = ft_rows(d[0]);
+        int avail = limit_f - fixed - 64 - region[0];
+        int ot0 = (int)((lb[1] + FT_R - 1) / FT_R) * FT_R;
+        auto stage0_floats = [&](int ot) {
+            long long cols = (ft_need_len(d[0], ot) + rows0 + rows0 - 1) / rows0 + FT_R + 2;
+            return cols * rows0 * d[0].es;
+        };
+        // prefer a staging buffer that gives every thread of the CTA a unit of FT_R outputs
+        const int want = fcfg.threads * FT_R;
+        if (ot0 > want) { ot0 = want; }
+        while (ot0 >= FT_R && std::max<long long>(stage0_floats(ot0), region[0]) > (long long)limit_f - fixed - 64) { ot0 -= FT_R; }
+        (void)avail;
+        if (ot0 < FT_R) { continue; }
+        {
+            long long cols = (ft_need_len(d[0], ot0) + rows0 + rows0 - 1) / rows0 + FT_R + 2;
+            fp.pitch[0] = (int)cols;
+            region[0] = std::max(region[0], round4((int)stage0_floats(ot0)));
+        }
+        // arena: [taps | odd stages | even stages (incl. staging)]
+        for (int i = 0; i < nst; i++) { fp.buf[i] = (i & 1) ? toff : toff + region[1]; }
+        fp.smem = (size_t)(toff + region[0] + region[1] + 64) * sizeof(float);
+        fp.ob_max = ob;
+        fp.ot0 = ot0;
+        fp.end = end;
+        fp.active = true;
+        break;
+    }
+    if (!fp.active) { return 0; }
+    for (int i = 1; i < nst; i++) {
+        Stage* s = st[1 + i].get();
+        s->fmid = true;
+        for (int b = 0; b < 2; b++) {
+            const size_t need = ((size_t)s->hist + 8) * s->in_es * sizeof(float);
+            if (!s->fh[b].p || s->fh[b].bytes < need) {
+                int rc = s->fh[b].alloc(need);
+                if (rc) { return rc; }
+            }
+        }
+    }
+    return 0;
 }
 int Chain::plan(int n) {
     for (auto& s : st) { n = s->plan(n); }
@@ -299,11 +433,10 @@ void Chain::reset_state() {
         s->reset_state();
         if (s->inbuf.p && s->hist > 0) { cudaMemset(s->inbuf.p, 0, (size_t)s->hist * s->in_es * sizeof(float)); }
         if (s->inbuf_alt.p && s->hist > 0) { cudaMemset(s->inbuf_alt.p, 0, (size_t)s->hist * s->in_es * sizeof(float)); }
-        if (s->kind == K_QUAD) {
-            QuadStage* q = (QuadStage*)s.get();
-            cudaMemset(q->state.p, 0, 2 * sizeof(float));
-            q->flip = 0;
+        for (int i = 0; i < 2; i++) {
+            if (s->fh[i].p) { cudaMemset(s->fh[i].p, 0, s->fh[i].bytes); }
         }
+        s->fpar = 0;
         if (s->kind == K_SEQ) {
             SeqStage* q = (SeqStage*)s.get();
             // AM::reset / AGC::reset (am.h:90-98, agc.h:64-68), Deemphasis::reset; the SSB demodulator has no reset
@@ -503,9 +636,22 @@ static int apply_pending_taps(FirCStage* f, cudaStream_t s) {
         std::swap(f->inbuf_alt.p, nb2.p);
         std::swap(f->inbuf_alt.bytes, nb2.bytes);
     }
+    if (f->fmid) {
+        // fused tail: the stage's history lives in fh[fpar]
+        DevBuf h0, h1;
+        const size_t hb = ((size_t)newH + 8) * f->in_es * sizeof(float);
+        if ((rc = h0.alloc(hb)) || (rc = h1.alloc(hb))) { return rc; }
+        if (keep > 0) {
+            B200_CK(cudaMemcpy(h0.as<float>() + (size_t)(newH - keep) * f->in_es, f->fh[f->fpar].as<float>() + (size_t)(oldH - keep) * f->in_es,
+                               (size_t)keep * f->in_es * sizeof(float), cudaMemcpyDeviceToDevice));
+        }
+        std::swap(f->fh[f->fpar].p, h0.p); std::swap(f->fh[f->fpar].bytes, h0.bytes);
+        std::swap(f->fh[f->fpar ^ 1].p, h1.p); std::swap(f->fh[f->fpar ^ 1].bytes, h1.bytes);
+    }
     rc = f->taps.alloc((size_t)newT * sizeof(float));
     if (rc) { return rc; }
     B200_CK(cudaMemcpy(f->taps.p, f->pending.data(), (size_t)newT * sizeof(float), cudaMemcpyHostToDevice));
+    if ((rc = f->upload_pm(f->pending, f->decim, 1))) { return rc; }
     f->ntaps = newT;
     f->hist = newH;
     if (f->decim != 1) { f->offset = 0; }          // DecimatingFIR::setTaps (decimating_fir.h:18-25)
@@ -538,11 +684,18 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
     cudaStream_t ts = tail_stream ? tail_stream : stream;
     size_t depth = 0;
     for (Chain* c : chains) {
+        bool changed = false;
         for (auto& sp : c->st) {
-            if (sp->kind == K_FIRC) {
+            if (sp->kind == K_FIRC && !((FirCStage*)sp.get())->pending.empty()) {
                 int rc = apply_pending_taps((FirCStage*)sp.get(), stream);
                 if (rc) { return rc; }
+                changed = true;
             }
+        }
+        if (changed && c->fp.active) {
+            int rc = c->plan_fused();
+            if (rc) { return rc; }
+            if (!c->fp.active) { set_error("new filter does not fit the fused tail (set option tails=1 before adding VFOs)"); return B200_ECAP; }
         }
     }
     for (Chain* c : chains) {
@@ -671,6 +824,79 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
         B200_CK(cudaStreamWaitEvent(ts, ev_stage1[parity], 0));
     }
     trace_mark("tails start", ts);
+    // ---- fused tails: every FIR-like stage after stage 1 of a VFO in one launch (kernels.cuh: FtJob) ----
+    {
+        std::vector<Chain*> fc;
+        for (Chain* c : chains) {
+            if (c->fp.active && c->st[1]->n_in > 0) { fc.push_back(c); }
+        }
+        if (!fc.empty()) {
+            // slab size: the fewest waves the largest slabs allow, then the smallest slab that keeps that wave count
+            // (less halo-free work per CTA; the halo a slab recomputes is a fixed cost)
+            const int threads = (fuse.threads == 512 || fuse.threads == 256) ? fuse.threads : 128;
+            size_t smem = 0;
+            int ob_cap = 1 << 30;
+            for (Chain* c : fc) { smem = std::max(smem, c->fp.smem); ob_cap = std::min(ob_cap, c->fp.ob_max); }
+            int cps = (int)((227 * 1024) / (smem + 1024));
+            cps = std::max(1, std::min(cps, 2048 / threads));
+            const long long slots = (long long)sm_count * cps;
+            auto total_slabs = [&](int ob) {
+                long long t = 0;
+                for (Chain* c : fc) { t += std::max(1, (c->st[c->fp.end - 1]->n_out + ob - 1) / ob); }
+                return t;
+            };
+            int ob = ob_cap;
+            if (fuse.ob_force <= 0) {
+                const long long waves = (total_slabs(ob_cap) + slots - 1) / slots;
+                int lo_ob = 4 * FT_R, hi_ob = ob_cap;           // smallest ob with total_slabs(ob) <= waves * slots
+                while (lo_ob < hi_ob) {
+                    int mid = (lo_ob + hi_ob) / 2;
+                    if (total_slabs(mid) <= waves * slots) { hi_ob = mid; } else { lo_ob = mid + 1; }
+                }
+                ob = hi_ob;
+            }
+            FtParams fpar;
+            fpar.njobs = 0; fpar.pad = 0;
+            int max_slabs = 0;
+            auto flush = [&]() -> int {
+                if (fpar.njobs == 0) { return 0; }
+                cudaError_t e = launch_tail_fused(fpar, max_slabs, threads, smem, ts);
+                if (e != cudaSuccess) { return cuda_fail(e, "launch_tail_fused"); }
+                launches++;
+                fpar.njobs = 0;
+                max_slabs = 0;
+                return 0;
+            };
+            for (Chain* c : fc) {
+                FtJob& J = fpar.job[fpar.njobs++];
+                const int nst = c->fp.end - 1;
+                J.nst = nst;
+                J.OB = ob;
+                J.OT0 = c->fp.ot0;
+                for (int i = 0; i < nst; i++) {
+                    Stage* sg = c->st[1 + i].get();
+                    FtStage& d = J.st[i];
+                    ft_describe(sg, d);
+                    d.n_in = sg->n_in; d.n_out = sg->n_out;
+                    d.buf = c->fp.buf[i]; d.pitch = c->fp.pitch[i]; d.tap_off = c->fp.tap_off[i]; d.qpitch = c->fp.qpitch[i];
+                    if (sg->kind == K_FIRC) { d.off = ((FirCStage*)sg)->chunk_offset; }
+                    if (sg->kind == K_POLY) { d.off = ((PolyStage*)sg)->chunk_offset; d.phase = ((PolyStage*)sg)->chunk_phase; }
+                    if (i > 0) {
+                        d.hist_rd = sg->fh[sg->fpar].as<float>();
+                        d.hist_wr = sg->fh[sg->fpar ^ 1].as<float>();
+                        sg->fpar ^= 1;
+                    }
+                }
+                J.src = c->st[1]->base();
+                J.out = c->st[c->fp.end - 1]->out_ptr;
+                J.slabs = std::max(1, (J.st[nst - 1].n_out + ob - 1) / ob);
+                max_slabs = std::max(max_slabs, J.slabs);
+                if (fpar.njobs == B200_BATCH) { int rc = flush(); if (rc) { return rc; } }
+            }
+            int rc = flush();
+            if (rc) { return rc; }
+        }
+    }
     // ---- remaining stages level by level: one launch per stage kind per level (batches of 16 VFOs) ----
     for (size_t lvl = 0; lvl < depth; lvl++) {
         FirParams fp; fp.njobs = 0; fp.max_out = 0;
@@ -681,6 +907,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
         M2SParams mp; mp.njobs = 0; mp.max_n = 0;
         for (Chain* c : chains) {
             if (lvl >= c->st.size()) { continue; }
+            if (c->fp.active && lvl >= 1 && (int)lvl < c->fp.end) { continue; }     // done by the fused launch
             Stage* s = c->st[lvl].get();
             int rc = 0;
             switch (s->kind) {
@@ -710,8 +937,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
                 QuadStage* f = (QuadStage*)s;
                 if (f->n_out <= 0) { break; }
                 QuadJob& j = qp.job[qp.njobs++];
-                j.in = (const float2*)f->in_data(); j.out = f->out_ptr;
-                j.state_in = f->state.as<float>() + f->chunk_flip; j.state_out = f->state.as<float>() + (f->chunk_flip ^ 1);
+                j.in = (const float2*)f->base(); j.out = f->out_ptr;
                 j.inv_dev = f->inv_dev; j.n = f->n_out;
                 qp.max_n = std::max(qp.max_n, f->n_out);
                 if (qp.njobs == B200_BATCH) { rc = flush_batch(qp, launch_quad, ts, launches); qp.max_n = 0; }
@@ -766,7 +992,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
     for (Chain* c : chains) {
         for (auto& sp : c->st) {
             Stage* s = sp.get();
-            if (s->kind == K_XD || s->hist <= 0) { continue; }
+            if (s->kind == K_XD || s->hist <= 0 || s->fmid) { continue; }
             if (s->n_in <= 0 && !s->dbl) { continue; }      // a double-buffered stage always hands its history over
             CarryJob j;
             j.dst = s->other_base(); j.a = s->base(); j.b = s->in_data();

@@ -53,6 +53,13 @@ struct Stage {
     int par = 0;                 // which buffer this chunk uses (dbl only)
     int n_in = 0, n_out = 0;     // this chunk
     float* out_ptr = nullptr;    // where this chunk's output goes (set by the scheduler)
+    // fused tail (kernels.cuh: FtStage): an intermediate stage keeps only its history, ping-pong between chunks
+    DevBuf fh[2];
+    int fpar = 0;                // read fh[fpar], write fh[fpar ^ 1]
+    bool fmid = false;
+    DevBuf taps_pm;              // taps in the fused kernel's phase-major order: row r = taps[q*D + r], pitch ceil(T/D)
+    int pm_floats = 0;           // multiple of 4
+    int upload_pm(const std::vector<float>& t, int rows_per_set, int sets);
     virtual ~Stage() {}
     virtual int plan(int n) = 0;             // host: output count for n inputs, advances the mirrored state
     virtual int max_out(int n) const = 0;    // upper bound
@@ -108,11 +115,9 @@ struct PolyStage : Stage {
 
 struct QuadStage : Stage {
     float inv_dev = 1.0f;
-    DevBuf state;                // 2 floats, ping-pong
-    int flip = 0, chunk_flip = 0;
-    QuadStage() { kind = K_QUAD; out_es = 1; }
+    QuadStage() { kind = K_QUAD; out_es = 1; hist = 1; }   // history = the previous chunk's last sample (Quadrature::phase)
     int configure(double deviationHz, double samplerate);
-    int plan(int n) override;
+    int plan(int n) override { n_in = n; n_out = n; return n; }
     int max_out(int n) const override { return n; }
 };
 
@@ -143,6 +148,16 @@ struct M2SStage : Stage {
     int max_out(int n) const override { return n; }
 };
 
+// Static part of a chain's fused-tail launch: which stages, the shared-memory arena, the slab size limit.
+struct FusedPlan {
+    bool active = false;
+    int end = 0;                 // stages [1, end) run in k_tail_fused
+    int ob_max = 0, ot0 = 0;
+    size_t smem = 0;
+    int buf[FT_MAXST], pitch[FT_MAXST], tap_off[FT_MAXST], qpitch[FT_MAXST];
+};
+struct FuseCfg { bool on = false; int ob_max = 1280; int smem_limit = 110 * 1024; int threads = 256; int ob_force = 0; };
+
 // A chain = one VFO (+ demodulator) or one stand-alone block.
 struct Chain {
     std::vector<std::unique_ptr<Stage>> st;
@@ -152,7 +167,10 @@ struct Chain {
     int n_out = 0;               // this chunk
     float* out_override = nullptr;   // this chunk: final stage writes straight into the caller's device buffer
     bool raw_input() const { return !st.empty() && st[0]->kind == K_XD; }
-    int finalize(int max_in, bool dbl_first = false);    // allocates stage buffers for chunks of up to max_in samples
+    FusedPlan fp;
+    FuseCfg fcfg;
+    int plan_fused();            // (re)builds fp from the stage list; clears fp.active when the chain cannot be fused
+    int finalize(int max_in, bool dbl_first = false, const FuseCfg* fuse = nullptr);    // allocates stage buffers for chunks of up to max_in samples
     int plan(int n);             // all stages; returns final count
     int max_out(int n) const;
     void reset_state();
@@ -186,6 +204,8 @@ struct Scheduler {
     int enable_overlap(cudaStream_t tail);
     long long launches = 0;
     int s1_variant = 6;
+    FuseCfg fuse;                // tails: one fused launch per <= 16 VFOs instead of one launch per stage kind
+    int sm_count = 148;
     bool pair_conjugates = true;   // stage 1: VFOs at +f / -f share their multiply-accumulates (exact identity)
     // optional device-side timing of the stage-1 launches (bench.py's roofline leg): CUDA events on `stream`
     bool time_s1 = false;

@@ -209,8 +209,10 @@ __global__ void __launch_bounds__(256) k_xd_tile(const __grid_constant__ XdParam
 }
 
 
+#define FL_M_PI_REF 3.1415926535f   // math::normalizePhase (normalize_phase.h:6-10)
 #include "xd_pipe.cuh"
 #include "tails.cuh"
+#include "fused_tail.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // retune edge: outputs whose tap window straddles the chunk start when the VFO offset changed at this
@@ -283,24 +285,19 @@ __global__ void __launch_bounds__(256) k_poly(const __grid_constant__ PolyParams
 // FM discriminator: out[i] = wrap(atan2f(x[i]) - atan2f(x[i-1])) * invDeviation
 // wrap rule and the constant 3.1415926535f follow math::normalizePhase (normalize_phase.h:6-10)
 // ------------------------------------------------------------------------------------------------
-#define FL_M_PI_REF 3.1415926535f
 __global__ void __launch_bounds__(256) k_quad(const __grid_constant__ QuadParams p) {
     const QuadJob& J = p.job[blockIdx.y];
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= J.n) { return; }
-    float2 c = __ldg(J.in + i);
+    // J.in[0] is the last sample of the previous chunk (zero at start: atan2f(0,0) = 0 = Quadrature's initial phase)
+    float2 c = __ldg(J.in + i + 1);
+    float2 q = __ldg(J.in + i);
     float cur = atan2f(c.y, c.x);
-    float prev;
-    if (i == 0) { prev = *J.state_in; }
-    else {
-        float2 q = __ldg(J.in + i - 1);
-        prev = atan2f(q.y, q.x);
-    }
+    float prev = atan2f(q.y, q.x);
     float diff = __fsub_rn(cur, prev);
     if (diff > FL_M_PI_REF) { diff = __fsub_rn(diff, 2.0f * FL_M_PI_REF); }
     else if (diff <= -FL_M_PI_REF) { diff = __fadd_rn(diff, 2.0f * FL_M_PI_REF); }
     J.out[i] = __fmul_rn(diff, J.inv_dev);
-    if (i == J.n - 1) { *J.state_out = cur; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1044,6 +1041,26 @@ cudaError_t launch_quad(const QuadParams& p, cudaStream_t s) {
     if (p.max_n <= 0 || p.njobs <= 0) { return cudaSuccess; }
     dim3 grid(cdiv(p.max_n, 256), p.njobs);
     k_quad<<<grid, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_tail_fused(const FtParams& p, int max_slabs, int threads, size_t smem_bytes, cudaStream_t s) {
+    if (p.njobs <= 0 || max_slabs <= 0) { return cudaSuccess; }
+    if ((int)smem_bytes > kernels_max_smem_optin()) { return cudaErrorInvalidValue; }
+    dim3 grid(max_slabs, p.njobs);
+    static size_t attr[3] = { 0, 0, 0 };
+#define FT_LAUNCH(NTV, SLOT)                                                                                                   \
+    do {                                                                                                                       \
+        if (smem_bytes > attr[SLOT]) {                                                                                         \
+            cudaError_t e = cudaFuncSetAttribute(k_tail_fused<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); \
+            if (e != cudaSuccess) { return e; }                                                                                \
+            attr[SLOT] = smem_bytes;                                                                                           \
+        }                                                                                                                      \
+        k_tail_fused<NTV><<<grid, NTV, smem_bytes, s>>>(p);                                                                    \
+    } while (0)
+    if (threads == 512) { FT_LAUNCH(512, 2); }
+    else if (threads == 256) { FT_LAUNCH(256, 1); }
+    else { FT_LAUNCH(128, 0); }
+#undef FT_LAUNCH
     return cudaGetLastError();
 }
 cudaError_t launch_fir_r(const FirRParams& p, cudaStream_t s) {

@@ -69,10 +69,8 @@ struct PolyParams { int njobs; int max_out; PolyJob job[B200_BATCH]; };
 
 // ---- FM discriminator (Quadrature::process, quadrature.h:39-46) ----
 struct QuadJob {
-    const float2* in;       // n samples (no history)
+    const float2* in;       // [1 history sample | n samples]
     float* out;
-    const float* state_in;  // previous chunk's last phase
-    float* state_out;       // this chunk's last phase (ping-pong: != state_in)
     float inv_dev;
     int n;
 };
@@ -86,6 +84,99 @@ struct FirRJob {
     int ntaps, n_out, stereo;
 };
 struct FirRParams { int njobs; int max_out; FirRJob job[B200_BATCH]; };
+
+// ---- fused tail: every FIR-like stage after stage 1 of one VFO in ONE launch ----
+// A CTA owns a slab of `OB` final outputs of one VFO and walks the stage list forward; what one stage produces for
+// the slab (plus the halo the next stage's taps need, recomputed per slab) stays in shared memory.  Each stage keeps
+// the reference's [history | data] semantics: samples with a negative chunk-relative index come from a small
+// per-stage history buffer (ping-pong: read `hist_rd`, the CTA of the last slab writes `hist_wr`).
+// Index conventions (chunk-relative "data" coordinates, i < 0 = history):
+//   FIRC/FIRR  out[m] = sum_k taps[k] * in[m*D + off - (T-1) + k]          (decimating_fir.h:45-68, fir.h:62-83)
+//   POLY       t = phase + m*D; out[m] = sum_k bank[t%L][k] * in[off + t/L - (T-1) + k]   (polyphase_resampler.h:69-99)
+//   QUAD       out[m] = wrap(arg(in[m]) - arg(in[m-1])) * scale              (quadrature.h:39-46)
+//   M2S        out[m] = (in[m], in[m])
+#define FT_MAXST 8
+#define FT_R 9              // outputs per thread (odd: lanes R apart hit distinct banks without padding)
+enum { FT_FIRC = 0, FT_POLY = 1, FT_QUAD = 2, FT_FIRR = 3, FT_M2S = 4 };
+struct FtStage {
+    int kind;
+    int T;                  // taps (FIRC/FIRR) or taps per phase (POLY)
+    int D;                  // decimation (FIRC), polyphase decimation (POLY), else 1
+    int L;                  // POLY interpolation
+    int off;                // FIRC: DecimatingFIR::offset of this chunk; POLY: offset
+    int phase;              // POLY: phase
+    int n_in, n_out;        // this chunk
+    int hist;               // history samples in front of the input: T-1, QUAD 1, M2S 0
+    int es;                 // floats per INPUT sample
+    int buf;                // float offset of the input buffer in the shared-memory arena (stage 0: staging buffer)
+    int pitch;              // row pitch (samples) of the phase-major layout (D rows)
+    int tap_off, qpitch;    // taps in shared memory: row r holds taps[q*D + r] (POLY: row (ph*D + r)), qpitch = ceil(T/D)
+    int ntap_f;             // floats of the phase-major tap array (multiple of 4)
+    int dup;                // output is mono duplicated to (l, r)
+    float scale;            // QUAD: 1/deviation
+    const float* taps;      // global, phase-major as in shared memory (Stage::taps_pm)
+    const float* hist_rd;   // stages 1..: hist*es floats
+    float* hist_wr;
+};
+struct FtJob {
+    int nst, slabs, OB, OT0;    // OT0: stage-0 outputs per staging sub-tile
+    const float* src;           // stage 0 input: [hist | data] in global memory
+    float* out;                 // final output
+    FtStage st[FT_MAXST];
+};
+struct FtParams { int njobs; int pad; FtJob job[B200_BATCH]; };
+
+#if defined(__CUDACC__)
+#define FT_HD __host__ __device__
+#else
+#define FT_HD
+#endif
+FT_HD inline int ft_posmod(long long a, int m) { long long r = a % m; return (int)(r < 0 ? r + m : r); }
+// input range [ilo, ihi) (data coordinates) that outputs [mlo, mhi) of stage s read; mhi > mlo
+FT_HD inline void ft_need_in(const FtStage& s, int mlo, int mhi, int& ilo, int& ihi) {
+    switch (s.kind) {
+    case FT_FIRC: case FT_FIRR:
+        ilo = s.off + mlo * s.D - (s.T - 1);
+        ihi = s.off + (mhi - 1) * s.D + 1;
+        break;
+    case FT_POLY:
+        ilo = s.off + (int)(((long long)s.phase + (long long)mlo * s.D) / s.L) - (s.T - 1);
+        ihi = s.off + (int)(((long long)s.phase + (long long)(mhi - 1) * s.D) / s.L) + 1;
+        break;
+    case FT_QUAD: ilo = mlo - 1; ihi = mhi; break;
+    default: ilo = mlo; ihi = mhi; break;
+    }
+}
+// origin of the phase-major shared-memory layout of stage s's input when the range starts at lo
+FT_HD inline int ft_origin(const FtStage& s, int lo) {
+    if (s.kind == FT_FIRC && s.D > 1) { return lo - ft_posmod((long long)lo - (s.off - (s.T - 1)), s.D); }
+    return lo;
+}
+FT_HD inline int ft_rows(const FtStage& s) { return (s.kind == FT_FIRC || s.kind == FT_POLY) ? s.D : 1; }
+// lo[s], hi[s]: input range of stage s for this slab (s = nst: the final output range)
+FT_HD inline void ft_ranges(const FtJob& J, int slab, int* lo, int* hi) {
+    const int nst = J.nst;
+    const int n_last = J.st[nst - 1].n_out;
+    int m0 = slab * J.OB, m1 = m0 + J.OB;
+    if (m1 > n_last) { m1 = n_last; }
+    if (m0 > m1) { m0 = m1; }
+    lo[nst] = m0; hi[nst] = m1;
+    const bool last = (slab == J.slabs - 1);
+    for (int s = nst - 1; s >= 0; s--) {
+        const FtStage& S = J.st[s];
+        const int pl = lo[s + 1] > 0 ? lo[s + 1] : 0, ph = hi[s + 1];
+        int ilo = 0, ihi = 0;
+        if (ph > pl) { ft_need_in(S, pl, ph, ilo, ihi); }
+        if (last && s > 0) {
+            // the last slab also hands the next chunk its history: the final `hist` inputs of every stage
+            const int hl = S.n_in - S.hist, hh = S.n_in;
+            if (ihi <= ilo) { ilo = hl; ihi = hh; }
+            else { if (hl < ilo) { ilo = hl; } if (hh > ihi) { ihi = hh; } }
+        }
+        lo[s] = ilo; hi[s] = ihi;
+    }
+}
+cudaError_t launch_tail_fused(const FtParams& p, int max_slabs, int threads, size_t smem_bytes, cudaStream_t s);
 
 // ---- sequential audio-rate tails (one thread per job): AM envelope + DC block + AGC, SSB rotate + AGC ----
 struct AgcState { float amp; };

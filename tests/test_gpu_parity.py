@@ -490,10 +490,14 @@ def test_frontend_multi_vfo_100msps(sb, oracle, report):
     fe.close()
 
 
-@pytest.mark.parametrize("variant,fft_async,overlap,pair", [(4, 1, 1, 1), (3, 0, 0, 1), (1, 1, 0, 0), (3, 1, 1, 0), (3, 1, 0, 1), (5, 1, 1, 1), (5, 1, 0, 0), (6, 1, 1, 1), (6, 1, 0, 0)])
-def test_frontend_variants_100msps(sb, oracle, report, variant, fft_async, overlap, pair):
+@pytest.mark.parametrize("variant,fft_async,overlap,pair,tails", [
+    (4, 1, 1, 1, {}), (3, 0, 0, 1, {}), (1, 1, 0, 0, {}), (3, 1, 1, 0, {"tails": 1}), (3, 1, 0, 1, {"tails": 0}), (5, 1, 1, 1, {}),
+    (5, 1, 0, 0, {"tails": 1}), (6, 1, 1, 1, {"tails": 1}), (6, 1, 0, 0, {}), (6, 1, 1, 1, {"ft_threads": 256}),
+    (6, 1, 1, 1, {"ft_ob": 301}), (6, 1, 0, 1, {"ft_ob": 64, "ft_smem_kb": 48}), (6, 1, 1, 1, {"ft_obmax": 2500, "ft_smem_kb": 200})])
+def test_frontend_variants_100msps(sb, oracle, report, variant, fft_async, overlap, pair, tails):
     """kernel / scheduling A-B on the config-2 geometry (short): 16-warp stage 1, synchronous spectrum branch,
-    tails on the main stream, conjugate-pair sharing off."""
+    tails on the main stream, conjugate-pair sharing off, per-stage tail launches instead of the fused tail,
+    forced fused-tail slab sizes."""
     fs, chunk, nch = 100e6, 1000000, 4
     n = chunk * nch
     offs = [5e6, -5e6, 15e6, -25e6, 35e6, 25e6]
@@ -505,6 +509,8 @@ def test_frontend_variants_100msps(sb, oracle, report, variant, fft_async, overl
     fe.set_option("s1", variant)
     fe.set_option("pair", pair)
     fe.set_option("fft_async", fft_async)
+    for k, v in tails.items():
+        fe.set_option(k, v)
     fe.set_fft(1 << 18, 200.0, 2)              # 500000-sample interval: frames inside chunks and across them
     cfgs = [sb.VfoConfig.wfm(o) for o in offs]
     ids = [fe.add_vfo(c) for c in cfgs]
@@ -518,7 +524,8 @@ def test_frontend_variants_100msps(sb, oracle, report, variant, fft_async, overl
         ya = _oracle_chain(oracle, x, fs, chunk, c).reshape(-1, 2)
         assert outs[vid].shape == ya.shape
         errs.append(rel_rms(outs[vid][1500:], ya[1500:]))
-    report["frontend_s1v%d_fftasync%d_overlap%d_pair%d" % (variant, fft_async, overlap, pair)] = {"wfm_audio_rel_rms": errs, "fft_power_rel_max": e_fft}
+    tag = "".join("_%s%d" % kv for kv in sorted(tails.items()))
+    report["frontend_s1v%d_fftasync%d_overlap%d_pair%d%s" % (variant, fft_async, overlap, pair, tag)] = {"wfm_audio_rel_rms": errs, "fft_power_rel_max": e_fft}
     assert e_fft < TOL, e_fft
     assert max(errs) < TOL, errs
     fe.close()
