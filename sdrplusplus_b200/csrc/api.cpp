@@ -106,7 +106,7 @@ static int ilog2(int n) { int l = 0; while ((1 << l) < n) { l++; } return l; }
 
 struct FftCore {
     FftPlanDev plan;
-    DevBuf tw, win, work;
+    DevBuf tw, twf, win, work;
     int size = 0, nz = 0, window = 0;
     int create(int size_, int nz_, int window_, int max_batch = 1) {
         if (size_ < 8 || size_ > (1 << 22) || (size_ & (size_ - 1))) { set_error("FFT size %d must be a power of two in [8, 4194304]", size_); return B200_EINVAL; }
@@ -133,6 +133,19 @@ struct FftCore {
         B200_CK(cudaMemcpy(win.p, w.data(), (size_t)nz * sizeof(float), cudaMemcpyHostToDevice));
         if ((rc = work.alloc((size_t)size * sizeof(float2) * (size_t)(max_batch > 0 ? max_batch : 1)))) { return rc; }
         plan.tw = tw.as<float2>(); plan.window = win.as<float>(); plan.nz = nz;
+        plan.tw_fine = nullptr;
+        if (plan.N2 > 1) {
+            // four-step twiddle W_N^e = tw[e >> s] * fine[e & (2^s - 1)], 2^s = N / TW
+            const int nf = size / plan.TW;
+            std::vector<float2> f((size_t)nf);
+            for (int j = 0; j < nf; j++) {
+                double a = -2.0 * 3.14159265358979323846 * (double)j / (double)size;
+                f[j] = make_float2((float)std::cos(a), (float)std::sin(a));
+            }
+            if ((rc = twf.alloc(f.size() * sizeof(float2)))) { return rc; }
+            B200_CK(cudaMemcpy(twf.p, f.data(), f.size() * sizeof(float2), cudaMemcpyHostToDevice));
+            plan.tw_fine = twf.as<float2>();
+        }
         return 0;
     }
 };
@@ -383,6 +396,7 @@ extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
         if (!strcmp(key, "ft_smem_kb")) { fe->sch.fuse.smem_limit = value * 1024; return 0; }
         if (!strcmp(key, "ft_threads")) { fe->sch.fuse.threads = value; return 0; }
     }
+    if (!strcmp(key, "fft")) { kernels_set_fft_variant(value); return 0; }
     if (!strcmp(key, "time_s1")) { fe->sch.time_s1 = value != 0; fe->sch.ev_used = 0; return 0; }
     set_error("unknown option %s", key);
     return B200_EINVAL;

@@ -681,6 +681,8 @@ __global__ void __launch_bounds__(512) k_fft_p2(const __grid_constant__ FftPlanD
     }
 }
 
+#include "fft_reg.cuh"
+
 template <int FMT>
 __global__ void __launch_bounds__(256) k_convert(const void* __restrict__ src, float2* __restrict__ dst, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -711,6 +713,8 @@ __global__ void __launch_bounds__(256) k_zoom_hold(const float* __restrict__ lin
 // launch wrappers
 // ------------------------------------------------------------------------------------------------
 static int g_smem_optin = -1;
+static int g_fft_variant = 1;     // 1: register-resident four-step passes where they apply; 0: shared-memory radix-8 passes
+void kernels_set_fft_variant(int v) { g_fft_variant = v; }
 int kernels_max_smem_optin() {
     if (g_smem_optin < 0) {
         int dev = 0, v = 0;
@@ -1114,6 +1118,32 @@ static cudaError_t launch_fft_fmt(const FftPlanDev& pl, const void* src, float2*
         return cudaGetLastError();
     }
     // two passes
+    if (g_fft_variant >= 1 && !out_raw && pl.tw_fine && pl.logN1 >= 8 && pl.logN1 <= 10 && pl.logN2 >= 8 && pl.logN2 <= 10) {
+        // register-resident column / row transforms (fft_reg.cuh)
+        constexpr int CC = 8, RR = 8;
+#define FR_P1(RA, RB)                                                                                          \
+        do {                                                                                                   \
+            const size_t sm = (size_t)CC * FrGeom<RA, RB>::pitch * sizeof(float2);                             \
+            e = set_smem(k_fftr_p1<FMT, RA, RB, CC>, sm);                                                      \
+            if (e != cudaSuccess) { return e; }                                                                \
+            k_fftr_p1<FMT, RA, RB, CC><<<dim3(pl.N2 / CC, nbatch), CC * FrGeom<RA, RB>::TP, sm, s>>>(pl, src, work, src_stride_bytes); \
+        } while (0)
+#define FR_P2(RA, RB)                                                                                          \
+        do {                                                                                                   \
+            const size_t sm = (size_t)RR * FrGeom<RA, RB>::pitch * sizeof(float2);                             \
+            e = set_smem(k_fftr_p2<RA, RB, RR>, sm);                                                           \
+            if (e != cudaSuccess) { return e; }                                                                \
+            k_fftr_p2<RA, RB, RR><<<dim3(pl.N1 / RR, nbatch), RR * FrGeom<RA, RB>::TP, sm, s>>>(pl, work, out_db); \
+        } while (0)
+        if (pl.logN1 == 10) { FR_P1(32, 32); } else if (pl.logN1 == 9) { FR_P1(16, 32); } else { FR_P1(16, 16); }
+        e = cudaGetLastError();
+        if (e != cudaSuccess) { return e; }
+        if (pl.logN2 == 10) { FR_P2(32, 32); } else if (pl.logN2 == 9) { FR_P2(16, 32); } else { FR_P2(16, 16); }
+#undef FR_P1
+#undef FR_P2
+        if (nlaunch) { (*nlaunch) += 2; }
+        return cudaGetLastError();
+    }
     // columns / rows per CTA: enough CTAs to fill the chip about twice, at least 4 (32-byte segments)
     int C = 16;
     while (C > 4 && (pl.N2 / C) * nbatch < 2 * num_sms()) { C >>= 1; }

@@ -217,6 +217,7 @@ struct FftPlanDev {
     int N2, logN2;          // pass 2 (row) length
     const float2* tw;       // twiddle table exp(-2 pi i k / TW), k < TW
     int TW, logTW;
+    const float2* tw_fine;  // exp(-2 pi i j / N), j < N / TW (two-pass plans; null otherwise)
     const float* window;    // nz floats: window(i,nz) * (-1)^i
     int nz;
 };
@@ -243,4 +244,5 @@ cudaError_t launch_zoom_hold_tbl(const float* line, const int* start, const int*
                                  float* hold, float hold_speed, cudaStream_t s);
 int kernels_max_smem_optin();
 void kernels_set_tail_variant(int v);
+void kernels_set_fft_variant(int v);
 void kernels_set_xd_tile(int mt);     // 0 = automatic

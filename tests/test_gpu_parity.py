@@ -31,7 +31,8 @@ def sb():
 
 # ---------------------------------------------------------------------------------------------- FFT branch
 @pytest.mark.parametrize("N,nz", [(8, 8), (64, 64), (1024, 1024), (4096, 3000), (8192, 8192), (16384, 16384),
-                                  (65536, 65536), (65536, 40000), (1 << 20, 1 << 20)])
+                                  (65536, 65536), (65536, 40000), (1 << 17, 1 << 17), (1 << 18, 200000), (1 << 19, 1 << 19),
+                                  (1 << 20, 1 << 20), (1 << 21, 1 << 21)])
 def test_fft_line_vs_oracle(sb, oracle, report, N, nz):
     x = noise_iq(nz, 11 + N, 1.0).copy()
     n = np.arange(nz)
