@@ -7,6 +7,7 @@
 #include <cstring>
 #include <algorithm>
 #include <map>
+#include <functional>
 #include <cstdlib>
 
 namespace b200 {
@@ -300,7 +301,8 @@ int Chain::finalize(int max_in, bool dbl_first, const FuseCfg* fuse) {
 // ---- fused tail: static plan ----
 static bool ft_fusable(const Stage* s) {
     switch (s->kind) {
-    case K_FIRC: case K_POLY: return s->in_es == 2;
+    case K_FIRC: return s->in_es == 2;
+    case K_POLY: return s->in_es == 2 && ((const PolyStage*)s)->interp <= 64;    // FT_MAX_L (fused_tail.cuh)
     case K_QUAD: case K_FIRR: case K_M2S: return true;
     default: return false;
     }
@@ -356,6 +358,10 @@ int Chain::plan_fused() {
             toff += d[i].ntap_f;
         }
     }
+    // direct first stage: decimating FIR by 2 or 4 on the complex stream
+    fp.s0_direct = fcfg.direct && d[0].kind == FT_FIRC && (d[0].D == 2 || d[0].D == 4) && d[0].T <= 512;
+    fp.nat_off = toff;
+    if (fp.s0_direct) { toff += round4(d[0].T); }
     const int limit_f = fcfg.smem_limit / 4;
     int ob = fcfg.ob_force > 0 ? fcfg.ob_force : fcfg.ob_max;
     for (; ob >= 4 * FT_R; ob = (ob * 3 / 4) / FT_R * FT_R) {
@@ -381,20 +387,26 @@ int Chain::plan_fused() {
         const int rows0 = ft_rows(d[0]);
         int avail = limit_f - fixed - 64 - region[0];
         int ot0 = (int)((lb[1] + FT_R - 1) / FT_R) * FT_R;
-        auto stage0_floats = [&](int ot) {
+        std::function<long long(int)> stage0_floats = [&](int ot) {
             long long cols = (ft_need_len(d[0], ot) + rows0 + rows0 - 1) / rows0 + FT_R + 2;
             return cols * rows0 * d[0].es;
         };
-        // prefer a staging buffer that gives every thread of the CTA a unit of FT_R outputs
-        const int want = fcfg.threads * FT_R;
+        // two staging buffers (double-buffered cp.async); sub-tiles that give every thread of the CTA a 5-output unit.
+        // direct first stage: three raw ring buffers, 3 outputs per thread and sub-tile.
+        const int nbuf = fp.s0_direct ? 3 : 2;
+        if (fp.s0_direct) {
+            stage0_floats = [&](int ot) { return (long long)((((long long)(ot - 1) * d[0].D + d[0].T + 3) & ~1LL) * 2); };
+        }
+        const int want = fcfg.threads * (fp.s0_direct ? 3 : 5);
         if (ot0 > want) { ot0 = want; }
-        while (ot0 >= FT_R && std::max<long long>(stage0_floats(ot0), region[0]) > (long long)limit_f - fixed - 64) { ot0 -= FT_R; }
+        while (ot0 >= FT_R && std::max<long long>(nbuf * (long long)round4((int)stage0_floats(ot0)), region[0]) > (long long)limit_f - fixed - 64) { ot0 -= FT_R; }
         (void)avail;
         if (ot0 < FT_R) { continue; }
         {
             long long cols = (ft_need_len(d[0], ot0) + rows0 + rows0 - 1) / rows0 + FT_R + 2;
             fp.pitch[0] = (int)cols;
-            region[0] = std::max(region[0], round4((int)stage0_floats(ot0)));
+            fp.stg2_rel = round4((int)stage0_floats(ot0));
+            region[0] = std::max(region[0], nbuf * fp.stg2_rel);
         }
         // arena: [taps | odd stages | even stages (incl. staging)]
         for (int i = 0; i < nst; i++) { fp.buf[i] = (i & 1) ? toff : toff + region[1]; }
@@ -857,6 +869,25 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
             }
             FtParams fpar;
             fpar.njobs = 0; fpar.pad = 0;
+            fpar.dbg = nullptr;
+            static long long* g_ft_dbg = nullptr;
+            static int g_ft_dbg_on = -1;
+            if (g_ft_dbg_on < 0) { const char* e = getenv("B200_FT_CLOCKS"); g_ft_dbg_on = (e && *e == '1') ? 1 : 0; }
+            if (g_ft_dbg_on) {
+                if (!g_ft_dbg) { cudaMalloc(&g_ft_dbg, 32 * sizeof(long long)); cudaMemset(g_ft_dbg, 0, 32 * sizeof(long long)); }
+                else {
+                    long long h[32];
+                    cudaMemcpy(h, g_ft_dbg, sizeof(h), cudaMemcpyDeviceToHost);      // previous launch (synchronising: debug only)
+                    fprintf(stderr, "[b200 ft clocks]");
+                    for (int i = 1; i < 10 && h[i]; i++) { fprintf(stderr, " s%d %lld", i - 1, h[i] - h[i - 1]); }
+                    fprintf(stderr, " | sub-tiles (wait, compute, sync):");
+                    for (int k = 0; k < 4 && h[16 + 3 * k]; k++) {
+                        fprintf(stderr, " [%lld %lld %lld]", h[16 + 3 * k] - (k ? h[15 + 3 * k] : h[0]), h[17 + 3 * k] - h[16 + 3 * k], h[18 + 3 * k] - h[17 + 3 * k]);
+                    }
+                    fprintf(stderr, "\n");
+                }
+                fpar.dbg = g_ft_dbg;
+            }
             int max_slabs = 0;
             auto flush = [&]() -> int {
                 if (fpar.njobs == 0) { return 0; }
@@ -873,6 +904,12 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
                 J.nst = nst;
                 J.OB = ob;
                 J.OT0 = c->fp.ot0;
+                J.stg2 = c->fp.buf[0] + c->fp.stg2_rel; J.pad = 0;
+                J.s0_direct = c->fp.s0_direct ? 1 : 0;
+                J.stg3 = c->fp.buf[0] + 2 * c->fp.stg2_rel;
+                J.nat_off = c->fp.nat_off;
+                J.stg_floats = c->fp.stg2_rel;
+                J.taps_nat = c->fp.s0_direct ? ((FirCStage*)c->st[1].get())->taps.as<float>() : nullptr;
                 for (int i = 0; i < nst; i++) {
                     Stage* sg = c->st[1 + i].get();
                     FtStage& d = J.st[i];

@@ -152,11 +152,13 @@ struct M2SStage : Stage {
 struct FusedPlan {
     bool active = false;
     int end = 0;                 // stages [1, end) run in k_tail_fused
-    int ob_max = 0, ot0 = 0;
+    int ob_max = 0, ot0 = 0, stg2_rel = 0;
+    bool s0_direct = false;      // first fused stage filters the raw stream from a cp.async.bulk ring (kernels.cuh: FtJob)
+    int nat_off = 0;
     size_t smem = 0;
     int buf[FT_MAXST], pitch[FT_MAXST], tap_off[FT_MAXST], qpitch[FT_MAXST];
 };
-struct FuseCfg { bool on = false; int ob_max = 1280; int smem_limit = 110 * 1024; int threads = 256; int ob_force = 0; };
+struct FuseCfg { bool on = false; int ob_max = 1280; int smem_limit = 110 * 1024; int threads = 256; int ob_force = 0; bool direct = true; };
 
 // A chain = one VFO (+ demodulator) or one stand-alone block.
 struct Chain {

@@ -87,8 +87,8 @@ __device__ __forceinline__ void fr_transform(float2 (&v)[RA > RB ? RA : RB], flo
 }
 
 // pass 1: CTA = C adjacent columns n2, every row n1:  A[k1][n2] = W_N^(k1 n2) * sum_n1 x[n1 N2 + n2] W_N1^(n1 k1)
-template <int FMT, int RA, int RB, int C>
-__global__ void __launch_bounds__(C * FrGeom<RA, RB>::TP) k_fftr_p1(const __grid_constant__ FftPlanDev pl, const void* __restrict__ src0,
+template <int FMT, int RA, int RB, int C, int MINB>
+__global__ void __launch_bounds__(C * FrGeom<RA, RB>::TP, MINB) k_fftr_p1(const __grid_constant__ FftPlanDev pl, const void* __restrict__ src0,
                                                                     float2* __restrict__ work0, long long src_stride_bytes) {
     using G = FrGeom<RA, RB>;
     extern __shared__ __align__(16) float2 smem[];

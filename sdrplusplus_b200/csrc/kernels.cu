@@ -1124,9 +1124,16 @@ static cudaError_t launch_fft_fmt(const FftPlanDev& pl, const void* src, float2*
 #define FR_P1(RA, RB)                                                                                          \
         do {                                                                                                   \
             const size_t sm = (size_t)CC * FrGeom<RA, RB>::pitch * sizeof(float2);                             \
-            e = set_smem(k_fftr_p1<FMT, RA, RB, CC>, sm);                                                      \
-            if (e != cudaSuccess) { return e; }                                                                \
-            k_fftr_p1<FMT, RA, RB, CC><<<dim3(pl.N2 / CC, nbatch), CC * FrGeom<RA, RB>::TP, sm, s>>>(pl, src, work, src_stride_bytes); \
+            if (g_fft_variant >= 2) {                                                                          \
+                e = set_smem(k_fftr_p1<FMT, RA, RB, CC, 3>, sm);                                               \
+                if (e != cudaSuccess) { return e; }                                                            \
+                k_fftr_p1<FMT, RA, RB, CC, 3><<<dim3(pl.N2 / CC, nbatch), CC * FrGeom<RA, RB>::TP, sm, s>>>(pl, src, work, src_stride_bytes); \
+            }                                                                                                  \
+            else {                                                                                             \
+                e = set_smem(k_fftr_p1<FMT, RA, RB, CC, 2>, sm);                                               \
+                if (e != cudaSuccess) { return e; }                                                            \
+                k_fftr_p1<FMT, RA, RB, CC, 2><<<dim3(pl.N2 / CC, nbatch), CC * FrGeom<RA, RB>::TP, sm, s>>>(pl, src, work, src_stride_bytes); \
+            }                                                                                                  \
         } while (0)
 #define FR_P2(RA, RB)                                                                                          \
         do {                                                                                                   \

@@ -120,11 +120,17 @@ struct FtStage {
 };
 struct FtJob {
     int nst, slabs, OB, OT0;    // OT0: stage-0 outputs per staging sub-tile
+    int stg2, pad;              // float offset of the second staging buffer (the first is st[0].buf)
+    // "direct" first stage (decimating FIR with D in {2,4} fed from global memory): the raw input streams into a ring
+    // of three shared-memory buffers with cp.async.bulk and is filtered in its natural (interleaved) order
+    int s0_direct, stg3;        // third ring buffer (float offset)
+    int nat_off, stg_floats;    // natural-order taps of stage 0 in the tap region; floats per ring buffer
+    const float* taps_nat;
     const float* src;           // stage 0 input: [hist | data] in global memory
     float* out;                 // final output
     FtStage st[FT_MAXST];
 };
-struct FtParams { int njobs; int pad; FtJob job[B200_BATCH]; };
+struct FtParams { int njobs; int pad; long long* dbg; FtJob job[B200_BATCH]; };   // dbg: optional per-stage clock64() of CTA (1,0)
 
 #if defined(__CUDACC__)
 #define FT_HD __host__ __device__

@@ -93,6 +93,19 @@ __global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdPar
                 src += nthr;
             }
         }
+        else if (FMT != FMT_CF32 && ibase >= 0 && ibase + ntile_samples <= (long long)p.count && (nthr & dmask) == 0) {
+            // interior tile of an integer stream: same walk, converted in registers (8 loads in flight per thread)
+            const int r = tid & dmask;
+            const int jstep = nthr >> g.logD;
+            float2* dst = X + r * JP + (tid >> g.logD);
+            long long i = ibase + tid;
+#pragma unroll 8
+            for (int idx = tid; idx < ntile_samples; idx += nthr) {
+                *dst = load_iq<FMT>(p.in, i);
+                dst += jstep;
+                i += nthr;
+            }
+        }
         else {
             for (int idx = tid; idx < ntile_samples; idx += nthr) {
                 const int j = idx >> g.logD, r = idx & dmask;
