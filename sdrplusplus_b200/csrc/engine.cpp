@@ -792,6 +792,44 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
                     p.nslots++;
                 }
             }
+            // polyphase-filter-bank form (xd_pfb.cuh): every job on a common frequency grid fs / (2 PS), same prototype,
+            // same alignment.  Accept when e^{j w_v PS} is within a few 1e-6 rad (over one tap window) of the same sign.
+            p.pfb_ps = 0; p.pfb_sigma = 1;
+            if (s1_variant >= 7 && p.njobs >= 1) {
+                bool same = true;
+                XdStage* x0 = g[b];
+                for (int v = 1; v < p.njobs; v++) {
+                    XdStage* xv = g[b + v];
+                    if (xv->T != x0->T || xv->chunk_offset != x0->chunk_offset || xv->n_out != x0->n_out || xv->h != x0->h) { same = false; }
+                }
+                if (same && x0->n_out > 0) {
+                    for (int P = 1; P <= 10 && !p.pfb_ps; P++) {
+                        // drift allowed per P samples so that it stays below 8e-6 rad over the T-tap window
+                        const double tol_turns = (8e-6 / 6.283185307179586) * (double)P / (double)x0->T;
+                        const double tol = tol_turns * 18446744073709551616.0;
+                        int sg = 0;
+                        bool ok = true;
+                        for (int v = 0; v < p.njobs && ok; v++) {
+                            const unsigned long long r = g[b + v]->w * (unsigned long long)P;
+                            const double d0 = (double)(long long)r;                                    // distance to 0 (signed)
+                            const double d1 = (double)(long long)(r - 0x8000000000000000ULL);            // distance to 1/2 turn
+                            int sv = 0;
+                            if (std::fabs(d0) <= tol) { sv = 1; } else if (std::fabs(d1) <= tol) { sv = -1; }
+                            if (sv == 0 || (sg != 0 && sv != sg)) { ok = false; }
+                            sg = sv;
+                        }
+                        if (!ok) { continue; }
+                        // run the kernel's PS = 8 or 10 instantiation: sigma' = sigma^(PS / P)
+                        for (int PS : { 8, 10 }) {
+                            if (PS % P == 0) {
+                                p.pfb_ps = PS;
+                                p.pfb_sigma = (sg < 0 && ((PS / P) & 1)) ? -1 : 1;
+                                break;
+                            }
+                        }
+                    }
+                }
+            }
             // the tiled kernel pads every job to the group's QP: all jobs of a batch must have room for it
             int variant = s1_variant;
             for (int v = 0; v < p.njobs; v++) {

@@ -205,7 +205,7 @@ struct Scheduler {
     cudaStream_t out_stream() const { return tail_stream ? tail_stream : stream; }
     int enable_overlap(cudaStream_t tail);
     long long launches = 0;
-    int s1_variant = 6;
+    int s1_variant = 7;          // 7: polyphase-filter-bank stage 1 when the VFO plan allows it, else 6
     FuseCfg fuse;                // tails: one fused launch per <= 16 VFOs instead of one launch per stage kind
     int sm_count = 148;
     bool pair_conjugates = true;   // stage 1: VFOs at +f / -f share their multiply-accumulates (exact identity)

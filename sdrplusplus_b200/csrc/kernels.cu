@@ -18,6 +18,8 @@
 //   k_zoom_hold               doZoom + peak hold (waterfall.cpp:65-90, 935-939)
 #include "kernels.cuh"
 #include <math.h>
+#include <string.h>
+#include <algorithm>
 
 // ------------------------------------------------------------------------------------------------
 // helpers
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(256) k_xd_tile(const __grid_constant__ XdParam
 
 #define FL_M_PI_REF 3.1415926535f   // math::normalizePhase (normalize_phase.h:6-10)
 #include "xd_pipe.cuh"
+#include "xd_pfb.cuh"
 #include "tails.cuh"
 #include "fused_tail.cuh"
 
@@ -872,12 +875,73 @@ static bool try_xd_pipe(const XdParams& p, cudaStream_t s, cudaError_t* err, int
     return true;
 }
 
+
+// ---- polyphase-filter-bank stage 1 (xd_pfb.cuh); returns true when it was launched ----
+template <int LOGD, int QC, int PS>
+static cudaError_t launch_xd_pfb_t(const XdParams& p, const XpGeom& g, int fmt, cudaStream_t s) {
+    constexpr int D = 1 << LOGD, GQ = (QC + 3) & ~3, XP = 4 * 2 * PS * 32;
+    const size_t xf = (size_t)std::max(D * g.JP, XP);
+    const size_t smem = (xf + (size_t)B200_BATCH * PS + (size_t)p.njobs * 128 + 3 * B200_BATCH) * sizeof(float2) + (size_t)D * GQ * sizeof(float);
+    cudaError_t e = set_smem(k_xd_pfb<LOGD, QC, PS>, smem);
+    if (e != cudaSuccess) { return e; }
+    int per_sm = (int)((size_t)233472 / (smem + 1024));
+    if (per_sm > 3) { per_sm = 3; }
+    if (per_sm < 1) { per_sm = 1; }
+    int grid = num_sms() * per_sm;
+    if (grid > g.ntiles) { grid = g.ntiles; }
+    k_xd_pfb<LOGD, QC, PS><<<grid, 128, smem, s>>>(p, g, fmt);
+    return cudaGetLastError();
+}
+static bool try_xd_pfb(const XdParams& p, int fmt, cudaStream_t s, cudaError_t* err) {
+    const int D = p.D, PS = p.pfb_ps;
+    if ((PS != 8 && PS != 10) || D < 4 || (D & (D - 1))) { return false; }
+    int logD = 0;
+    while ((1 << logD) < D) { logD++; }
+    const int T = p.job[0].T;
+    const int org = (((p.job[0].offset - (T - 1)) % D) + D) % D;
+    long long jmin = (1LL << 60), jmax = -(1LL << 60);
+    for (int v = 0; v < p.njobs; v++) {
+        const int a = p.job[v].offset - (p.job[v].T - 1) - org;
+        if (p.job[v].T != T || (a % D) != 0 || p.job[v].n_out <= 0) { return false; }
+        const long long c = a / D;
+        if (c < jmin) { jmin = c; }
+        if (c + p.job[v].n_out > jmax) { jmax = c + p.job[v].n_out; }
+    }
+    const int QC = (T + D - 1) / D;
+    if (jmin & 1) { jmin -= 1; }
+    XpGeom g;
+    memset(&g, 0, sizeof(g));
+    int jp = 128 + QC + 2;
+    jp += (jp & 1);
+    if ((jp & 3) == 0) { jp += 2; }
+    g.MT = 128; g.JP = jp; g.QPC = QC; g.org = org; g.logD = logD; g.jmin = jmin; g.RS = 4; g.single = 1;
+    g.ntiles = cdiv(jmax - jmin, 128);
+    cudaError_t e;
+#define PFB_CASE(LD, Q)                                                                  \
+    if (logD == LD && QC == Q) {                                                         \
+        e = (PS == 10) ? launch_xd_pfb_t<LD, Q, 10>(p, g, fmt, s) : launch_xd_pfb_t<LD, Q, 8>(p, g, fmt, s); \
+        *err = e;                                                                        \
+        return true;                                                                     \
+    }
+    PFB_CASE(5, 5) PFB_CASE(6, 5) PFB_CASE(4, 5) PFB_CASE(3, 7) PFB_CASE(2, 7)
+#undef PFB_CASE
+    return false;
+}
+
 template <int FMT>
 static cudaError_t launch_xd_fmt(const XdParams& p, int variant, cudaStream_t s, int* nlaunch) {
     int max_out = 0;
     for (int v = 0; v < p.njobs; v++) { max_out = p.job[v].n_out > max_out ? p.job[v].n_out : max_out; }
     if (max_out <= 0) { return cudaSuccess; }
     const int D = p.D;
+    if (variant >= 7) {
+        cudaError_t e = cudaSuccess;
+        if (p.pfb_ps > 0 && try_xd_pfb(p, FMT, s, &e)) {
+            if (nlaunch) { (*nlaunch)++; }
+            return e;
+        }
+        variant = 6;
+    }
     if (variant >= 3) {
         cudaError_t e = cudaSuccess;
         if (try_xd_pipe<FMT>(p, s, &e, variant == 4 ? 16 : (variant >= 5 ? 4 : 8), variant == 6)) {

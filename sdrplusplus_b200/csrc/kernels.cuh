@@ -43,6 +43,9 @@ struct XdParams {
     // B = sum Im(g) x;  y(+f) = (A.x - B.y, A.y + B.x),  y(-f) = (A.x + B.y, A.y - B.x).  slot_b = -1: single.
     int nslots;
     signed char slot_a[B200_BATCH], slot_b[B200_BATCH];
+    // polyphase-filter-bank form of stage 1 (xd_pfb.cuh): e^{j w_v PS} = sigma for every job, same taps and alignment.
+    // pfb_ps = 0: not applicable
+    int pfb_ps, pfb_sigma;
     XdJob job[B200_BATCH];
 };
 

@@ -1,0 +1,201 @@
+// sdrplusplus_b200/csrc/xd_pfb.cuh -- stage 1 for VFO plans whose offsets are commensurate with the sample rate
+// ("s1" = 7, the default when it applies; falls back to k_xd_pipe).  Included by kernels.cu after xd_pipe.cuh.
+//
+// Stage 1 computes, for every VFO v,   y_v[m] = e^{j phi_v(i_m)} * sum_k h[k] e^{j w_v k} x[i_m + k]
+// (FrequencyXlator folded into the first DecimatingFIR: frequency_xlator.h:43-50, decimating_fir.h:45-68).
+// When e^{j w_v PS} = sigma (= +1 or -1) for EVERY VFO of the launch -- offsets on a grid of fs / (2 PS), e.g. the
+// +-5/15/25/35 MHz plan of BASELINE config 2 on a 100 MS/s stream: PS = 10, sigma = -1 -- the tap phasor only
+// depends on k mod PS:   e^{j w_v k} = sigma^floor(k / PS) * e^{j w_v (k mod PS)},   so
+//     S_a[m]  = sum_{k = a (mod PS)} sigma^floor(k/PS) h[k] x[i_m + k]        (a < PS; REAL taps, shared by all VFOs)
+//     y_v[m]  = e^{j phi_v(i_m)} * sum_a e^{j w_v a} S_a[m]                     (PS complex MACs per VFO)
+// i.e. a polyphase filter bank: 2 real FMAs per tap and sample for ALL VFOs together instead of 4 per VFO, which
+// moves stage 1 from the fp32 roof to the HBM roof.  The identity is exact for offsets that are exact multiples of
+// fs / (2 PS); the reference's phase increment is the angle of an fp32-rounded phasor, a few 1e-8 rad off that grid:
+// the host accepts a plan when the phase drift across one tap window stays below 1e-6 rad (Scheduler::run), and the
+// output phase e^{j phi_v} keeps using the exact 64-bit phase, so nothing accumulates.
+//
+// Tile = 128 outputs; the D decimation phases of the de-interleaved tile are split over the 4 warps of the CTA; each
+// lane holds 4 outputs x PS complex accumulators; partial sums meet in shared memory (aliased onto the consumed tile).
+#pragma once
+
+template <int LOGD, int QC, int PS>
+__global__ void __launch_bounds__(128, 3) k_xd_pfb(const __grid_constant__ XdParams p, const XpGeom g, const int fmt) {
+    extern __shared__ __align__(16) float2 smem[];
+    constexpr int D = 1 << LOGD, NW = 4, RPER = D / NW, MT = 128;
+    constexpr int WN = (QC + 2) & ~1;             // window samples per output pair (QC + 1 needed, loaded as LDS.128)
+    constexpr int GQ = (QC + 3) & ~3;             // taps per phase row, padded to whole LDS.128
+    const int JP = g.JP;
+    const int tid = threadIdx.x, lane = tid & 31, h = tid >> 5;
+    float2* X = smem;                                               // [D][JP]  (later: partial sums [NW][2][PS][32])
+    constexpr int XP = NW * 2 * PS * 32;
+    float* Gs = reinterpret_cast<float*>(smem + (size_t)max(D * JP, XP));   // [D][GQ] signed real taps
+    float2* C = reinterpret_cast<float2*>(Gs + D * GQ);             // [njobs][PS]  e^{j w_v a}
+    float2* TB = C + (size_t)B200_BATCH * PS;                        // [njobs][MT] phase ramp
+    float2* BASE = TB + (size_t)p.njobs * MT;
+    int* CJ = reinterpret_cast<int*>(BASE + B200_BATCH);
+    int* JN = CJ + B200_BATCH;
+    float2** JOUT = reinterpret_cast<float2**>(BASE + 2 * B200_BATCH);
+
+    // ---- tables (once per CTA) ----
+    {
+        const XdJob& J0j = p.job[0];
+        for (int idx = tid; idx < D * GQ; idx += 128) {
+            const int r = idx / GQ, q = idx - r * GQ;
+            const int k = q * D + r;
+            float t = (q < QC && k < J0j.T) ? __ldg(J0j.h + k) : 0.0f;
+            if (p.pfb_sigma < 0 && ((k / PS) & 1)) { t = -t; }
+            Gs[idx] = t;
+        }
+        for (int idx = tid; idx < p.njobs * PS; idx += 128) {
+            const int v = idx / PS, a = idx - v * PS;
+            C[idx] = phasor_u64(p.job[v].w * (unsigned long long)a);
+        }
+        if (tid < p.njobs) {
+            const XdJob& Jv = p.job[tid];
+            const int a = Jv.offset - (Jv.T - 1) - g.org;            // == 0 (mod D): every job shares job 0's alignment
+            CJ[tid] = a / D;
+            JN[tid] = Jv.n_out;
+            JOUT[tid] = Jv.out;
+        }
+        for (int idx = tid; idx < p.njobs * MT; idx += 128) {
+            const int v = idx / MT, k = idx - v * MT;
+            TB[idx] = phasor_u64(p.job[v].w * (unsigned long long)((long long)k * D));
+        }
+    }
+    const int ntile_samples = D * (MT + QC);
+    const int jl0 = 2 * lane;
+
+    for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+        const long long J0 = g.jmin + (long long)tile * MT;
+        // ---- tile fill: X[r][j] = x((J0 + j) * D + org + r) ----
+        {
+            const long long ibase = J0 * D + g.org;
+            const bool interior = ibase >= 0 && ibase + ntile_samples <= (long long)p.count;
+            const int r = tid & (D - 1);
+            constexpr int jstep = 128 >> LOGD;
+            if (interior && D <= 128) {
+                float2* dst = X + r * JP + (tid >> LOGD);
+                if (fmt == FMT_CF32) {
+                    const float2* src = reinterpret_cast<const float2*>(p.in) + ibase + tid;
+                    for (int idx = tid; idx < ntile_samples; idx += 128) { cp_async8(dst, src); dst += jstep; src += 128; }
+                }
+                else if (fmt == FMT_CS16) {
+                    long long i = ibase + tid;
+#pragma unroll 8
+                    for (int idx = tid; idx < ntile_samples; idx += 128) { *dst = load_iq<FMT_CS16>(p.in, i); dst += jstep; i += 128; }
+                }
+                else {
+                    long long i = ibase + tid;
+#pragma unroll 8
+                    for (int idx = tid; idx < ntile_samples; idx += 128) { *dst = load_iq<FMT_CS8>(p.in, i); dst += jstep; i += 128; }
+                }
+            }
+            else {
+                for (int idx = tid; idx < ntile_samples; idx += 128) {
+                    const long long i = ibase + idx;
+                    float2 v;
+                    if (fmt == FMT_CF32) { v = load_x<FMT_CF32>(p, i); }
+                    else if (fmt == FMT_CS16) { v = load_x<FMT_CS16>(p, i); }
+                    else { v = load_x<FMT_CS8>(p, i); }
+                    X[(idx & (D - 1)) * JP + (idx >> LOGD)] = v;
+                }
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+        }
+        if (tid < p.njobs) {
+            const XdJob& Jv = p.job[tid];
+            const int a0 = Jv.offset - (Jv.T - 1);
+            const long long im0 = (long long)a0 + (J0 - (long long)CJ[tid]) * D;
+            // centre the (tiny) drift of e^{j w PS n} against sigma^n on the middle of the tap window
+            unsigned long long dr = Jv.w * (unsigned long long)PS;
+            if (p.pfb_sigma < 0) { dr -= 0x8000000000000000ULL; }
+            const long long corr = (long long)dr * (long long)(Jv.T / (2 * PS));
+            BASE[tid] = phasor_u64(Jv.phase0 + Jv.w * (unsigned long long)im0 + (unsigned long long)corr);
+        }
+        __syncthreads();
+
+        // ---- accumulate: this warp's RPER phases, 4 outputs x PS accumulators per lane ----
+        float2 acc[4][PS];
+#pragma unroll
+        for (int o = 0; o < 4; o++)
+#pragma unroll
+            for (int a = 0; a < PS; a++) { acc[o][a] = make_float2(0.f, 0.f); }
+#pragma unroll
+        for (int rr = 0; rr < RPER; rr++) {
+            const int r = h * RPER + rr;
+            const float2* row = X + r * JP + jl0;
+            float2 xs[2][WN];
+#pragma unroll
+            for (int pi = 0; pi < 2; pi++) {
+                const float4* src = reinterpret_cast<const float4*>(row + 64 * pi);
+#pragma unroll
+                for (int u = 0; u < WN / 2; u++) {
+                    const float4 t = src[u];
+                    xs[pi][2 * u] = make_float2(t.x, t.y);
+                    xs[pi][2 * u + 1] = make_float2(t.z, t.w);
+                }
+            }
+            float gq[GQ];
+            const float4* gp = reinterpret_cast<const float4*>(Gs + r * GQ);
+#pragma unroll
+            for (int u = 0; u < GQ / 4; u++) {
+                const float4 t = gp[u];
+                gq[4 * u] = t.x; gq[4 * u + 1] = t.y; gq[4 * u + 2] = t.z; gq[4 * u + 3] = t.w;
+            }
+#pragma unroll
+            for (int q = 0; q < QC; q++) {
+                const int a = (q * D + rr) % PS;          // compile-time after unrolling (rot adds the warp's share)
+#pragma unroll
+                for (int pi = 0; pi < 2; pi++)
+#pragma unroll
+                    for (int o = 0; o < 2; o++) {
+                        acc[pi * 2 + o][a] = ffma2(make_float2(gq[q], gq[q]), xs[pi][q + o], acc[pi * 2 + o][a]);
+                    }
+            }
+        }
+
+        // ---- two exchange rounds (outputs {0,1} then {2,3}): publish, sum the 4 warps' partials, combine per VFO ----
+        float2* Pb = X;
+#pragma unroll
+        for (int round = 0; round < 2; round++) {
+            __syncthreads();                                   // tile (round 0) / previous partials (round 1) consumed
+#pragma unroll
+            for (int oo = 0; oo < 2; oo++)
+#pragma unroll
+                for (int a = 0; a < PS; a++) { Pb[((h * 2 + oo) * PS + a) * 32 + lane] = acc[round * 2 + oo][a]; }
+            __syncthreads();
+            const int oo = h & 1, vs = h >> 1;
+            float2 S[PS];
+#pragma unroll
+            for (int a = 0; a < PS; a++) { S[a] = make_float2(0.f, 0.f); }
+#pragma unroll
+            for (int hh = 0; hh < NW; hh++) {
+                const int rh = (hh * RPER) % PS;               // warp hh holds a at a' = (a - rh) mod PS
+#pragma unroll
+                for (int a = 0; a < PS; a++) {
+                    const int ap = (a - rh + PS) % PS;
+                    const float2 t = Pb[((hh * 2 + oo) * PS + ap) * 32 + lane];
+                    S[a].x += t.x; S[a].y += t.y;
+                }
+            }
+            const int jl = jl0 + 64 * round + oo;
+            for (int v = vs; v < p.njobs; v += 2) {
+                float2 A = make_float2(0.f, 0.f), B = make_float2(0.f, 0.f);
+                const float2* cv = C + v * PS;
+#pragma unroll
+                for (int a = 0; a < PS; a++) {
+                    const float2 c = cv[a];
+                    A = ffma2(make_float2(c.x, c.x), S[a], A);
+                    B = ffma2(make_float2(c.y, c.y), S[a], B);
+                }
+                const long long m = J0 + jl - (long long)CJ[v];
+                if (m >= 0 && m < JN[v]) {
+                    const float2 ph = cmulf(BASE[v], TB[(size_t)v * MT + jl]);
+                    JOUT[v][m] = cmulf(make_float2(A.x - B.y, A.y + B.x), ph);
+                }
+            }
+        }
+        __syncthreads();                                       // partial sums consumed before the next tile fill
+    }
+}
