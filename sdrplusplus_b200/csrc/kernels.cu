@@ -879,9 +879,10 @@ static bool try_xd_pipe(const XdParams& p, cudaStream_t s, cudaError_t* err, int
 // ---- polyphase-filter-bank stage 1 (xd_pfb.cuh); returns true when it was launched ----
 template <int LOGD, int QC, int PS>
 static cudaError_t launch_xd_pfb_t(const XdParams& p, const XpGeom& g, int fmt, cudaStream_t s) {
-    constexpr int D = 1 << LOGD, GQ = (QC + 3) & ~3, XP = 4 * 2 * PS * 32;
-    const size_t xf = (size_t)std::max(D * g.JP, XP);
-    const size_t smem = (xf + (size_t)B200_BATCH * PS + (size_t)p.njobs * 128 + 3 * B200_BATCH) * sizeof(float2) + (size_t)D * GQ * sizeof(float);
+    constexpr int D = 1 << LOGD, GQ = (QC + 3) & ~3;
+    const size_t smem = ((size_t)D * g.JP + (size_t)B200_BATCH * (PS + PFB_MT / 16 + 16) + 3 * B200_BATCH) * sizeof(float2) +
+                        (size_t)D * GQ * sizeof(float);
+    if ((int)smem > kernels_max_smem_optin()) { return cudaErrorInvalidValue; }
     cudaError_t e = set_smem(k_xd_pfb<LOGD, QC, PS>, smem);
     if (e != cudaSuccess) { return e; }
     int per_sm = (int)((size_t)233472 / (smem + 1024));
@@ -911,11 +912,11 @@ static bool try_xd_pfb(const XdParams& p, int fmt, cudaStream_t s, cudaError_t* 
     if (jmin & 1) { jmin -= 1; }
     XpGeom g;
     memset(&g, 0, sizeof(g));
-    int jp = 128 + QC + 2;
+    int jp = PFB_MT + QC + 2;
     jp += (jp & 1);
     if ((jp & 3) == 0) { jp += 2; }
-    g.MT = 128; g.JP = jp; g.QPC = QC; g.org = org; g.logD = logD; g.jmin = jmin; g.RS = 4; g.single = 1;
-    g.ntiles = cdiv(jmax - jmin, 128);
+    g.MT = PFB_MT; g.JP = jp; g.QPC = QC; g.org = org; g.logD = logD; g.jmin = jmin; g.RS = 1; g.single = 1;
+    g.ntiles = cdiv(jmax - jmin, PFB_MT);
     cudaError_t e;
 #define PFB_CASE(LD, Q)                                                                  \
     if (logD == LD && QC == Q) {                                                         \

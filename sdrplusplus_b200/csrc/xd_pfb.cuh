@@ -14,24 +14,26 @@
 // the host accepts a plan when the phase drift across one tap window stays below 1e-6 rad (Scheduler::run), and the
 // output phase e^{j phi_v} keeps using the exact 64-bit phase, so nothing accumulates.
 //
-// Tile = 128 outputs; the D decimation phases of the de-interleaved tile are split over the 4 warps of the CTA; each
-// lane holds 4 outputs x PS complex accumulators; partial sums meet in shared memory (aliased onto the consumed tile).
+// Tile = 256 outputs, 64 per warp: a lane walks all D decimation phases of the de-interleaved tile for its 2 outputs
+// (PS complex accumulators each), so no partial sums cross warps; VFOs at +f / -f share the combination sums
+// (XdParams slots).  The per-output phase e^{j phi_v} comes from the exact 64-bit phase: base * ramp_hi * ramp_lo.
 #pragma once
 
+#define PFB_MT 256
 template <int LOGD, int QC, int PS>
 __global__ void __launch_bounds__(128, 3) k_xd_pfb(const __grid_constant__ XdParams p, const XpGeom g, const int fmt) {
     extern __shared__ __align__(16) float2 smem[];
-    constexpr int D = 1 << LOGD, NW = 4, RPER = D / NW, MT = 128;
+    constexpr int D = 1 << LOGD, MT = PFB_MT;
     constexpr int WN = (QC + 2) & ~1;             // window samples per output pair (QC + 1 needed, loaded as LDS.128)
     constexpr int GQ = (QC + 3) & ~3;             // taps per phase row, padded to whole LDS.128
     const int JP = g.JP;
     const int tid = threadIdx.x, lane = tid & 31, h = tid >> 5;
-    float2* X = smem;                                               // [D][JP]  (later: partial sums [NW][2][PS][32])
-    constexpr int XP = NW * 2 * PS * 32;
-    float* Gs = reinterpret_cast<float*>(smem + (size_t)max(D * JP, XP));   // [D][GQ] signed real taps
+    float2* X = smem;                                               // [D][JP]
+    float* Gs = reinterpret_cast<float*>(smem + (size_t)D * JP);    // [D][GQ] signed real taps
     float2* C = reinterpret_cast<float2*>(Gs + D * GQ);             // [njobs][PS]  e^{j w_v a}
-    float2* TB = C + (size_t)B200_BATCH * PS;                        // [njobs][MT] phase ramp
-    float2* BASE = TB + (size_t)p.njobs * MT;
+    float2* TH = C + (size_t)B200_BATCH * PS;                        // [njobs][MT/16] e^{j w_v D 16 i}
+    float2* TL = TH + (size_t)B200_BATCH * (MT / 16);                // [njobs][16]    e^{j w_v D j}
+    float2* BASE = TL + (size_t)B200_BATCH * 16;
     int* CJ = reinterpret_cast<int*>(BASE + B200_BATCH);
     int* JN = CJ + B200_BATCH;
     float2** JOUT = reinterpret_cast<float2**>(BASE + 2 * B200_BATCH);
@@ -57,13 +59,17 @@ __global__ void __launch_bounds__(128, 3) k_xd_pfb(const __grid_constant__ XdPar
             JN[tid] = Jv.n_out;
             JOUT[tid] = Jv.out;
         }
-        for (int idx = tid; idx < p.njobs * MT; idx += 128) {
-            const int v = idx / MT, k = idx - v * MT;
-            TB[idx] = phasor_u64(p.job[v].w * (unsigned long long)((long long)k * D));
+        for (int idx = tid; idx < p.njobs * (MT / 16); idx += 128) {
+            const int v = idx / (MT / 16), i = idx - v * (MT / 16);
+            TH[v * (MT / 16) + i] = phasor_u64(p.job[v].w * (unsigned long long)((long long)i * 16 * D));
+        }
+        for (int idx = tid; idx < p.njobs * 16; idx += 128) {
+            const int v = idx >> 4, j = idx & 15;
+            TL[idx] = phasor_u64(p.job[v].w * (unsigned long long)((long long)j * D));
         }
     }
     const int ntile_samples = D * (MT + QC);
-    const int jl0 = 2 * lane;
+    const int jlw = h * 64 + 2 * lane;              // this lane's first output of the tile
 
     for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
         const long long J0 = g.jmin + (long long)tile * MT;
@@ -77,6 +83,7 @@ __global__ void __launch_bounds__(128, 3) k_xd_pfb(const __grid_constant__ XdPar
                 float2* dst = X + r * JP + (tid >> LOGD);
                 if (fmt == FMT_CF32) {
                     const float2* src = reinterpret_cast<const float2*>(p.in) + ibase + tid;
+#pragma unroll 4
                     for (int idx = tid; idx < ntile_samples; idx += 128) { cp_async8(dst, src); dst += jstep; src += 128; }
                 }
                 else if (fmt == FMT_CS16) {
@@ -115,26 +122,21 @@ __global__ void __launch_bounds__(128, 3) k_xd_pfb(const __grid_constant__ XdPar
         }
         __syncthreads();
 
-        // ---- accumulate: this warp's RPER phases, 4 outputs x PS accumulators per lane ----
-        float2 acc[4][PS];
+        // ---- accumulate: all D phases, 2 outputs x PS accumulators per lane ----
+        float2 S[2][PS];
 #pragma unroll
-        for (int o = 0; o < 4; o++)
+        for (int o = 0; o < 2; o++)
 #pragma unroll
-            for (int a = 0; a < PS; a++) { acc[o][a] = make_float2(0.f, 0.f); }
+            for (int a = 0; a < PS; a++) { S[o][a] = make_float2(0.f, 0.f); }
 #pragma unroll
-        for (int rr = 0; rr < RPER; rr++) {
-            const int r = h * RPER + rr;
-            const float2* row = X + r * JP + jl0;
-            float2 xs[2][WN];
+        for (int r = 0; r < D; r++) {
+            const float4* src = reinterpret_cast<const float4*>(X + r * JP + jlw);
+            float2 xs[WN];
 #pragma unroll
-            for (int pi = 0; pi < 2; pi++) {
-                const float4* src = reinterpret_cast<const float4*>(row + 64 * pi);
-#pragma unroll
-                for (int u = 0; u < WN / 2; u++) {
-                    const float4 t = src[u];
-                    xs[pi][2 * u] = make_float2(t.x, t.y);
-                    xs[pi][2 * u + 1] = make_float2(t.z, t.w);
-                }
+            for (int u = 0; u < WN / 2; u++) {
+                const float4 t = src[u];
+                xs[2 * u] = make_float2(t.x, t.y);
+                xs[2 * u + 1] = make_float2(t.z, t.w);
             }
             float gq[GQ];
             const float4* gp = reinterpret_cast<const float4*>(Gs + r * GQ);
@@ -145,57 +147,42 @@ __global__ void __launch_bounds__(128, 3) k_xd_pfb(const __grid_constant__ XdPar
             }
 #pragma unroll
             for (int q = 0; q < QC; q++) {
-                const int a = (q * D + rr) % PS;          // compile-time after unrolling (rot adds the warp's share)
+                const int a = (q * D + r) % PS;              // compile-time after unrolling
 #pragma unroll
-                for (int pi = 0; pi < 2; pi++)
-#pragma unroll
-                    for (int o = 0; o < 2; o++) {
-                        acc[pi * 2 + o][a] = ffma2(make_float2(gq[q], gq[q]), xs[pi][q + o], acc[pi * 2 + o][a]);
-                    }
+                for (int o = 0; o < 2; o++) { S[o][a] = ffma2(make_float2(gq[q], gq[q]), xs[q + o], S[o][a]); }
             }
         }
 
-        // ---- two exchange rounds (outputs {0,1} then {2,3}): publish, sum the 4 warps' partials, combine per VFO ----
-        float2* Pb = X;
+        // ---- combine per slot (a VFO, or a +f / -f pair sharing A = sum cos*S and B = sum sin*S), rotate, store ----
 #pragma unroll
-        for (int round = 0; round < 2; round++) {
-            __syncthreads();                                   // tile (round 0) / previous partials (round 1) consumed
-#pragma unroll
-            for (int oo = 0; oo < 2; oo++)
-#pragma unroll
-                for (int a = 0; a < PS; a++) { Pb[((h * 2 + oo) * PS + a) * 32 + lane] = acc[round * 2 + oo][a]; }
-            __syncthreads();
-            const int oo = h & 1, vs = h >> 1;
-            float2 S[PS];
-#pragma unroll
-            for (int a = 0; a < PS; a++) { S[a] = make_float2(0.f, 0.f); }
-#pragma unroll
-            for (int hh = 0; hh < NW; hh++) {
-                const int rh = (hh * RPER) % PS;               // warp hh holds a at a' = (a - rh) mod PS
-#pragma unroll
-                for (int a = 0; a < PS; a++) {
-                    const int ap = (a - rh + PS) % PS;
-                    const float2 t = Pb[((hh * 2 + oo) * PS + ap) * 32 + lane];
-                    S[a].x += t.x; S[a].y += t.y;
-                }
-            }
-            const int jl = jl0 + 64 * round + oo;
-            for (int v = vs; v < p.njobs; v += 2) {
+        for (int o = 0; o < 2; o++) {
+            const int jl = jlw + o;
+            for (int sl = 0; sl < p.nslots; sl++) {
+                const int ja = p.slot_a[sl], jb = p.slot_b[sl];
                 float2 A = make_float2(0.f, 0.f), B = make_float2(0.f, 0.f);
-                const float2* cv = C + v * PS;
+                const float2* cv = C + ja * PS;
 #pragma unroll
                 for (int a = 0; a < PS; a++) {
                     const float2 c = cv[a];
-                    A = ffma2(make_float2(c.x, c.x), S[a], A);
-                    B = ffma2(make_float2(c.y, c.y), S[a], B);
+                    A = ffma2(make_float2(c.x, c.x), S[o][a], A);
+                    B = ffma2(make_float2(c.y, c.y), S[o][a], B);
                 }
-                const long long m = J0 + jl - (long long)CJ[v];
-                if (m >= 0 && m < JN[v]) {
-                    const float2 ph = cmulf(BASE[v], TB[(size_t)v * MT + jl]);
-                    JOUT[v][m] = cmulf(make_float2(A.x - B.y, A.y + B.x), ph);
+                {
+                    const long long m = J0 + jl - (long long)CJ[ja];
+                    if (m >= 0 && m < JN[ja]) {
+                        const float2 ph = cmulf(cmulf(BASE[ja], TH[ja * (MT / 16) + (jl >> 4)]), TL[ja * 16 + (jl & 15)]);
+                        JOUT[ja][m] = cmulf(make_float2(A.x - B.y, A.y + B.x), ph);
+                    }
+                }
+                if (jb >= 0) {
+                    const long long m = J0 + jl - (long long)CJ[jb];
+                    if (m >= 0 && m < JN[jb]) {
+                        const float2 ph = cmulf(cmulf(BASE[jb], TH[jb * (MT / 16) + (jl >> 4)]), TL[jb * 16 + (jl & 15)]);
+                        JOUT[jb][m] = cmulf(make_float2(A.x + B.y, A.y - B.x), ph);      // conjugate coefficients
+                    }
                 }
             }
         }
-        __syncthreads();                                       // partial sums consumed before the next tile fill
+        __syncthreads();                                       // tile consumed before the next fill
     }
 }
