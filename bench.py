@@ -373,6 +373,26 @@ def run_b200(args):
                 t.free()
         clk = clocks.stop()
         fe.close()
+        # ---------------- the dominant kernel with nothing else running (explains roofline.frac) ----------------
+        s1_alone = None
+        if rank == 0:
+            fe2 = sb.FrontEnd(FS, chunk)
+            fe2.set_stream(stream.cuda_stream)
+            fe2.set_option("overlap", 0)
+            fe2.set_option("pair", args.pair)
+            fe2.set_option("s1", args.s1)
+            fe2.set_option("tails", args.tails)
+            for o in offsets:
+                fe2.add_vfo(sb.VfoConfig.wfm(o))
+            o2 = make_outputs(False)
+            for k in range(3):
+                fe2.submit_ptr(ptrs[k % nbuf], chunk, lib.FMT_CF32, lib.MEM_DEVICE, o2[0]); fe2.wait()
+            fe2.set_option("time_s1", 1)
+            for k in range(10):
+                fe2.submit_ptr(ptrs[k % nbuf], chunk, lib.FMT_CF32, lib.MEM_DEVICE, o2[0]); fe2.wait()
+            a_ms, a_n = fe2.s1_stats()
+            fe2.close()
+            s1_alone = a_ms / max(a_n, 1)
 
     if rank != 0:
         if world > 1:
@@ -396,15 +416,20 @@ def run_b200(args):
                     host_buffers="b200_host_alloc (cudaHostAlloc)"),
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": "k_xd_pipe (stage 1: translate + first decimating FIR of all VFOs, IQ read once)",
+        "roofline": {"bound": "hbm", "kernel": ("k_xd_pfb" if args.s1 >= 7 and args.offsets == "sym" else "k_xd_pipe") +
+                     " (stage 1: translate + first decimating FIR of all VFOs, IQ read once)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None,
-                     "traffic": 151213056 if (chunk == 1 << 24 and args.offsets == "sym") else None,
-                     "traffic_source": "ncu --set full: dram__bytes_read.sum 134.31 MB + dram__bytes_write.sum 16.91 MB per launch (profiles/r01_ncu_full_xd_pipe_paired.txt)",
+                     "traffic": 151075840 if (chunk == 1 << 24 and args.offsets == "sym") else None,
+                     "traffic_source": "ncu --set full: dram__bytes_read.sum 135.62 MB + dram__bytes_write.sum 15.46 MB per launch (profiles/r01_ncu_full_xd_pfb.txt)",
                      "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": s1_avg, "launches_timed": s1_n,
                      "share_of_step": (s1_ms / ms) if ms else None,
                      "step_level": {"achieved": algo_bytes * args.steps / (ms * 1e-3) / 1e9, "frac": algo_bytes * args.steps / (ms * 1e-3) / 1e9 / peak},
-                     "note": "fp32-FMA bound, not HBM bound: 8 VFOs x 143 complex taps / 32 = 143 FMA per input sample vs 9 B (see DESIGN.md)"},
+                     "alone": ({"avg_launch_ms": s1_alone, "achieved": algo_bytes / (s1_alone * 1e-3) / 1e9,
+                                "frac": algo_bytes / (s1_alone * 1e-3) / 1e9 / peak,
+                                "what": "same kernel, same inputs, no spectrum branch and no overlapped tail kernels on the GPU"} if s1_alone else None),
+                     "note": "avg_launch_ms is measured inside the timed region, where the spectrum and tail kernels of neighbouring chunks share the SMs; "
+                             "'alone' times the same launch with nothing else running. Filter-bank form: 14 FMA per input sample vs 9 B (DESIGN.md section 5)"},
     }
     if world == 1 and not args.no_cpu:
         try:

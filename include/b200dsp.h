@@ -190,8 +190,16 @@ int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt, int in_me
 int b200_fe_wait(b200_fe* fe);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 long long b200_fe_launch_count(b200_fe* fe);
-/* "s1": stage-1 kernel variant for A/B parity runs (0 plain per-output kernel, 1 tiled 4 outputs/lane,
- * 2 tiled 2 outputs/lane); "time_s1": 1 = bracket every stage-1 launch with CUDA events on the handle's stream */
+/* Tuning / A-B switches (defaults are the fast paths; every variant is held to the same parity tests):
+ *  "s1"      stage-1 kernel: 7 polyphase-filter-bank form when the VFO offsets share a frequency grid, else 6 (default);
+ *            6/5/4/3 per-VFO complex taps on cp.async tiles (4-warp x3 per SM / 4-warp / 16-warp / 8-warp CTAs);
+ *            2, 1 single-buffered tiles; 0 one thread per output
+ *  "pair"    1 = VFOs at +f / -f share their stage-1 sums (default)
+ *  "tails"   2 = one fused launch for the stages after stage 1 (default), 1 = one tiled kernel per stage, 0 = plain;
+ *            "ft_threads", "ft_obmax", "ft_ob", "ft_smem_kb", "ft_direct" tune the fused launch.  Before VFOs are added.
+ *  "overlap" 1 = tails of chunk k overlap stage 1 of chunk k+1 on a second stream (default).  Before VFOs are added.
+ *  "fft"     1 = register-resident four-step passes (default), 0 = shared-memory radix-8 passes; "fft_async" 1 = own stream
+ *  "time_s1" 1 = bracket every stage-1 launch with CUDA events on the handle's stream (b200_fe_s1_stats) */
 int b200_fe_set_option(b200_fe* fe, const char* key, int value);
 /* device time spent in the stage-1 (translate + first decimation) launches since the last call, and their count;
  * synchronises on the recorded events ("time_s1" must be on).  bench.py's roofline leg reads this. */
