@@ -912,9 +912,7 @@ static bool try_xd_pfb(const XdParams& p, int fmt, cudaStream_t s, cudaError_t* 
     if (jmin & 1) { jmin -= 1; }
     XpGeom g;
     memset(&g, 0, sizeof(g));
-    int jp = PFB_MT + QC + 2;
-    jp += (jp & 1);
-    if ((jp & 3) == 0) { jp += 2; }
+    int jp = (PFB_MT + QC + 3) | 1;       // odd pitch: the 8-byte de-interleaving stores of a warp hit 32 distinct banks
     g.MT = PFB_MT; g.JP = jp; g.QPC = QC; g.org = org; g.logD = logD; g.jmin = jmin; g.RS = 1; g.single = 1;
     g.ntiles = cdiv(jmax - jmin, PFB_MT);
     cudaError_t e;

@@ -16,7 +16,8 @@
 //
 // Tile = 256 outputs, 64 per warp: a lane walks all D decimation phases of the de-interleaved tile for its 2 outputs
 // (PS complex accumulators each), so no partial sums cross warps; VFOs at +f / -f share the combination sums
-// (XdParams slots).  The per-output phase e^{j phi_v} comes from the exact 64-bit phase: base * ramp_hi * ramp_lo.
+// (XdParams slots).  The per-output phase e^{j phi_v} comes from the exact 64-bit phase: a per-tile table of 16 coarse
+// phases per VFO times a 16-entry fine ramp.
 #pragma once
 
 #define PFB_MT 256
@@ -31,9 +32,9 @@ __global__ void __launch_bounds__(128, 3) k_xd_pfb(const __grid_constant__ XdPar
     float2* X = smem;                                               // [D][JP]
     float* Gs = reinterpret_cast<float*>(smem + (size_t)D * JP);    // [D][GQ] signed real taps
     float2* C = reinterpret_cast<float2*>(Gs + D * GQ);             // [njobs][PS]  e^{j w_v a}
-    float2* TH = C + (size_t)B200_BATCH * PS;                        // [njobs][MT/16] e^{j w_v D 16 i}
-    float2* TL = TH + (size_t)B200_BATCH * (MT / 16);                // [njobs][16]    e^{j w_v D j}
-    float2* BASE = TL + (size_t)B200_BATCH * 16;
+    float2* TL = C + (size_t)B200_BATCH * PS;                        // [njobs][16]    e^{j w_v D j}
+    float2* PHT = TL + (size_t)B200_BATCH * 16;                      // [njobs][MT/16] per tile: base phase * coarse ramp
+    float2* BASE = PHT + (size_t)B200_BATCH * (MT / 16);
     int* CJ = reinterpret_cast<int*>(BASE + B200_BATCH);
     int* JN = CJ + B200_BATCH;
     float2** JOUT = reinterpret_cast<float2**>(BASE + 2 * B200_BATCH);
@@ -58,10 +59,6 @@ __global__ void __launch_bounds__(128, 3) k_xd_pfb(const __grid_constant__ XdPar
             CJ[tid] = a / D;
             JN[tid] = Jv.n_out;
             JOUT[tid] = Jv.out;
-        }
-        for (int idx = tid; idx < p.njobs * (MT / 16); idx += 128) {
-            const int v = idx / (MT / 16), i = idx - v * (MT / 16);
-            TH[v * (MT / 16) + i] = phasor_u64(p.job[v].w * (unsigned long long)((long long)i * 16 * D));
         }
         for (int idx = tid; idx < p.njobs * 16; idx += 128) {
             const int v = idx >> 4, j = idx & 15;
@@ -110,15 +107,19 @@ __global__ void __launch_bounds__(128, 3) k_xd_pfb(const __grid_constant__ XdPar
             cp_async_commit();
             cp_async_wait<0>();
         }
-        if (tid < p.njobs) {
-            const XdJob& Jv = p.job[tid];
-            const int a0 = Jv.offset - (Jv.T - 1);
-            const long long im0 = (long long)a0 + (J0 - (long long)CJ[tid]) * D;
-            // centre the (tiny) drift of e^{j w PS n} against sigma^n on the middle of the tap window
-            unsigned long long dr = Jv.w * (unsigned long long)PS;
-            if (p.pfb_sigma < 0) { dr -= 0x8000000000000000ULL; }
-            const long long corr = (long long)dr * (long long)(Jv.T / (2 * PS));
-            BASE[tid] = phasor_u64(Jv.phase0 + Jv.w * (unsigned long long)im0 + (unsigned long long)corr);
+        {
+            // per-tile phase of every job at the tile's first output, times the coarse ramp: 16 entries per job
+            const int v = tid >> 4, i = tid & 15;                    // MT / 16 == 16 entries, 8 jobs per pass of 128 threads
+            for (int vv = v; vv < p.njobs; vv += 8) {
+                const XdJob& Jv = p.job[vv];
+                const int a0 = Jv.offset - (Jv.T - 1);
+                const long long im0 = (long long)a0 + (J0 - (long long)CJ[vv]) * D;
+                // centre the (tiny) drift of e^{j w PS n} against sigma^n on the middle of the tap window
+                unsigned long long dr = Jv.w * (unsigned long long)PS;
+                if (p.pfb_sigma < 0) { dr -= 0x8000000000000000ULL; }
+                const long long corr = (long long)dr * (long long)(Jv.T / (2 * PS));
+                PHT[vv * (MT / 16) + i] = phasor_u64(Jv.phase0 + Jv.w * (unsigned long long)(im0 + (long long)i * 16 * D) + (unsigned long long)corr);
+            }
         }
         __syncthreads();
 
@@ -130,13 +131,19 @@ __global__ void __launch_bounds__(128, 3) k_xd_pfb(const __grid_constant__ XdPar
             for (int a = 0; a < PS; a++) { S[o][a] = make_float2(0.f, 0.f); }
 #pragma unroll
         for (int r = 0; r < D; r++) {
-            const float4* src = reinterpret_cast<const float4*>(X + r * JP + jlw);
-            float2 xs[WN];
+            // JP is odd (conflict-free de-interleaving stores): odd rows start 8 bytes off a 16-byte boundary, their
+            // window is loaded from one column earlier (sh = 1)
+            constexpr int WNO = (QC + 3) & ~1;
+            const int sh = r & 1;
+            const float4* src = reinterpret_cast<const float4*>(X + r * JP + jlw - sh);
+            float2 xs[WNO];
 #pragma unroll
-            for (int u = 0; u < WN / 2; u++) {
-                const float4 t = src[u];
-                xs[2 * u] = make_float2(t.x, t.y);
-                xs[2 * u + 1] = make_float2(t.z, t.w);
+            for (int u = 0; u < WNO / 2; u++) {
+                if (2 * u < WN + 2 * sh) {
+                    const float4 t = src[u];
+                    xs[2 * u] = make_float2(t.x, t.y);
+                    xs[2 * u + 1] = make_float2(t.z, t.w);
+                }
             }
             float gq[GQ];
             const float4* gp = reinterpret_cast<const float4*>(Gs + r * GQ);
@@ -149,40 +156,43 @@ __global__ void __launch_bounds__(128, 3) k_xd_pfb(const __grid_constant__ XdPar
             for (int q = 0; q < QC; q++) {
                 const int a = (q * D + r) % PS;              // compile-time after unrolling
 #pragma unroll
-                for (int o = 0; o < 2; o++) { S[o][a] = ffma2(make_float2(gq[q], gq[q]), xs[q + o], S[o][a]); }
+                for (int o = 0; o < 2; o++) { S[o][a] = ffma2(make_float2(gq[q], gq[q]), xs[q + o + sh], S[o][a]); }
             }
         }
 
         // ---- combine per slot (a VFO, or a +f / -f pair sharing A = sum cos*S and B = sum sin*S), rotate, store ----
+        // every job of a filter-bank launch has the same alignment and length: one bounds test per output
+        const long long m0 = J0 + jlw - (long long)CJ[0];
+        const bool ok0 = m0 >= 0 && m0 < JN[0], ok1 = (m0 + 1) >= 0 && (m0 + 1) < JN[0];
+        const int ih = jlw >> 4, il = jlw & 15;                 // jlw is even: both outputs share the coarse ramp entry
+        for (int sl = 0; sl < p.nslots; sl++) {
+            const int ja = p.slot_a[sl], jb = p.slot_b[sl];
+            float2 A0 = make_float2(0.f, 0.f), B0 = A0, A1 = A0, B1 = A0;
+            const float2* cv = C + ja * PS;
 #pragma unroll
-        for (int o = 0; o < 2; o++) {
-            const int jl = jlw + o;
-            for (int sl = 0; sl < p.nslots; sl++) {
-                const int ja = p.slot_a[sl], jb = p.slot_b[sl];
-                float2 A = make_float2(0.f, 0.f), B = make_float2(0.f, 0.f);
-                const float2* cv = C + ja * PS;
-#pragma unroll
-                for (int a = 0; a < PS; a++) {
-                    const float2 c = cv[a];
-                    A = ffma2(make_float2(c.x, c.x), S[o][a], A);
-                    B = ffma2(make_float2(c.y, c.y), S[o][a], B);
-                }
-                {
-                    const long long m = J0 + jl - (long long)CJ[ja];
-                    if (m >= 0 && m < JN[ja]) {
-                        const float2 ph = cmulf(cmulf(BASE[ja], TH[ja * (MT / 16) + (jl >> 4)]), TL[ja * 16 + (jl & 15)]);
-                        JOUT[ja][m] = cmulf(make_float2(A.x - B.y, A.y + B.x), ph);
-                    }
-                }
-                if (jb >= 0) {
-                    const long long m = J0 + jl - (long long)CJ[jb];
-                    if (m >= 0 && m < JN[jb]) {
-                        const float2 ph = cmulf(cmulf(BASE[jb], TH[jb * (MT / 16) + (jl >> 4)]), TL[jb * 16 + (jl & 15)]);
-                        JOUT[jb][m] = cmulf(make_float2(A.x + B.y, A.y - B.x), ph);      // conjugate coefficients
-                    }
-                }
+            for (int a = 0; a < PS; a++) {
+                const float2 c = cv[a];
+                A0 = ffma2(make_float2(c.x, c.x), S[0][a], A0);
+                B0 = ffma2(make_float2(c.y, c.y), S[0][a], B0);
+                A1 = ffma2(make_float2(c.x, c.x), S[1][a], A1);
+                B1 = ffma2(make_float2(c.y, c.y), S[1][a], B1);
+            }
+            {
+                const float2 pc = PHT[ja * (MT / 16) + ih];
+                const float2 p0 = cmulf(pc, TL[ja * 16 + il]), p1 = cmulf(pc, TL[ja * 16 + il + 1]);
+                float2* out = JOUT[ja] + m0;
+                if (ok0) { out[0] = cmulf(make_float2(A0.x - B0.y, A0.y + B0.x), p0); }
+                if (ok1) { out[1] = cmulf(make_float2(A1.x - B1.y, A1.y + B1.x), p1); }
+            }
+            if (jb >= 0) {
+                const float2 pc = PHT[jb * (MT / 16) + ih];
+                const float2 p0 = cmulf(pc, TL[jb * 16 + il]), p1 = cmulf(pc, TL[jb * 16 + il + 1]);
+                float2* out = JOUT[jb] + m0;
+                if (ok0) { out[0] = cmulf(make_float2(A0.x + B0.y, A0.y - B0.x), p0); }      // conjugate coefficients
+                if (ok1) { out[1] = cmulf(make_float2(A1.x + B1.y, A1.y - B1.x), p1); }
             }
         }
         __syncthreads();                                       // tile consumed before the next fill
     }
 }
+
