@@ -251,6 +251,30 @@ void      b200_fft_destroy(b200_fft* f);
 void* b200_host_alloc(uint64_t bytes);
 void  b200_host_free(void* p);
 
+/* ------------------------------------------------------------------------------------------
+ * Data formats either side of the path
+ * ------------------------------------------------------------------------------------------ */
+/* Compressed-stream ingest: dsp::compression::SampleStreamDecompressor::process
+ * (core/src/dsp/compression/sample_stream_decompressor.h:15-37).  A packet is an 8-byte header
+ * {u16 compression, u16 PCMType, f32 scaler} + int8 / int16 / float32 I,Q pairs.  b200_pcm_packet_info reads
+ * the header (host memory) and returns the B200_FMT_* of the payload, the conversion factor
+ * 1 / (32768/scaler) resp. 1 / (128/scaler) the reference hands to volk_16i/8i_s32f_convert_32f, the sample
+ * count and the payload offset; b200_fe_set_ingest_scale makes the front end convert the next integer chunks
+ * with that factor (scale <= 0 restores 1/32768, 1/128).  The payload then goes to b200_fe_process as is. */
+int b200_pcm_packet_info(const void* packet, int bytes, int* fmt, float* scale, int* count, int* data_offset);
+int b200_fe_set_ingest_scale(b200_fe* fe, int fmt, float scale);
+/* IQ export: dsp::compression::SampleStreamCompressor::process (sample_stream_compressor.h:30-66): finds the
+ * maximum VALUE of the 2*count floats (volk_32f_index_max_32u), writes header + payload scaled by 32768/max
+ * (int16) or 128/max (int8), rounded like rintf and saturated; B200_FMT_CF32 copies.  Returns the packet size. */
+int b200_pcm_compress(const float* iq, int count, int pcm_fmt, void* packet, int cap_bytes, int mem);
+/* Recorder sample types: wav::Writer::write (core/src/utils/wav.cpp:150-183): uint8 = x*127 + 128 (truncated),
+ * int16 = rint(x*32767) saturated, int32 = rint(x*2147483647) saturated (the device saturates at INT_MAX where the
+ * CPU conversion overflows).  in/out are n floats / n samples in `mem`. */
+#define B200_EXPORT_U8  0
+#define B200_EXPORT_I16 1
+#define B200_EXPORT_I32 2
+int b200_export_convert(const float* in, long long n, int sample_type, void* out, int mem);
+
 #ifdef __cplusplus
 }
 #endif

@@ -128,6 +128,9 @@ class Oracle:
             "orc_zoom": (None, [i, i, i, i, vp, vp]),
             "orc_hold": (None, [vp, vp, i, C.c_float]),
             "orc_i16_to_f32": (None, [vp, vp, i]),
+            "orc_pcm_compress": (i, [i, i, vp, vp]),
+            "orc_pcm_decompress": (i, [i, vp, vp]),
+            "orc_export_convert": (None, [vp, i, i, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -287,6 +290,25 @@ class Oracle:
         latest = _f32(latest)
         self.lib.orc_hold(hold.ctypes.data_as(C.c_void_p), latest.ctypes.data_as(C.c_void_p), hold.size, speed)
         return hold
+
+    def pcm_compress(self, iq, pcm_type):
+        """SampleStreamCompressor::process: complex64 -> packet bytes; pcm_type 0 int8, 1 int16, 2 float32"""
+        x = np.ascontiguousarray(iq, np.complex64)
+        out = np.zeros(8 + x.size * 8, np.uint8)
+        n = self.lib.orc_pcm_compress(int(x.size), int(pcm_type), x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        return out[:n].copy()
+
+    def pcm_decompress(self, packet):
+        b = np.ascontiguousarray(packet, np.uint8)
+        out = np.zeros(max(b.size, 8), np.float32)
+        n = self.lib.orc_pcm_decompress(int(b.size), b.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        return out[: 2 * n].view(np.complex64).copy()
+
+    def export_convert(self, x, typ):
+        a = np.ascontiguousarray(x, np.float32).reshape(-1)
+        out = np.zeros(a.size, {0: np.uint8, 1: np.int16, 2: np.int32}[typ])
+        self.lib.orc_export_convert(a.ctypes.data_as(C.c_void_p), int(a.size), int(typ), out.ctypes.data_as(C.c_void_p))
+        return out
 
     def i16_to_f32(self, x):
         x = np.ascontiguousarray(x, np.int16)

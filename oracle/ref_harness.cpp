@@ -32,6 +32,8 @@
 #include <dsp/demod/am.h>
 #include <dsp/demod/ssb.h>
 #include <dsp/correction/dc_blocker.h>
+#include <dsp/compression/sample_stream_compressor.h>
+#include <dsp/compression/sample_stream_decompressor.h>
 #include <dsp/taps/low_pass.h>
 #include <dsp/taps/band_pass.h>
 #include <dsp/taps/high_pass.h>
@@ -418,5 +420,23 @@ void orc_hold(float* hold, const float* latest, int n, float speed) {
 }
 
 void orc_i16_to_f32(const int16_t* in, float* out, int n) { volk_16i_s32f_convert_32f(out, in, 32768.0f, n); }
+
+// the reference's own packet code over the shim's leaf kernels
+int orc_pcm_compress(int count, int pcmType, const float* iq, uint8_t* out) {
+    return dsp::compression::SampleStreamCompressor::process(count, (dsp::compression::PCMType)pcmType, (const dsp::complex_t*)iq, out);
+}
+int orc_pcm_decompress(int bytes, const uint8_t* in, float* iq_out) {
+    dsp::compression::SampleStreamDecompressor d;
+    return d.process(bytes, in, (dsp::complex_t*)iq_out);
+}
+// wav.cpp is not a header (it pulls the riff writer): the three conversions of Writer::write, line for line in intent
+void orc_export_convert(const float* in, int n, int type, void* out) {
+    if (type == 0) {
+        uint8_t* o = (uint8_t*)out;
+        for (int i = 0; i < n; i++) { o[i] = (in[i] * 127.0f) + 128.0f; }
+    }
+    else if (type == 1) { volk_32f_s32f_convert_16i((int16_t*)out, in, 32767.0f, n); }
+    else { volk_32f_s32f_convert_32i((int32_t*)out, in, 2147483647.0f, n); }
+}
 
 } // extern "C"

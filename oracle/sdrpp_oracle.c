@@ -1014,3 +1014,55 @@ void orc_hold(float* hold, const float* latest, int n, float speed) {
 
 /* file_source int16 ingest  (source_modules/file_source/src/main.cpp:162) */
 void orc_i16_to_f32(const int16_t* in, float* out, int n) { ovk_16i_to_32f(out, in, 32768.0f, (unsigned)n); }
+
+/* SampleStreamCompressor::process (dsp/compression/sample_stream_compressor.h:30-66) */
+int orc_pcm_compress(int count, int pcmType, const float* iq, uint8_t* out) {
+    uint16_t ct = 0, st = (uint16_t)pcmType;
+    memcpy(out, &ct, 2);
+    memcpy(out + 2, &st, 2);
+    if (pcmType == 2) {                                   /* PCM_TYPE_F32: scaler 0, plain copy (:44-48) */
+        float z = 0.0f;
+        memcpy(out + 4, &z, 4);
+        memcpy(out + 8, iq, (size_t)count * 8);
+        return 8 + count * 8;
+    }
+    unsigned int maxIdx = ovk_index_max(iq, (unsigned)count * 2);     /* :51-54: the largest VALUE, not magnitude */
+    float maxVal = iq[maxIdx];
+    memcpy(out + 4, &maxVal, 4);
+    if (pcmType == 0) {                                   /* PCM_TYPE_I8 (:57-59) */
+        ovk_32f_to_8i((int8_t*)(out + 8), iq, 128.0f / maxVal, (unsigned)count * 2);
+        return 8 + count * 2;
+    }
+    ovk_32f_to_16i((int16_t*)(out + 8), iq, 32768.0f / maxVal, (unsigned)count * 2);     /* :61-63 */
+    return 8 + count * 4;
+}
+
+/* SampleStreamDecompressor::process (dsp/compression/sample_stream_decompressor.h:15-37) */
+int orc_pcm_decompress(int bytes, const uint8_t* in, float* iq_out) {
+    uint16_t st;
+    float scaler;
+    memcpy(&st, in + 2, 2);
+    memcpy(&scaler, in + 4, 4);
+    if (st == 2) { memcpy(iq_out, in + 8, (size_t)(bytes - 8)); return (bytes - 8) / 8; }
+    if (st == 1) {
+        int n = (bytes - 8) / 4;
+        ovk_16i_to_32f(iq_out, (const int16_t*)(in + 8), 32768.0f / scaler, (unsigned)n * 2);
+        return n;
+    }
+    if (st == 0) {
+        int n = (bytes - 8) / 2;
+        ovk_8i_to_32f(iq_out, (const int8_t*)(in + 8), 128.0f / scaler, (unsigned)n * 2);
+        return n;
+    }
+    return 0;
+}
+
+/* wav::Writer::write sample conversion (core/src/utils/wav.cpp:150-183) */
+void orc_export_convert(const float* in, int n, int type, void* out) {
+    if (type == 0) {
+        uint8_t* o = (uint8_t*)out;
+        for (int i = 0; i < n; i++) { o[i] = (uint8_t)((in[i] * 127.0f) + 128.0f); }          /* :160-163 */
+    }
+    else if (type == 1) { ovk_32f_to_16i((int16_t*)out, in, 32767.0f, (unsigned)n); }          /* :168 */
+    else { ovk_32f_to_32i((int32_t*)out, in, 2147483647.0f, (unsigned)n); }                    /* :172 */
+}

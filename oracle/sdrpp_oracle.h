@@ -97,6 +97,12 @@ void  orc_hold(float* hold, const float* latest, int n, float speed);
 
 /* file_source int16 ingest (source_modules/file_source/src/main.cpp:162) */
 void  orc_i16_to_f32(const int16_t* in, float* out, int n);
+/* compressed sample stream (dsp/compression/sample_stream_{compressor,decompressor}.h): pcmType 0 int8, 1 int16, 2 float32.
+ * compress: count complex in -> packet bytes (returned); decompress: packet of `bytes` -> complex count (returned) */
+int   orc_pcm_compress(int count, int pcmType, const float* iq, uint8_t* out);
+int   orc_pcm_decompress(int bytes, const uint8_t* in, float* iq_out);
+/* recorder sample conversion (core/src/utils/wav.cpp:150-183): type 0 uint8, 1 int16, 2 int32 */
+void  orc_export_convert(const float* in, int n, int type, void* out);
 
 #ifdef __cplusplus
 }

@@ -105,6 +105,9 @@ static inline void volk_32f_s32f_convert_16i(int16_t* out, const float* in, cons
         out[k] = (int16_t)rintf(r);
     }
 }
+static inline void volk_32f_s32f_convert_32i(int32_t* out, const float* in, const float scalar, unsigned int n) {
+    ovk_32f_to_32i(out, in, scalar, n);
+}
 static inline void volk_32f_s32f_convert_8i(int8_t* out, const float* in, const float scalar, unsigned int n) {
     for (unsigned int k = 0; k < n; k++) {
         float r = in[k] * scalar;

@@ -173,6 +173,37 @@ static inline void ovk_8i_to_32f(float* out, const int8_t* in, float scalar, uns
     for (unsigned int i = 0; i < n; i++) { out[i] = (float)in[i] * inv; }
 }
 
+/* volk_32f_s32f_convert_{8i,16i,32i}: r = in * scalar, clamped to the type's range, rounded with rintf
+ * (call sites: sample_stream_compressor.h:56,60; wav.cpp:168,172) */
+static inline void ovk_32f_to_8i(int8_t* out, const float* in, float scalar, unsigned int n) {
+    for (unsigned int i = 0; i < n; i++) {
+        float r = in[i] * scalar;
+        if (r > 127.0f) { r = 127.0f; } else if (r < -128.0f) { r = -128.0f; }
+        out[i] = (int8_t)rintf(r);
+    }
+}
+static inline void ovk_32f_to_16i(int16_t* out, const float* in, float scalar, unsigned int n) {
+    for (unsigned int i = 0; i < n; i++) {
+        float r = in[i] * scalar;
+        if (r > 32767.0f) { r = 32767.0f; } else if (r < -32768.0f) { r = -32768.0f; }
+        out[i] = (int16_t)rintf(r);
+    }
+}
+static inline void ovk_32f_to_32i(int32_t* out, const float* in, float scalar, unsigned int n) {
+    for (unsigned int i = 0; i < n; i++) {
+        float r = in[i] * scalar;
+        if (r > 2147483647.0f) { r = 2147483647.0f; } else if (r < -2147483648.0f) { r = -2147483648.0f; }
+        /* (float)INT_MAX is 2^31: the conversion of a clamped top value is out of range on the CPU; pin it */
+        out[i] = (r >= 2147483648.0f) ? 2147483647 : (int32_t)rintf(r);
+    }
+}
+/* volk_32f_index_max_32u: first index of the largest value */
+static inline unsigned int ovk_index_max(const float* in, unsigned int n) {
+    float mx = in[0]; unsigned int idx = 0;
+    for (unsigned int i = 1; i < n; i++) { if (in[i] > mx) { mx = in[i]; idx = i; } }
+    return idx;
+}
+
 #ifdef __cplusplus
 }
 #endif

@@ -185,7 +185,16 @@ struct b200_fe {
     cudaEvent_t ev_h2d[2] = { nullptr, nullptr }, ev_compute[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
     bool slot_used[2] = { false, false };
     unsigned long long nsub = 0, nwait = 0;
+    float scale16 = 1.0f / 32768.0f, scale8 = 1.0f / 128.0f;
 };
+
+// (float)x * scale for the integer input formats: 1/32768 and 1/128 unless the caller set the scale of a
+// compressed-stream packet (b200_fe_set_ingest_scale)
+static float fe_ingest_scale(const b200_fe* fe, int fmt) {
+    if (fmt == B200_FMT_CS16) { return fe->scale16; }
+    if (fmt == B200_FMT_CS8) { return fe->scale8; }
+    return 0.0f;
+}
 
 static int fe_alloc_fft(b200_fe* fe) {
     int rc;
@@ -457,6 +466,8 @@ static int fe_fft_chunk(b200_fe* fe, const void* dptr, int fmt, int count, int* 
     const unsigned long long pos = fe->pos, end = pos + (unsigned long long)count;
     const unsigned long long nz = (unsigned long long)fe->fft.nz, interval = nz + (unsigned long long)fe->skip;
     const int bps = bytes_per_sample(fmt);
+    const float isc = fe_ingest_scale(fe, fmt);
+    fe->fft.plan.in_scale = isc;
     cudaStream_t main_s = fe->sch.stream;
     // with overlapped tails the spectrum branch must be on its own stream (its output leaves through the tail stream)
     const bool async = fe->fft_async || fe->sch.tail_stream != nullptr;
@@ -482,7 +493,7 @@ static int fe_fft_chunk(b200_fe* fe, const void* dptr, int fmt, int count, int* 
         const unsigned long long lo = pos, hi = std::min(fend, end);
         if (hi > lo) {
             if ((rc = fork())) { return rc; }
-            cudaError_t e = launch_convert_cf32(dptr, fmt, fe->frame.as<float2>() + (size_t)(lo - fe->fstart), (int)(hi - lo), s);
+            cudaError_t e = launch_convert_cf32(dptr, fmt, fe->frame.as<float2>() + (size_t)(lo - fe->fstart), (int)(hi - lo), isc, s);
             if (e != cudaSuccess) { return cuda_fail(e, "launch_convert_cf32"); }
             fe->sch.launches++;
         }
@@ -517,7 +528,7 @@ static int fe_fft_chunk(b200_fe* fe, const void* dptr, int fmt, int count, int* 
         if (hi > lo) {
             if ((rc = fork())) { return rc; }
             const char* src = (const char*)dptr + (size_t)(lo - pos) * bps;
-            cudaError_t e = launch_convert_cf32(src, fmt, fe->frame.as<float2>(), (int)(hi - lo), s);
+            cudaError_t e = launch_convert_cf32(src, fmt, fe->frame.as<float2>(), (int)(hi - lo), isc, s);
             if (e != cudaSuccess) { return cuda_fail(e, "launch_convert_cf32"); }
             fe->sch.launches++;
         }
@@ -593,6 +604,7 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
     // fork the spectrum branch first; its join (a wait on the main stream) comes after the VFO branch has been
     // enqueued, so the two overlap on the device
     if ((rc = fe_fft_chunk(fe, dptr, in_fmt, count, &nlines))) { return rc; }
+    fe->sch.in_scale = fe_ingest_scale(fe, in_fmt);
     if ((rc = fe->sch.run(chains, dptr, in_fmt, count, true))) { return rc; }
     cudaStream_t os = fe->sch.out_stream();       // tail stream in overlapped mode, else the main stream
     if (fe->fft_join_pending) {
@@ -906,4 +918,108 @@ extern "C" void* b200_host_alloc(uint64_t bytes) {
 }
 extern "C" void b200_host_free(void* p) {
     if (p) { cudaFreeHost(p); }
+}
+
+
+// ------------------------------------------------------------------ data formats either side of the path
+extern "C" int b200_fe_set_ingest_scale(b200_fe* fe, int fmt, float scale) {
+    if (!fe) { set_error("null fe"); return B200_EINVAL; }
+    std::lock_guard<std::mutex> lck(fe->mtx);
+    if (fmt == B200_FMT_CS16) { fe->scale16 = scale > 0.0f ? scale : 1.0f / 32768.0f; return 0; }
+    if (fmt == B200_FMT_CS8) { fe->scale8 = scale > 0.0f ? scale : 1.0f / 128.0f; return 0; }
+    set_error("ingest scale applies to B200_FMT_CS16 / B200_FMT_CS8");
+    return B200_EINVAL;
+}
+
+// SampleStreamDecompressor::process header (sample_stream_decompressor.h:15-33)
+extern "C" int b200_pcm_packet_info(const void* packet, int bytes, int* fmt, float* scale, int* count, int* data_offset) {
+    if (!packet || bytes < 8 || !fmt || !scale || !count || !data_offset) { set_error("bad packet"); return B200_EINVAL; }
+    const unsigned char* b = (const unsigned char*)packet;
+    unsigned short sampleType;
+    float scaler;
+    memcpy(&sampleType, b + 2, 2);
+    memcpy(&scaler, b + 4, 4);
+    *data_offset = 8;
+    if (sampleType == 2) { *fmt = B200_FMT_CF32; *scale = 0.0f; *count = (bytes - 8) / 8; return 0; }          // PCM_TYPE_F32
+    if (sampleType == 1) { *fmt = B200_FMT_CS16; *scale = 1.0f / (32768.0f / scaler); *count = (bytes - 8) / 4; return 0; }
+    if (sampleType == 0) { *fmt = B200_FMT_CS8; *scale = 1.0f / (128.0f / scaler); *count = (bytes - 8) / 2; return 0; }
+    set_error("unknown PCM sample type %d", (int)sampleType);
+    return B200_EINVAL;
+}
+
+static int export_scalar(int type, float* scalar) {
+    switch (type) {
+    case B200_EXPORT_U8: *scalar = 0.0f; return EXP_U8;
+    case B200_EXPORT_I16: *scalar = 32767.0f; return EXP_I16;            // wav.cpp:168
+    case B200_EXPORT_I32: *scalar = 2147483647.0f; return EXP_I32;       // wav.cpp:172
+    default: return -1;
+    }
+}
+static size_t export_bytes(int t) { return t == EXP_I32 ? 4 : (t == EXP_I16 ? 2 : 1); }
+
+// wav::Writer::write sample conversion (core/src/utils/wav.cpp:150-183) on the device
+extern "C" int b200_export_convert(const float* in, long long n, int sample_type, void* out, int mem) {
+    if (!in || !out || n < 0) { set_error("null argument"); return B200_EINVAL; }
+    float scalar;
+    const int t = export_scalar(sample_type, &scalar);
+    if (t < 0) { set_error("bad sample type %d", sample_type); return B200_EINVAL; }
+    if (n == 0) { return 0; }
+    if (mem == B200_MEM_DEVICE) {
+        cudaError_t e = launch_export(in, n, t, scalar, out, nullptr);
+        if (e != cudaSuccess) { return cuda_fail(e, "launch_export"); }
+        B200_CK(cudaStreamSynchronize(nullptr));
+        return 0;
+    }
+    DevBuf di, dout;
+    int rc;
+    if ((rc = di.alloc((size_t)n * sizeof(float), false)) || (rc = dout.alloc((size_t)n * export_bytes(t), false))) { return rc; }
+    B200_CK(cudaMemcpy(di.p, in, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    cudaError_t e = launch_export(di.as<float>(), n, t, scalar, dout.p, nullptr);
+    if (e != cudaSuccess) { return cuda_fail(e, "launch_export"); }
+    B200_CK(cudaMemcpy(out, dout.p, (size_t)n * export_bytes(t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// SampleStreamCompressor::process (sample_stream_compressor.h:30-66): 8-byte header + PCM payload
+extern "C" int b200_pcm_compress(const float* iq, int count, int pcm_fmt, void* packet, int cap_bytes, int mem) {
+    if (!iq || !packet || count < 0) { set_error("null argument"); return B200_EINVAL; }
+    const int bps = pcm_fmt == B200_FMT_CF32 ? 8 : (pcm_fmt == B200_FMT_CS16 ? 4 : (pcm_fmt == B200_FMT_CS8 ? 2 : 0));
+    if (!bps) { set_error("bad pcm format %d", pcm_fmt); return B200_EINVAL; }
+    const int bytes = 8 + count * bps;
+    if (cap_bytes < bytes) { set_error("packet buffer too small"); return B200_ECAP; }
+    const unsigned short sampleType = pcm_fmt == B200_FMT_CF32 ? 2 : (pcm_fmt == B200_FMT_CS16 ? 1 : 0);
+    const bool dev = mem == B200_MEM_DEVICE;
+    DevBuf di, dout, dmax;
+    int rc;
+    const float* src = iq;
+    if (!dev) {
+        if ((rc = di.alloc((size_t)count * 8 + 16, false))) { return rc; }
+        B200_CK(cudaMemcpy(di.p, iq, (size_t)count * 8, cudaMemcpyHostToDevice));
+        src = di.as<float>();
+    }
+    unsigned char hdr[8] = { 0 };
+    memcpy(hdr + 2, &sampleType, 2);
+    unsigned char* dst = (unsigned char*)packet;
+    if ((rc = dout.alloc((size_t)bytes + 16, false))) { return rc; }
+    unsigned char* dpk = dev ? dst : dout.as<unsigned char>();
+    if (pcm_fmt == B200_FMT_CF32) {
+        B200_CK(cudaMemcpy(dpk + 8, src, (size_t)count * 8, cudaMemcpyDeviceToDevice));
+    }
+    else {
+        if ((rc = dmax.alloc(16, true))) { return rc; }
+        float maxVal = 0.0f;
+        if (count > 0) {
+            cudaError_t e = launch_index_max(src, (long long)count * 2, dmax.as<float>(), nullptr);
+            if (e != cudaSuccess) { return cuda_fail(e, "launch_index_max"); }
+            B200_CK(cudaMemcpy(&maxVal, dmax.p, sizeof(float), cudaMemcpyDeviceToHost));
+        }
+        memcpy(hdr + 4, &maxVal, 4);
+        const float scalar = (pcm_fmt == B200_FMT_CS16 ? 32768.0f : 128.0f) / maxVal;
+        cudaError_t e = launch_export(src, (long long)count * 2, pcm_fmt == B200_FMT_CS16 ? EXP_I16 : EXP_I8, scalar, dpk + 8, nullptr);
+        if (e != cudaSuccess) { return cuda_fail(e, "launch_export"); }
+    }
+    B200_CK(cudaMemcpy(dpk, hdr, 8, cudaMemcpyHostToDevice));
+    if (!dev) { B200_CK(cudaMemcpy(dst, dpk, (size_t)bytes, cudaMemcpyDeviceToHost)); }
+    else { B200_CK(cudaStreamSynchronize(nullptr)); }
+    return bytes;
 }

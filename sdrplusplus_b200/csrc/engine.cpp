@@ -750,6 +750,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
             p.hist_len = RAW_HIST;
             p.count = count;
             p.D = kv.first;
+            p.in_scale = in_scale;
             p.QP = 1;
             p.njobs = (int)std::min<size_t>(B200_BATCH, g.size() - b);
             for (int v = 0; v < p.njobs; v++) {
@@ -864,7 +865,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
         rc1.njobs = 1;
         CarryJob& j = rc1.job[0];
         j.dst = raw_hist.as<float>(); j.a = raw_hist.as<float>(); j.b = raw;
-        j.h = RAW_HIST; j.la = RAW_HIST; j.lb = count; j.esize = 2; j.bfmt = fmt;
+        j.h = RAW_HIST; j.la = RAW_HIST; j.lb = count; j.esize = 2; j.bfmt = fmt; j.scale = in_scale;
         cudaError_t e = launch_carry(rc1, stream);
         if (e != cudaSuccess) { return cuda_fail(e, "launch_carry"); }
         launches++;
@@ -1071,7 +1072,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
             if (s->n_in <= 0 && !s->dbl) { continue; }      // a double-buffered stage always hands its history over
             CarryJob j;
             j.dst = s->other_base(); j.a = s->base(); j.b = s->in_data();
-            j.h = s->hist; j.la = s->hist; j.lb = s->n_in; j.esize = s->in_es; j.bfmt = -1;
+            j.h = s->hist; j.la = s->hist; j.lb = s->n_in; j.esize = s->in_es; j.bfmt = -1; j.scale = 0.0f;
             int rc = push(j);
             if (rc) { return rc; }
         }

@@ -208,6 +208,7 @@ struct Scheduler {
     int s1_variant = 7;          // 7: polyphase-filter-bank stage 1 when the VFO plan allows it, else 6
     FuseCfg fuse;                // tails: one fused launch per <= 16 VFOs instead of one launch per stage kind
     int sm_count = 148;
+    float in_scale = 1.0f / 32768.0f;   // integer raw formats of this chunk: sample = (float)x * in_scale (set by the caller)
     bool pair_conjugates = true;   // stage 1: VFOs at +f / -f share their multiply-accumulates (exact identity)
     // optional device-side timing of the stage-1 launches (bench.py's roofline leg): CUDA events on `stream`
     bool time_s1 = false;

@@ -24,19 +24,21 @@
 // ------------------------------------------------------------------------------------------------
 // helpers
 // ------------------------------------------------------------------------------------------------
+// sc = 1 / scalar of volk_16i_s32f_convert_32f / volk_8i_s32f_convert_32f: 1/32768 for file_source's int16
+// (file_source main.cpp:162), 1/128 for int8, scaler/32768 resp. scaler/128 for a compressed-stream packet
+// (sample_stream_decompressor.h:24-33); unused for cf32
 template <int FMT>
-__device__ __forceinline__ float2 load_iq(const void* __restrict__ p, long long i) {
+__device__ __forceinline__ float2 load_iq(const void* __restrict__ p, long long i, float sc) {
     if (FMT == FMT_CF32) {
         return __ldg(reinterpret_cast<const float2*>(p) + i);
     }
     else if (FMT == FMT_CS16) {
         short2 v = __ldg(reinterpret_cast<const short2*>(p) + i);
-        // volk_16i_s32f_convert_32f(.., 32768.0f): (float)x * (1/32768)  (file_source main.cpp:162)
-        return make_float2((float)v.x * (1.0f / 32768.0f), (float)v.y * (1.0f / 32768.0f));
+        return make_float2((float)v.x * sc, (float)v.y * sc);
     }
     else {
         char2 v = __ldg(reinterpret_cast<const char2*>(p) + i);
-        return make_float2((float)v.x * (1.0f / 128.0f), (float)v.y * (1.0f / 128.0f));
+        return make_float2((float)v.x * sc, (float)v.y * sc);
     }
 }
 
@@ -44,7 +46,7 @@ __device__ __forceinline__ float2 load_iq(const void* __restrict__ p, long long 
 template <int FMT>
 __device__ __forceinline__ float2 load_x(const XdParams& p, long long i) {
     if (i >= 0) {
-        if (i < p.count) { return load_iq<FMT>(p.in, i); }
+        if (i < p.count) { return load_iq<FMT>(p.in, i, p.in_scale); }
         return make_float2(0.0f, 0.0f);
     }
     long long h = (long long)p.hist_len + i;
@@ -460,9 +462,9 @@ __device__ __forceinline__ float carry_elem(const CarryJob& J, long long s, int 
     long long b = s - J.la;
     if (J.bfmt < 0) { return reinterpret_cast<const float*>(J.b)[b * J.esize + comp]; }
     float2 v;
-    if (J.bfmt == FMT_CF32) { v = load_iq<FMT_CF32>(J.b, b); }
-    else if (J.bfmt == FMT_CS16) { v = load_iq<FMT_CS16>(J.b, b); }
-    else { v = load_iq<FMT_CS8>(J.b, b); }
+    if (J.bfmt == FMT_CF32) { v = load_iq<FMT_CF32>(J.b, b, 0.0f); }
+    else if (J.bfmt == FMT_CS16) { v = load_iq<FMT_CS16>(J.b, b, J.scale); }
+    else { v = load_iq<FMT_CS8>(J.b, b, J.scale); }
     return comp ? v.y : v.x;
 }
 __global__ void __launch_bounds__(256) k_carry(const __grid_constant__ CarryParams p) {
@@ -604,7 +606,7 @@ __device__ __forceinline__ float power_db(float2 X, float normFactSq) {
 template <int FMT>
 __device__ __forceinline__ float2 load_windowed(const FftPlanDev& pl, const void* __restrict__ src, int n) {
     if (n >= pl.nz) { return make_float2(0.0f, 0.0f); }    // zero padding [nz, N)  (iq_frontend.cpp:301)
-    float2 x = load_iq<FMT>(src, n);
+    float2 x = load_iq<FMT>(src, n, pl.in_scale);
     float w = __ldg(pl.window + n);
     return make_float2(x.x * w, x.y * w);
 }
@@ -687,9 +689,9 @@ __global__ void __launch_bounds__(512) k_fft_p2(const __grid_constant__ FftPlanD
 #include "fft_reg.cuh"
 
 template <int FMT>
-__global__ void __launch_bounds__(256) k_convert(const void* __restrict__ src, float2* __restrict__ dst, int n) {
+__global__ void __launch_bounds__(256) k_convert(const void* __restrict__ src, float2* __restrict__ dst, int n, float sc) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { dst[i] = load_iq<FMT>(src, i); }
+    if (i < n) { dst[i] = load_iq<FMT>(src, i, sc); }
 }
 
 // doZoom + hold; start/len come from the host, which runs the reference's fp32 index loop verbatim so the
@@ -1250,12 +1252,79 @@ cudaError_t launch_fft_frame(const FftPlanDev& pl, const void* src, int fmt, flo
     return launch_fft_frames(pl, src, fmt, work, out_db, out_raw, s, nlaunch, 1, 0);
 }
 
-cudaError_t launch_convert_cf32(const void* src, int fmt, float2* dst, int n, cudaStream_t s) {
+cudaError_t launch_convert_cf32(const void* src, int fmt, float2* dst, int n, float scale, cudaStream_t s) {
     if (n <= 0) { return cudaSuccess; }
     int grid = cdiv(n, 256);
-    if (fmt == FMT_CF32) { k_convert<FMT_CF32><<<grid, 256, 0, s>>>(src, dst, n); }
-    else if (fmt == FMT_CS16) { k_convert<FMT_CS16><<<grid, 256, 0, s>>>(src, dst, n); }
-    else { k_convert<FMT_CS8><<<grid, 256, 0, s>>>(src, dst, n); }
+    if (fmt == FMT_CF32) { k_convert<FMT_CF32><<<grid, 256, 0, s>>>(src, dst, n, scale); }
+    else if (fmt == FMT_CS16) { k_convert<FMT_CS16><<<grid, 256, 0, s>>>(src, dst, n, scale); }
+    else { k_convert<FMT_CS8><<<grid, 256, 0, s>>>(src, dst, n, scale); }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// export formats: recorder sample types (wav.cpp:150-183) and the compressed-stream packet payload
+// (sample_stream_compressor.h:30-66).  r = x * scalar, clamped, rounded to nearest-even like rintf.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_export(const float* __restrict__ in, long long n, int type, float scalar, void* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) { return; }
+    const float x = __ldg(in + i);
+    if (type == EXP_U8) {
+        // bufU8[i] = (samples[i] * 127.0f) + 128.0f   (float -> uint8_t conversion truncates)
+        const float v = __fadd_rn(__fmul_rn(x, 127.0f), 128.0f);
+        reinterpret_cast<unsigned char*>(out)[i] = (unsigned char)__float2int_rz(v);
+    }
+    else if (type == EXP_I8) {
+        float r = __fmul_rn(x, scalar);
+        r = fminf(fmaxf(r, -128.0f), 127.0f);
+        reinterpret_cast<signed char*>(out)[i] = (signed char)__float2int_rn(r);
+    }
+    else if (type == EXP_I16) {
+        float r = __fmul_rn(x, scalar);
+        r = fminf(fmaxf(r, -32768.0f), 32767.0f);
+        reinterpret_cast<short*>(out)[i] = (short)__float2int_rn(r);
+    }
+    else {
+        float r = __fmul_rn(x, scalar);
+        r = fminf(fmaxf(r, -2147483648.0f), 2147483648.0f);
+        reinterpret_cast<int*>(out)[i] = __float2int_rn(r);          // saturates at INT_MAX where the CPU conversion overflows
+    }
+}
+cudaError_t launch_export(const float* in, long long n, int type, float scalar, void* out, cudaStream_t s) {
+    if (n <= 0) { return cudaSuccess; }
+    k_export<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, n, type, scalar, out);
+    return cudaGetLastError();
+}
+// first index of the maximum VALUE (not magnitude) of n floats: volk_32f_index_max_32u.  One CTA; key = (value, -index).
+__global__ void __launch_bounds__(1024) k_index_max(const float* __restrict__ in, long long n, float* __restrict__ out_val) {
+    __shared__ float sv[32];
+    __shared__ long long si[32];
+    float best = -INFINITY;
+    long long bi = 0x7fffffffffffffffLL;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = __ldg(in + i);
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        const float ov = __shfl_down_sync(0xffffffffu, best, d);
+        const long long oi = __shfl_down_sync(0xffffffffu, bi, d);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = (threadIdx.x < (blockDim.x >> 5)) ? sv[threadIdx.x] : -INFINITY;
+        bi = (threadIdx.x < (blockDim.x >> 5)) ? si[threadIdx.x] : 0x7fffffffffffffffLL;
+        for (int d = 16; d > 0; d >>= 1) {
+            const float ov = __shfl_down_sync(0xffffffffu, best, d);
+            const long long oi = __shfl_down_sync(0xffffffffu, bi, d);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (threadIdx.x == 0) { *out_val = best; }
+    }
+}
+cudaError_t launch_index_max(const float* in, long long n, float* out_val, cudaStream_t s) {
+    k_index_max<<<1, 1024, 0, s>>>(in, n, out_val);
     return cudaGetLastError();
 }
 

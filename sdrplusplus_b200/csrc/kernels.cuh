@@ -46,6 +46,7 @@ struct XdParams {
     // polyphase-filter-bank form of stage 1 (xd_pfb.cuh): e^{j w_v PS} = sigma for every job, same taps and alignment.
     // pfb_ps = 0: not applicable
     int pfb_ps, pfb_sigma;
+    float in_scale;         // integer formats: sample = (float)x * in_scale
     XdJob job[B200_BATCH];
 };
 
@@ -215,6 +216,7 @@ struct CarryJob {
     int h, la, lb;          // element counts
     int esize;              // floats per element (1 or 2)
     int bfmt;               // format of b: -1 = float elements of esize, else FMT_* (IQ input -> cf32)
+    float scale;            // integer formats: sample = (float)x * scale
 };
 #define CARRY_BATCH 64
 struct CarryParams { int njobs; CarryJob job[CARRY_BATCH]; };
@@ -228,6 +230,7 @@ struct FftPlanDev {
     int TW, logTW;
     const float2* tw_fine;  // exp(-2 pi i j / N), j < N / TW (two-pass plans; null otherwise)
     const float* window;    // nz floats: window(i,nz) * (-1)^i
+    float in_scale;         // integer input formats: sample = (float)x * in_scale
     int nz;
 };
 
@@ -247,7 +250,10 @@ cudaError_t launch_fft_frame(const FftPlanDev& pl, const void* src, int fmt, flo
 // nbatch equally spaced frames (src_stride_bytes apart) in one launch pair; work: nbatch*N float2, out_db: nbatch*N
 cudaError_t launch_fft_frames(const FftPlanDev& pl, const void* src, int fmt, float2* work, float* out_db,
                               float2* out_raw, cudaStream_t s, int* nlaunch, int nbatch, long long src_stride_bytes);
-cudaError_t launch_convert_cf32(const void* src, int fmt, float2* dst, int n, cudaStream_t s);
+cudaError_t launch_convert_cf32(const void* src, int fmt, float2* dst, int n, float scale, cudaStream_t s);
+enum { EXP_U8 = 0, EXP_I8 = 1, EXP_I16 = 2, EXP_I32 = 3 };
+cudaError_t launch_export(const float* in, long long n, int type, float scalar, void* out, cudaStream_t s);
+cudaError_t launch_index_max(const float* in, long long n, float* out_val, cudaStream_t s);
 // start/len: per-pixel bin ranges built on the host with the reference's fp32 index loop
 cudaError_t launch_zoom_hold_tbl(const float* line, const int* start, const int* len, int out_size, float* out,
                                  float* hold, float hold_speed, cudaStream_t s);

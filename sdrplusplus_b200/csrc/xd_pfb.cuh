@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(128, 3) k_xd_pfb(const __grid_constant__ XdPar
             TL[idx] = phasor_u64(p.job[v].w * (unsigned long long)((long long)j * D));
         }
     }
+    __syncthreads();                                // CJ is read by other threads when the first tile's phase table is built
     const int ntile_samples = D * (MT + QC);
     const int jlw = h * 64 + 2 * lane;              // this lane's first output of the tile
 
@@ -86,12 +87,12 @@ __global__ void __launch_bounds__(128, 3) k_xd_pfb(const __grid_constant__ XdPar
                 else if (fmt == FMT_CS16) {
                     long long i = ibase + tid;
 #pragma unroll 8
-                    for (int idx = tid; idx < ntile_samples; idx += 128) { *dst = load_iq<FMT_CS16>(p.in, i); dst += jstep; i += 128; }
+                    for (int idx = tid; idx < ntile_samples; idx += 128) { *dst = load_iq<FMT_CS16>(p.in, i, p.in_scale); dst += jstep; i += 128; }
                 }
                 else {
                     long long i = ibase + tid;
 #pragma unroll 8
-                    for (int idx = tid; idx < ntile_samples; idx += 128) { *dst = load_iq<FMT_CS8>(p.in, i); dst += jstep; i += 128; }
+                    for (int idx = tid; idx < ntile_samples; idx += 128) { *dst = load_iq<FMT_CS8>(p.in, i, p.in_scale); dst += jstep; i += 128; }
                 }
             }
             else {

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(NT, 1) k_xd_pipe(const __grid_constant__ XdPar
             long long i = ibase + tid;
 #pragma unroll 8
             for (int idx = tid; idx < ntile_samples; idx += nthr) {
-                *dst = load_iq<FMT>(p.in, i);
+                *dst = load_iq<FMT>(p.in, i, p.in_scale);
                 dst += jstep;
                 i += nthr;
             }

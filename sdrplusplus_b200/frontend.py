@@ -120,6 +120,10 @@ class FrontEnd:
     def set_vfo_bandwidth(self, vid, bw):
         L.check(self._l.b200_fe_set_vfo_bandwidth(self._h, vid, float(bw)))
 
+    def set_ingest_scale(self, fmt, scale):
+        """Conversion factor of the next int16 / int8 chunks (a compressed-stream packet's scaler); <= 0: default."""
+        L.check(self._l.b200_fe_set_ingest_scale(self._h, int(fmt), float(scale)))
+
     def set_option(self, key, value):
         L.check(self._l.b200_fe_set_option(self._h, key.encode(), int(value)))
 
@@ -370,3 +374,33 @@ def fft_frame_params(sr, size, rate):
     nz, skip = C.c_int(), C.c_int()
     L.check(l.b200_fft_frame_params(sr, size, rate, C.byref(nz), C.byref(skip)))
     return nz.value, skip.value
+
+
+# ---------------------------------------------------------------------------------------------- data formats
+EXPORT_U8, EXPORT_I16, EXPORT_I32 = 0, 1, 2
+
+
+def pcm_packet_info(packet):
+    """(fmt, scale, count, data_offset) of a SampleStreamCompressor packet (bytes / uint8 array)."""
+    b = np.ascontiguousarray(np.frombuffer(packet, np.uint8) if isinstance(packet, (bytes, bytearray)) else packet, np.uint8)
+    fmt, cnt, off = C.c_int(), C.c_int(), C.c_int()
+    sc = C.c_float()
+    L.check(L.load().b200_pcm_packet_info(b.ctypes.data, int(b.size), C.byref(fmt), C.byref(sc), C.byref(cnt), C.byref(off)))
+    return fmt.value, sc.value, cnt.value, off.value
+
+
+def pcm_compress(iq, pcm_fmt):
+    """SampleStreamCompressor::process on the device: complex64 in, packet bytes (uint8 array) out."""
+    x = np.ascontiguousarray(iq, np.complex64)
+    out = np.empty(8 + x.size * 8, np.uint8)
+    n = L.check(L.load().b200_pcm_compress(x.ctypes.data, int(x.size), int(pcm_fmt), out.ctypes.data, int(out.size), L.MEM_HOST))
+    return out[:n].copy()
+
+
+def export_convert(x, sample_type):
+    """wav::Writer sample conversion on the device: float32 in, uint8 / int16 / int32 out."""
+    a = np.ascontiguousarray(x, np.float32).reshape(-1)
+    dt = {EXPORT_U8: np.uint8, EXPORT_I16: np.int16, EXPORT_I32: np.int32}[sample_type]
+    out = np.empty(a.size, dt)
+    L.check(L.load().b200_export_convert(a.ctypes.data, int(a.size), int(sample_type), out.ctypes.data, L.MEM_HOST))
+    return out

@@ -98,6 +98,10 @@ SIGNATURES = {
     "b200_fft_destroy": (None, [_vp]),
     "b200_host_alloc": (_vp, [C.c_uint64]),
     "b200_host_free": (None, [_vp]),
+    "b200_pcm_packet_info": (_i, [_vp, _i, _ip, C.POINTER(C.c_float), _ip, _ip]),
+    "b200_fe_set_ingest_scale": (_i, [_vp, _i, C.c_float]),
+    "b200_pcm_compress": (_i, [_vp, _i, _i, _vp, _i, _i]),
+    "b200_export_convert": (_i, [_vp, C.c_longlong, _i, _vp, _i]),
 }
 
 _lib = None

@@ -397,6 +397,47 @@ def test_frontend_many_vfos_batching(sb, oracle, report):
     fe.close()
 
 
+def test_compressed_stream_ingest_and_export(sb, oracle, report):
+    """SURVEY section 8f data formats: a SampleStreamCompressor packet (int16 / int8 payload + scaler) fed to the front
+    end gives what the reference's decompressor + cf32 path gives; the device-side compressor and the recorder sample
+    conversions are bit-exact with the oracle."""
+    from sdrplusplus_b200 import frontend, lib as L
+    n, chunk = 120000, 12000
+    x = _sig(n, 23)
+    for pcm, fmt in ((1, L.FMT_CS16), (0, L.FMT_CS8)):
+        fe_p, fe_f = sb.FrontEnd(FS, chunk), sb.FrontEnd(FS, chunk)
+        for fe in (fe_p, fe_f):
+            fe.set_fft(65536, 20.0, 2)
+        cfg = sb.VfoConfig.wfm(300e3)
+        vp, vf = fe_p.add_vfo(cfg), fe_f.add_vfo(cfg)
+        yp, yf, lp, lf = [], [], [], []
+        for c in range(0, n, chunk):
+            pkt = oracle.pcm_compress(x[c:c + chunk], pcm)                   # what the server puts on the wire
+            pf, sc, cnt, off = frontend.pcm_packet_info(pkt)
+            assert pf == fmt and cnt == chunk and off == 8
+            fe_p.set_ingest_scale(fmt, sc)
+            payload = pkt[off:].view(np.int16 if pcm == 1 else np.int8)
+            o1, l1 = fe_p.process(payload, fmt=fmt)
+            o2, l2 = fe_f.process(oracle.pcm_decompress(pkt))                # reference: decompress, then the cf32 path
+            yp.append(o1[vp]); yf.append(o2[vf]); lp.append(l1); lf.append(l2)
+        yp, yf = np.concatenate(yp), np.concatenate(yf)
+        e = rel_rms(yp[4000:], yf[4000:])
+        lines_p, lines_f = np.concatenate([l for l in lp if l.size]), np.concatenate([l for l in lf if l.size])
+        e_l = float(np.max(np.abs(lines_p - lines_f)))
+        report["packet_ingest_pcm%d" % pcm] = {"wfm_audio_rel_rms": e, "fft_db_abs_max": e_l}
+        assert e < 1e-6 and e_l < 1e-3
+        fe_p.close(); fe_f.close()
+    # device-side compressor: header and payload byte for byte
+    for pcm, fmt in ((1, L.FMT_CS16), (0, L.FMT_CS8), (2, L.FMT_CF32)):
+        assert np.array_equal(frontend.pcm_compress(x[:50001], fmt), oracle.pcm_compress(x[:50001], pcm))
+    # recorder sample types
+    a = np.concatenate([x.view(np.float32)[:100001] * 0.9, np.array([1.0, -1.0, 2.0, -2.0, 0.5, -0.5, 1.5e-5], np.float32)])
+    for t, ot in ((frontend.EXPORT_I16, 1), (frontend.EXPORT_I32, 2)):
+        assert np.array_equal(frontend.export_convert(a, t), oracle.export_convert(a, ot))
+    a8 = np.clip(a, -1.0, 1.0)
+    assert np.array_equal(frontend.export_convert(a8, frontend.EXPORT_U8), oracle.export_convert(a8, 0))
+
+
 def test_deemphasis_block_bit_exact(sb, oracle):
     n = 20000
     x = noise_iq(n, 15, 0.5).view(np.float32)            # (l, r) pairs

@@ -58,3 +58,28 @@ def test_design_and_spectrum_bit_identical(oracle, ref_oracle):
     line = R.fft_frame(65536, 65536, 2, x)
     for args in ((0, 65536, 1000), (1000, 60000, 1280), (60000, 8000, 777)):
         assert _same(R.zoom(args[0], args[1], args[2], line), S.zoom(args[0], args[1], args[2], line))
+
+
+def test_packet_and_export_formats_bit_identical(oracle, ref_oracle):
+    """compressed sample stream (sample_stream_compressor.h / _decompressor.h) and the recorder conversions: the
+    restatement against the reference's own code, plus known answers."""
+    x = (noise_iq(5000, 3, 0.4) + fm_carrier(5000, FS, 300e3)).astype(np.complex64)
+    for t in (0, 1, 2):
+        pr, ps = ref_oracle.pcm_compress(x, t), oracle.pcm_compress(x, t)
+        assert np.array_equal(pr, ps)
+        assert np.array_equal(ref_oracle.pcm_decompress(pr).view(np.uint32), oracle.pcm_decompress(ps).view(np.uint32))
+        y = oracle.pcm_decompress(ps)
+        # the scaler is the largest sample VALUE (not magnitude): samples inside (-max, max) come back within half a
+        # step, more negative ones saturate -- the reference's behaviour, kept
+        xf, yf = x.view(np.float32), y.view(np.float32)
+        mx = float(np.max(xf))
+        step = {0: mx / 128.0, 1: mx / 32768.0, 2: 0.0}[t]
+        inside = np.abs(xf) < mx * (1.0 - 1.0 / 128.0)
+        assert np.max(np.abs(yf[inside] - xf[inside])) <= step * 0.51 + 1e-9
+        assert ps.size == 8 + x.size * {0: 2, 1: 4, 2: 8}[t]
+        assert int(ps[2]) + 256 * int(ps[3]) == t and int(ps[0]) == 0 and int(ps[1]) == 0
+    a = np.array([0.0, 0.5, -0.5, 1.0, -1.0, 2.0, -2.0, 1.5e-5, 0.25000763], np.float32)
+    for t in (0, 1, 2):
+        assert np.array_equal(ref_oracle.export_convert(a[:5] if t == 0 else a, t), oracle.export_convert(a[:5] if t == 0 else a, t))
+    assert list(oracle.export_convert(a, 1)[:7]) == [0, 16384, -16384, 32767, -32767, 32767, -32768]     # rintf: ties to even, saturation
+    assert list(oracle.export_convert(a[:5], 0)) == [128, 191, 64, 255, 1]
