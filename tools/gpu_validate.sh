@@ -1,4 +1,5 @@
 #!/bin/bash
+# full validation on one B200: every GPU test, smoke(), the default bench line, a launch timeline
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.log
