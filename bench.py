@@ -356,6 +356,9 @@ def run_b200(args):
         outs_host = [make_outputs(True), make_outputs(True)]
         e2e = {}
         for name, fmt, bps in (("cs16", lib.FMT_CS16, 4), ("cf32", lib.FMT_CF32, 8), ("cs8", lib.FMT_CS8, 2)):
+            if args.quick and name != "cs16":
+                e2e[name] = {"value": None}
+                continue
             host_in = [Pinned(chunk * bps) for _ in range(2)]
             for k, t in enumerate(host_in):
                 if name == "cs16":
@@ -463,6 +466,7 @@ def main():
                     help="sym = BASELINE config 2 (+-5/15/25/35 MHz); asym = 8 offsets without conjugate pairs")
     ap.add_argument("--cpu-ms", type=int, default=12000, help="duration of the CPU reference sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="diagnostic: only the int16 end-to-end leg")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region (diagnostic)")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -396,6 +396,7 @@ extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
     if (!strcmp(key, "pair")) { fe->sch.pair_conjugates = value != 0; return 0; }
     if (!strcmp(key, "fft_async")) { fe->fft_async = value != 0; return 0; }
     if (!strcmp(key, "s1_mt")) { kernels_set_xd_tile(value); return 0; }
+    if (!strcmp(key, "s1_cps")) { kernels_set_xd_cps(value); return 0; }
     if (!strcmp(key, "tails") || !strncmp(key, "ft_", 3)) {
         // 0: one thread per output; 1: shared-memory tiled kernels, one launch per stage; 2: one fused launch per <= 16 VFOs
         if (b200_fe_vfo_count(fe) > 0) { set_error("'%s' must be chosen before VFOs are added", key); return B200_ESTATE; }

@@ -749,6 +749,8 @@ static cudaError_t launch_xd_tile_t(const XdParams& p, int MT, int JP, int QPC, 
 }
 
 
+int g_xd_cps = 0;                 // cap on stage-1 CTAs per SM (0 = as many as fit): leaves room for the other streams
+void kernels_set_xd_cps(int v) { g_xd_cps = v; }
 int g_xd_mt_override = 0;
 void kernels_set_xd_tile(int mt) { g_xd_mt_override = mt; }
 static int g_num_sms = -1;
@@ -889,6 +891,7 @@ static cudaError_t launch_xd_pfb_t(const XdParams& p, const XpGeom& g, int fmt, 
     if (e != cudaSuccess) { return e; }
     int per_sm = (int)((size_t)233472 / (smem + 1024));
     if (per_sm > 3) { per_sm = 3; }
+    if (g_xd_cps > 0 && per_sm > g_xd_cps) { per_sm = g_xd_cps; }
     if (per_sm < 1) { per_sm = 1; }
     int grid = num_sms() * per_sm;
     if (grid > g.ntiles) { grid = g.ntiles; }

@@ -261,3 +261,4 @@ int kernels_max_smem_optin();
 void kernels_set_tail_variant(int v);
 void kernels_set_fft_variant(int v);
 void kernels_set_xd_tile(int mt);     // 0 = automatic
+void kernels_set_xd_cps(int v);       // cap on stage-1 CTAs per SM, 0 = automatic
