@@ -385,7 +385,6 @@ int Chain::plan_fused() {
         const int fixed = toff + region[1];
         // stage 0 streams through what is left of the budget, at most what one pass over the slab needs
         const int rows0 = ft_rows(d[0]);
-        int avail = limit_f - fixed - 64 - region[0];
         int ot0 = (int)((lb[1] + FT_R - 1) / FT_R) * FT_R;
         std::function<long long(int)> stage0_floats = [&](int ot) {
             long long cols = (ft_need_len(d[0], ot) + rows0 + rows0 - 1) / rows0 + FT_R + 2;
@@ -400,7 +399,6 @@ int Chain::plan_fused() {
         const int want = fcfg.threads * (fp.s0_direct ? 3 : 5);
         if (ot0 > want) { ot0 = want; }
         while (ot0 >= FT_R && std::max<long long>(nbuf * (long long)round4((int)stage0_floats(ot0)), region[0]) > (long long)limit_f - fixed - 64) { ot0 -= FT_R; }
-        (void)avail;
         if (ot0 < FT_R) { continue; }
         {
             long long cols = (ft_need_len(d[0], ot0) + rows0 + rows0 - 1) / rows0 + FT_R + 2;

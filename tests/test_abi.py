@@ -82,3 +82,15 @@ def test_decim_plan_table_loads():
     L = lib.load()
     assert L.b200_load_decim_plans(None) == 0
     assert L.b200_load_decim_plans(b"/nonexistent/file") == -6
+
+
+def test_fused_tail_range_arithmetic_invariants():
+    """csrc/kernels.cuh ft_ranges / ft_need_in (shared by the CUDA kernel and the scheduler): slabs tile the outputs,
+    every stage's needs are met by what the previous stage produces, the last slab hands over every history."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "test_ft_ranges")
+    assert os.path.exists(exe), "run python __graft_entry__.py first"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "ok" in r.stdout
