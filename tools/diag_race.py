@@ -23,4 +23,8 @@ xf = x.view(np.float32)
 for vid, off in zip(ids, (300e3, -300e3)):
     v = o.rxvfo(fs, 250e3, 150e3, off); d = o.wfm(75e3, 250e3, False, True)
     ref = np.concatenate([d.process(v.process(xf[2 * i: 2 * (i + chunk)])) for i in range(0, n, chunk)]).reshape(-1, 2)
-    print(sys.argv[1:], "vfo", vid, "rel rms %.3g" % rel_rms(outs[vid][1000:], ref[1000:]), flush=True)
+    y = outs[vid]
+    bad = np.nonzero(np.abs(y[:, 0] - ref[:, 0]) > 1e-3)[0]
+    print(sys.argv[1:], "vfo", vid, "rel rms %.3g" % rel_rms(y[1000:], ref[1000:]), "bad samples %d of %d" % (bad.size, y.shape[0]),
+          ("first %d last %d, per 1250-sample chunk: %s" % (bad[0], bad[-1], np.bincount(bad // 1250, minlength=y.shape[0] // 1250).tolist())) if bad.size else "",
+          "zeros %d nan %d" % (int(np.sum(y[:, 0] == 0)), int(np.sum(~np.isfinite(y[:, 0])))), flush=True)
