@@ -143,6 +143,10 @@ typedef struct {
     double af_samplerate;     /* 0 = no AF chain (output at out_samplerate); e.g. 48000                      */
     int    af_high_pass;      /* taps::highPass(300, 100, af_samplerate)                                     */
     double af_deemph_tau;     /* seconds, 0 = off (50e-6 EU / 75e-6 US, radio_module.h deempTaus)            */
+    /* dsp::audio::Volume at the very end (core/src/dsp/audio/volume.h:13-17,39-42): out = in * (muted ? 0 : powf(volume, 2)) */
+    int    af_volume_on;      /* 0 = no volume block                                                         */
+    int    af_muted;
+    double af_volume;
 } b200_vfo_cfg;
 
 typedef struct {

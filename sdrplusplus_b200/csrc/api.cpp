@@ -146,6 +146,7 @@ struct FftCore {
             B200_CK(cudaMemcpy(twf.p, f.data(), f.size() * sizeof(float2), cudaMemcpyHostToDevice));
             plan.tw_fine = twf.as<float2>();
         }
+        B200_CK(cudaDeviceSynchronize());       // tables uploaded on the legacy stream; the spectrum branch runs on a non-blocking one
         return 0;
     }
 };
@@ -303,6 +304,9 @@ static int build_vfo_chain(b200_fe* fe, VfoSlot* v) {
     if (rc) { return rc; }
     if (c.af_samplerate > 0 && c.demod != B200_DEMOD_RAW) {
         if ((rc = v->chain.add_af_chain(c.out_samplerate, c.af_samplerate, c.af_high_pass != 0, c.af_deemph_tau))) { return rc; }
+    }
+    if (c.af_volume_on && c.demod != B200_DEMOD_RAW) {
+        if ((rc = v->chain.add_volume(c.af_volume, c.af_muted != 0))) { return rc; }
     }
     const bool ov = fe->sch.tail_stream != nullptr;
     if (ov && v->chain.st.size() == 1) {

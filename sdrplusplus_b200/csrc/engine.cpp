@@ -63,7 +63,11 @@ int DevBuf::alloc(size_t n, bool zero) {
     if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaMalloc"); }
     bytes = n;
     if (zero) {
+        // cudaMemset is asynchronous on the legacy default stream, which the library's non-blocking streams do not
+        // wait for: without the synchronisation a later cudaMemcpyAsync / kernel on those streams can be overtaken by
+        // the zero fill (seen as an intermittent all-zero tap table)
         e = cudaMemset(p, 0, n);
+        if (e == cudaSuccess) { e = cudaDeviceSynchronize(); }
         if (e != cudaSuccess) { return cuda_fail(e, "cudaMemset"); }
     }
     return 0;
@@ -295,7 +299,11 @@ int Chain::finalize(int max_in, bool dbl_first, const FuseCfg* fuse) {
     int rc = out.alloc(((size_t)cap + 8) * out_es * sizeof(float));
     if (rc) { return rc; }
     if (fuse) { fcfg = *fuse; }
-    return plan_fused();
+    rc = plan_fused();
+    if (rc) { return rc; }
+    // every table was uploaded with legacy-stream copies / memsets; the data path runs on non-blocking streams
+    B200_CK(cudaDeviceSynchronize());
+    return 0;
 }
 
 // ---- fused tail: static plan ----
@@ -453,6 +461,7 @@ void Chain::reset_state() {
             cudaMemcpy(q->state.p, q->init_state, sizeof(q->init_state), cudaMemcpyHostToDevice);
         }
     }
+    cudaDeviceSynchronize();      // the memsets above run on the legacy stream: finish them before the library's streams go on
 }
 
 int Chain::add_xlator(double offsetHz, double samplerate) {
@@ -594,6 +603,12 @@ int Chain::add_af_chain(double afSR, double audioSR, bool highPass, double deemp
     return 0;
 }
 
+int Chain::add_volume(double volume, bool muted) {
+    const float v = powf((float)volume, 2);                                  // volume.h:14: _volume = powf(volume, 2)
+    st.push_back(std::make_unique<ScaleStage>(st.empty() ? 2 : st.back()->out_es, muted ? 0.0f : v));
+    return 0;
+}
+
 // ------------------------------------------------------------------ Scheduler
 int Scheduler::init_raw() {
     if (raw_hist.p) { return 0; }
@@ -616,7 +631,7 @@ int Scheduler::s1_stats(double* ms_total, int* n) {
     return 0;
 }
 int Scheduler::reset_raw() {
-    if (raw_hist.p) { B200_CK(cudaMemset(raw_hist.p, 0, raw_hist.bytes)); }
+    if (raw_hist.p) { B200_CK(cudaMemset(raw_hist.p, 0, raw_hist.bytes)); B200_CK(cudaDeviceSynchronize()); }
     return 0;
 }
 
@@ -666,6 +681,7 @@ static int apply_pending_taps(FirCStage* f, cudaStream_t s) {
     f->hist = newH;
     if (f->decim != 1) { f->offset = 0; }          // DecimatingFIR::setTaps (decimating_fir.h:18-25)
     f->pending.clear();
+    B200_CK(cudaDeviceSynchronize());              // the device-to-device copies above ran on the legacy stream
     return 0;
 }
 
@@ -979,6 +995,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
         FirRParams rp; rp.njobs = 0; rp.max_out = 0;
         SeqParams sp; sp.njobs = 0;
         M2SParams mp; mp.njobs = 0; mp.max_n = 0;
+        ScaleParams cp2; cp2.njobs = 0; cp2.max_n = 0;
         for (Chain* c : chains) {
             if (lvl >= c->st.size()) { continue; }
             if (c->fp.active && lvl >= 1 && (int)lvl < c->fp.end) { continue; }     // done by the fused launch
@@ -1036,6 +1053,14 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
                 if (sp.njobs == B200_BATCH) { rc = flush_batch(sp, launch_seq, ts, launches); }
                 break;
             }
+            case K_SCALE: {
+                if (s->n_out <= 0) { break; }
+                ScaleJob& j = cp2.job[cp2.njobs++];
+                j.in = s->in_data(); j.out = s->out_ptr; j.n = s->n_out * s->in_es; j.gain = ((ScaleStage*)s)->gain;
+                cp2.max_n = std::max(cp2.max_n, j.n);
+                if (cp2.njobs == B200_BATCH) { rc = flush_batch(cp2, launch_scale, ts, launches); cp2.max_n = 0; }
+                break;
+            }
             case K_M2S: {
                 if (s->n_out <= 0) { break; }
                 M2SJob& j = mp.job[mp.njobs++];
@@ -1054,6 +1079,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
         if ((rc = flush_batch(rp, launch_fir_r, ts, launches))) { return rc; }
         if ((rc = flush_batch(sp, launch_seq, ts, launches))) { return rc; }
         if ((rc = flush_batch(mp, launch_m2s, ts, launches))) { return rc; }
+        if ((rc = flush_batch(cp2, launch_scale, ts, launches))) { return rc; }
     }
     // ---- history carry (the memmove at the end of every reference process()) ----
     CarryParams cp;

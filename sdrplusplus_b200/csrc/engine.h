@@ -40,7 +40,7 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
-enum StageKind { K_XD, K_FIRC, K_POLY, K_QUAD, K_FIRR, K_SEQ, K_M2S };
+enum StageKind { K_XD, K_FIRC, K_POLY, K_QUAD, K_FIRR, K_SEQ, K_M2S, K_SCALE };
 
 struct Stage {
     StageKind kind;
@@ -160,6 +160,13 @@ struct FusedPlan {
 };
 struct FuseCfg { bool on = false; int ob_max = 1280; int smem_limit = 110 * 1024; int threads = 256; int ob_force = 0; bool direct = true; };
 
+struct ScaleStage : Stage {
+    float gain = 1.0f;
+    ScaleStage(int es, float g) { kind = K_SCALE; in_es = es; out_es = es; gain = g; }
+    int plan(int n) override { n_in = n; n_out = n; return n; }
+    int max_out(int n) const override { return n; }
+};
+
 // A chain = one VFO (+ demodulator) or one stand-alone block.
 struct Chain {
     std::vector<std::unique_ptr<Stage>> st;
@@ -191,6 +198,7 @@ struct Chain {
     int add_deemph(double tau, double samplerate);                          // filter::Deemphasis<stereo_t> (deephasis.h:14-28)
     // radio AF chain: RationalResampler<stereo_t> -> [300 Hz high-pass FIR] -> [Deemphasis]  (radio_module.h:99-110,546-553)
     int add_af_chain(double afSamplerate, double audioSamplerate, bool highPass, double deemphTau);
+    int add_volume(double volume, bool muted);                              // dsp::audio::Volume (volume.h:13-17,39-42)
 };
 
 // Runs a set of chains over one chunk: stage-1 launches grouped by decimation, then level by level one

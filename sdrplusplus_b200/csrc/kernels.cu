@@ -320,6 +320,13 @@ __global__ void __launch_bounds__(256) k_fir_r(const __grid_constant__ FirRParam
     else { J.out[m] = acc; }
 }
 
+__global__ void __launch_bounds__(256) k_scale(const __grid_constant__ ScaleParams p) {
+    const ScaleJob& J = p.job[blockIdx.y];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= J.n) { return; }
+    J.out[i] = __fmul_rn(__ldg(J.in + i), J.gain);
+}
+
 __global__ void __launch_bounds__(256) k_m2s(const __grid_constant__ M2SParams p) {
     const M2SJob& J = p.job[blockIdx.y];
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1164,6 +1171,12 @@ cudaError_t launch_m2s(const M2SParams& p, cudaStream_t s) {
     if (p.max_n <= 0 || p.njobs <= 0) { return cudaSuccess; }
     dim3 grid(cdiv(p.max_n, 256), p.njobs);
     k_m2s<<<grid, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_scale(const ScaleParams& p, cudaStream_t s) {
+    if (p.max_n <= 0 || p.njobs <= 0) { return cudaSuccess; }
+    dim3 grid(cdiv(p.max_n, 256), p.njobs);
+    k_scale<<<grid, 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 cudaError_t launch_carry(const CarryParams& p, cudaStream_t s) {

@@ -205,6 +205,10 @@ struct SeqJob {
 struct SeqParams { int njobs; SeqJob job[B200_BATCH]; };
 #define SEQ_STATE_FLOATS 8   // [0] carrier amp [1] audio amp [2] dc offset [3] rot re [4] rot im [5] deemph last l [6] last r
 
+// ---- elementwise gain (dsp::audio::Volume, volume.h:39-42: volk_32f_s32f_multiply_32f) ----
+struct ScaleJob { const float* in; float* out; int n; float gain; };      // n floats
+struct ScaleParams { int njobs; int max_n; ScaleJob job[B200_BATCH]; };
+
 // ---- mono -> stereo copy (convert::MonoToStereo) ----
 struct M2SJob { const float* in; float* out; int n; };
 struct M2SParams { int njobs; int max_n; M2SJob job[B200_BATCH]; };
@@ -243,6 +247,7 @@ cudaError_t launch_quad(const QuadParams& p, cudaStream_t s);
 cudaError_t launch_fir_r(const FirRParams& p, cudaStream_t s);
 cudaError_t launch_seq(const SeqParams& p, cudaStream_t s);
 cudaError_t launch_m2s(const M2SParams& p, cudaStream_t s);
+cudaError_t launch_scale(const ScaleParams& p, cudaStream_t s);
 cudaError_t launch_carry(const CarryParams& p, cudaStream_t s);
 // src: nz samples of format fmt (chunk data), read directly; out_db: N floats; work: N float2 scratch
 cudaError_t launch_fft_frame(const FftPlanDev& pl, const void* src, int fmt, float2* work, float* out_db,

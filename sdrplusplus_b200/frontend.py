@@ -28,6 +28,13 @@ class VfoConfig:
     af_samplerate: float = 0.0       # radio AF chain: resample to this rate (0 = off) ...
     af_high_pass: bool = False       # ... 300 Hz high-pass ...
     af_deemph_tau: float = 0.0       # ... deemphasis time constant in seconds (0 = off)
+    af_volume_on: bool = False       # dsp::audio::Volume at the end: out = in * (muted ? 0 : volume^2)
+    af_muted: bool = False
+    af_volume: float = 1.0
+
+    def with_volume(self, volume, muted=False):
+        self.af_volume_on, self.af_volume, self.af_muted = True, volume, muted
+        return self
 
     def with_af(self, audio_sr=48000.0, high_pass=False, deemph_tau=50e-6):
         self.af_samplerate, self.af_high_pass, self.af_deemph_tau = audio_sr, high_pass, deemph_tau
@@ -60,7 +67,7 @@ class VfoConfig:
     def to_c(self):
         return L.VfoCfg(self.offset, self.out_samplerate, self.bandwidth, self.demod, self.deviation, int(self.low_pass),
                         self.agc_mode, self.agc_attack, self.agc_decay, self.dc_block_rate, self.af_samplerate,
-                        int(self.af_high_pass), self.af_deemph_tau)
+                        int(self.af_high_pass), self.af_deemph_tau, int(self.af_volume_on), int(self.af_muted), float(self.af_volume))
 
 
 _NP_FMT = {L.FMT_CF32: (np.complex64, 1), L.FMT_CS16: (np.int16, 2), L.FMT_CS8: (np.int8, 2)}

@@ -26,7 +26,8 @@ class VfoCfg(C.Structure):
     _fields_ = [("offset", C.c_double), ("out_samplerate", C.c_double), ("bandwidth", C.c_double), ("demod", C.c_int),
                 ("deviation", C.c_double), ("low_pass", C.c_int), ("agc_mode", C.c_int), ("agc_attack", C.c_double),
                 ("agc_decay", C.c_double), ("dc_block_rate", C.c_double), ("af_samplerate", C.c_double),
-                ("af_high_pass", C.c_int), ("af_deemph_tau", C.c_double)]
+                ("af_high_pass", C.c_int), ("af_deemph_tau", C.c_double), ("af_volume_on", C.c_int), ("af_muted", C.c_int),
+                ("af_volume", C.c_double)]
 
 
 class Outputs(C.Structure):

@@ -475,6 +475,30 @@ def test_frontend_af_chain(sb, oracle, report, high_pass):
     fe.close()
 
 
+def test_af_volume_block_bit_exact(sb):
+    """dsp::audio::Volume at the end of the AF chain (volume.h:13-17,39-42): out = in * powf(volume, 2), muted -> 0;
+    one fp32 multiply per sample, so the check is bit for bit against the same chain without the block."""
+    n = 120000
+    x = _sig(n, 18)
+    outs = {}
+    for name, cfg in (("plain", sb.VfoConfig.wfm(300e3).with_af(48000.0, True, 50e-6)),
+                      ("vol", sb.VfoConfig.wfm(300e3).with_af(48000.0, True, 50e-6).with_volume(0.7)),
+                      ("muted", sb.VfoConfig.wfm(300e3).with_af(48000.0, True, 50e-6).with_volume(0.7, True)),
+                      ("vol_noaf", sb.VfoConfig.nfm(200e3).with_volume(1.3))):
+        fe = sb.FrontEnd(FS, 12000)
+        vid = fe.add_vfo(cfg)
+        outs[name] = fe.process_chunks(x, 12000)[0][vid]
+        fe.close()
+    g = np.float32(np.float32(0.7) ** np.float32(2))
+    assert np.array_equal((outs["plain"] * g).view(np.uint32), outs["vol"].view(np.uint32))
+    assert outs["muted"].shape == outs["plain"].shape and not np.any(outs["muted"])
+    fe = sb.FrontEnd(FS, 12000)
+    vid = fe.add_vfo(sb.VfoConfig.nfm(200e3))
+    ref = fe.process_chunks(x, 12000)[0][vid]
+    fe.close()
+    assert np.array_equal((ref * np.float32(np.float32(1.3) ** np.float32(2))).view(np.uint32), outs["vol_noaf"].view(np.uint32))
+
+
 def test_frontend_retune_and_bandwidth(sb, oracle, report):
     """RxVFO::setOffset / setBandwidth mid-stream, applied at a chunk boundary like the reference's ctrlMtx."""
     n = 480000
