@@ -94,3 +94,26 @@ def test_fused_tail_range_arithmetic_invariants():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "ok" in r.stdout
+
+
+def test_pcm_packet_header_parsing_matches_reference_decompressor(oracle):
+    """b200_pcm_packet_info is host-only: format, sample count and the conversion factor must be what
+    SampleStreamDecompressor::process (sample_stream_decompressor.h:15-33) derives from the same header."""
+    import numpy as np
+    from sdrplusplus_b200 import frontend, lib as L
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal(777) + 1j * rng.standard_normal(777)).astype(np.complex64) * 0.2
+    for pcm, fmt, dt in ((1, L.FMT_CS16, np.int16), (0, L.FMT_CS8, np.int8), (2, L.FMT_CF32, np.float32)):
+        pkt = oracle.pcm_compress(x, pcm)
+        f, sc, cnt, off = frontend.pcm_packet_info(pkt)
+        assert (f, cnt, off) == (fmt, x.size, 8)
+        ref = oracle.pcm_decompress(pkt).view(np.float32)
+        payload = pkt[off:].view(dt)
+        mine = payload.astype(np.float32) * np.float32(sc) if pcm != 2 else payload
+        assert np.array_equal(mine.view(np.uint32), ref.view(np.uint32))      # (float)x * scale, bit for bit
+    with pytest.raises(L.B200Error):
+        frontend.pcm_packet_info(np.zeros(4, np.uint8))
+    bad = oracle.pcm_compress(x, 1).copy()
+    bad[2] = 9
+    with pytest.raises(L.B200Error):
+        frontend.pcm_packet_info(bad)
