@@ -117,17 +117,22 @@ def test_broadcast_and_vfo_group_sharding_gloo():
 # ---------------------------------------------------------------------------------------------- on the GPU
 def _gpu_worker(rank, world, port, outdir):
     """config-4 sharding with the real kernels: rank 0 owns the stream and broadcasts every raw chunk, each rank runs
-    the CUDA front end for its VFO group (both ranks share cuda:0 here, so the transport is gloo; on a multi-GPU box
-    the same code broadcasts device buffers over NCCL)."""
+    the CUDA front end for its VFO group.  With one GPU per rank the chunk is broadcast device-to-device over NCCL and
+    processed from device memory; when the ranks have to share cuda:0 (the single-GPU test box) the transport is gloo."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nccl = torch.cuda.device_count() >= world
+    dev = rank if nccl else 0
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl" if nccl else "gloo", rank=rank, world_size=world)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import sdrplusplus_b200 as sb
     from sdrplusplus_b200 import lib as L
     from test_multi_rank import _sharding_case
-    assert L.load().b200_init(0) == 0
+    assert L.load().b200_init(dev) == 0
     fs, n, chunk, cfgs, x = _sharding_case(sb, L)
     buf = torch.from_numpy(x.view(np.float32).copy()) if rank == 0 else torch.empty(2 * n, dtype=torch.float32)
+    if nccl:
+        buf = buf.cuda()
     mine = partition_vfos(len(cfgs), world, rank)
     fe = sb.FrontEnd(fs, chunk)
     if rank == 0:
@@ -138,14 +143,33 @@ def _gpu_worker(rank, world, port, outdir):
     for c in range(0, n, chunk):
         seg = buf[2 * c: 2 * (c + chunk)].clone()
         dist.broadcast(seg, src=0)
-        o, ln = fe.process(seg.numpy().view(np.complex64))
-        for i, vid in ids.items():
-            outs[i].append(o[vid])
-        if ln.size:
-            lines.append(ln)
+        if nccl:
+            # device in, device out: the path a multi-GPU deployment runs
+            torch.cuda.synchronize()
+            o = L.Outputs()
+            keep = {}
+            for i, vid in ids.items():
+                cap = fe.vfo_max_out(vid, chunk)
+                keep[i] = torch.empty(2 * cap, device="cuda", dtype=torch.float32)
+                o.vfo_out[vid] = keep[i].data_ptr(); o.vfo_cap[vid] = cap
+            nl = max(1, fe.fft_max_lines(chunk))
+            lt = torch.empty(nl * 65536, device="cuda", dtype=torch.float32)
+            o.fft_out = lt.data_ptr(); o.fft_cap_lines = nl; o.out_mem = L.MEM_DEVICE
+            fe.process_ptr(seg.data_ptr(), chunk, L.FMT_CF32, L.MEM_DEVICE, o)
+            for i, vid in ids.items():
+                y = keep[i][: 2 * o.vfo_count[vid]].cpu().numpy()
+                outs[i].append(y.view(np.complex64) if cfgs[i].demod == L.DEMOD_RAW else y.reshape(-1, 2))
+            if o.fft_lines:
+                lines.append(lt[: o.fft_lines * 65536].cpu().numpy().reshape(-1, 65536))
+        else:
+            o, ln = fe.process(seg.numpy().view(np.complex64))
+            for i, vid in ids.items():
+                outs[i].append(o[vid])
+            if ln.size:
+                lines.append(ln)
     fe.close()
     np.savez(os.path.join(outdir, "rank%d.npz" % rank), lines=np.concatenate(lines) if lines else np.empty((0, 0), np.float32),
-             **{"vfo%d" % i: np.concatenate(v) for i, v in outs.items()})
+             transport=np.array([1 if nccl else 0]), **{"vfo%d" % i: np.concatenate(v) for i, v in outs.items()})
     dist.barrier()
     dist.destroy_process_group()
 
@@ -186,6 +210,8 @@ def test_vfo_group_sharding_matches_single_process(tmp_path):
             if k == "lines":
                 if r == 0:
                     lines = z[k]
+            elif k == "transport":
+                pass
             else:
                 got[int(k[3:])] = z[k]
     assert sorted(got) == list(range(len(cfgs)))
