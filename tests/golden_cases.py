@@ -93,4 +93,15 @@ def run_cases(R):
     i16 = np.random.default_rng(3).integers(-32768, 32767, 512).astype(np.int16)
     g["i16_in"] = i16
     g["i16_out"] = R.i16_to_f32(i16)
+    # ---- data formats either side of the path (compressed sample stream; recorder sample types) ----
+    xs = signal(4096, 77).astype(np.complex64)
+    for t, name in ((0, "i8"), (1, "i16"), (2, "f32")):
+        pkt = R.pcm_compress(xs, t)
+        g["pcm_packet_%s_head" % name] = pkt[:72].copy()
+        g["pcm_packet_%s_digest" % name] = digest(pkt.astype(np.float32))
+        g["pcm_roundtrip_%s_digest" % name] = digest(R.pcm_decompress(pkt).view(np.float32))
+    a = np.concatenate([xs.view(np.float32) * 3.0, np.array([1.0, -1.0, 0.5, -0.5, 2.5e-5], np.float32)])
+    g["export_i16_digest"] = digest(R.export_convert(a, 1).astype(np.float32))
+    g["export_i32_head"] = R.export_convert(a[:64], 2)
+    g["export_u8_head"] = R.export_convert(np.clip(a[:64], -1.0, 1.0), 0)
     return g
