@@ -10,6 +10,7 @@
 #include "dsp/channel/rx_vfo.h"
 #include "dsp/demod/broadcast_fm.h"
 #include "dsp/b200/frontend.h"
+#include "dsp/compression/sample_stream_compressor.h"   // compiled here; exercised through the C ABI in tests/test_gpu_parity.py
 
 static std::vector<float> g_line(65536);
 static int g_lines = 0;
