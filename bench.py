@@ -379,23 +379,27 @@ def run_b200(args):
         # ---------------- the dominant kernel with nothing else running (explains roofline.frac) ----------------
         s1_alone = None
         if rank == 0:
-            fe2 = sb.FrontEnd(FS, chunk)
-            fe2.set_stream(stream.cuda_stream)
-            fe2.set_option("overlap", 0)
-            fe2.set_option("pair", args.pair)
-            fe2.set_option("s1", args.s1)
-            fe2.set_option("tails", args.tails)
-            for o in offsets:
-                fe2.add_vfo(sb.VfoConfig.wfm(o))
-            o2 = make_outputs(False)
-            for k in range(3):
-                fe2.submit_ptr(ptrs[k % nbuf], chunk, lib.FMT_CF32, lib.MEM_DEVICE, o2[0]); fe2.wait()
-            fe2.set_option("time_s1", 1)
-            for k in range(10):
-                fe2.submit_ptr(ptrs[k % nbuf], chunk, lib.FMT_CF32, lib.MEM_DEVICE, o2[0]); fe2.wait()
-            a_ms, a_n = fe2.s1_stats()
-            fe2.close()
-            s1_alone = a_ms / max(a_n, 1)
+            try:                                     # an explanatory extra: never let it take the bench line down
+                fe2 = sb.FrontEnd(FS, chunk)
+                fe2.set_stream(stream.cuda_stream)
+                fe2.set_option("overlap", 0)
+                fe2.set_option("pair", args.pair)
+                fe2.set_option("s1", args.s1)
+                fe2.set_option("tails", args.tails)
+                for o in offsets:
+                    fe2.add_vfo(sb.VfoConfig.wfm(o))
+                o2 = make_outputs(False)
+                for k in range(3):
+                    fe2.submit_ptr(ptrs[k % nbuf], chunk, lib.FMT_CF32, lib.MEM_DEVICE, o2[0]); fe2.wait()
+                fe2.set_option("time_s1", 1)
+                for k in range(10):
+                    fe2.submit_ptr(ptrs[k % nbuf], chunk, lib.FMT_CF32, lib.MEM_DEVICE, o2[0]); fe2.wait()
+                a_ms, a_n = fe2.s1_stats()
+                fe2.close()
+                s1_alone = a_ms / max(a_n, 1)
+            except Exception as ex:                  # noqa: BLE001
+                print("roofline.alone skipped: %r" % (ex,), file=sys.stderr)
+                s1_alone = None
 
     if rank != 0:
         if world > 1:
