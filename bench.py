@@ -460,7 +460,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunk", type=int, default=1 << 24, help="IQ samples per step (default 16 Mi = 128 MiB cf32 > L2)")
-    ap.add_argument("--s1", type=int, default=7, help="stage-1 kernel variant (7 = polyphase-filter-bank form when the VFO plan allows it, else 6 = 4-warp CTAs, 3 per SM, cp.async tiles)")
+    ap.add_argument("--s1", type=int, default=8, help="stage-1 kernel variant (8 = filter-bank form fed by the TMA engine, 7 = filter bank on cp.async tiles, when the VFO plan allows it; else 6 = per-VFO complex taps)")
     ap.add_argument("--tails", type=int, default=2, help="2 = one fused tail launch per <= 16 VFOs (default), 1 = shared-memory tiled kernel per stage, 0 = one thread per output")
     ap.add_argument("--ft", default="", help="fused-tail tuning, e.g. ft_threads=256,ft_obmax=1024,ft_smem_kb=72")
     ap.add_argument("--s1-mt", type=int, default=0, help="force the stage-1 tile size (outputs per tile), 0 = automatic")

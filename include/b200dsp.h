@@ -194,8 +194,12 @@ int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt, int in_me
 int b200_fe_wait(b200_fe* fe);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 long long b200_fe_launch_count(b200_fe* fe);
+/* counters by name: "launches", "chunks", "s1_tma_launches" (stage-1 launches of this process that ran the TMA-fed
+ * filter-bank kernel); -1 for an unknown key */
+long long b200_fe_stat(b200_fe* fe, const char* key);
 /* Tuning / A-B switches (defaults are the fast paths; every variant is held to the same parity tests):
- *  "s1"      stage-1 kernel: 7 polyphase-filter-bank form when the VFO offsets share a frequency grid, else 6 (default);
+ *  "s1"      stage-1 kernel: 8 (default) filter-bank form fed by the TMA engine (cf32 chunks, VFO offsets on a common
+ *            frequency grid, first decimation 32 or 64), else 7: the same form on cp.async tiles, else 6;
  *            6/5/4/3 per-VFO complex taps on cp.async tiles (4-warp x3 per SM / 4-warp / 16-warp / 8-warp CTAs);
  *            2, 1 single-buffered tiles; 0 one thread per output
  *  "pair"    1 = VFOs at +f / -f share their stage-1 sums (default)
@@ -227,6 +231,9 @@ int         b200_xlator_set_offset(b200_block* b, double offsetHz, double sample
 b200_block* b200_decim_create(int ratio);                                       /* multirate::PowerDecimator<complex_t> (power_decimator.h:51-67) */
 b200_block* b200_resamp_create(double inSamplerate, double outSamplerate);      /* multirate::RationalResampler<complex_t|stereo_t> (rational_resampler.h:82-96) */
 b200_block* b200_fir_cr_create(const float* taps, int ntaps, int decimation);   /* filter::FIR / DecimatingFIR<complex_t,float> (fir.h:62-83, decimating_fir.h:45-68) */
+/* FIR::setTaps (fir.h:31-52) of a block made by b200_fir_cr_create: new coefficients at the next chunk boundary, the
+ * most recent delay-line samples are kept (a decimating filter restarts its decimation phase, decimating_fir.h:18-25) */
+int         b200_fir_cr_set_taps(b200_block* b, const float* taps, int ntaps);
 b200_block* b200_fir_rr_create(const float* taps, int ntaps);                   /* filter::FIR<float,float> */
 b200_block* b200_rxvfo_create(double inSamplerate, double outSamplerate, double bandwidth, double offset); /* channel::RxVFO (rx_vfo.h:89-100) */
 int         b200_rxvfo_set_offset(b200_block* b, double offset);

@@ -388,6 +388,14 @@ extern "C" int b200_fe_fft_max_lines(b200_fe* fe, int count) {
     return (int)(count / ((long long)fe->fft.nz + fe->skip)) + 2;
 }
 extern "C" long long b200_fe_launch_count(b200_fe* fe) { return fe ? fe->sch.launches : 0; }
+extern int g_xd_tma_launches;
+extern "C" long long b200_fe_stat(b200_fe* fe, const char* key) {
+    if (!fe || !key) { return -1; }
+    if (!strcmp(key, "launches")) { return fe->sch.launches; }
+    if (!strcmp(key, "s1_tma_launches")) { return g_xd_tma_launches; }      // process-wide: stage-1 launches that took the TMA kernel
+    if (!strcmp(key, "chunks")) { return (long long)fe->nsub; }
+    return -1;
+}
 extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
     if (!fe || !key) { set_error("null argument"); return B200_EINVAL; }
     if (!strcmp(key, "s1")) { fe->sch.s1_variant = value; return 0; }
@@ -446,19 +454,13 @@ static void apply_pending(b200_fe* fe) {
             v->pend_offset = false;
         }
         if (v->pend_bw) {
-            // only the channel filter follows the bandwidth (rx_vfo.h:60-70); it exists iff bw != outSR at creation
-            bool had_filter = (v->cfg.bandwidth != v->cfg.out_samplerate);
-            if (had_filter && v->new_bw != v->cfg.out_samplerate) {
-                // locate the channel FIR: the last FirC stage with decim == 1 before the demodulator stages
-                FirCStage* f = nullptr;
-                for (auto& s : v->chain.st) {
-                    if (s->kind == K_FIRC && ((FirCStage*)s.get())->decim == 1) { f = (FirCStage*)s.get(); }
-                }
-                if (f) {
-                    double fw = v->new_bw / 2.0;
-                    f->pending = lowpass_taps(fw, fw * 0.1, v->cfg.out_samplerate);
-                    v->cfg.bandwidth = v->new_bw;
-                }
+            // RxVFO::setBandwidth (rx_vfo.h:60-70): only the channel filter follows the bandwidth; bandwidth == outSR
+            // bypasses it (identity tap here, Chain::add_rxvfo)
+            FirCStage* f = v->chain.chan_fir >= 0 ? (FirCStage*)v->chain.st[v->chain.chan_fir].get() : nullptr;
+            if (f) {
+                double fw = v->new_bw / 2.0;
+                f->pending = (v->new_bw != v->cfg.out_samplerate) ? lowpass_taps(fw, fw * 0.1, v->cfg.out_samplerate) : std::vector<float>{ 1.0f };
+                v->cfg.bandwidth = v->new_bw;
             }
             v->pend_bw = false;
         }
@@ -557,6 +559,31 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
     const int slot = (int)(fe->nsub & 1);
     cudaStream_t s = fe->sch.stream;
     const size_t in_bytes = (size_t)count * bytes_per_sample(in_fmt);
+    // ---- capacity checks against the exact counts, before anything is enqueued and before any state moves ----
+    std::vector<Chain*> chains;
+    std::vector<int> ids;
+    for (size_t i = 0; i < fe->vfos.size(); i++) {
+        if (fe->vfos[i]->used) { chains.push_back(&fe->vfos[i]->chain); ids.push_back((int)i); }
+    }
+    for (size_t k = 0; k < chains.size(); k++) {
+        int bound = chains[k]->max_out(count);
+        if (out->vfo_out[ids[k]] == nullptr || out->vfo_cap[ids[k]] < bound) {
+            set_error("VFO %d output buffer too small: need room for %d samples (b200_fe_vfo_max_out)", ids[k], bound);
+            return B200_ECAP;
+        }
+    }
+    if (fe->fft_on) {
+        // exact count of lines this chunk completes
+        unsigned long long end = fe->pos + (unsigned long long)count, f = fe->fstart;
+        unsigned long long nz = (unsigned long long)fe->fft.nz, iv = nz + (unsigned long long)fe->skip;
+        int need = 0;
+        while (f + nz <= end) { need++; f += iv; }
+        if (need > fe->max_lines) { set_error("FFT line buffer overflow: %d lines complete in this chunk, room for %d", need, fe->max_lines); return B200_ECAP; }
+        if (need > 0 && (out->fft_out == nullptr || out->fft_cap_lines < need)) {
+            set_error("FFT output buffer too small: %d lines complete in this chunk", need);
+            return B200_ECAP;
+        }
+    }
     const void* dptr = iq;
     if (in_mem == B200_MEM_HOST && count > 0) {
         if (fe->in_dev[slot].bytes < in_bytes) {
@@ -572,33 +599,7 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
         B200_CK(cudaStreamWaitEvent(s, fe->ev_h2d[slot], 0));
         dptr = fe->in_dev[slot].p;
     }
-    // ---- capacity checks against the exact counts, before any state moves ----
-    std::vector<Chain*> chains;
-    std::vector<int> ids;
-    for (size_t i = 0; i < fe->vfos.size(); i++) {
-        if (fe->vfos[i]->used) { chains.push_back(&fe->vfos[i]->chain); ids.push_back((int)i); }
-    }
-    for (size_t k = 0; k < chains.size(); k++) {
-        int bound = chains[k]->max_out(count);
-        if (out->vfo_out[ids[k]] == nullptr || out->vfo_cap[ids[k]] < bound) {
-            set_error("VFO %d output buffer too small: need room for %d samples (b200_fe_vfo_max_out)", ids[k], bound);
-            return B200_ECAP;
-        }
-    }
-    if (fe->fft_on) {
-        int bound = b200_fe_fft_max_lines(fe, count);
-        if (out->fft_out == nullptr || out->fft_cap_lines < std::min(bound, fe->max_lines)) {
-            // exact count of lines this chunk completes
-            unsigned long long end = fe->pos + (unsigned long long)count, f = fe->fstart;
-            unsigned long long nz = (unsigned long long)fe->fft.nz, iv = nz + (unsigned long long)fe->skip;
-            int need = 0;
-            while (f + nz <= end) { need++; f += iv; }
-            if (need > 0 && (out->fft_out == nullptr || out->fft_cap_lines < need)) {
-                set_error("FFT output buffer too small: %d lines complete in this chunk", need);
-                return B200_ECAP;
-            }
-        }
-    }
+    { int rcd = fe->sch.apply_deferred(chains); if (rcd) { return rcd; } }
     for (Chain* c : chains) { c->plan(count); }
     // device-resident outputs: the last stage of every chain (and the FFT epilogue) write straight into the caller's buffers
     const bool direct = (out->out_mem == B200_MEM_DEVICE);
@@ -721,6 +722,13 @@ struct b200_block {
     // rxvfo bookkeeping for the setters
     double inSR = 0, outSR = 0, bw = 0;
     bool is_rxvfo = false, is_xlator = false;
+    // setters may come from another thread than the worker running b200_block_process (b200dsp.h conventions): they only
+    // stage a value under `mtx`; process() applies it at its next chunk boundary, like the reference's ctrlMtx
+    std::mutex mtx;
+    bool pend_off = false, pend_bw = false;
+    double new_off_rad = 0, new_bw = 0;
+    bool is_fir_c = false;
+    std::vector<float> pend_taps;   // FIR::setTaps of a stand-alone complex-data filter
 };
 
 static b200_block* block_new() {
@@ -761,7 +769,9 @@ extern "C" b200_block* b200_xlator_create(double offsetHz, double sr) {
 }
 extern "C" int b200_xlator_set_offset(b200_block* b, double offsetHz, double sr) {
     if (!b || !b->is_xlator) { set_error("not an xlator block"); return B200_EINVAL; }
-    ((XdStage*)b->chain.st[0].get())->set_offset_rad(hz_to_rads(offsetHz, sr));
+    std::lock_guard<std::mutex> lck(b->mtx);
+    b->pend_off = true;
+    b->new_off_rad = hz_to_rads(offsetHz, sr);
     return 0;
 }
 extern "C" b200_block* b200_decim_create(int ratio) {
@@ -780,7 +790,14 @@ extern "C" b200_block* b200_fir_cr_create(const float* taps, int n, int decim) {
     if (!taps || n < 1 || decim < 1) { set_error("bad taps"); return nullptr; }
     b200_block* b = block_new();
     if (!b) { return nullptr; }
+    b->is_fir_c = true;
     return block_finish(b, b->chain.add_fir_c(std::vector<float>(taps, taps + n), decim));
+}
+extern "C" int b200_fir_cr_set_taps(b200_block* b, const float* taps, int n) {
+    if (!b || !b->is_fir_c || !taps || n < 1) { set_error("not a complex-data FIR block / bad taps"); return B200_EINVAL; }
+    std::lock_guard<std::mutex> lck(b->mtx);
+    b->pend_taps.assign(taps, taps + n);
+    return 0;
 }
 extern "C" b200_block* b200_fir_rr_create(const float* taps, int n) {
     if (!taps || n < 1) { set_error("bad taps"); return nullptr; }
@@ -797,21 +814,37 @@ extern "C" b200_block* b200_rxvfo_create(double inSR, double outSR, double bw, d
 }
 extern "C" int b200_rxvfo_set_offset(b200_block* b, double offset) {
     if (!b || !b->is_rxvfo) { set_error("not an RxVFO block"); return B200_EINVAL; }
-    ((XdStage*)b->chain.st[0].get())->set_offset_rad(hz_to_rads(-offset, b->inSR));
+    std::lock_guard<std::mutex> lck(b->mtx);
+    b->pend_off = true;
+    b->new_off_rad = hz_to_rads(-offset, b->inSR);
     return 0;
 }
 extern "C" int b200_rxvfo_set_bandwidth(b200_block* b, double bw) {
     if (!b || !b->is_rxvfo || bw <= 0) { set_error("not an RxVFO block / bad bandwidth"); return B200_EINVAL; }
-    if (b->bw == b->outSR || bw == b->outSR) { set_error("channel filter presence cannot change after creation"); return B200_EINVAL; }
-    FirCStage* f = nullptr;
-    for (auto& s : b->chain.st) {
-        if (s->kind == K_FIRC && ((FirCStage*)s.get())->decim == 1) { f = (FirCStage*)s.get(); }
-    }
-    if (!f) { set_error("no channel filter"); return B200_EINVAL; }
-    double fw = bw / 2.0;
-    f->pending = lowpass_taps(fw, fw * 0.1, b->outSR);
-    b->bw = bw;
+    if (b->chain.chan_fir < 0) { set_error("no channel filter"); return B200_EINVAL; }
+    std::lock_guard<std::mutex> lck(b->mtx);
+    b->pend_bw = true;
+    b->new_bw = bw;
     return 0;
+}
+// staged setter values -> stages; called by the worker at the top of process()
+static void block_apply_pending(b200_block* b) {
+    std::lock_guard<std::mutex> lck(b->mtx);
+    if (b->pend_off) {
+        ((XdStage*)b->chain.st[0].get())->set_offset_rad(b->new_off_rad);
+        b->pend_off = false;
+    }
+    if (!b->pend_taps.empty()) {
+        ((FirCStage*)b->chain.st[0].get())->pending.swap(b->pend_taps);
+        b->pend_taps.clear();
+    }
+    if (b->pend_bw) {
+        FirCStage* f = (FirCStage*)b->chain.st[b->chain.chan_fir].get();
+        const double fw = b->new_bw / 2.0;
+        f->pending = (b->new_bw != b->outSR) ? lowpass_taps(fw, fw * 0.1, b->outSR) : std::vector<float>{ 1.0f };
+        b->bw = b->new_bw;
+        b->pend_bw = false;
+    }
 }
 extern "C" b200_block* b200_quad_create(double dev, double sr) {
     b200_block* b = block_new();
@@ -856,6 +889,9 @@ extern "C" int b200_block_max_out(b200_block* b, int count) {
 extern "C" int b200_block_process(b200_block* b, int count, const void* in, void* out) {
     if (!b || (count > 0 && (!in || !out))) { set_error("null argument"); return B200_EINVAL; }
     if (count < 0 || count > b->max_chunk) { set_error("count %d exceeds the block's chunk limit %d", count, b->max_chunk); return B200_ECAP; }
+    block_apply_pending(b);
+    std::vector<Chain*> chains{ &b->chain };
+    { int rcd = b->sch.apply_deferred(chains); if (rcd) { return rcd; } }     // may move stage buffers: before the input copy
     cudaStream_t s = b->stream;
     const bool raw = b->chain.raw_input();
     const size_t in_bytes = (size_t)count * b->in_es * sizeof(float);
@@ -864,7 +900,6 @@ extern "C" int b200_block_process(b200_block* b, int count, const void* in, void
         B200_CK(cudaMemcpyAsync(dst, in, in_bytes, cudaMemcpyHostToDevice, s));
     }
     b->chain.plan(count);
-    std::vector<Chain*> chains{ &b->chain };
     int rc = b->sch.run(chains, raw ? b->in_dev.p : nullptr, FMT_CF32, count, raw);
     if (rc) { return rc; }
     if (b->chain.n_out > 0) {

@@ -523,6 +523,11 @@ int Chain::add_rxvfo(double inSR, double outSR, double bw, double offset) {
     if (pl.use_decim) {
         dp = find_decim_plan(pl.predec_ratio);
         if (!dp) { set_error("no decimation plan for ratio %d (decim_plans.bin not found?)", pl.predec_ratio); return B200_ENOPLAN; }
+        if ((int)dp->stages[0].taps.size() - 1 > Scheduler::RAW_HIST) {
+            set_error("first decimation stage of ratio %d has %d taps: more than the %d samples of raw history kept", pl.predec_ratio,
+                      (int)dp->stages[0].taps.size(), Scheduler::RAW_HIST + 1);
+            return B200_ECAP;
+        }
         x->configure(dp->stages[0].decim, dp->stages[0].taps);     // xlator fused with the first DecimatingFIR
         first_other = 1;
     }
@@ -543,10 +548,15 @@ int Chain::add_rxvfo(double inSR, double outSR, double bw, double offset) {
         if (rc) { return rc; }
         st.push_back(std::move(r));
     }
-    if (bw != outSR) {
+    // The reference always owns the channel filter and bypasses it while bandwidth == outSamplerate (rx_vfo.h:24,60-70,
+    // 91-93).  Here the stage always exists; bypass = the exact identity tap {1.0f}, so setBandwidth can switch between
+    // the two at a chunk boundary.  (The reference's bypassed filter keeps a stale delay line; after identity -> low-pass
+    // this one starts from the cleared history a fresh block has.)
+    {
         double fw = bw / 2.0;
-        int rc = add_fir_c(lowpass_taps(fw, fw * 0.1, outSR), 1);
+        int rc = add_fir_c(bw != outSR ? lowpass_taps(fw, fw * 0.1, outSR) : std::vector<float>{ 1.0f }, 1);
         if (rc) { return rc; }
+        chan_fir = (int)st.size() - 1;
     }
     return 0;
 }
@@ -704,11 +714,8 @@ int Scheduler::enable_overlap(cudaStream_t tail) {
     return 0;
 }
 
-int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int count, bool carry_raw) {
-    // ---- wiring + deferred parameter changes ----
-    const int parity = (int)(chunk_idx & 1);
-    cudaStream_t ts = tail_stream ? tail_stream : stream;
-    size_t depth = 0;
+// deferred parameter changes (FIR::setTaps at a chunk boundary); fallible, so callers run it BEFORE Chain::plan()
+int Scheduler::apply_deferred(std::vector<Chain*>& chains) {
     for (Chain* c : chains) {
         bool changed = false;
         for (auto& sp : c->st) {
@@ -723,6 +730,18 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
             if (rc) { return rc; }
             if (!c->fp.active) { set_error("new filter does not fit the fused tail (set option tails=1 before adding VFOs)"); return B200_ECAP; }
         }
+    }
+    return 0;
+}
+
+int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int count, bool carry_raw) {
+    // ---- wiring ----
+    const int parity = (int)(chunk_idx & 1);
+    cudaStream_t ts = tail_stream ? tail_stream : stream;
+    size_t depth = 0;
+    {
+        int rc = apply_deferred(chains);          // no-op when the caller already did it
+        if (rc) { return rc; }
     }
     for (Chain* c : chains) {
         for (auto& sp : c->st) { sp->par = parity; }
@@ -809,7 +828,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
             }
             // polyphase-filter-bank form (xd_pfb.cuh): every job on a common frequency grid fs / (2 PS), same prototype,
             // same alignment.  Accept when e^{j w_v PS} is within a few 1e-6 rad (over one tap window) of the same sign.
-            p.pfb_ps = 0; p.pfb_sigma = 1;
+            p.pfb_ps = 0; p.pfb_sigma = 1; p.taps_host = nullptr;
             if (s1_variant >= 7 && p.njobs >= 1) {
                 bool same = true;
                 XdStage* x0 = g[b];
@@ -818,6 +837,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
                     if (xv->T != x0->T || xv->chunk_offset != x0->chunk_offset || xv->n_out != x0->n_out || xv->h != x0->h) { same = false; }
                 }
                 if (same && x0->n_out > 0) {
+                    p.taps_host = x0->h.data();
                     for (int P = 1; P <= 10 && !p.pfb_ps; P++) {
                         // drift allowed per P samples so that it stays below 8e-6 rad over the T-tap window
                         const double tol_turns = (8e-6 / 6.283185307179586) * (double)P / (double)x0->T;

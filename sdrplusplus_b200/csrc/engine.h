@@ -176,6 +176,7 @@ struct Chain {
     int n_out = 0;               // this chunk
     float* out_override = nullptr;   // this chunk: final stage writes straight into the caller's device buffer
     bool raw_input() const { return !st.empty() && st[0]->kind == K_XD; }
+    int chan_fir = -1;           // stage index of RxVFO's channel filter (rx_vfo.h:28-31), set by add_rxvfo
     FusedPlan fp;
     FuseCfg fcfg;
     int plan_fused();            // (re)builds fp from the stage list; clears fp.active when the chain cannot be fused
@@ -213,7 +214,7 @@ struct Scheduler {
     cudaStream_t out_stream() const { return tail_stream ? tail_stream : stream; }
     int enable_overlap(cudaStream_t tail);
     long long launches = 0;
-    int s1_variant = 7;          // 7: polyphase-filter-bank stage 1 when the VFO plan allows it, else 6
+    int s1_variant = 8;          // 8: filter-bank stage 1 fed by the TMA engine (cf32 chunks), 7: cp.async filter bank, when the VFO plan allows it; else 6
     FuseCfg fuse;                // tails: one fused launch per <= 16 VFOs instead of one launch per stage kind
     int sm_count = 148;
     float in_scale = 1.0f / 32768.0f;   // integer raw formats of this chunk: sample = (float)x * in_scale (set by the caller)
@@ -230,6 +231,7 @@ struct Scheduler {
     // raw: device pointer to the chunk (format fmt) for chains with raw_input(); typed chains were fed by
     // copying into st[0]->in_data() beforehand.  counts were planned already (Chain::plan).
     int run(std::vector<Chain*>& chains, const void* raw, int fmt, int count, bool carry_raw);
+    int apply_deferred(std::vector<Chain*>& chains);   // pending FIR taps; call before Chain::plan()
     int reset_raw();
 };
 

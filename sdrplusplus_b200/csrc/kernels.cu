@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(256) k_xd_tile(const __grid_constant__ XdParam
 #define FL_M_PI_REF 3.1415926535f   // math::normalizePhase (normalize_phase.h:6-10)
 #include "xd_pipe.cuh"
 #include "xd_pfb.cuh"
+#include "xd_tma.cuh"
 #include "tails.cuh"
 #include "fused_tail.cuh"
 
@@ -939,6 +940,104 @@ static bool try_xd_pfb(const XdParams& p, int fmt, cudaStream_t s, cudaError_t* 
     return false;
 }
 
+
+// ---- filter-bank stage 1 fed by the TMA engine (xd_tma.cuh); returns true when it was launched ----
+typedef CUresult (*PFN_tmap_encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmap_encode tmap_encode_fn() {
+    static PFN_tmap_encode fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) {
+            fn = (PFN_tmap_encode)f;
+        }
+        else { cudaGetLastError(); }
+    }
+    return fn;
+}
+int g_xd_tma_launches = 0;        // diagnostic: how many stage-1 launches took the TMA path
+template <int LOGD, int QC, int PS, int MT>
+static cudaError_t launch_xd_tma_t(const XdParams& p, const XtGeom& g, const CUtensorMap& tm, cudaStream_t s) {
+    using Lay = XtLay<LOGD, QC, MT>;
+    const size_t smem = (size_t)XT_STAGES * Lay::STAGE + ((size_t)B200_BATCH * (PS + 16) + (size_t)Lay::NW * B200_BATCH * 4) * sizeof(float2) +
+                        2 * XT_STAGES * sizeof(unsigned long long) + 1024;
+    if ((int)smem > kernels_max_smem_optin()) { return cudaErrorInvalidValue; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = set_smem(k_xd_tma<LOGD, QC, PS, MT>, smem);
+        if (e != cudaSuccess) { return e; }
+        attr_set = true;
+    }
+    int grid = num_sms();
+    if (grid > g.ntiles) { grid = g.ntiles; }
+    k_xd_tma<LOGD, QC, PS, MT><<<grid, (Lay::NW + 1) * 32, smem, s>>>(p, g, tm);
+    g_xd_tma_launches++;
+    return cudaGetLastError();
+}
+static bool try_xd_tma(const XdParams& p, cudaStream_t s, cudaError_t* err) {
+    const int D = p.D, PS = p.pfb_ps;
+    if ((PS != 8 && PS != 10) || (D != 32 && D != 64) || !p.taps_host) { return false; }
+    if (((uintptr_t)p.in & 15) != 0) { return false; }
+    PFN_tmap_encode enc = tmap_encode_fn();
+    if (!enc) { return false; }
+    const int T = p.job[0].T;
+    const int a0 = p.job[0].offset - (T - 1);
+    const int org = ((a0 % D) + D) % D;
+    for (int v = 0; v < p.njobs; v++) {
+        const int a = p.job[v].offset - (p.job[v].T - 1);
+        if (p.job[v].T != T || a != a0 || p.job[v].n_out != p.job[0].n_out || p.job[v].n_out <= 0) { return false; }
+    }
+    // row origin: 128-byte aligned when that costs no extra tap block, else 16-byte aligned (s leading zero taps)
+    const int QC = (T + (org & 1) + D - 1) / D;
+    int sh = org & 1;
+    for (int al = 16; al >= 2; al >>= 1) {
+        const int c = org & (al - 1);
+        if ((T + c + D - 1) / D == QC) { sh = c; break; }
+    }
+    if (QC * D > XT_MAXTAPS) { return false; }
+    XtGeom g;
+    memset(&g, 0, sizeof(g));
+    g.org = org - sh;
+    g.s = sh;
+    g.cj = (a0 - org) / D;                        // exact: a0 - org is a multiple of D
+    long long jmin = g.cj;
+    if (jmin & 1) { jmin -= 1; }
+    g.jmin = jmin;
+    for (int q = 0; q < QC * D; q++) {
+        const int k = q - sh;
+        float t = (k >= 0 && k < T) ? p.taps_host[k] : 0.0f;
+        if (p.pfb_sigma < 0 && k >= 0 && ((k / PS) & 1)) { t = -t; }
+        g.g[q] = t;
+    }
+    const long long avail = (long long)p.count - g.org;
+    g.rows_tma = avail > 0 ? (int)(avail / (2 * D)) : 0;
+    const int MT = (D == 32) ? 256 : 128;
+    g.ntiles = cdiv((long long)g.cj + p.job[0].n_out - jmin, MT);
+    if (g.rows_tma < 8) { return false; }
+    CUtensorMap tm;
+    const cuuint64_t gdim[2] = { (cuuint64_t)(4 * D), (cuuint64_t)g.rows_tma };
+    const cuuint64_t gstr[1] = { (cuuint64_t)(4 * D) * sizeof(float) };
+    const int NR = (((MT + QC + 2) / 2) + 7) & ~7;
+    const cuuint32_t box[2] = { 32u, (cuuint32_t)NR };
+    const cuuint32_t estr[2] = { 1u, 1u };
+    void* base = (void*)((const float2*)p.in + g.org);
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { return false; }
+#define XT_CASE(LD, Q, MTV)                                                                    \
+    if (D == (1 << LD) && QC == Q) {                                                           \
+        *err = (PS == 10) ? launch_xd_tma_t<LD, Q, 10, MTV>(p, g, tm, s) : launch_xd_tma_t<LD, Q, 8, MTV>(p, g, tm, s); \
+        return true;                                                                           \
+    }
+    XT_CASE(5, 5, 256) XT_CASE(6, 5, 128) XT_CASE(6, 6, 128) XT_CASE(6, 7, 128)
+#undef XT_CASE
+    return false;
+}
+
 template <int FMT>
 static cudaError_t launch_xd_fmt(const XdParams& p, int variant, cudaStream_t s, int* nlaunch) {
     int max_out = 0;
@@ -947,6 +1046,10 @@ static cudaError_t launch_xd_fmt(const XdParams& p, int variant, cudaStream_t s,
     const int D = p.D;
     if (variant >= 7) {
         cudaError_t e = cudaSuccess;
+        if (variant >= 8 && FMT == FMT_CF32 && p.pfb_ps > 0 && try_xd_tma(p, s, &e)) {
+            if (nlaunch) { (*nlaunch)++; }
+            return e;
+        }
         if (p.pfb_ps > 0 && try_xd_pfb(p, FMT, s, &e)) {
             if (nlaunch) { (*nlaunch)++; }
             return e;

@@ -47,6 +47,7 @@ struct XdParams {
     // pfb_ps = 0: not applicable
     int pfb_ps, pfb_sigma;
     float in_scale;         // integer formats: sample = (float)x * in_scale
+    const float* taps_host; // HOST copy of the real prototype taps shared by the jobs of a filter-bank launch (launcher only)
     XdJob job[B200_BATCH];
 };
 

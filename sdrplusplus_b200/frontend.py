@@ -145,6 +145,9 @@ class FrontEnd:
     def launch_count(self):
         return self._l.b200_fe_launch_count(self._h)
 
+    def stat(self, key):
+        return self._l.b200_fe_stat(self._h, key.encode())
+
     def vfo_max_out(self, vid, count):
         return L.check(self._l.b200_fe_vfo_max_out(self._h, vid, count))
 

@@ -1,6 +1,6 @@
-// host/dsp/block.h -- worker-thread block base and the typed Processor<I,O> of the operator API
-// (start / stop / tempStart / tempStop / run, core/src/dsp/block.h:18-131, processor.h:42-73), for adapters whose
-// process() forwards to libb200dsp.  One worker thread per started block, `while (run() >= 0)`.
+// host/dsp/block.h -- worker-thread block base of the operator API (start / stop / tempStart / tempStop / run,
+// core/src/dsp/block.h:18-131), for adapters whose process() forwards to libb200dsp.  One worker thread per started
+// block, `while (run() >= 0)`.  The typed bases live in processor.h / sink.h / source.h / operator.h like the reference.
 #pragma once
 #include <algorithm>
 #include <cassert>
@@ -11,16 +11,25 @@
 #include "types.h"
 
 namespace dsp {
-    class block {
+    // what hier_block and chain hold: anything that can be started and stopped (block.h:10-16)
+    class generic_block {
     public:
-        virtual ~block() { if (inited) { stop(); } }
-        virtual void start() {
+        virtual ~generic_block() {}
+        virtual void start() {}
+        virtual void stop() {}
+        virtual int run() { return -1; }
+    };
+
+    class block : public generic_block {
+    public:
+        ~block() override { if (inited) { stop(); } }
+        void start() override {
             std::lock_guard<std::recursive_mutex> lk(ctrlMtx);
             if (running) { return; }
             running = true;
             launch();
         }
-        virtual void stop() {
+        void stop() override {
             std::lock_guard<std::recursive_mutex> lk(ctrlMtx);
             if (!running) { return; }
             halt();
@@ -32,7 +41,7 @@ namespace dsp {
         void tempStart() {
             if (depth > 0 && --depth == 0 && paused) { launch(); paused = false; }
         }
-        virtual int run() = 0;
+        int run() override = 0;
 
     protected:
         void registerInput(untyped_stream* s) { ins.push_back(s); }
@@ -57,27 +66,5 @@ namespace dsp {
         bool running = false, paused = false;
         int depth = 0;
     };
-
-    template <class I, class O>
-    class Processor : public block {
-    public:
-        void init(stream<I>* in) {
-            _in = in;
-            registerInput(_in);
-            registerOutput(&out);
-            inited = true;
-        }
-        virtual void setInput(stream<I>* in) {
-            std::lock_guard<std::recursive_mutex> lk(ctrlMtx);
-            tempStop();
-            unregisterInput(_in);
-            _in = in;
-            registerInput(_in);
-            tempStart();
-        }
-        stream<O> out;
-
-    protected:
-        stream<I>* _in = nullptr;
-    };
 }
+#include "processor.h"

@@ -1,8 +1,13 @@
-// host/dsp/demod/broadcast_fm.h -- dsp::demod::BroadcastFM (mono branch) with the reference's interface
-// (init(in, deviation, samplerate, stereo, lowPass, rdsOut) / process / run, core/src/dsp/demod/broadcast_fm.h:36-215),
-// forwarding to libb200dsp (b200_wfm_*).  Stereo / RDS are not built yet: init() reports failure through ok().
+// host/dsp/demod/broadcast_fm.h -- dsp::demod::BroadcastFM with the reference's interface (init(in, deviation,
+// samplerate, stereo, lowPass, rdsOut) / setDeviation / setSamplerate / setStereo / setLowPass / setRDSOut / reset /
+// process(count, in, out, rdsOutCount, rdsout) / run / rdsOut, core/src/dsp/demod/broadcast_fm.h:20-240), forwarding to
+// libb200dsp (b200_wfm_*): discriminator, 19 kHz pilot filter + PLL + L-R recovery (stereo), audio low-pass.
+// The RDS side output is the discriminator output as complex samples (broadcast_fm.h:156-160: rtoc of the demodulated
+// signal); it is produced on request from the same pass.
 #pragma once
-#include "../block.h"
+#include <vector>
+#include "../processor.h"
+#include "../b200/handle.h"
 
 namespace dsp::demod {
     class BroadcastFM : public Processor<complex_t, stereo_t> {
@@ -12,32 +17,67 @@ namespace dsp::demod {
         BroadcastFM(stream<complex_t>* in, double deviation, double samplerate, bool stereo = true, bool lowPass = true, bool rdsOut = false) {
             init(in, deviation, samplerate, stereo, lowPass, rdsOut);
         }
-        ~BroadcastFM() override {
-            if (inited) { stop(); }
-            b200_block_destroy(h);
-        }
         void init(stream<complex_t>* in, double deviation, double samplerate, bool stereo = true, bool lowPass = true, bool rdsOut = false) {
-            (void)rdsOut;
-            h = b200_wfm_create(deviation, samplerate, stereo ? 1 : 0, lowPass ? 1 : 0);
+            _dev = deviation; _sr = samplerate; _stereo = stereo; _lowPass = lowPass; _rds = rdsOut;
+            make();
+            registerOutput(&this->rdsOut);
             base_type::init(in);
         }
-        bool ok() const { return h != nullptr; }
+        bool ok() const { return blk.ok() && (!_rds || quad.ok()); }
+        void setDeviation(double deviation) { _dev = deviation; rebuild(); }
+        void setSamplerate(double samplerate) { _sr = samplerate; rebuild(); }
+        void setStereo(bool stereo) { _stereo = stereo; rebuild(); }
+        void setLowPass(bool lowPass) { _lowPass = lowPass; rebuild(); }
+        void setRDSOut(bool rdsOut) { _rds = rdsOut; rebuild(); }
         void reset() {
             std::lock_guard<std::recursive_mutex> lk(ctrlMtx);
             tempStop();
-            b200_block_reset(h);
+            blk.reset();
+            quad.reset();
             tempStart();
         }
-        inline int process(int count, complex_t* in, stereo_t* out_) { return b200_block_process(h, count, in, out_); }
+        // the reference's signature: rdsOutCount / rdsout receive the RDS branch (0 samples while it is off)
+        inline int process(int count, complex_t* in, stereo_t* out_, int& rdsOutCount, complex_t* rdsout = nullptr) {
+            rdsOutCount = 0;
+            if (_rds && rdsout && quad.ok()) {
+                if ((int)mono.size() < count) { mono.resize((size_t)count); }
+                const int n = quad.process(count, in, mono.data());
+                for (int i = 0; i < n; i++) { rdsout[i].re = mono[(size_t)i]; rdsout[i].im = 0.0f; }
+                rdsOutCount = n > 0 ? n : 0;
+            }
+            return blk.process(count, in, out_);
+        }
+        inline int process(int count, complex_t* in, stereo_t* out_) {
+            int unused = 0;
+            return process(count, in, out_, unused, nullptr);
+        }
         int run() override {
-            int count = _in->read();
+            const int count = _in->read();
             if (count < 0) { return -1; }
-            int n = process(count, _in->readBuf, out.writeBuf);
+            int rdsCount = 0;
+            const int n = process(count, _in->readBuf, out.writeBuf, rdsCount, rdsOut.writeBuf);
             _in->flush();
-            if (n < 0 || !out.swap(n)) { return -1; }
+            if (n < 0) { return -1; }
+            if (rdsCount && !rdsOut.swap(rdsCount)) { return -1; }
+            if (!out.swap(n)) { return -1; }
             return n;
         }
+        stream<complex_t> rdsOut;
+
     private:
-        b200_block* h = nullptr;
+        void make() {
+            blk.adopt(b200_wfm_create(_dev, _sr, _stereo ? 1 : 0, _lowPass ? 1 : 0));
+            quad.adopt(_rds ? b200_quad_create(_dev, _sr) : nullptr);
+        }
+        void rebuild() {
+            std::lock_guard<std::recursive_mutex> lk(ctrlMtx);
+            tempStop();
+            make();
+            tempStart();
+        }
+        double _dev = 75000.0, _sr = 250000.0;
+        bool _stereo = false, _lowPass = true, _rds = false;
+        std::vector<float> mono;
+        b200::Handle blk, quad;
     };
 }

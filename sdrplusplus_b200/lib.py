@@ -71,6 +71,7 @@ SIGNATURES = {
     "b200_fe_submit": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(Outputs)]),
     "b200_fe_wait": (_i, [_vp]),
     "b200_fe_launch_count": (_ll, [_vp]),
+    "b200_fe_stat": (_ll, [_vp, C.c_char_p]),
     "b200_fe_set_option": (_i, [_vp, C.c_char_p, _i]),
     "b200_fe_s1_stats": (_i, [_vp, C.POINTER(C.c_double), _ip]),
     "b200_fft_zoom_hold": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, C.c_float, _i]),
@@ -79,6 +80,7 @@ SIGNATURES = {
     "b200_decim_create": (_vp, [_i]),
     "b200_resamp_create": (_vp, [_d, _d]),
     "b200_fir_cr_create": (_vp, [_vp, _i, _i]),
+    "b200_fir_cr_set_taps": (_i, [_vp, _vp, _i]),
     "b200_fir_rr_create": (_vp, [_vp, _i]),
     "b200_rxvfo_create": (_vp, [_d, _d, _d, _d]),
     "b200_rxvfo_set_offset": (_i, [_vp, _d]),

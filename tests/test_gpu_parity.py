@@ -250,7 +250,7 @@ def _oracle_lines(oracle, x, fs, size, rate):
     return np.array(lines)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 def test_frontend_c1_geometry(sb, oracle, report, variant):
     """BASELINE config 1: 2.4 MS/s, chunk 12000, 65536-pt FFT @ 20 fps, one WFM VFO at +300 kHz."""
     n = 600000
@@ -559,7 +559,8 @@ def test_frontend_multi_vfo_100msps(sb, oracle, report):
 @pytest.mark.parametrize("variant,fft_async,overlap,pair,tails", [
     (4, 1, 1, 1, {}), (3, 0, 0, 1, {}), (1, 1, 0, 0, {}), (3, 1, 1, 0, {"tails": 1}), (3, 1, 0, 1, {"tails": 0}), (5, 1, 1, 1, {}),
     (5, 1, 0, 0, {"tails": 1}), (6, 1, 1, 1, {"tails": 1}), (6, 1, 0, 0, {}), (6, 1, 1, 1, {"ft_threads": 256}),
-    (6, 1, 1, 1, {"ft_ob": 301}), (7, 1, 1, 1, {}), (7, 1, 0, 0, {"tails": 1}), (7, 0, 0, 1, {"ft_direct": 0}), (6, 1, 0, 1, {"ft_ob": 64, "ft_smem_kb": 48}), (6, 1, 1, 1, {"ft_obmax": 2500, "ft_smem_kb": 200})])
+    (6, 1, 1, 1, {"ft_ob": 301}), (7, 1, 1, 1, {}), (7, 1, 0, 0, {"tails": 1}), (7, 0, 0, 1, {"ft_direct": 0}), (6, 1, 0, 1, {"ft_ob": 64, "ft_smem_kb": 48}), (6, 1, 1, 1, {"ft_obmax": 2500, "ft_smem_kb": 200}),
+    (8, 1, 1, 1, {}), (8, 0, 0, 0, {"tails": 1})])
 def test_frontend_variants_100msps(sb, oracle, report, variant, fft_async, overlap, pair, tails):
     """kernel / scheduling A-B on the config-2 geometry (short): 16-warp stage 1, synchronous spectrum branch,
     tails on the main stream, conjugate-pair sharing off, per-stage tail launches instead of the fused tail,
