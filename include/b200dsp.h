@@ -171,6 +171,14 @@ int b200_fe_set_stream(b200_fe* fe, void* cuda_stream);
 /* IQFrontEnd::setFFTSize/Rate/Window (iq_frontend.h:37-39); size 0 disables the branch. size must be a
  * power of two in [8, 4194304]. */
 int b200_fe_set_fft(b200_fe* fe, int size, double rate, int window);
+/* IQFrontEnd's pre-processing chain in front of the FFT branch and every VFO (core/src/signal_path/iq_frontend.cpp:32-39):
+ * PowerDecimator -> correction::DCBlocker<complex_t> (rate 50 / effective samplerate, iq_frontend.h:55-57) -> math::Conjugate;
+ * all off by default like the reference's.  setDecimation (iq_frontend.cpp:100-115): ratio = power of two <= 8192; it
+ * changes the effective sample rate (samplerate / ratio) every later setting is interpreted with, so it must come before
+ * b200_fe_set_fft / b200_fe_add_vfo.  setDCBlocking / setInvertIQ (:117-123) may change between chunks. */
+int b200_fe_set_decimation(b200_fe* fe, int ratio);
+int b200_fe_set_dc_blocking(b200_fe* fe, int enabled);
+int b200_fe_set_invert_iq(b200_fe* fe, int enabled);
 /* IQFrontEnd::addVFO / removeVFO (iq_frontend.h:32-33) + radio demodulator selection: returns vfo id */
 int b200_fe_add_vfo(b200_fe* fe, const b200_vfo_cfg* cfg);
 int b200_fe_remove_vfo(b200_fe* fe, int id);

@@ -187,6 +187,15 @@ struct b200_fe {
     bool slot_used[2] = { false, false };
     unsigned long long nsub = 0, nwait = 0;
     float scale16 = 1.0f / 32768.0f, scale8 = 1.0f / 128.0f;
+    // IQFrontEnd pre-processing chain (iq_frontend.cpp:32-39): PowerDecimator -> DCBlocker -> Conjugate, off by default
+    int decim = 1;               // setDecimation: everything behind it runs at fs_eff = fs / decim
+    double fs_eff = 0;
+    bool dc_block = false, invert_iq = false;
+    Chain pre;                   // the decimator (typed cf32 chain), built when decim > 1
+    Scheduler sch_pre;
+    DevBuf pp[2];                // chunk after DC blocker / conjugate (one per chunk in flight)
+    DevBuf dc_state, dc_segA, dc_segB;
+    int max_eff = 0;             // largest chunk behind the decimator
 };
 
 // (float)x * scale for the integer input formats: 1/32768 and 1/128 unless the caller set the scale of a
@@ -201,7 +210,7 @@ static int fe_alloc_fft(b200_fe* fe) {
     int rc;
     if ((rc = fe->frame.alloc((size_t)fe->fft.nz * sizeof(float2)))) { return rc; }
     long long interval = (long long)fe->fft.nz + fe->skip;
-    fe->max_lines = (int)(fe->max_chunk / interval) + 2;
+    fe->max_lines = (int)(fe->max_eff / interval) + 2;
     return fe->lines.alloc((size_t)fe->max_lines * fe->fft.size * sizeof(float));
 }
 
@@ -210,7 +219,9 @@ extern "C" b200_fe* b200_fe_create(double samplerate, int max_chunk) {
     if (samplerate <= 0 || max_chunk < 1) { set_error("bad samplerate/max_chunk"); return nullptr; }
     b200_fe* fe = new b200_fe;
     fe->fs = samplerate;
+    fe->fs_eff = samplerate;
     fe->max_chunk = max_chunk;
+    fe->max_eff = max_chunk;
     bool ok = cudaStreamCreateWithFlags(&fe->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&fe->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&fe->fft_stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -268,6 +279,42 @@ extern "C" int b200_fe_set_stream(b200_fe* fe, void* s) {
     return 0;
 }
 
+// IQFrontEnd::setDecimation / setDCBlocking / setInvertIQ (iq_frontend.cpp:100-119)
+extern "C" int b200_fe_set_decimation(b200_fe* fe, int ratio) {
+    if (!fe) { set_error("null fe"); return B200_EINVAL; }
+    if (ratio < 1 || (ratio & (ratio - 1)) || ratio > 8192) { set_error("decimation must be a power of two <= 8192"); return B200_EINVAL; }
+    std::lock_guard<std::mutex> lck(fe->mtx);
+    if (b200_fe_vfo_count(fe) > 0 || fe->fft_on || fe->nsub > 0) {
+        set_error("the input decimation changes the effective sample rate: set it before the FFT and the VFOs are configured");
+        return B200_ESTATE;
+    }
+    B200_CK(cudaDeviceSynchronize());
+    fe->pre.st.clear();
+    fe->decim = ratio;
+    fe->fs_eff = fe->fs / (double)ratio;
+    fe->max_eff = fe->max_chunk;
+    if (ratio > 1) {
+        int rc = fe->pre.add_power_decim(ratio);
+        if (!rc) { rc = fe->pre.finalize(fe->max_chunk); }
+        if (rc) { fe->pre.st.clear(); fe->decim = 1; fe->fs_eff = fe->fs; return rc; }
+        fe->max_eff = fe->pre.max_out(fe->max_chunk);
+        fe->sch_pre.stream = fe->sch.stream;
+    }
+    return 0;
+}
+extern "C" int b200_fe_set_dc_blocking(b200_fe* fe, int enabled) {
+    if (!fe) { set_error("null fe"); return B200_EINVAL; }
+    std::lock_guard<std::mutex> lck(fe->mtx);
+    fe->dc_block = enabled != 0;
+    return 0;
+}
+extern "C" int b200_fe_set_invert_iq(b200_fe* fe, int enabled) {
+    if (!fe) { set_error("null fe"); return B200_EINVAL; }
+    std::lock_guard<std::mutex> lck(fe->mtx);
+    fe->invert_iq = enabled != 0;
+    return 0;
+}
+
 extern "C" int b200_fe_set_fft(b200_fe* fe, int size, double rate, int window) {
     if (!fe) { set_error("null fe"); return B200_EINVAL; }
     std::lock_guard<std::mutex> lck(fe->mtx);
@@ -275,8 +322,8 @@ extern "C" int b200_fe_set_fft(b200_fe* fe, int size, double rate, int window) {
     if (size == 0) { fe->fft_on = false; return 0; }
     if (rate <= 0) { set_error("bad fft rate"); return B200_EINVAL; }
     int nz, skip;
-    fft_frame_params(fe->fs, size, rate, nz, skip);
-    int rc = fe->fft.create(size, nz, window, (int)(fe->max_chunk / ((long long)nz + skip)) + 2);
+    fft_frame_params(fe->fs_eff, size, rate, nz, skip);
+    int rc = fe->fft.create(size, nz, window, (int)(fe->max_eff / ((long long)nz + skip)) + 2);
     if (rc) { return rc; }
     fe->skip = skip;
     fe->fft_rate = rate;
@@ -289,7 +336,7 @@ extern "C" int b200_fe_set_fft(b200_fe* fe, int size, double rate, int window) {
 
 static int build_vfo_chain(b200_fe* fe, VfoSlot* v) {
     const b200_vfo_cfg& c = v->cfg;
-    int rc = v->chain.add_rxvfo(fe->fs, c.out_samplerate, c.bandwidth, c.offset);
+    int rc = v->chain.add_rxvfo(fe->fs_eff, c.out_samplerate, c.bandwidth, c.offset);
     if (rc) { return rc; }
     switch (c.demod) {
     case B200_DEMOD_RAW: break;
@@ -313,7 +360,7 @@ static int build_vfo_chain(b200_fe* fe, VfoSlot* v) {
         // overlapped mode hands every chain's output to the tail stream: give a stage-1-only chain an exact copy stage
         if ((rc = v->chain.add_fir_c(std::vector<float>{ 1.0f }, 1))) { return rc; }
     }
-    return v->chain.finalize(fe->max_chunk, ov, &fe->sch.fuse);
+    return v->chain.finalize(fe->max_eff, ov, &fe->sch.fuse);
 }
 
 extern "C" int b200_fe_add_vfo(b200_fe* fe, const b200_vfo_cfg* cfg) {
@@ -438,6 +485,8 @@ extern "C" int b200_fe_reset(b200_fe* fe) {
         if (v->used) { v->chain.reset_state(); }
     }
     int rc = fe->sch.reset_raw();
+    if (!fe->pre.st.empty()) { fe->pre.reset_state(); }
+    if (fe->dc_state.p) { B200_CK(cudaMemset(fe->dc_state.p, 0, 16)); B200_CK(cudaDeviceSynchronize()); }
     fe->pos = 0;
     fe->fstart = 0;
     return rc;
@@ -450,7 +499,7 @@ static void apply_pending(b200_fe* fe) {
         if (!v->used) { continue; }
         if (v->pend_offset) {
             v->cfg.offset = v->new_offset;
-            ((XdStage*)v->chain.st[0].get())->set_offset_rad(hz_to_rads(-v->cfg.offset, fe->fs));
+            ((XdStage*)v->chain.st[0].get())->set_offset_rad(hz_to_rads(-v->cfg.offset, fe->fs_eff));
             v->pend_offset = false;
         }
         if (v->pend_bw) {
@@ -565,8 +614,11 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
     for (size_t i = 0; i < fe->vfos.size(); i++) {
         if (fe->vfos[i]->used) { chains.push_back(&fe->vfos[i]->chain); ids.push_back((int)i); }
     }
+    // samples that reach the FFT branch and the VFOs: the chunk itself, or what the input decimator makes of it
+    const int ecount = (fe->decim > 1) ? fe->pre.peek(count) : count;
+    if (ecount < 0) { set_error("input decimator is not a FIR cascade"); return B200_ESTATE; }
     for (size_t k = 0; k < chains.size(); k++) {
-        int bound = chains[k]->max_out(count);
+        int bound = chains[k]->max_out(ecount);
         if (out->vfo_out[ids[k]] == nullptr || out->vfo_cap[ids[k]] < bound) {
             set_error("VFO %d output buffer too small: need room for %d samples (b200_fe_vfo_max_out)", ids[k], bound);
             return B200_ECAP;
@@ -574,7 +626,7 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
     }
     if (fe->fft_on) {
         // exact count of lines this chunk completes
-        unsigned long long end = fe->pos + (unsigned long long)count, f = fe->fstart;
+        unsigned long long end = fe->pos + (unsigned long long)ecount, f = fe->fstart;
         unsigned long long nz = (unsigned long long)fe->fft.nz, iv = nz + (unsigned long long)fe->skip;
         int need = 0;
         while (f + nz <= end) { need++; f += iv; }
@@ -600,6 +652,53 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
         dptr = fe->in_dev[slot].p;
     }
     { int rcd = fe->sch.apply_deferred(chains); if (rcd) { return rcd; } }
+    // ---- IQFrontEnd pre-processing chain (iq_frontend.cpp:32-39): decimator -> DC blocker -> conjugate ----
+    if (fe->decim > 1 || fe->dc_block || fe->invert_iq) {
+        if (fe->slot_used[slot]) { B200_CK(cudaStreamWaitEvent(s, fe->ev_compute[slot], 0)); }     // pp[slot] of two chunks ago
+        const void* cur = dptr;
+        int cur_fmt = in_fmt;
+        if (fe->decim > 1) {
+            cudaError_t e = launch_convert_cf32(dptr, in_fmt, (float2*)fe->pre.st[0]->in_data(), count, fe_ingest_scale(fe, in_fmt), s);
+            if (e != cudaSuccess) { return cuda_fail(e, "launch_convert_cf32"); }
+            fe->sch.launches++;
+            fe->pre.plan(count);
+            std::vector<Chain*> pc{ &fe->pre };
+            const long long l0 = fe->sch_pre.launches;
+            fe->sch_pre.stream = s;
+            int rcp = fe->sch_pre.run(pc, nullptr, FMT_CF32, count, false);
+            if (rcp) { return rcp; }
+            fe->sch.launches += fe->sch_pre.launches - l0;
+            cur = fe->pre.out.p;
+            cur_fmt = FMT_CF32;
+        }
+        if (fe->dc_block || fe->invert_iq) {
+            const size_t need = ((size_t)fe->max_eff + 8) * sizeof(float2);
+            if (fe->pp[slot].bytes < need) { int rca = fe->pp[slot].alloc(need, false); if (rca) { return rca; } }
+            const int nseg_max = fe->max_eff / 4096 + 2;
+            if (!fe->dc_state.p) {
+                int rca;
+                if ((rca = fe->dc_state.alloc(16)) || (rca = fe->dc_segA.alloc((size_t)nseg_max * sizeof(float), false)) ||
+                    (rca = fe->dc_segB.alloc((size_t)nseg_max * sizeof(float2), false))) { return rca; }
+            }
+            DcbParams dp;
+            memset(&dp, 0, sizeof(dp));
+            dp.in = cur; dp.out = fe->pp[slot].as<float2>(); dp.fmt = cur_fmt; dp.count = ecount;
+            dp.in_scale = fe_ingest_scale(fe, cur_fmt);
+            dp.rate = (float)(50.0 / fe->fs_eff);                      // genDCBlockRate (iq_frontend.h:55-57)
+            dp.dc_on = fe->dc_block ? 1 : 0; dp.conj_on = fe->invert_iq ? 1 : 0;
+            dp.state = fe->dc_state.as<float2>(); dp.segA = fe->dc_segA.as<float>(); dp.segB = fe->dc_segB.as<float2>();
+            dp.nseg = (ecount + 4095) / 4096;
+            int nl = 0;
+            cudaError_t e = launch_preproc(dp, s, &nl);
+            if (e != cudaSuccess) { return cuda_fail(e, "launch_preproc"); }
+            fe->sch.launches += nl;
+            cur = fe->pp[slot].p;
+            cur_fmt = FMT_CF32;
+        }
+        dptr = cur;
+        in_fmt = cur_fmt;
+        count = ecount;
+    }
     for (Chain* c : chains) { c->plan(count); }
     // device-resident outputs: the last stage of every chain (and the FFT epilogue) write straight into the caller's buffers
     const bool direct = (out->out_mem == B200_MEM_DEVICE);

@@ -446,6 +446,14 @@ int Chain::max_out(int n) const {
     for (auto& s : st) { n = s->max_out(n); }
     return n;
 }
+int Chain::peek(int n) const {
+    for (auto& s : st) {
+        if (s->kind != K_FIRC) { return -1; }
+        const FirCStage* f = (const FirCStage*)s.get();
+        n = (f->offset < n) ? (n - f->offset + f->decim - 1) / f->decim : 0;
+    }
+    return n;
+}
 void Chain::reset_state() {
     for (auto& s : st) {
         s->reset_state();

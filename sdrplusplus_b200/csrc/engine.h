@@ -183,6 +183,7 @@ struct Chain {
     int finalize(int max_in, bool dbl_first = false, const FuseCfg* fuse = nullptr);    // allocates stage buffers for chunks of up to max_in samples
     int plan(int n);             // all stages; returns final count
     int max_out(int n) const;
+    int peek(int n) const;       // output count Chain::plan(n) would return, without moving any state (FIR-only chains; else -1)
     void reset_state();
     // builders (reference block -> stage list)
     int add_rxvfo(double inSR, double outSR, double bw, double offset);     // rx_vfo.h:17-31

@@ -695,6 +695,7 @@ __global__ void __launch_bounds__(512) k_fft_p2(const __grid_constant__ FftPlanD
 }
 
 #include "fft_reg.cuh"
+#include "preproc.cuh"
 
 template <int FMT>
 __global__ void __launch_bounds__(256) k_convert(const void* __restrict__ src, float2* __restrict__ dst, int n, float sc) {

@@ -256,6 +256,21 @@ cudaError_t launch_fft_frame(const FftPlanDev& pl, const void* src, int fmt, flo
 // nbatch equally spaced frames (src_stride_bytes apart) in one launch pair; work: nbatch*N float2, out_db: nbatch*N
 cudaError_t launch_fft_frames(const FftPlanDev& pl, const void* src, int fmt, float2* work, float* out_db,
                               float2* out_raw, cudaStream_t s, int* nlaunch, int nbatch, long long src_stride_bytes);
+// IQFrontEnd pre-processing at the input rate: DC blocker + conjugate (preproc.cuh)
+struct DcbParams {
+    const void* in;          // chunk (format fmt)
+    float2* out;             // cf32 chunk after the chain
+    int fmt;
+    int count;
+    float in_scale;
+    float rate;              // DCBlocker::_rate (float, dc_blocker.h:88)
+    int dc_on, conj_on;
+    float2* state;           // [0] offset carried across chunks
+    float2* segB;            // [nseg] per-segment B, then rewritten by the scan to the offset at each segment start
+    float* segA;             // [nseg] per-segment slope complement c
+    int nseg;
+};
+cudaError_t launch_preproc(const DcbParams& p, cudaStream_t s, int* nlaunch);
 cudaError_t launch_convert_cf32(const void* src, int fmt, float2* dst, int n, float scale, cudaStream_t s);
 enum { EXP_U8 = 0, EXP_I8 = 1, EXP_I16 = 2, EXP_I32 = 3 };
 cudaError_t launch_export(const float* in, long long n, int type, float scalar, void* out, cudaStream_t s);

@@ -108,6 +108,16 @@ class FrontEnd:
         L.check(self._l.b200_fe_set_fft(self._h, int(size), float(rate), int(window)))
         self.fft_size = int(size)
 
+    # IQFrontEnd::setDecimation / setDCBlocking / setInvertIQ
+    def set_decimation(self, ratio):
+        L.check(self._l.b200_fe_set_decimation(self._h, int(ratio)))
+
+    def set_dc_blocking(self, on):
+        L.check(self._l.b200_fe_set_dc_blocking(self._h, int(bool(on))))
+
+    def set_invert_iq(self, on):
+        L.check(self._l.b200_fe_set_invert_iq(self._h, int(bool(on))))
+
     def set_stream(self, cuda_stream):
         L.check(self._l.b200_fe_set_stream(self._h, C.c_void_p(cuda_stream)))
 

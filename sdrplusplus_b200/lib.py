@@ -59,6 +59,9 @@ SIGNATURES = {
     "b200_fe_destroy": (None, [_vp]),
     "b200_fe_set_stream": (_i, [_vp, _vp]),
     "b200_fe_set_fft": (_i, [_vp, _i, _d, _i]),
+    "b200_fe_set_decimation": (_i, [_vp, _i]),
+    "b200_fe_set_dc_blocking": (_i, [_vp, _i]),
+    "b200_fe_set_invert_iq": (_i, [_vp, _i]),
     "b200_fe_add_vfo": (_i, [_vp, C.POINTER(VfoCfg)]),
     "b200_fe_remove_vfo": (_i, [_vp, _i]),
     "b200_fe_set_vfo_offset": (_i, [_vp, _i, _d]),

@@ -1,0 +1,105 @@
+"""GPU parity of IQFrontEnd's pre-processing chain (SURVEY.md 8a row a19 + iq_frontend.cpp:32-39): input PowerDecimator ->
+full-rate complex DCBlocker (rate 50 / fs) -> Conjugate, in front of the FFT branch and the VFOs.  Oracle: the same
+reference blocks chained on the CPU (correction::DCBlocker<complex_t>, multirate::PowerDecimator, conj), then the usual
+RxVFO -> WFM graph and the spectrum handler."""
+import numpy as np
+import pytest
+
+from util import rel_rms, noise_iq, fm_carrier
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+FS = 2.4e6
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import sdrplusplus_b200 as m
+    from sdrplusplus_b200 import lib
+    L = lib.load()
+    assert L.b200_device_count() > 0
+    assert L.b200_init(0) == 0
+    return m
+
+
+def _lines(oracle, x, fs, size, rate):
+    skip, nz = oracle.fft_params(fs, size, rate)
+    return np.array([oracle.fft_frame(size, nz, 2, x[f:f + nz]) for f in range(0, x.size - nz + 1, nz + skip)])
+
+
+@pytest.mark.parametrize("dc,conj,chunk", [(True, False, 12000), (False, True, 12000), (True, True, 36000), (True, True, 7001)])
+def test_dc_blocker_and_conjugate_full_rate(sb, oracle, report, dc, conj, chunk):
+    n = 480000
+    x = noise_iq(n, 51, 0.02).copy()
+    x += fm_carrier(n, FS, -300e3 if conj else 300e3)         # mirrored by the conjugate
+    x += np.complex64(0.05 - 0.03j)                          # the DC the blocker is there for
+    fe = sb.FrontEnd(FS, 40000)
+    fe.set_dc_blocking(dc)
+    fe.set_invert_iq(conj)
+    fe.set_fft(65536, 20.0, 2)
+    cfg = sb.VfoConfig.wfm(300e3)
+    vid = fe.add_vfo(cfg)
+    raw = fe.add_vfo(sb.VfoConfig.raw(0.0, 300e3, 300e3))     # the pre-processed stream itself, decimated by 8
+    outs, lines = fe.process_chunks(x, chunk)
+    # oracle: the reference blocks, chunked the same way (the blocker is a plain recurrence: chunking does not matter)
+    dcb = oracle.dcblock_c(50.0 / FS)
+    v, d = oracle.rxvfo(FS, 250e3, 150e3, 300e3), oracle.wfm(75e3, 250e3)
+    vr = oracle.rxvfo(FS, 300e3, 300e3, 0.0)
+    ya, yr, xs = [], [], []
+    for i in range(0, n, chunk):
+        seg = x[i:i + chunk].view(np.float32)
+        if dc:
+            seg = dcb.process(seg)
+        if conj:
+            seg = np.conj(seg.view(np.complex64)).view(np.float32)
+        xs.append(seg.view(np.complex64).copy())
+        ya.append(d.process(v.process(seg)).reshape(-1, 2))
+        yr.append(vr.process(seg).view(np.complex64))
+    ya, yr, xp = np.concatenate(ya), np.concatenate(yr), np.concatenate(xs)
+    la = _lines(oracle, xp, FS, 65536, 20.0)
+    assert outs[vid].shape == ya.shape and outs[raw].shape == yr.shape
+    e_audio = rel_rms(outs[vid][4000:], ya[4000:])
+    e_raw = rel_rms(outs[raw][2000:], yr[2000:])
+    p, pr = 10.0 ** (lines.astype(np.float64) / 10), 10.0 ** (la.astype(np.float64) / 10)
+    e_fft = float(np.max(np.abs(p - pr)) / np.max(pr))
+    report["preproc_dc%d_conj%d_chunk%d" % (dc, conj, chunk)] = {"wfm_audio_rel_rms": e_audio, "raw_vfo_rel_rms": e_raw, "fft_power_rel_max": e_fft}
+    assert lines.shape == la.shape
+    assert e_fft < TOL, e_fft
+    assert e_raw < TOL, e_raw
+    assert e_audio < TOL, e_audio
+    if dc:
+        # the residual DC of the blocked stream is far below the 0.058 that went in
+        assert abs(np.mean(outs[raw][20000:])) < 2e-3
+    fe.close()
+
+
+def test_input_decimation_then_dc_block(sb, oracle, report):
+    """IQFrontEnd::setDecimation(4): everything behind the decimator runs at fs / 4 (iq_frontend.cpp:100-115)."""
+    fs, n, chunk, ratio = 9.6e6, 960000, 48000, 4
+    x = noise_iq(n, 52, 0.02).copy()
+    x += fm_carrier(n, fs, 300e3)
+    x += np.complex64(0.02 + 0.01j)
+    fe = sb.FrontEnd(fs, chunk)
+    fe.set_decimation(ratio)
+    fe.set_dc_blocking(True)
+    fe.set_fft(65536, 20.0, 2)
+    vid = fe.add_vfo(sb.VfoConfig.wfm(300e3))
+    outs, lines = fe.process_chunks(x, chunk)
+    dec = oracle.decim(ratio)
+    dcb = oracle.dcblock_c(50.0 / (fs / ratio))
+    v, d = oracle.rxvfo(fs / ratio, 250e3, 150e3, 300e3), oracle.wfm(75e3, 250e3)
+    ya, xs = [], []
+    for i in range(0, n, chunk):
+        seg = dcb.process(dec.process(x[i:i + chunk].view(np.float32)))
+        xs.append(seg.view(np.complex64).copy())
+        ya.append(d.process(v.process(seg)).reshape(-1, 2))
+    ya, xp = np.concatenate(ya), np.concatenate(xs)
+    la = _lines(oracle, xp, fs / ratio, 65536, 20.0)
+    assert outs[vid].shape == ya.shape
+    e = rel_rms(outs[vid][4000:], ya[4000:])
+    p, pr = 10.0 ** (lines.astype(np.float64) / 10), 10.0 ** (la.astype(np.float64) / 10)
+    e_fft = float(np.max(np.abs(p - pr)) / np.max(pr))
+    report["preproc_decim4_dc"] = {"wfm_audio_rel_rms": e, "fft_power_rel_max": e_fft}
+    assert lines.shape == la.shape and lines.shape[0] >= 1
+    assert e_fft < TOL and e < TOL, (e_fft, e)
+    fe.close()
