@@ -212,7 +212,8 @@ long long b200_fe_stat(b200_fe* fe, const char* key);
  *            2, 1 single-buffered tiles; 0 one thread per output
  *  "pair"    1 = VFOs at +f / -f share their stage-1 sums (default)
  *  "tails"   2 = one fused launch for the stages after stage 1 (default), 1 = one tiled kernel per stage, 0 = plain;
- *            "ft_threads", "ft_obmax", "ft_ob", "ft_smem_kb", "ft_direct" tune the fused launch.  Before VFOs are added.
+ *            "ft_threads", "ft_obmax", "ft_ob", "ft_smem_kb", "ft_direct" tune the fused launch; "ft_prereg" 1 (default) = the
+ *            short decimating FIR stages run with their window in registers (k_dfir_reg).  Before VFOs are added.
  *  "overlap" 1 = tails of chunk k overlap stage 1 of chunk k+1 on a second stream (default).  Before VFOs are added.
  *  "fft"     1 = register-resident four-step passes (default), 0 = shared-memory radix-8 passes; "fft_async" 1 = own stream
  *  "time_s1" 1 = bracket every stage-1 launch with CUDA events on the handle's stream (b200_fe_s1_stats) */

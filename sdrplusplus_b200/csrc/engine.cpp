@@ -80,8 +80,9 @@ void DevBuf::release() {
 
 int Stage::alloc_in(int cap) {
     cap_in = cap;
-    int rc = inbuf.alloc(((size_t)hist + (size_t)cap + 8) * in_es * sizeof(float));
-    if (!rc && dbl) { rc = inbuf_alt.alloc(((size_t)hist + (size_t)cap + 8) * in_es * sizeof(float)); }
+    const size_t bytes = ((size_t)hist + (size_t)cap + Scheduler::STAGE_SPARE) * in_es * sizeof(float);
+    int rc = inbuf.alloc(bytes);
+    if (!rc && dbl) { rc = inbuf_alt.alloc(bytes); }
     return rc;
 }
 
@@ -170,6 +171,7 @@ int FirCStage::configure(const std::vector<float>& t, int decim_) {
     ntaps = (int)t.size();
     decim = decim_;
     hist = ntaps - 1;
+    htaps = t;
     int rc = taps.alloc((size_t)ntaps * sizeof(float));
     if (rc) { return rc; }
     B200_CK(cudaMemcpy(taps.p, t.data(), (size_t)ntaps * sizeof(float), cudaMemcpyHostToDevice));
@@ -349,13 +351,27 @@ static int round4(int x) { return (x + 3) & ~3; }
 int Chain::plan_fused() {
     fp.active = false;
     for (auto& s : st) { s->fmid = false; }
+    fp.beg = 1;
     if (!fcfg.on || st.size() < 3 || st[0]->kind != K_XD) { return 0; }
-    int end = 1;
-    while (end < (int)st.size() && end - 1 < FT_MAXST && ft_fusable(st[end].get())) { end++; }
-    const int nst = end - 1;
+    // the short decimating FIRs right behind stage 1 run in registers (k_dfir_reg), one launch each, in front of the fused
+    // launch -- as long as at least two stages are left to fuse
+    int beg = 1;
+    if (fcfg.pre_reg) {
+        while (beg < (int)st.size() && st[beg]->kind == K_FIRC && st[beg]->in_es == 2 && ((FirCStage*)st[beg].get())->decim > 1 &&
+               dfir_reg_supported(((FirCStage*)st[beg].get())->decim, ((FirCStage*)st[beg].get())->ntaps)) { beg++; }
+    }
+    int end = beg;
+    for (;;) {
+        end = beg;
+        while (end < (int)st.size() && end - beg < FT_MAXST && ft_fusable(st[end].get())) { end++; }
+        if (end - beg >= 2 || beg == 1) { break; }
+        beg--;                                   // too little left behind the register stages: give one back
+    }
+    const int nst = end - beg;
     if (nst < 2) { return 0; }
+    fp.beg = beg;
     FtStage d[FT_MAXST];
-    for (int i = 0; i < nst; i++) { ft_describe(st[1 + i].get(), d[i]); }
+    for (int i = 0; i < nst; i++) { ft_describe(st[beg + i].get(), d[i]); }
     // taps region
     int toff = 0;
     for (int i = 0; i < nst; i++) {
@@ -425,7 +441,7 @@ int Chain::plan_fused() {
     }
     if (!fp.active) { return 0; }
     for (int i = 1; i < nst; i++) {
-        Stage* s = st[1 + i].get();
+        Stage* s = st[fp.beg + i].get();
         s->fmid = true;
         for (int b = 0; b < 2; b++) {
             const size_t need = ((size_t)s->hist + 8) * s->in_es * sizeof(float);
@@ -660,7 +676,7 @@ static int apply_pending_taps(FirCStage* f, cudaStream_t s) {
     B200_CK(cudaDeviceSynchronize());
     const int newT = (int)f->pending.size(), oldT = f->ntaps;
     const int newH = newT - 1, oldH = oldT - 1;
-    const size_t bytes = ((size_t)newH + f->cap_in + 8) * f->in_es * sizeof(float);
+    const size_t bytes = ((size_t)newH + f->cap_in + Scheduler::STAGE_SPARE) * f->in_es * sizeof(float);
     DevBuf nb, nb2;
     int rc = nb.alloc(bytes);
     if (rc) { return rc; }
@@ -695,6 +711,7 @@ static int apply_pending_taps(FirCStage* f, cudaStream_t s) {
     if (rc) { return rc; }
     B200_CK(cudaMemcpy(f->taps.p, f->pending.data(), (size_t)newT * sizeof(float), cudaMemcpyHostToDevice));
     if ((rc = f->upload_pm(f->pending, f->decim, 1))) { return rc; }
+    f->htaps = f->pending;
     f->ntaps = newT;
     f->hist = newH;
     if (f->decim != 1) { f->offset = 0; }          // DecimatingFIR::setTaps (decimating_fir.h:18-25)
@@ -917,11 +934,59 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
         B200_CK(cudaStreamWaitEvent(ts, ev_stage1[parity], 0));
     }
     trace_mark("tails start", ts);
+    // ---- short decimating FIRs with the window in registers (k_dfir_reg): one launch per level and plan stage ----
+    DfrParams dfr;
+    dfr.njobs = 0; dfr.max_out = 0;
+    int dfr_D = 0, dfr_T = 0;
+    const std::vector<float>* dfr_taps = nullptr;
+    auto dfr_flush = [&]() -> int {
+        if (dfr.njobs == 0) { return 0; }
+        cudaError_t e = launch_dfir_reg(dfr, dfr_D, dfr_T, ts);
+        if (e != cudaSuccess) { return cuda_fail(e, "launch_dfir_reg"); }
+        launches++;
+        dfr.njobs = 0; dfr.max_out = 0;
+        return 0;
+    };
+    auto dfr_push = [&](FirCStage* f) -> int {
+        if (dfr.njobs > 0 && (dfr_D != f->decim || dfr_T != f->ntaps || *dfr_taps != f->htaps || dfr.njobs == B200_BATCH)) {
+            int rc = dfr_flush();
+            if (rc) { return rc; }
+        }
+        if (dfr.njobs == 0) {
+            dfr_D = f->decim; dfr_T = f->ntaps; dfr_taps = &f->htaps;
+            memcpy(dfr.taps, f->htaps.data(), (size_t)f->ntaps * sizeof(float));
+        }
+        FirJob& j = dfr.job[dfr.njobs++];
+        j.in = (const float2*)f->base(); j.out = (float2*)f->out_ptr; j.taps = f->taps.as<float>();
+        j.ntaps = f->ntaps; j.decim = f->decim; j.offset = f->chunk_offset; j.n_out = f->n_out;
+        dfr.max_out = std::max(dfr.max_out, f->n_out);
+        return 0;
+    };
+    auto dfr_ok = [&](const Stage* s) {
+        if (!fuse.pre_reg || s->kind != K_FIRC || s->in_es != 2) { return false; }
+        const FirCStage* f = (const FirCStage*)s;
+        return f->decim > 1 && f->ntaps <= DFR_MAXT && dfir_reg_supported(f->decim, f->ntaps);
+    };
+    {
+        int max_beg = 1;
+        for (Chain* c : chains) { if (c->fp.active) { max_beg = std::max(max_beg, c->fp.beg); } }
+        for (int lvl = 1; lvl < max_beg; lvl++) {
+            for (Chain* c : chains) {
+                if (!c->fp.active || lvl >= c->fp.beg) { continue; }
+                FirCStage* f = (FirCStage*)c->st[lvl].get();
+                if (f->n_out <= 0) { continue; }
+                int rc = dfr_push(f);
+                if (rc) { return rc; }
+            }
+            int rc = dfr_flush();
+            if (rc) { return rc; }
+        }
+    }
     // ---- fused tails: every FIR-like stage after stage 1 of a VFO in one launch (kernels.cuh: FtJob) ----
     {
         std::vector<Chain*> fc;
         for (Chain* c : chains) {
-            if (c->fp.active && c->st[1]->n_in > 0) { fc.push_back(c); }
+            if (c->fp.active && c->st[c->fp.beg]->n_in > 0) { fc.push_back(c); }
         }
         if (!fc.empty()) {
             // slab size: the fewest waves the largest slabs allow, then the smallest slab that keeps that wave count
@@ -981,7 +1046,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
             };
             for (Chain* c : fc) {
                 FtJob& J = fpar.job[fpar.njobs++];
-                const int nst = c->fp.end - 1;
+                const int nst = c->fp.end - c->fp.beg;
                 J.nst = nst;
                 J.OB = ob;
                 J.OT0 = c->fp.ot0;
@@ -990,9 +1055,9 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
                 J.stg3 = c->fp.buf[0] + 2 * c->fp.stg2_rel;
                 J.nat_off = c->fp.nat_off;
                 J.stg_floats = c->fp.stg2_rel;
-                J.taps_nat = c->fp.s0_direct ? ((FirCStage*)c->st[1].get())->taps.as<float>() : nullptr;
+                J.taps_nat = c->fp.s0_direct ? ((FirCStage*)c->st[c->fp.beg].get())->taps.as<float>() : nullptr;
                 for (int i = 0; i < nst; i++) {
-                    Stage* sg = c->st[1 + i].get();
+                    Stage* sg = c->st[c->fp.beg + i].get();
                     FtStage& d = J.st[i];
                     ft_describe(sg, d);
                     d.n_in = sg->n_in; d.n_out = sg->n_out;
@@ -1005,7 +1070,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
                         sg->fpar ^= 1;
                     }
                 }
-                J.src = c->st[1]->base();
+                J.src = c->st[c->fp.beg]->base();
                 J.out = c->st[c->fp.end - 1]->out_ptr;
                 J.slabs = std::max(1, (J.st[nst - 1].n_out + ob - 1) / ob);
                 max_slabs = std::max(max_slabs, J.slabs);
@@ -1034,6 +1099,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
             case K_FIRC: {
                 FirCStage* f = (FirCStage*)s;
                 if (f->n_out <= 0) { break; }
+                if (dfr_ok(f)) { rc = dfr_push(f); break; }
                 FirJob& j = fp.job[fp.njobs++];
                 j.in = (const float2*)f->base(); j.out = (float2*)f->out_ptr; j.taps = f->taps.as<float>();
                 j.ntaps = f->ntaps; j.decim = f->decim; j.offset = f->chunk_offset; j.n_out = f->n_out;
@@ -1101,6 +1167,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
             if (rc) { return rc; }
         }
         int rc;
+        if ((rc = dfr_flush())) { return rc; }
         if ((rc = flush_batch(fp, launch_fir_c, ts, launches))) { return rc; }
         if ((rc = flush_batch(pp, launch_poly, ts, launches))) { return rc; }
         if ((rc = flush_batch(qp, launch_quad, ts, launches))) { return rc; }

@@ -95,6 +95,7 @@ struct XdStage : Stage {
 struct FirCStage : Stage {
     int ntaps = 1, decim = 1, offset = 0, chunk_offset = 0;
     DevBuf taps;
+    std::vector<float> htaps;    // host copy of the taps in use
     std::vector<float> pending;  // FIR::setTaps applied at the next chunk boundary
     FirCStage() { kind = K_FIRC; }
     int configure(const std::vector<float>& t, int decim_);
@@ -151,14 +152,15 @@ struct M2SStage : Stage {
 // Static part of a chain's fused-tail launch: which stages, the shared-memory arena, the slab size limit.
 struct FusedPlan {
     bool active = false;
-    int end = 0;                 // stages [1, end) run in k_tail_fused
+    int beg = 1;                 // stages [1, beg): short decimating FIRs run by k_dfir_reg in front of the fused launch
+    int end = 0;                 // stages [beg, end) run in k_tail_fused
     int ob_max = 0, ot0 = 0, stg2_rel = 0;
     bool s0_direct = false;      // first fused stage filters the raw stream from a cp.async.bulk ring (kernels.cuh: FtJob)
     int nat_off = 0;
     size_t smem = 0;
     int buf[FT_MAXST], pitch[FT_MAXST], tap_off[FT_MAXST], qpitch[FT_MAXST];
 };
-struct FuseCfg { bool on = false; int ob_max = 1280; int smem_limit = 110 * 1024; int threads = 256; int ob_force = 0; bool direct = true; };
+struct FuseCfg { bool on = false; int ob_max = 1280; int smem_limit = 110 * 1024; int threads = 256; int ob_force = 0; bool direct = true; bool pre_reg = true; };
 
 struct ScaleStage : Stage {
     float gain = 1.0f;
@@ -228,6 +230,7 @@ struct Scheduler {
     ~Scheduler();
     DevBuf raw_hist;             // last RAW_HIST samples of the raw IQ stream (cf32)
     static const int RAW_HIST = 1024;
+    static const int STAGE_SPARE = 72;  // samples past the data of a stage buffer that vector loads may touch (k_dfir_reg)
     int init_raw();
     // raw: device pointer to the chunk (format fmt) for chains with raw_input(); typed chains were fed by
     // copying into st[0]->in_data() beforehand.  counts were planned already (Chain::plan).

@@ -218,6 +218,7 @@ __global__ void __launch_bounds__(256) k_xd_tile(const __grid_constant__ XdParam
 #include "xd_pfb.cuh"
 #include "xd_tma.cuh"
 #include "tails.cuh"
+#include "dfir_reg.cuh"
 #include "fused_tail.cuh"
 
 // ------------------------------------------------------------------------------------------------

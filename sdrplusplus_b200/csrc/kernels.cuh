@@ -61,6 +61,20 @@ struct FirJob {
 };
 struct FirParams { int njobs; int max_out; FirJob job[B200_BATCH]; };
 
+// ---- short decimating FIR stages with the input window in registers (dfir_reg.cuh) ----
+#define DFR_THREADS 128
+#define DFR_MAXT 72
+
+struct DfrParams {
+    int njobs;
+    int max_out;
+    float taps[DFR_MAXT];        // shared by every job of the launch (same plan stage)
+    FirJob job[B200_BATCH];
+};
+
+bool dfir_reg_supported(int D, int T);
+cudaError_t launch_dfir_reg(const DfrParams& p, int D, int T, cudaStream_t s);
+
 // ---- polyphase rational resampler (PolyphaseResampler::process, polyphase_resampler.h:69-99) ----
 // output m: t = phase0 + m*decim; off = offset0 + t/interp; ph = t%interp;
 // out[m] = sum_k in[off + k] * bank[ph*tpp + k]

@@ -89,9 +89,9 @@ __device__ __forceinline__ DcbMap dcb_block_exclusive(DcbMap mine, DcbMap* warp_
 __global__ void __launch_bounds__(DCB_THREADS) k_dcb_reduce(const __grid_constant__ DcbParams p) {
     __shared__ DcbMap wt[DCB_THREADS / 32];
     const long long s0 = (long long)blockIdx.x * DCB_SEG + (long long)threadIdx.x * DCB_RUN;
-    long long s1 = s0 + DCB_RUN;
-    if (s1 > p.count) { s1 = p.count; }
-    DcbMap mine = dcb_run_map(p, s0 < p.count ? s0 : p.count, s1 > s0 ? s1 : s0);
+    const long long lo = s0 < p.count ? s0 : (long long)p.count;
+    const long long hi = s0 + DCB_RUN < p.count ? s0 + DCB_RUN : (long long)p.count;
+    DcbMap mine = dcb_run_map(p, lo, hi > lo ? hi : lo);          // threads past the end of the chunk: the identity
     DcbMap total;
     dcb_block_exclusive(mine, wt, total);
     if (threadIdx.x == 0) { p.segA[blockIdx.x] = total.c; p.segB[blockIdx.x] = total.b; }

@@ -78,18 +78,7 @@ k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, c
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);     // full[s] = bar0 + 8 s, empty[s] = bar0 + 8 (XT_STAGES + s)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NT = (NW + 1) * 32;
 
-    for (int idx = tid; idx < p.njobs * PS; idx += NT) {
-        const int v = idx / PS, b = idx - v * PS;
-        int a = (b - g.s) % PS;
-        if (a < 0) { a += PS; }
-        C[idx] = phasor_u64(p.job[v].w * (unsigned long long)a);
-    }
-    for (int idx = tid; idx < p.njobs * 16; idx += NT) {
-        const int v = idx >> 4, j = idx & 15;
-        TL[idx] = phasor_u64(p.job[v].w * (unsigned long long)((long long)j * D));
-    }
     if (tid == 0) {
         for (int s = 0; s < XT_STAGES; s++) {
             xt_mbar_init(bar0 + 8 * s, 1);
@@ -98,9 +87,23 @@ k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, c
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
+    // the producer starts the first tiles right away; the consumers build their tables under those loads
+    if (warp < NW) {
+        for (int idx = tid; idx < p.njobs * PS; idx += NW * 32) {
+            const int v = idx / PS, b = idx - v * PS;
+            int a = (b - g.s) % PS;
+            if (a < 0) { a += PS; }
+            C[idx] = phasor_u64(p.job[v].w * (unsigned long long)a);
+        }
+        for (int idx = tid; idx < p.njobs * 16; idx += NW * 32) {
+            const int v = idx >> 4, j = idx & 15;
+            TL[idx] = phasor_u64(p.job[v].w * (unsigned long long)((long long)j * D));
+        }
+        asm volatile("bar.sync 1, %0;\n" ::"n"(NW * 32) : "memory");
+    }
 
     // a tile is "fast" when every row it reads lies inside the tensor map; the few others (stream history in front of
-    // the chunk, the ragged end) are filled by the consumer warps with plain loads into the same swizzled layout
+    // the chunk, the ragged end) get their missing samples patched in by the consumer warps after the TMA boxes landed
     auto tile_fast = [&](long long J0) { return J0 >= 0 && (J0 >> 1) + Lay::NEED <= (long long)g.rows_tma; };
 
     if (warp == NW) {
@@ -113,19 +116,18 @@ k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, c
                 xt_mbar_wait(bar0 + 8 * (XT_STAGES + st), ph ^ 1u);
                 const long long J0 = g.jmin + (long long)tile * MT;
                 const unsigned full = bar0 + 8 * st;
-                if (tile_fast(J0)) {
-                    xt_mbar_expect(full, (unsigned)STAGE);
-                    const unsigned dst = sbase + (unsigned)(st * STAGE);
-                    const int row0 = (int)(J0 >> 1);
+                // every tile comes in through the TMA engine; rows outside the tensor (negative: stream history in front of
+                // the chunk; past its last full super-row: the ragged end) arrive zero-filled and are patched by the consumers
+                xt_mbar_expect(full, (unsigned)STAGE);
+                const unsigned dst = sbase + (unsigned)(st * STAGE);
+                const int row0 = (int)(J0 >> 1);
 #pragma unroll
-                    for (int sg = 0; sg < NSEG; sg++) {
+                for (int sg = 0; sg < NSEG; sg++) {
 #pragma unroll
-                        for (int par = 0; par < 2; par++) {
-                            xt_tma_2d(dst + (unsigned)((sg * 2 + par) * REGION), &tm, full, par * 2 * D + sg * 32, row0);
-                        }
+                    for (int par = 0; par < 2; par++) {
+                        xt_tma_2d(dst + (unsigned)((sg * 2 + par) * REGION), &tm, full, par * 2 * D + sg * 32, row0);
                     }
                 }
-                else { xt_mbar_arrive(full); }
             }
         }
         return;
@@ -161,39 +163,24 @@ k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, c
         xt_mbar_wait(bar0 + 8 * st, ph);
         const unsigned sb = sbase + (unsigned)(st * STAGE);
         if (!tile_fast(J0)) {
-            // stream history in front of the chunk / ragged end: the consumer warps fill the stage themselves, two samples
-            // (one 16-byte swizzle chunk) per load, eight independent loads in flight per thread
-            const long long ibase = J0 * D + g.org;                // even: rows start 16-byte aligned
+            // patch what the tensor map does not cover: samples before the chunk (from the carried raw history) and the
+            // samples of the last, partial super-row.  A few hundred at most, once or twice per launch.
+            const long long ibase = J0 * D + g.org;
             unsigned char* stg = gbase + st * STAGE;
-            constexpr int NPAIR = (MT + QC + 1) * D / 2;
-            const float4* in4 = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(p.in) + ibase);
-            const float4* hs4 = reinterpret_cast<const float4*>(p.hist + ((long long)p.hist_len + ibase));
-            for (int base = tid; base < NPAIR; base += NW * 32 * 8) {
-                float4 v[8];
-                bool edge[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int pi = base + u * NW * 32;
-                    const long long i = ibase + 2LL * pi;
-                    const bool in_chunk = pi < NPAIR && i >= 0 && i + 1 < (long long)p.count;
-                    const bool in_hist = pi < NPAIR && i + 1 < 0 && i >= -(long long)p.hist_len;
-                    const float4* ptr = in_chunk ? in4 + pi : hs4 + pi;
-                    v[u] = (in_chunk || in_hist) ? __ldg(ptr) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    edge[u] = pi < NPAIR && !(in_chunk || in_hist);
-                }
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int pi = base + u * NW * 32;
-                    if (pi >= NPAIR) { continue; }
-                    if (edge[u]) {                                  // a pair that straddles the end of the chunk or of the history
-                        const float2 a = load_x<FMT_CF32>(p, ibase + 2LL * pi), b = load_x<FMT_CF32>(p, ibase + 2LL * pi + 1);
-                        v[u] = make_float4(a.x, a.y, b.x, b.y);
-                    }
-                    const int idx = 2 * pi, j = idx >> LOGD, r = idx & (D - 1), row = j >> 1;
-                    const int off = ((r >> 4) * 2 + (j & 1)) * REGION + row * 128 + ((((r >> 1) & 7) ^ (row & 7)) << 4);
-                    *reinterpret_cast<float4*>(stg + off) = v[u];
-                }
-            }
+            constexpr int NSAMP = (MT + QC + 1) * D;
+            const long long tensor_end = (long long)g.org + (long long)g.rows_tma * (2 * D);
+            const int head = (int)(ibase < 0 ? (-ibase < NSAMP ? -ibase : NSAMP) : 0);
+            long long t0 = tensor_end - ibase, t1 = (long long)p.count - ibase;
+            if (t0 < head) { t0 = head; }
+            if (t1 > NSAMP) { t1 = NSAMP; }
+            auto patch = [&](int idx) {
+                const float2 v = load_x<FMT_CF32>(p, ibase + idx);
+                const int j = idx >> LOGD, r = idx & (D - 1), row = j >> 1;
+                const int off = ((r >> 4) * 2 + (j & 1)) * REGION + row * 128 + ((((r >> 1) & 7) ^ (row & 7)) << 4) + (r & 1) * 8;
+                *reinterpret_cast<float2*>(stg + off) = v;
+            };
+            for (int idx = tid; idx < head; idx += NW * 32) { patch(idx); }
+            for (long long idx = t0 + tid; idx < t1; idx += NW * 32) { patch((int)idx); }
             asm volatile("bar.sync 1, %0;\n" ::"n"(NW * 32) : "memory");
         }
 

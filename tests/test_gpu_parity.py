@@ -560,7 +560,7 @@ def test_frontend_multi_vfo_100msps(sb, oracle, report):
     (4, 1, 1, 1, {}), (3, 0, 0, 1, {}), (1, 1, 0, 0, {}), (3, 1, 1, 0, {"tails": 1}), (3, 1, 0, 1, {"tails": 0}), (5, 1, 1, 1, {}),
     (5, 1, 0, 0, {"tails": 1}), (6, 1, 1, 1, {"tails": 1}), (6, 1, 0, 0, {}), (6, 1, 1, 1, {"ft_threads": 256}),
     (6, 1, 1, 1, {"ft_ob": 301}), (7, 1, 1, 1, {}), (7, 1, 0, 0, {"tails": 1}), (7, 0, 0, 1, {"ft_direct": 0}), (6, 1, 0, 1, {"ft_ob": 64, "ft_smem_kb": 48}), (6, 1, 1, 1, {"ft_obmax": 2500, "ft_smem_kb": 200}),
-    (8, 1, 1, 1, {}), (8, 0, 0, 0, {"tails": 1})])
+    (8, 1, 1, 1, {}), (8, 0, 0, 0, {"tails": 1}), (8, 1, 1, 1, {"ft_prereg": 0}), (7, 1, 0, 1, {"tails": 1, "ft_prereg": 0})])
 def test_frontend_variants_100msps(sb, oracle, report, variant, fft_async, overlap, pair, tails):
     """kernel / scheduling A-B on the config-2 geometry (short): 16-warp stage 1, synchronous spectrum branch,
     tails on the main stream, conjugate-pair sharing off, per-stage tail launches instead of the fused tail,
