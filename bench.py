@@ -201,6 +201,96 @@ def run_reference(args):
     return 0
 
 
+C4_FS = 1.024e9
+C4_WORKLOAD = "C4: 1.024 GS/s complex IQ, 64 mixed AM/NFM/USB VFOs on a 12.5 MHz grid (+ 1048576-pt FFT on rank 0), VFO groups per GPU, raw IQ broadcast over NCCL"
+
+
+def c4_vfos(sb, lib):
+    """BASELINE config 4: 64 VFOs, offsets k * 12.5 MHz (k = -32..-1, 1..32), modes cycling AM / NFM / USB."""
+    ks = list(range(-32, 0)) + list(range(1, 33))
+    mk = [lambda o: sb.VfoConfig.am(o), lambda o: sb.VfoConfig.nfm(o), lambda o: sb.VfoConfig.ssb(o, lib.DEMOD_USB)]
+    return [mk[i % 3](12.5e6 * k) for i, k in enumerate(ks)]
+
+
+def c4_leg(torch, dist, sb, lib, rank, world, local, steps, warm=3, chunk=1 << 23):
+    """Strong scaling of ONE stream: the same 64 VFOs + FFT whatever the GPU count; rank 0 owns the stream, the library
+    broadcasts every raw chunk (b200_shard_*), every rank demodulates its VFO group.  value = samples / max-over-ranks time."""
+    import ctypes as C
+    from sdrplusplus_b200.sharding import ShardedFrontEnd, make_unique_id, partition_vfos
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        cfgs = c4_vfos(sb, lib)
+        mine = partition_vfos(len(cfgs), world, rank)
+        fe = sb.FrontEnd(C4_FS, chunk)
+        fe.set_stream(stream.cuda_stream)
+        if rank == 0:
+            fe.set_fft(FFT_SIZE, FFT_RATE, lib.WIN_NUTTALL)
+        ids = [fe.add_vfo(cfgs[i]) for i in mine]
+        uid = [make_unique_id() if rank == 0 else None]
+        if world > 1:
+            dist.broadcast_object_list(uid, src=0)
+        sh = ShardedFrontEnd(fe, rank, world, uid[0])
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(0xC4)
+        ins = [(torch.rand(2 * chunk, device="cuda", generator=gen, dtype=torch.float32) * 2.0 - 1.0) for _ in range(3)] if rank == 0 else []
+        outs = []
+        for _ in range(2):
+            o = lib.Outputs()
+            keep = []
+            for v in ids:
+                cap = fe.vfo_max_out(v, chunk)
+                t = torch.empty(2 * cap, device="cuda", dtype=torch.float32)
+                keep.append(t)
+                o.vfo_out[v] = t.data_ptr()
+                o.vfo_cap[v] = cap
+            nl = max(1, fe.fft_max_lines(chunk))
+            t = torch.empty(nl * FFT_SIZE, device="cuda", dtype=torch.float32)
+            keep.append(t)
+            o.fft_out = t.data_ptr()
+            o.fft_cap_lines = nl
+            o.out_mem = lib.MEM_DEVICE
+            outs.append((o, keep))
+
+        def loop(n):
+            infl = 0
+            for i in range(n):
+                ptr = ins[i % 3].data_ptr() if rank == 0 else 0
+                sh.submit_ptr(ptr, chunk, lib.FMT_CF32, lib.MEM_DEVICE, outs[i % 2][0])
+                infl += 1
+                if infl == 2:
+                    sh.wait()
+                    infl -= 1
+            while infl:
+                sh.wait()
+                infl -= 1
+
+        loop(warm)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        b0 = sh.bytes_broadcast()
+        l0 = fe.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        loop(steps)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            dist.barrier()
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        res = {"workload": C4_WORKLOAD, "scaling": "strong", "value": chunk * steps / (ms * 1e-3) / 1e6, "unit": "MS/s", "n_gpus": world,
+               "ms_per_step": ms / steps, "steps": steps, "chunk_samples": chunk, "vfos_total": len(cfgs), "vfos_this_rank": len(ids),
+               "collective": "ncclBroadcast of the raw chunk from rank 0 (b200_shard_submit), one chunk ahead of the compute" if world > 1 else "none (one GPU)",
+               "nvlink_bytes_per_step_per_receiver": (sh.bytes_broadcast() - b0) // max(steps, 1), "gpu_launches_rank0": int(fe.launch_count() - l0),
+               "timing": "CUDA events on each rank's stream, max over ranks"}
+        sh.close()
+        fe.close()
+    return res
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -401,6 +491,12 @@ def run_b200(args):
                 print("roofline.alone skipped: %r" % (ex,), file=sys.stderr)
                 s1_alone = None
 
+    c4 = None
+    if args.c4 and not args.quick:
+        try:
+            c4 = c4_leg(torch, dist, sb, lib, rank, world, local, max(6, min(args.steps, 12)))
+        except Exception as ex:                      # noqa: BLE001 -- a secondary leg: never take the bench line down (all ranks fail alike)
+            c4 = {"workload": C4_WORKLOAD, "value": None, "error": repr(ex)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -438,6 +534,8 @@ def run_b200(args):
                      "note": "avg_launch_ms is measured inside the timed region, where the spectrum and tail kernels of neighbouring chunks share the SMs; "
                              "'alone' times the same launch with nothing else running. Filter-bank form: 14 FMA per input sample vs 9 B (DESIGN.md section 5)"},
     }
+    if c4 is not None:
+        line["c4"] = c4
     if world == 1 and not args.no_cpu:
         try:
             v, threads, kind, what = cpu_reference_run(args.cpu_ms)
@@ -471,6 +569,7 @@ def main():
     ap.add_argument("--cpu-ms", type=int, default=12000, help="duration of the CPU reference sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--quick", action="store_true", help="diagnostic: only the int16 end-to-end leg")
+    ap.add_argument("--c4", type=int, default=1, help="1 = also time BASELINE config 4 (one 1.024 GS/s stream, 64 VFOs sharded over the GPUs with an NCCL broadcast) and report it under 'c4'")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region (diagnostic)")
     args = ap.parse_args()
     if args.warmup < 3:

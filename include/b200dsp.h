@@ -222,6 +222,23 @@ int b200_fe_set_option(b200_fe* fe, const char* key, int value);
  * synchronises on the recorded events ("time_s1" must be on).  bench.py's roofline leg reads this. */
 int b200_fe_s1_stats(b200_fe* fe, double* ms_total, int* launches);
 
+/* ------------------------------------------------------------------------------------------
+ * One IQ stream, VFO groups on several GPUs (BASELINE config 4).  Replaces the Splitter fan-out
+ * (core/src/dsp/routing/splitter.h:46-61: every bound consumer gets a memcpy of every chunk) ACROSS devices: one process per
+ * GPU, each with its own b200_fe holding its VFO group (rank 0 also keeps the FFT branch); rank 0 ingests the chunk and
+ * ncclBroadcasts the raw IQ on a communication stream, one chunk ahead of the compute.  There is no other exchange.
+ * b200_shard_unique_id: rank 0 makes the 128-byte NCCL id, the caller hands it to the other ranks (any side channel);
+ * every rank then calls b200_shard_create, and b200_shard_submit / b200_shard_wait with the SAME count and format per
+ * chunk (iq is read on rank 0 only).  NCCL is bound at run time (libnccl.so.2).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b200_shard b200_shard;
+int         b200_shard_unique_id(void* id128);
+b200_shard* b200_shard_create(b200_fe* fe, int rank, int world, const void* id128);
+int         b200_shard_submit(b200_shard* sh, const void* iq, int count, int in_fmt, int in_mem, b200_outputs* out);
+int         b200_shard_wait(b200_shard* sh);
+long long   b200_shard_bytes_broadcast(b200_shard* sh);      /* bytes this rank has put through ncclBroadcast so far */
+void        b200_shard_destroy(b200_shard* sh);
+
 /* waterfall zoom (max-decimate) + peak hold on the device line, bit-exact with
  * doZoom / pushFFT hold loop (core/src/gui/widgets/waterfall.cpp:65-90, 935-939).
  * line: fft_size dB values (mem), out/hold: out_size floats (same mem). hold may be NULL. */

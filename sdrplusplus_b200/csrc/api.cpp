@@ -1163,3 +1163,150 @@ extern "C" int b200_pcm_compress(const float* iq, int count, int pcm_fmt, void* 
     else { B200_CK(cudaStreamSynchronize(nullptr)); }
     return bytes;
 }
+
+// ------------------------------------------------------------------ one stream, VFO groups on several GPUs (BASELINE config 4)
+// The path has no exchange step: every VFO consumes the same raw IQ -- the reference's Splitter
+// memcpy fan-out (core/src/dsp/routing/splitter.h:46-61).  Across GPUs the fan-out is one ncclBroadcast of each raw chunk
+// from the ingest rank, on a communication stream, one chunk ahead of the compute (two chunk buffers per rank).
+// NCCL is bound at run time (dlopen "libnccl.so.2": the process's own copy when a framework already loaded one).
+#include <dlfcn.h>
+namespace {
+struct NcclId { char internal[128]; };
+typedef void* NcclComm;
+struct NcclApi {
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl() {
+    static NcclApi a;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!h) { h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL); }
+        if (h) {
+            a.GetUniqueId = (int (*)(NcclId*))dlsym(h, "ncclGetUniqueId");
+            a.CommInitRank = (int (*)(NcclComm*, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+            a.CommDestroy = (int (*)(NcclComm))dlsym(h, "ncclCommDestroy");
+            a.Broadcast = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(h, "ncclBroadcast");
+            a.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+            a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.Broadcast;
+        }
+    }
+    return a;
+}
+int nccl_fail(int r, const char* what) {
+    set_error("NCCL error %d (%s) in %s", r, nccl().GetErrorString ? nccl().GetErrorString(r) : "?", what);
+    return B200_ECUDA;
+}
+}
+
+struct b200_shard {
+    b200_fe* fe = nullptr;
+    int rank = 0, world = 1;
+    NcclComm comm = nullptr;
+    cudaStream_t comm_stream = nullptr;
+    DevBuf buf[2];                       // the raw chunk on this rank (root: staged host input or the caller's device chunk)
+    cudaEvent_t ev_bcast[2] = { nullptr, nullptr }, ev_src[2] = { nullptr, nullptr };
+    unsigned long long nsub = 0;
+    long long bytes_broadcast = 0;
+};
+
+extern "C" int b200_shard_unique_id(void* id128) {
+    if (!id128) { set_error("null id"); return B200_EINVAL; }
+    if (!nccl().ok) { set_error("libnccl.so.2 not found: the sharded front end needs NCCL"); return B200_ENODEV; }
+    NcclId id;
+    int r = nccl().GetUniqueId(&id);
+    if (r) { return nccl_fail(r, "ncclGetUniqueId"); }
+    memcpy(id128, &id, sizeof(id));
+    return 0;
+}
+
+extern "C" void b200_shard_destroy(b200_shard* sh) {
+    if (!sh) { return; }
+    cudaDeviceSynchronize();
+    if (sh->comm) { nccl().CommDestroy(sh->comm); }
+    for (int i = 0; i < 2; i++) {
+        if (sh->ev_bcast[i]) { cudaEventDestroy(sh->ev_bcast[i]); }
+        if (sh->ev_src[i]) { cudaEventDestroy(sh->ev_src[i]); }
+    }
+    if (sh->comm_stream) { cudaStreamDestroy(sh->comm_stream); }
+    delete sh;
+}
+
+extern "C" b200_shard* b200_shard_create(b200_fe* fe, int rank, int world, const void* id128) {
+    if (!fe || !id128 || world < 1 || rank < 0 || rank >= world) { set_error("bad shard arguments"); return nullptr; }
+    if (!nccl().ok) { set_error("libnccl.so.2 not found: the sharded front end needs NCCL"); return nullptr; }
+    b200_shard* sh = new b200_shard;
+    sh->fe = fe; sh->rank = rank; sh->world = world;
+    bool ok = cudaStreamCreateWithFlags(&sh->comm_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; i++) {
+        ok = cudaEventCreateWithFlags(&sh->ev_bcast[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&sh->ev_src[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) { cuda_fail(cudaGetLastError(), "shard stream/event creation"); b200_shard_destroy(sh); return nullptr; }
+    NcclId id;
+    memcpy(&id, id128, sizeof(id));
+    int r = nccl().CommInitRank(&sh->comm, world, id, rank);
+    if (r) { nccl_fail(r, "ncclCommInitRank"); sh->comm = nullptr; b200_shard_destroy(sh); return nullptr; }
+    return sh;
+}
+
+// Every rank calls submit with the same count and format; `iq` is read on rank 0 only.  Values and counts per VFO are
+// those of b200_fe_submit on the rank that owns the VFO.
+extern "C" int b200_shard_submit(b200_shard* sh, const void* iq, int count, int in_fmt, int in_mem, b200_outputs* out) {
+    if (!sh || !out) { set_error("null argument"); return B200_EINVAL; }
+    b200_fe* fe = sh->fe;
+    if (count < 0 || count > fe->max_chunk) { set_error("count %d exceeds max_chunk %d", count, fe->max_chunk); return B200_ECAP; }
+    if (in_fmt < 0 || in_fmt > 2) { set_error("bad input format"); return B200_EINVAL; }
+    if (sh->rank == 0 && count > 0 && !iq) { set_error("rank 0 needs the chunk"); return B200_EINVAL; }
+    if (fe->nsub - fe->nwait >= 2) { set_error("two chunks already in flight: call b200_shard_wait"); return B200_ESTATE; }
+    if (sh->world == 1) {                                   // nothing to fan out: the plain front end
+        int rc1 = b200_fe_submit(fe, iq, count, in_fmt, in_mem, out);
+        if (!rc1) { sh->nsub++; }
+        return rc1;
+    }
+    const int slot = (int)(fe->nsub & 1);                   // the front end's own input slot of this chunk
+    const size_t bytes = (size_t)count * bytes_per_sample(in_fmt);
+    cudaStream_t cs = sh->comm_stream, ms = fe->sch.stream;
+    if (sh->buf[slot].bytes < bytes) {
+        B200_CK(cudaDeviceSynchronize());
+        int rc = sh->buf[slot].alloc(std::max(bytes, (size_t)fe->max_chunk * bytes_per_sample(in_fmt)), false);
+        if (rc) { return rc; }
+    }
+    // buf[slot] was the input of the chunk two submissions ago: its compute has to be over before it is overwritten
+    if (fe->slot_used[slot]) { B200_CK(cudaStreamWaitEvent(cs, fe->ev_compute[slot], 0)); }
+    if (count > 0) {
+        if (sh->rank == 0) {
+            if (in_mem == B200_MEM_HOST) {
+                B200_CK(cudaMemcpyAsync(sh->buf[slot].p, iq, bytes, cudaMemcpyHostToDevice, cs));
+            }
+            else {
+                // the caller's device chunk is valid on the stream it submits on
+                B200_CK(cudaEventRecord(sh->ev_src[slot], ms));
+                B200_CK(cudaStreamWaitEvent(cs, sh->ev_src[slot], 0));
+                B200_CK(cudaMemcpyAsync(sh->buf[slot].p, iq, bytes, cudaMemcpyDeviceToDevice, cs));
+            }
+        }
+        if (sh->world > 1) {
+            int r = nccl().Broadcast(sh->buf[slot].p, sh->buf[slot].p, bytes, 1 /* ncclUint8 */, 0, sh->comm, cs);
+            if (r) { return nccl_fail(r, "ncclBroadcast"); }
+            sh->bytes_broadcast += (long long)bytes;
+        }
+    }
+    B200_CK(cudaEventRecord(sh->ev_bcast[slot], cs));
+    B200_CK(cudaStreamWaitEvent(ms, sh->ev_bcast[slot], 0));
+    int rc = b200_fe_submit(fe, sh->buf[slot].p, count, in_fmt, B200_MEM_DEVICE, out);
+    if (rc) { return rc; }
+    sh->nsub++;
+    return 0;
+}
+extern "C" int b200_shard_wait(b200_shard* sh) {
+    if (!sh) { set_error("null shard"); return B200_EINVAL; }
+    return b200_fe_wait(sh->fe);
+}
+extern "C" long long b200_shard_bytes_broadcast(b200_shard* sh) { return sh ? sh->bytes_broadcast : 0; }

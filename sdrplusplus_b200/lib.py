@@ -77,6 +77,12 @@ SIGNATURES = {
     "b200_fe_stat": (_ll, [_vp, C.c_char_p]),
     "b200_fe_set_option": (_i, [_vp, C.c_char_p, _i]),
     "b200_fe_s1_stats": (_i, [_vp, C.POINTER(C.c_double), _ip]),
+    "b200_shard_unique_id": (_i, [_vp]),
+    "b200_shard_create": (_vp, [_vp, _i, _i, _vp]),
+    "b200_shard_submit": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(Outputs)]),
+    "b200_shard_wait": (_i, [_vp]),
+    "b200_shard_bytes_broadcast": (_ll, [_vp]),
+    "b200_shard_destroy": (None, [_vp]),
     "b200_fft_zoom_hold": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, C.c_float, _i]),
     "b200_xlator_create": (_vp, [_d, _d]),
     "b200_xlator_set_offset": (_i, [_vp, _d, _d]),
