@@ -465,7 +465,7 @@ extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
         if (!strcmp(key, "ft_smem_kb")) { fe->sch.fuse.smem_limit = value * 1024; return 0; }
         if (!strcmp(key, "ft_threads")) { fe->sch.fuse.threads = value; return 0; }
         if (!strcmp(key, "ft_direct")) { fe->sch.fuse.direct = value != 0; return 0; }
-        if (!strcmp(key, "ft_prereg")) { fe->sch.fuse.pre_reg = value != 0; return 0; }
+        if (!strcmp(key, "ft_prereg")) { fe->sch.fuse.pre_reg = value; return 0; }
     }
     if (!strcmp(key, "fft")) { kernels_set_fft_variant(value); return 0; }
     if (!strcmp(key, "time_s1")) { fe->sch.time_s1 = value != 0; fe->sch.ev_used = 0; return 0; }

@@ -4,29 +4,64 @@
 //
 // Every non-first stage of the reference's decimation plans is one of six (decimation, taps) pairs
 // (decim/plans.h:24-140: (2,69) (2,12) (4,27) (8,54) (8,44) (8,36)), so the kernel is instantiated per pair: a thread
-// produces R consecutive outputs, loads the (R-1)*D + T samples they read ONCE with 16-byte loads (the stage-1 output was
-// just written: L2 hits; neighbouring threads share lines through L1), and runs T*R fully unrolled packed FMAs whose tap
-// operand comes from the kernel parameter block (constant bank -> uniform register): no shared memory, no barrier, no
-// address arithmetic in the loop.  This replaces the fused tail's first stages, where the same work was LSU-bound
+// produces R consecutive outputs, loads the (R-1)*D + T samples they read ONCE with 16-byte loads (staged once per CTA in shared memory by
+// coalesced 16-byte loads -- the stage-1 output was just written: L2 hits -- in a padded layout that makes every thread's
+// window loads conflict-free), and runs T*R fully unrolled packed FMAs whose tap
+// operand comes from the kernel parameter block (constant bank -> uniform register): one barrier, no address arithmetic in the loop.  This replaces the fused tail's first stages, where the same work was LSU-bound
 // (profiles/r01_ncu_full_tail_fused.txt: 37 % of the tail in the (4,27) stage).
 //
 // Index convention as in kernels.cuh (FirJob): out[m] = sum_k taps[k] * in[offset + m*D + k], `in` = oldest history sample.
 #pragma once
 
 template <int D, int T, int R>
+struct DfrGeom {
+    static constexpr int S = R * D / 2;                       // 16-byte pairs between the windows of neighbouring threads
+    static constexpr int LS = (S == 1) ? 0 : (S == 2) ? 1 : (S == 4) ? 2 : (S == 8) ? 3 : (S == 16) ? 4 : (S == 32) ? 5 : 6;
+    static_assert((1 << LS) == S, "R*D/2 must be a power of two");
+    static constexpr int NS = (R - 1) * D + T;                // samples the R outputs of a thread read
+    static constexpr int NV = (NS + 2) / 2;                   // pairs per thread (one spare for an odd start)
+    static constexpr int NPT = (DFR_THREADS - 1) * S + NV;    // pairs per CTA tile
+    static constexpr int SMEM = (NPT + (NPT >> LS) + 2) * 16; // one pad pair per S pairs: thread stride S + 1 (odd) -> conflict-free
+};
+
+template <int D, int T, int R>
 __global__ void __launch_bounds__(DFR_THREADS) k_dfir_reg(const __grid_constant__ DfrParams p) {
+    using G = DfrGeom<D, T, R>;
+    extern __shared__ __align__(16) float4 dfr_sm[];
     const FirJob& J = p.job[blockIdx.y];
-    const int m0 = (blockIdx.x * DFR_THREADS + threadIdx.x) * R;
-    if (m0 >= J.n_out) { return; }
-    constexpr int NS = (R - 1) * D + T;              // samples the R outputs read
-    constexpr int NV = (NS + 2) / 2;                 // 16-byte loads, one spare for an odd start
-    const long long first = (long long)J.offset + (long long)m0 * D;
-    const int sh = (int)(first & 1);                 // odd start: load from the even sample below
-    const float4* __restrict__ src = reinterpret_cast<const float4*>(J.in + (first - sh));
-    float2 x[2 * NV];
+    const int mt = blockIdx.x * DFR_THREADS * R;              // first output of this CTA
+    if (mt >= J.n_out) { return; }
+    const long long first = (long long)J.offset + (long long)mt * D;
+    const int sh = (int)(first & 1);                          // odd start: the tile begins at the even sample below
+    // ---- the tile: coalesced 16-byte loads, padded layout ----
+    {
+        const float4* __restrict__ src = reinterpret_cast<const float4*>(J.in + (first - sh));
+        // pairs past the data of the last tile stay inside the stage buffer (Scheduler::STAGE_SPARE) as long as they
+        // belong to an output that exists; beyond that they are not read
+        const long long last_out = (long long)J.n_out - 1 - mt;
+        const int need = (int)((last_out < (long long)DFR_THREADS * R - 1 ? last_out : (long long)DFR_THREADS * R - 1) * D + T + 1 + sh + 1) / 2;
+        // every load of the tile in flight at once (the fill is one round trip to L2 / HBM, not NPT / 128 of them)
+        constexpr int NIT = (G::NPT + DFR_THREADS - 1) / DFR_THREADS;
+        float4 t[NIT];
 #pragma unroll
-    for (int v = 0; v < NV; v++) {
-        const float4 t = __ldg(src + v);
+        for (int u = 0; u < NIT; u++) {
+            const int i = threadIdx.x + u * DFR_THREADS;
+            t[u] = (i < G::NPT && i < need) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < NIT; u++) {
+            const int i = threadIdx.x + u * DFR_THREADS;
+            if (i < G::NPT) { dfr_sm[i + (i >> G::LS)] = t[u]; }
+        }
+    }
+    __syncthreads();
+    const int m0 = mt + threadIdx.x * R;
+    if (m0 >= J.n_out) { return; }
+    const float4* win = dfr_sm + threadIdx.x * (G::S + 1);
+    float2 x[2 * G::NV];
+#pragma unroll
+    for (int v = 0; v < G::NV; v++) {
+        const float4 t = win[v + (v >> G::LS)];
         x[2 * v] = make_float2(t.x, t.y);
         x[2 * v + 1] = make_float2(t.z, t.w);
     }
@@ -58,7 +93,7 @@ __global__ void __launch_bounds__(DFR_THREADS) k_dfir_reg(const __grid_constant_
 template <int D, int T, int R>
 static cudaError_t launch_dfir_reg_t(const DfrParams& p, cudaStream_t s) {
     dim3 grid((unsigned)((p.max_out + DFR_THREADS * R - 1) / (DFR_THREADS * R)), (unsigned)p.njobs);
-    k_dfir_reg<D, T, R><<<grid, DFR_THREADS, 0, s>>>(p);
+    k_dfir_reg<D, T, R><<<grid, DFR_THREADS, DfrGeom<D, T, R>::SMEM, s>>>(p);
     return cudaGetLastError();
 }
 // true when (D, T) is one of the plan stages the kernel is built for

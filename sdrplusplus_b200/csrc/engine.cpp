@@ -356,8 +356,8 @@ int Chain::plan_fused() {
     // the short decimating FIRs right behind stage 1 run in registers (k_dfir_reg), one launch each, in front of the fused
     // launch -- as long as at least two stages are left to fuse
     int beg = 1;
-    if (fcfg.pre_reg) {
-        while (beg < (int)st.size() && st[beg]->kind == K_FIRC && st[beg]->in_es == 2 && ((FirCStage*)st[beg].get())->decim > 1 &&
+    if (fcfg.pre_reg > 0) {
+        while (beg - 1 < fcfg.pre_reg && beg < (int)st.size() && st[beg]->kind == K_FIRC && st[beg]->in_es == 2 && ((FirCStage*)st[beg].get())->decim > 1 &&
                dfir_reg_supported(((FirCStage*)st[beg].get())->decim, ((FirCStage*)st[beg].get())->ntaps)) { beg++; }
     }
     int end = beg;
@@ -963,7 +963,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
         return 0;
     };
     auto dfr_ok = [&](const Stage* s) {
-        if (!fuse.pre_reg || s->kind != K_FIRC || s->in_es != 2) { return false; }
+        if (fuse.pre_reg <= 0 || s->kind != K_FIRC || s->in_es != 2) { return false; }
         const FirCStage* f = (const FirCStage*)s;
         return f->decim > 1 && f->ntaps <= DFR_MAXT && dfir_reg_supported(f->decim, f->ntaps);
     };
@@ -995,8 +995,16 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
             size_t smem = 0;
             int ob_cap = 1 << 30;
             for (Chain* c : fc) { smem = std::max(smem, c->fp.smem); ob_cap = std::min(ob_cap, c->fp.ob_max); }
-            int cps = (int)((227 * 1024) / (smem + 1024));
-            cps = std::max(1, std::min(cps, 2048 / threads));
+            // resident CTAs per SM as the device will actually place them (registers bound the 256-thread build at two)
+            static std::map<std::pair<int, size_t>, int> occ_cache;
+            int cps;
+            {
+                auto key = std::make_pair(threads, smem);
+                auto it = occ_cache.find(key);
+                if (it == occ_cache.end()) { it = occ_cache.emplace(key, tail_fused_ctas_per_sm(threads, smem)).first; }
+                cps = it->second;
+            }
+            if (cps < 1) { cps = std::max(1, std::min((int)((227 * 1024) / (smem + 1024)), 2048 / threads)); }
             const long long slots = (long long)sm_count * cps;
             auto total_slabs = [&](int ob) {
                 long long t = 0;

@@ -160,7 +160,7 @@ struct FusedPlan {
     size_t smem = 0;
     int buf[FT_MAXST], pitch[FT_MAXST], tap_off[FT_MAXST], qpitch[FT_MAXST];
 };
-struct FuseCfg { bool on = false; int ob_max = 1280; int smem_limit = 110 * 1024; int threads = 256; int ob_force = 0; bool direct = true; bool pre_reg = true; };
+struct FuseCfg { bool on = false; int ob_max = 1280; int smem_limit = 110 * 1024; int threads = 256; int ob_force = 0; bool direct = true; int pre_reg = 8; };   // pre_reg: how many short decimating FIR stages may run in registers in front of the fused launch
 
 struct ScaleStage : Stage {
     float gain = 1.0f;

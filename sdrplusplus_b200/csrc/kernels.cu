@@ -1227,6 +1227,25 @@ cudaError_t launch_quad(const QuadParams& p, cudaStream_t s) {
     k_quad<<<grid, 256, 0, s>>>(p);
     return cudaGetLastError();
 }
+// resident CTAs of the fused tail per SM for a thread count and dynamic shared-memory size (registers included)
+int tail_fused_ctas_per_sm(int threads, size_t smem_bytes) {
+    int n = 0;
+    cudaError_t e;
+    if (threads == 512) {
+        cudaFuncSetAttribute(k_tail_fused<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_tail_fused<512>, 512, smem_bytes);
+    }
+    else if (threads == 256) {
+        cudaFuncSetAttribute(k_tail_fused<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_tail_fused<256>, 256, smem_bytes);
+    }
+    else {
+        cudaFuncSetAttribute(k_tail_fused<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_tail_fused<128>, 128, smem_bytes);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 cudaError_t launch_tail_fused(const FtParams& p, int max_slabs, int threads, size_t smem_bytes, cudaStream_t s) {
     if (p.njobs <= 0 || max_slabs <= 0) { return cudaSuccess; }
     if ((int)smem_bytes > kernels_max_smem_optin()) { return cudaErrorInvalidValue; }

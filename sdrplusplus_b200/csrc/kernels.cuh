@@ -202,6 +202,7 @@ FT_HD inline void ft_ranges(const FtJob& J, int slab, int* lo, int* hi) {
     }
 }
 cudaError_t launch_tail_fused(const FtParams& p, int max_slabs, int threads, size_t smem_bytes, cudaStream_t s);
+int tail_fused_ctas_per_sm(int threads, size_t smem_bytes);
 
 // ---- sequential audio-rate tails (one thread per job): AM envelope + DC block + AGC, SSB rotate + AGC ----
 struct AgcState { float amp; };

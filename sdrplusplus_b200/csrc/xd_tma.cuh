@@ -169,7 +169,10 @@ k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, c
             unsigned char* stg = gbase + st * STAGE;
             constexpr int NSAMP = (MT + QC + 1) * D;
             const long long tensor_end = (long long)g.org + (long long)g.rows_tma * (2 * D);
-            const int head = (int)(ibase < 0 ? (-ibase < NSAMP ? -ibase : NSAMP) : 0);
+            // the tensor's row 0 starts at sample g.org: everything of this tile in front of it was zero-filled -- stream
+            // history (index < 0) AND the first g.org samples of the chunk
+            const long long front = (long long)g.org - ibase;
+            const int head = (int)(front > 0 ? (front < NSAMP ? front : NSAMP) : 0);
             long long t0 = tensor_end - ibase, t1 = (long long)p.count - ibase;
             if (t0 < head) { t0 = head; }
             if (t1 > NSAMP) { t1 = NSAMP; }

@@ -39,13 +39,22 @@ def test_dc_blocker_and_conjugate_full_rate(sb, oracle, report, dc, conj, chunk)
     fe.set_fft(65536, 20.0, 2)
     cfg = sb.VfoConfig.wfm(300e3)
     vid = fe.add_vfo(cfg)
-    raw = fe.add_vfo(sb.VfoConfig.raw(0.0, 300e3, 300e3))     # the pre-processed stream itself, decimated by 8
+    raw = fe.add_vfo(sb.VfoConfig.raw(0.0, 300e3, 300e3))     # the pre-processed stream itself around DC, decimated by 8
+    raw2 = fe.add_vfo(sb.VfoConfig.raw(-900e3, 300e3, 300e3))  # ... and a slice of it away from DC
     outs, lines = fe.process_chunks(x, chunk)
     # oracle: the reference blocks, chunked the same way (the blocker is a plain recurrence: chunking does not matter)
     dcb = oracle.dcblock_c(50.0 / FS)
     v, d = oracle.rxvfo(FS, 250e3, 150e3, 300e3), oracle.wfm(75e3, 250e3)
-    vr = oracle.rxvfo(FS, 300e3, 300e3, 0.0)
-    ya, yr, xs = [], [], []
+    vr, vr2, vr64 = oracle.rxvfo(FS, 300e3, 300e3, 0.0), oracle.rxvfo(FS, 300e3, 300e3, -900e3), oracle.rxvfo(FS, 300e3, 300e3, 0.0)
+    # float64 blocker (same recurrence, no fp32 rounding of the offset): what the reference's fp32 loop itself drifts from
+    r = float(np.float32(50.0 / FS))
+    from scipy.signal import lfilter
+    x64 = x.astype(np.complex128)
+    y64 = (x64 - lfilter([0.0, r], [1.0, -(1.0 - r)], x64)) if dc else x64
+    if conj:
+        y64 = np.conj(y64)
+    y64 = y64.astype(np.complex64)
+    ya, yr, yr2, yr64, xs = [], [], [], [], []
     for i in range(0, n, chunk):
         seg = x[i:i + chunk].view(np.float32)
         if dc:
@@ -55,17 +64,26 @@ def test_dc_blocker_and_conjugate_full_rate(sb, oracle, report, dc, conj, chunk)
         xs.append(seg.view(np.complex64).copy())
         ya.append(d.process(v.process(seg)).reshape(-1, 2))
         yr.append(vr.process(seg).view(np.complex64))
-    ya, yr, xp = np.concatenate(ya), np.concatenate(yr), np.concatenate(xs)
+        yr2.append(vr2.process(seg).view(np.complex64))
+        yr64.append(vr64.process(y64[i:i + chunk].view(np.float32)).view(np.complex64))
+    ya, yr, yr2, yr64, xp = np.concatenate(ya), np.concatenate(yr), np.concatenate(yr2), np.concatenate(yr64), np.concatenate(xs)
     la = _lines(oracle, xp, FS, 65536, 20.0)
     assert outs[vid].shape == ya.shape and outs[raw].shape == yr.shape
     e_audio = rel_rms(outs[vid][4000:], ya[4000:])
     e_raw = rel_rms(outs[raw][2000:], yr[2000:])
+    e_raw2 = rel_rms(outs[raw2][2000:], yr2[2000:])
+    # The slice around DC carries the blocker's offset itself (0.058 here, held in fp32: ulp 3.7e-9) against 0.006 rms of
+    # signal: the reference's own sequential fp32 loop sits 2e-7 absolute (4e-5 of this output) from the exact recurrence,
+    # and so does any other fp32 evaluation order.  That floor is measured and bounds the gate of this one output.
+    floor_dc = rel_rms(yr[2000:], yr64[2000:])
     p, pr = 10.0 ** (lines.astype(np.float64) / 10), 10.0 ** (la.astype(np.float64) / 10)
     e_fft = float(np.max(np.abs(p - pr)) / np.max(pr))
-    report["preproc_dc%d_conj%d_chunk%d" % (dc, conj, chunk)] = {"wfm_audio_rel_rms": e_audio, "raw_vfo_rel_rms": e_raw, "fft_power_rel_max": e_fft}
+    report["preproc_dc%d_conj%d_chunk%d" % (dc, conj, chunk)] = {"wfm_audio_rel_rms": e_audio, "raw_vfo_at_dc_rel_rms": e_raw, "raw_vfo_off_dc_rel_rms": e_raw2,
+                                                              "reference_fp32_blocker_vs_exact_at_dc": floor_dc, "fft_power_rel_max": e_fft}
     assert lines.shape == la.shape
     assert e_fft < TOL, e_fft
-    assert e_raw < TOL, e_raw
+    assert e_raw2 < TOL, e_raw2
+    assert e_raw < floor_dc + TOL, (e_raw, floor_dc)
     assert e_audio < TOL, e_audio
     if dc:
         # the residual DC of the blocked stream is far below the 0.058 that went in
