@@ -380,10 +380,11 @@ def run_b200(args):
                 dist.barrier()
             torch.cuda.synchronize()
 
-        def timed_loop(ptrs, fmt, mem, outs, steps, warm):
-            """pipelined submit/wait (two chunks in flight); returns (ms by CUDA events on `stream`, wall ms, d2h bytes)."""
+        def timed_loop(ptrs, fmt, mem, outs, steps, warm, cps=1):
+            """pipelined submit/wait (two chunks in flight); a step = `cps` chunks.  Returns (ms by CUDA events on `stream`,
+            wall ms, d2h bytes of one chunk)."""
             inflight = 0
-            for i in range(warm):
+            for i in range(warm * cps):
                 fe.submit_ptr(ptrs[i % len(ptrs)], chunk, fmt, mem, outs[i % 2][0])
                 inflight += 1
                 if inflight == 2:
@@ -398,7 +399,7 @@ def run_b200(args):
             e0.record(stream)
             d2h = 0
             host_submit = 0.0
-            for i in range(steps):
+            for i in range(steps * cps):
                 o = outs[i % 2][0]
                 th = time.perf_counter()
                 fe.submit_ptr(ptrs[i % len(ptrs)], chunk, fmt, mem, o)
@@ -420,7 +421,7 @@ def run_b200(args):
                 t = torch.tensor([ms, wall], device="cuda", dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 ms, wall = float(t[0]), float(t[1])
-            timed_loop.host_submit_ms = host_submit * 1e3 / max(steps, 1)
+            timed_loop.host_submit_ms = host_submit * 1e3 / max(steps * cps, 1)
             return ms, wall, d2h
 
         probe = pcie_probe(torch)
@@ -430,17 +431,21 @@ def run_b200(args):
         ptrs = [t.data_ptr() for t in dev_in]
         fe.set_option("time_s1", 0)
         l0 = fe.launch_count()
-        timed_loop(ptrs, lib.FMT_CF32, lib.MEM_DEVICE, outs_dev, 0, args.warmup)       # warm-up only
+        cps = max(1, min(args.chunks_per_step, 32) if args.quick else args.chunks_per_step)
+        timed_loop(ptrs, lib.FMT_CF32, lib.MEM_DEVICE, outs_dev, 0, args.warmup, cps)       # warm-up only
         fe.set_option("time_s1", 1)
         if not args.no_clocks:
             clocks.start()
         l0 = fe.launch_count()
-        ms, wall, _ = timed_loop(ptrs, lib.FMT_CF32, lib.MEM_DEVICE, outs_dev, args.steps, 0)
+        ms, wall, _ = timed_loop(ptrs, lib.FMT_CF32, lib.MEM_DEVICE, outs_dev, args.steps, 0, cps)
         launches = fe.launch_count() - l0
         host_submit_ms = timed_loop.host_submit_ms
-        s1_ms, s1_n = fe.s1_stats()
+        s1_ms, s1_n = fe.group_stats(0)
+        tail_ms, tail_n = fe.group_stats(1)
+        fft_ms, fft_n = fe.group_stats(2)
+        tma_launches = fe.stat("s1_tma_launches")
         fe.set_option("time_s1", 0)
-        value = world * chunk * args.steps / (ms * 1e-3) / 1e6
+        value = world * chunk * cps * args.steps / (ms * 1e-3) / 1e6
 
         # ---------------- end-to-end legs (host pinned in, host pinned out) ----------------
         outs_host = [make_outputs(True), make_outputs(True)]
@@ -459,9 +464,11 @@ def run_b200(args):
                     t.array(np.float32)[:] = dev_in[k].cpu().numpy()
             hp = [t.data_ptr() for t in host_in]
             steps = max(8, args.steps)
-            ems, ewall, d2h = timed_loop(hp, fmt, lib.MEM_HOST, outs_host, steps, 3)
-            e2e[name] = {"value": world * chunk * steps / (ewall * 1e-3) / 1e6, "unit": "MS/s", "h2d_bytes_per_step": chunk * bps,
-                         "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step_wall": ewall / steps, "ms_per_step_events": ems / steps}
+            ecps = max(1, cps // 8)
+            ems, ewall, d2h = timed_loop(hp, fmt, lib.MEM_HOST, outs_host, steps, 3, ecps)
+            e2e[name] = {"value": world * chunk * ecps * steps / (ewall * 1e-3) / 1e6, "unit": "MS/s", "h2d_bytes_per_step": chunk * bps * ecps,
+                         "d2h_bytes_per_step": int(d2h) * ecps, "steps": steps, "chunks_per_step": ecps, "ms_per_step_wall": ewall / steps,
+                         "ms_per_step_events": ems / steps}
             for t in host_in:
                 t.free()
         clk = clocks.stop()
@@ -491,6 +498,55 @@ def run_b200(args):
                 print("roofline.alone skipped: %r" % (ex,), file=sys.stderr)
                 s1_alone = None
 
+        # ---------------- the small-chunk regime (the reference's own chunk sizes at 100 MS/s) ----------------
+        sweep = None
+        if rank == 0 and not args.quick:
+            sweep = {}
+            for csz, nchunks in ((500000, 400), (1000000, 300), (1 << 22, 120)):
+                try:
+                    fe3 = sb.FrontEnd(FS, csz)
+                    fe3.set_stream(stream.cuda_stream)
+                    fe3.set_fft(FFT_SIZE, FFT_RATE, lib.WIN_NUTTALL)
+                    ids3 = [fe3.add_vfo(sb.VfoConfig.wfm(o)) for o in offsets]
+                    o3 = []
+                    for _ in range(2):
+                        oo = lib.Outputs()
+                        keep3 = []
+                        for v in ids3:
+                            c3 = fe3.vfo_max_out(v, csz)
+                            t3 = torch.empty(2 * c3, device="cuda", dtype=torch.float32)
+                            keep3.append(t3); oo.vfo_out[v] = t3.data_ptr(); oo.vfo_cap[v] = c3
+                        nl3 = max(1, fe3.fft_max_lines(csz))
+                        t3 = torch.empty(nl3 * FFT_SIZE, device="cuda", dtype=torch.float32)
+                        keep3.append(t3); oo.fft_out = t3.data_ptr(); oo.fft_cap_lines = nl3; oo.out_mem = lib.MEM_DEVICE
+                        o3.append((oo, keep3))
+                    nslots = (2 * chunk) // (2 * csz)                      # walk through the big device buffers: larger than L2
+
+                    def run3(n):
+                        infl = 0
+                        for i in range(n):
+                            b = dev_in[(i // nslots) % nbuf]
+                            fe3.submit_ptr(b.data_ptr() + (i % nslots) * csz * 8, csz, lib.FMT_CF32, lib.MEM_DEVICE, o3[i % 2][0])
+                            infl += 1
+                            if infl == 2:
+                                fe3.wait(); infl -= 1
+                        while infl:
+                            fe3.wait(); infl -= 1
+                    run3(20)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream); run3(nchunks); e1.record(stream)
+                    torch.cuda.synchronize()
+                    sweep[str(csz)] = {"value": csz * nchunks / (e0.elapsed_time(e1) * 1e-3) / 1e6, "unit": "MS/s", "chunks": nchunks,
+                                       "us_per_chunk": e0.elapsed_time(e1) * 1e3 / nchunks}
+                    fe3.close()
+                except Exception as ex:              # noqa: BLE001
+                    sweep[str(csz)] = {"value": None, "error": repr(ex)}
+        numa_all = [numa]
+        if world > 1:
+            numa_all = [None] * world
+            dist.all_gather_object(numa_all, numa)
+
     c4 = None
     if args.c4 and not args.quick:
         try:
@@ -505,34 +561,69 @@ def run_b200(args):
     algo_bytes = ALGO_BYTES_PER_SAMPLE * chunk
     s1_avg = s1_ms / max(s1_n, 1)
     achieved = algo_bytes / (s1_avg * 1e-3) / 1e9 if s1_n else None
+    nchunks_timed = cps * args.steps
+    s1_kernel = ("k_xd_tma" if tma_launches > 0 else ("k_xd_pfb" if args.s1 >= 7 and args.offsets == "sym" else "k_xd_pipe"))
+    # DRAM traffic of the dominant kernel: from the tracked ncu capture of this round, never a constant in this file
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("kernel", "").startswith(s1_kernel) and tj.get("chunk_samples") == chunk:
+            traffic = int(tj["dram_bytes_read"] + tj["dram_bytes_write"])
+            traffic_src = "ncu --set full, %s: dram__bytes_read.sum %.2f MB + dram__bytes_write.sum %.2f MB per launch (%s)" % (
+                tj.get("kernel"), tj["dram_bytes_read"] / 1e6, tj["dram_bytes_write"] / 1e6, tj.get("source"))
+    except (OSError, ValueError, KeyError):
+        pass
+    # useful fp32 multiply-adds behind stage 1, per VFO output sample of the C2 chain (real FMA; a packed FFMA2 counts 2):
+    # audio FIR 237 + channel FIR 2*126 + polyphase 2*119 + (2,69) stage 2*69*1.5625 + (4,27) stage 2*27*3.125
+    tail_fma = 8 * chunk * (250e3 / FS) * (237 + 2 * 126 + 2 * 119 + 2 * 69 * 1.5625 + 2 * 27 * 3.125)
+    fma_peak = 35.0e12                      # measured FFMA / FFMA2 issue peak of this part (tools/ubench.cu), FMA/s
+    tail_avg = tail_ms / max(tail_n, 1)
+    fft_avg = fft_ms / max(fft_n, 1)
+    fft_bytes = chunk * (FFT_RATE / FS) * FFT_SIZE * (8 + 8 + 8 + 4)          # frames per chunk x (read IQ, work out, work in, dB out)
+    groups = [
+        {"group": "stage 1", "kernels": s1_kernel, "avg_ms": s1_avg, "timed": s1_n, "bound": "hbm", "achieved": achieved, "peak": peak,
+         "unit": "GB/s", "frac": (achieved / peak) if achieved else None},
+        {"group": "behind stage 1", "kernels": "k_dfir_reg x2, k_tail_fused, k_carry", "avg_ms": tail_avg, "timed": tail_n, "bound": "fp32 FMA issue",
+         "achieved": (tail_fma / (tail_avg * 1e-3) / 1e12) if tail_n else None, "peak": fma_peak / 1e12, "unit": "TFMA/s",
+         "frac": (tail_fma / (tail_avg * 1e-3) / fma_peak) if tail_n else None, "useful_fma_per_chunk": tail_fma},
+        {"group": "spectrum branch", "kernels": "k_fftr_p1, k_fftr_p2 (frames of a chunk batched)", "avg_ms": fft_avg, "timed": fft_n, "bound": "hbm / L2",
+         "achieved": (fft_bytes / (fft_avg * 1e-3) / 1e9) if fft_n else None, "peak": peak, "unit": "GB/s",
+         "frac": (fft_bytes / (fft_avg * 1e-3) / 1e9 / peak) if fft_n else None,
+         "bytes_per_chunk": fft_bytes},
+    ]
+    timed = [g for g in groups if g["timed"]]
+    dominant_by_time = max(timed, key=lambda g: g["avg_ms"])["group"] if timed else None
     line = {
         "metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "ms_per_step_wall": wall / args.steps, "host_ms_per_submit": host_submit_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "chunk_samples": chunk, "samplerate": FS, "parallelism": "replicas x%d (one IQ stream per GPU, no collective)" % world,
+        "config": {"workload": WORKLOAD, "chunk_samples": chunk, "chunks_per_step": cps, "samples_per_step": chunk * cps, "samplerate": FS,
+                   "parallelism": "replicas x%d (one IQ stream per GPU, no collective)" % world,
                    "l2": "inputs larger than L2: %d MiB cf32 chunk, %d rotating device buffers" % (chunk * 8 >> 20, nbuf),
                    "value_input": "cf32 resident in HBM, outputs to HBM", "e2e_input": "int16 IQ in pinned host memory (file_source format); cf32 and int8 also reported",
                    "pipelining": "b200_fe_submit/wait, 2 chunks in flight", "s1_variant": args.s1, "tails_variant": args.tails,
                    "vfo_offsets_hz": offsets, "conjugate_pair_sharing": bool(args.pair) and args.offsets == "sym",
-                   "tails_overlap_next_chunk": bool(args.overlap)},
-        "e2e": dict(e2e["cs16"], format="cs16", cf32=e2e["cf32"], cs8=e2e["cs8"], pcie_probe=probe, numa=numa,
+                   "tails_overlap_next_chunk": bool(args.overlap),
+                   "chunk_sweep": sweep, "chunk_sweep_note": "device-resident MS/s of the same graph at the reference's own chunk sizes (STREAM_BUFFER_SIZE caps a chunk at 1e6 samples, core/src/dsp/stream.h:9)"},
+        "e2e": dict(e2e["cs16"], format="cs16", cf32=e2e["cf32"], cs8=e2e["cs8"], pcie_probe=probe, numa=numa, numa_per_rank=numa_all,
                     host_buffers="b200_host_alloc (cudaHostAlloc)"),
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": ("k_xd_pfb" if args.s1 >= 7 and args.offsets == "sym" else "k_xd_pipe") +
-                     " (stage 1: translate + first decimating FIR of all VFOs, IQ read once)",
+        "roofline": {"bound": "hbm", "kernel": s1_kernel + " (stage 1: translate + first decimating FIR of all VFOs, IQ read once; the kernel that moves the algorithmic bytes)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None,
-                     "traffic": 151075840 if (chunk == 1 << 24 and args.offsets == "sym") else None,
-                     "traffic_source": "ncu --set full: dram__bytes_read.sum 135.62 MB + dram__bytes_write.sum 15.46 MB per launch (profiles/r01_ncu_full_xd_pfb.txt)",
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": s1_avg, "launches_timed": s1_n,
-                     "share_of_step": (s1_ms / ms) if ms else None,
-                     "step_level": {"achieved": algo_bytes * args.steps / (ms * 1e-3) / 1e9, "frac": algo_bytes * args.steps / (ms * 1e-3) / 1e9 / peak},
+                     "share_of_step": (s1_avg * nchunks_timed / ms) if ms else None,
+                     "step_level": {"achieved": algo_bytes * nchunks_timed / (ms * 1e-3) / 1e9, "frac": algo_bytes * nchunks_timed / (ms * 1e-3) / 1e9 / peak},
                      "alone": ({"avg_launch_ms": s1_alone, "achieved": algo_bytes / (s1_alone * 1e-3) / 1e9,
                                 "frac": algo_bytes / (s1_alone * 1e-3) / 1e9 / peak,
                                 "what": "same kernel, same inputs, no spectrum branch and no overlapped tail kernels on the GPU"} if s1_alone else None),
-                     "note": "avg_launch_ms is measured inside the timed region, where the spectrum and tail kernels of neighbouring chunks share the SMs; "
-                             "'alone' times the same launch with nothing else running. Filter-bank form: 14 FMA per input sample vs 9 B (DESIGN.md section 5)"},
+                     "by_group": groups, "dominant_by_time": dominant_by_time,
+                     "note": "avg_launch_ms of every group is measured live with CUDA events on the stream the group runs on, inside the timed region, "
+                             "where the three streams (stage 1 | behind stage 1 | spectrum) share the SMs; 'alone' times stage 1 with nothing else running. "
+                             "Timed: the first %d chunks of the region per group." % s1_n},
     }
     if c4 is not None:
         line["c4"] = c4
@@ -557,7 +648,8 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--chunk", type=int, default=1 << 24, help="IQ samples per step (default 16 Mi = 128 MiB cf32 > L2)")
+    ap.add_argument("--chunk", type=int, default=1 << 24, help="IQ samples per chunk (default 16 Mi = 128 MiB cf32 > L2)")
+    ap.add_argument("--chunks-per-step", type=int, default=512, help="a step = this many chunks through the pipelined submit/wait API (default 512: about 75 ms of device time per step)")
     ap.add_argument("--s1", type=int, default=8, help="stage-1 kernel variant (8 = filter-bank form fed by the TMA engine, 7 = filter bank on cp.async tiles, when the VFO plan allows it; else 6 = per-VFO complex taps)")
     ap.add_argument("--tails", type=int, default=2, help="2 = one fused tail launch per <= 16 VFOs (default), 1 = shared-memory tiled kernel per stage, 0 = one thread per output")
     ap.add_argument("--ft", default="", help="fused-tail tuning, e.g. ft_threads=256,ft_obmax=1024,ft_smem_kb=72")

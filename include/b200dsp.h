@@ -221,6 +221,9 @@ int b200_fe_set_option(b200_fe* fe, const char* key, int value);
 /* device time spent in the stage-1 (translate + first decimation) launches since the last call, and their count;
  * synchronises on the recorded events ("time_s1" must be on).  bench.py's roofline leg reads this. */
 int b200_fe_s1_stats(b200_fe* fe, double* ms_total, int* launches);
+/* the same for a launch group: 0 = stage 1, 1 = everything behind stage 1 of a chunk (register FIRs, fused tail, carries),
+ * 2 = the spectrum branch of a chunk.  At most 512 samples per group are kept between two calls. */
+int b200_fe_group_stats(b200_fe* fe, int group, double* ms_total, int* launches);
 
 /* ------------------------------------------------------------------------------------------
  * One IQ stream, VFO groups on several GPUs (BASELINE config 4).  Replaces the Splitter fan-out

@@ -468,7 +468,7 @@ extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
         if (!strcmp(key, "ft_prereg")) { fe->sch.fuse.pre_reg = value; return 0; }
     }
     if (!strcmp(key, "fft")) { kernels_set_fft_variant(value); return 0; }
-    if (!strcmp(key, "time_s1")) { fe->sch.time_s1 = value != 0; fe->sch.ev_used = 0; return 0; }
+    if (!strcmp(key, "time_s1")) { fe->sch.time_s1 = value != 0; for (auto& t : fe->sch.timers) { t.used = 0; } return 0; }
     set_error("unknown option %s", key);
     return B200_EINVAL;
 }
@@ -476,6 +476,10 @@ extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
 extern "C" int b200_fe_s1_stats(b200_fe* fe, double* ms_total, int* launches) {
     if (!fe || !ms_total || !launches) { set_error("null argument"); return B200_EINVAL; }
     return fe->sch.s1_stats(ms_total, launches);
+}
+extern "C" int b200_fe_group_stats(b200_fe* fe, int group, double* ms_total, int* launches) {
+    if (!fe || !ms_total || !launches) { set_error("null argument"); return B200_EINVAL; }
+    return fe->sch.group_stats(group, ms_total, launches);
 }
 
 extern "C" int b200_fe_reset(b200_fe* fe) {
@@ -531,6 +535,7 @@ static int fe_fft_chunk(b200_fe* fe, const void* dptr, int fmt, int count, int* 
     float* const lines_base = fe->lines_override ? fe->lines_override : fe->lines.as<float>();
     cudaStream_t s = async ? fe->fft_stream : main_s;
     bool forked = false;
+    cudaEvent_t t_fft = nullptr;
     auto fork = [&]() -> int {
         // the spectrum branch only reads the chunk: run it beside the VFO branch, join before the outputs
         if (async && !forked) {
@@ -539,6 +544,7 @@ static int fe_fft_chunk(b200_fe* fe, const void* dptr, int fmt, int count, int* 
             // the line buffer of the previous chunk may still be on its way out (tail stream)
             if (fe->lines_busy) { B200_CK(cudaStreamWaitEvent(s, fe->ev_lines_free, 0)); }
             trace_mark("fft start", s);
+            t_fft = fe->sch.timer_begin(2, s);
             forked = true;
         }
         return 0;
@@ -591,6 +597,7 @@ static int fe_fft_chunk(b200_fe* fe, const void* dptr, int fmt, int count, int* 
         }
     }
     if (forked) {
+        if (t_fft) { B200_CK(cudaEventRecord(t_fft, s)); }
         trace_mark("fft done", s);
         B200_CK(cudaEventRecord(fe->ev_fft_done, s));
         fe->fft_join_pending = true;     // joined by the caller after the VFO branch has been enqueued

@@ -649,19 +649,36 @@ int Scheduler::init_raw() {
     return raw_hist.alloc((size_t)RAW_HIST * sizeof(float2));
 }
 Scheduler::~Scheduler() {
-    for (cudaEvent_t e : ev_s1) { cudaEventDestroy(e); }
+    for (Timer& t : timers) { for (cudaEvent_t e : t.ev) { cudaEventDestroy(e); } }
 }
-int Scheduler::s1_stats(double* ms_total, int* n) {
+cudaEvent_t Scheduler::timer_begin(int group, cudaStream_t s) {
+    if (!time_s1) { return nullptr; }
+    Timer& t = timers[group];
+    if (t.used + 2 > 2 * TIMER_MAX) { return nullptr; }
+    if (t.used + 2 > t.ev.size()) {
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { return nullptr; }
+        t.ev.push_back(a);
+        t.ev.push_back(b);
+    }
+    cudaEvent_t t0 = t.ev[t.used], t1 = t.ev[t.used + 1];
+    t.used += 2;
+    cudaEventRecord(t0, s);
+    return t1;
+}
+int Scheduler::group_stats(int group, double* ms_total, int* n) {
+    if (group < 0 || group > 2) { set_error("bad timer group"); return B200_EINVAL; }
+    Timer& t = timers[group];
     double tot = 0.0;
-    for (size_t i = 0; i + 1 < ev_used; i += 2) {
-        B200_CK(cudaEventSynchronize(ev_s1[i + 1]));
+    for (size_t i = 0; i + 1 < t.used; i += 2) {
+        B200_CK(cudaEventSynchronize(t.ev[i + 1]));
         float ms = 0.0f;
-        B200_CK(cudaEventElapsedTime(&ms, ev_s1[i], ev_s1[i + 1]));
+        B200_CK(cudaEventElapsedTime(&ms, t.ev[i], t.ev[i + 1]));
         tot += ms;
     }
     *ms_total = tot;
-    *n = (int)(ev_used / 2);
-    ev_used = 0;
+    *n = (int)(t.used / 2);
+    t.used = 0;
     return 0;
 }
 int Scheduler::reset_raw() {
@@ -896,19 +913,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
                 if (g[b + v]->gpad_len < (p.D - 1) + (p.QP + 8) * p.D) { variant = 0; }
             }
             int nl = 0;
-            cudaEvent_t t0 = nullptr, t1 = nullptr;
-            if (time_s1) {
-                if (ev_used + 2 > ev_s1.size()) {
-                    cudaEvent_t a, b;
-                    B200_CK(cudaEventCreate(&a));
-                    B200_CK(cudaEventCreate(&b));
-                    ev_s1.push_back(a);
-                    ev_s1.push_back(b);
-                }
-                t0 = ev_s1[ev_used]; t1 = ev_s1[ev_used + 1];
-                ev_used += 2;
-                B200_CK(cudaEventRecord(t0, stream));
-            }
+            cudaEvent_t t1 = timer_begin(0, stream);
             cudaError_t e = launch_xlate_decim(p, fmt, variant, stream, &nl);
             if (e != cudaSuccess) { return cuda_fail(e, "launch_xlate_decim"); }
             if (t1) { B200_CK(cudaEventRecord(t1, stream)); }
@@ -934,6 +939,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
         B200_CK(cudaStreamWaitEvent(ts, ev_stage1[parity], 0));
     }
     trace_mark("tails start", ts);
+    cudaEvent_t t_tail = timer_begin(1, ts);
     // ---- short decimating FIRs with the window in registers (k_dfir_reg): one launch per level and plan stage ----
     DfrParams dfr;
     dfr.njobs = 0; dfr.max_out = 0;
@@ -1206,6 +1212,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
     }
     int rcf = flush_batch(cp, launch_carry, ts, launches);
     if (rcf) { return rcf; }
+    if (t_tail) { B200_CK(cudaEventRecord(t_tail, ts)); }
     trace_mark("tails+carry done", ts);
     if (tail_stream) { B200_CK(cudaEventRecord(ev_tail[parity], ts)); }
     chunk_idx++;

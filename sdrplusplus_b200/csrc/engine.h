@@ -222,11 +222,16 @@ struct Scheduler {
     int sm_count = 148;
     float in_scale = 1.0f / 32768.0f;   // integer raw formats of this chunk: sample = (float)x * in_scale (set by the caller)
     bool pair_conjugates = true;   // stage 1: VFOs at +f / -f share their multiply-accumulates (exact identity)
-    // optional device-side timing of the stage-1 launches (bench.py's roofline leg): CUDA events on `stream`
+    // optional device-side timing (bench.py's roofline legs): CUDA events around a launch group on the stream it runs on.
+    // group 0 = stage 1 (stream), 1 = everything behind stage 1 of a chunk: register FIRs, fused tail, carries (tail stream),
+    // 2 = the spectrum branch of a chunk (its own stream; recorded by the front end).  At most TIMER_MAX samples per group.
     bool time_s1 = false;
-    std::vector<cudaEvent_t> ev_s1;     // pairs (start, stop)
-    size_t ev_used = 0;
-    int s1_stats(double* ms_total, int* launches);   // synchronises the recorded events, then clears them
+    static const size_t TIMER_MAX = 512;
+    struct Timer { std::vector<cudaEvent_t> ev; size_t used = 0; };
+    Timer timers[3];
+    cudaEvent_t timer_begin(int group, cudaStream_t s);      // returns the stop event to record, nullptr when off / full
+    int group_stats(int group, double* ms_total, int* launches);   // synchronises the recorded events, then clears them
+    int s1_stats(double* ms_total, int* launches) { return group_stats(0, ms_total, launches); }
     ~Scheduler();
     DevBuf raw_hist;             // last RAW_HIST samples of the raw IQ stream (cf32)
     static const int RAW_HIST = 1024;

@@ -152,6 +152,12 @@ class FrontEnd:
         L.check(self._l.b200_fe_s1_stats(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def group_stats(self, group):
+        """(ms_total, launches) of a timed launch group since the last call: 0 stage 1, 1 behind stage 1, 2 spectrum branch"""
+        ms, n = C.c_double(), C.c_int()
+        L.check(self._l.b200_fe_group_stats(self._h, int(group), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def launch_count(self):
         return self._l.b200_fe_launch_count(self._h)
 

@@ -77,6 +77,7 @@ SIGNATURES = {
     "b200_fe_stat": (_ll, [_vp, C.c_char_p]),
     "b200_fe_set_option": (_i, [_vp, C.c_char_p, _i]),
     "b200_fe_s1_stats": (_i, [_vp, C.POINTER(C.c_double), _ip]),
+    "b200_fe_group_stats": (_i, [_vp, _i, C.POINTER(C.c_double), _ip]),
     "b200_shard_unique_id": (_i, [_vp]),
     "b200_shard_create": (_vp, [_vp, _i, _i, _vp]),
     "b200_shard_submit": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(Outputs)]),
