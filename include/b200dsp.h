@@ -64,6 +64,7 @@ extern "C" {
 #define B200_DEMOD_USB  4    /* demod::SSB<stereo_t> Mode::USB           -- ssb.h:77-92             */
 #define B200_DEMOD_LSB  5
 #define B200_DEMOD_DSB  6
+#define B200_DEMOD_WFM_STEREO 7  /* demod::BroadcastFM stereo branch: pilot filter + PLL + L-R recovery -- broadcast_fm.h:147-190 */
 
 #define B200_AGC_CARRIER 0   /* demod::AM::AGCMode (am.h:14-17) */
 #define B200_AGC_AUDIO   1
@@ -147,6 +148,11 @@ typedef struct {
     int    af_volume_on;      /* 0 = no volume block                                                         */
     int    af_muted;
     double af_volume;
+    /* radio IF chain between the VFO and the demodulator (decoder_modules/radio/src/radio_module.h:88-96): power squelch,
+     * noise_reduction::PowerSquelch (core/src/dsp/noise_reduction/power_squelch.h:33-50): a chunk whose mean amplitude is
+     * below squelch_level dB is zeroed before it reaches the demodulator */
+    int    squelch_on;
+    double squelch_level;
 } b200_vfo_cfg;
 
 typedef struct {
@@ -268,9 +274,10 @@ b200_block* b200_rxvfo_create(double inSamplerate, double outSamplerate, double 
 int         b200_rxvfo_set_offset(b200_block* b, double offset);
 int         b200_rxvfo_set_bandwidth(b200_block* b, double bandwidth);
 b200_block* b200_quad_create(double deviationHz, double samplerate);            /* demod::Quadrature (quadrature.h:39-46): complex -> float */
-b200_block* b200_wfm_create(double deviationHz, double samplerate, int stereo, int lowPass); /* demod::BroadcastFM: complex -> stereo */
+b200_block* b200_wfm_create(double deviationHz, double samplerate, int stereo, int lowPass); /* demod::BroadcastFM (mono or stereo branch, broadcast_fm.h:144-212): complex -> stereo */
 b200_block* b200_nfm_create(double samplerate, double bandwidth, int lowPass);  /* demod::FM<stereo_t> */
 b200_block* b200_am_create(int agcMode, double bandwidth, double agcAttack, double agcDecay, double dcBlockRate, double samplerate); /* demod::AM<stereo_t> */
+b200_block* b200_squelch_create(double level);                                       /* noise_reduction::PowerSquelch (power_squelch.h:33-50): complex -> complex */
 b200_block* b200_deemph_create(double tau, double samplerate);                       /* filter::Deemphasis<stereo_t> (deephasis.h:58-77): stereo -> stereo */
 b200_block* b200_ssb_create(int mode /*0 USB,1 LSB,2 DSB*/, double bandwidth, double samplerate, double agcAttack, double agcDecay); /* demod::SSB<stereo_t> */
 /* returns the output sample count; in/out are host pointers of the block's sample types */

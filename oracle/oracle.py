@@ -115,6 +115,7 @@ class Oracle:
             "orc_am_create": (vp, [i, d, d, d, d, d]),
             "orc_ssb_create": (vp, [i, d, d, d, d]),
             "orc_dcblock_c_create": (vp, [d]),
+            "orc_squelch_create": (vp, [d]),
             "orc_deemph_create": (vp, [d, d]),
             "orc_process": (i, [vp, i, vp, vp]),
             "orc_reset": (None, [vp]),
@@ -246,6 +247,9 @@ class Oracle:
 
     def dcblock_c(self, rate):
         return Block(self.lib, self.lib.orc_dcblock_c_create(rate), 2, 2)
+
+    def squelch(self, level):
+        return Block(self.lib, self.lib.orc_squelch_create(level), 2, 2)
 
     def deemph(self, tau, sr):
         return Block(self.lib, self.lib.orc_deemph_create(tau, sr), 2, 2)

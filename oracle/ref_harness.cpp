@@ -32,6 +32,7 @@
 #include <dsp/demod/am.h>
 #include <dsp/demod/ssb.h>
 #include <dsp/correction/dc_blocker.h>
+#include <dsp/noise_reduction/power_squelch.h>
 #include <dsp/compression/sample_stream_compressor.h>
 #include <dsp/compression/sample_stream_decompressor.h>
 #include <dsp/taps/low_pass.h>
@@ -168,6 +169,12 @@ namespace {
         DcNode(double rate) { b.init(NULL, rate); }
         int process(int count, const void* in, void* out) override { return b.process(count, s.load(in, count), (complex_t*)out); }
         void reset() override { b.reset(); }
+    };
+
+    struct SquelchNode : Node {
+        noise_reduction::PowerSquelch b;
+        SquelchNode(double level) { b.init(NULL, level); }
+        int process(int count, const void* in, void* out) override { return b.process(count, (const complex_t*)in, (complex_t*)out); }
     };
 
     struct DeemphNode : Node {
@@ -325,6 +332,7 @@ void* orc_am_create(int agcMode, double bw, double att, double dec, double dcr, 
 }
 void* orc_ssb_create(int mode, double bw, double sr, double att, double dec) { return new SsbNode(mode, bw, sr, att, dec); }
 void* orc_dcblock_c_create(double rate) { return new DcNode(rate); }
+void* orc_squelch_create(double level) { return new SquelchNode(level); }
 void* orc_deemph_create(double tau, double sr) { return new DeemphNode(tau, sr); }
 
 int orc_process(void* h, int count, const void* in, void* out) { return ((Node*)h)->process(count, in, out); }

@@ -791,8 +791,129 @@ static int n_wfm_proc(node* b, int count, const void* in, void* out) {
 }
 static void n_wfm_reset(node* b) { n_wfm* w = (n_wfm*)b; w->q.phase = 0.0f; fir_reset(&w->al); }
 static void n_wfm_destroy(node* b) { n_wfm* w = (n_wfm*)b; fir_free(&w->al); free(w->s.p); free(b); }
+/* ---- demod::BroadcastFM stereo branch  (core/src/dsp/demod/broadcast_fm.h:36-66,147-190): RealToComplex -> pilot band-pass
+ *      (FIR<complex_t,complex_t>, taps::bandPass<complex_t>(18750,19250,3000,fs,odd)) -> loop::PLL (pll.h:64-70 over
+ *      PhaseControlLoop, phase_control_loop.h:27-32,58-85) -> Delay x2 -> conj, two complex multiplies -> real part * 2 ->
+ *      L = (L+R) + (L-R), R = (L+R) - (L-R) -> two audio low-passes -> LRToStereo.  RDS output not restated (off). ---- */
+/* math::normalizePhase  (math/normalize_phase.h:6-10) */
+static float normalize_phase(float diff) {
+    if (diff > FL_M_PI) { diff -= 2.0f * FL_M_PI; }
+    else if (diff <= -FL_M_PI) { diff += 2.0f * FL_M_PI; }
+    return diff;
+}
+typedef struct { float alpha, beta, phase, freq, minFreq, maxFreq; } pll_t;
+static void pll_init(pll_t* p, double bandwidth, double initPhase, double initFreq, double minFreq, double maxFreq) {
+    /* PhaseControlLoop<float>::criticallyDamped with T = float: the arguments are narrowed to float first */
+    float bw = (float)bandwidth;
+    float damp = (float)(sqrt(2.0) / 2.0);
+    float den = (float)(1.0 + 2.0 * damp * bw + bw * bw);
+    p->alpha = (4 * damp * bw) / den;
+    p->beta = (4 * bw * bw) / den;
+    p->phase = (float)initPhase;
+    p->freq = (float)initFreq;
+    p->minFreq = (float)minFreq;
+    p->maxFreq = (float)maxFreq;
+}
+static void pll_process(pll_t* p, int count, const cf32* in, cf32* out) {
+    const float minPhase = -FL_M_PI, maxPhase = FL_M_PI, phaseDelta = maxPhase - minPhase;
+    for (int i = 0; i < count; i++) {
+        out[i].re = cosf(p->phase);                                  /* math::phasor */
+        out[i].im = sinf(p->phase);
+        float err = normalize_phase(atan2f(in[i].im, in[i].re) - p->phase);
+        p->freq += p->beta * err;                                    /* PhaseControlLoop::advance */
+        if (p->freq > p->maxFreq) { p->freq = p->maxFreq; }
+        else if (p->freq < p->minFreq) { p->freq = p->minFreq; }
+        p->phase += p->freq + (p->alpha * err);
+        while (p->phase > maxPhase) { p->phase -= phaseDelta; }
+        while (p->phase < minPhase) { p->phase += phaseDelta; }
+    }
+}
+/* math::Delay<T>  (math/delay.h:43-53) on `es` floats per element */
+typedef struct { int delay, es; float* buf; } delay_t;
+static void delay_init(delay_t* d, int delay, int es) {
+    d->delay = delay; d->es = es;
+    d->buf = (float*)calloc((size_t)(STREAM_BUFFER_SIZE + DELAY_EXTRA) * (size_t)es, sizeof(float));
+}
+static void delay_process(delay_t* d, int count, const float* in, float* out) {
+    size_t e = sizeof(float) * (size_t)d->es;
+    memcpy(d->buf + (size_t)d->delay * d->es, in, e * (size_t)count);
+    memcpy(out, d->buf, e * (size_t)count);
+    memmove(d->buf, d->buf + (size_t)count * d->es, e * (size_t)d->delay);
+}
+/* complex data, complex taps: FIR<complex_t,complex_t>  (fir.h:74-76: volk_32fc_x2_dot_prod_32fc) */
+static int fir_process_cc(fir_t* f, int count, const cf32* in, cf32* out) {
+    cf32* buf = (cf32*)f->buffer;
+    memcpy(&buf[f->ntaps - 1], in, sizeof(cf32) * (size_t)count);
+    for (int i = 0; i < count; i++) { ovk_dot_32fc_32fc((ovk_cf32*)&out[i], (const ovk_cf32*)&buf[i], (const ovk_cf32*)f->taps, (unsigned)f->ntaps); }
+    memmove(buf, &buf[count], sizeof(cf32) * (size_t)(f->ntaps - 1));
+    return count;
+}
+typedef struct {
+    node base; fmquad_t q; fir_t pilot, al, ar; pll_t pll; delay_t lpr, lmr; int lowPass;
+    scratch_t sm, sc, sp, sv, sd, sl, sr;
+    double sr_hz;
+} n_wfms;
+static int n_wfms_proc(node* b, int count, const void* in, void* out) {
+    n_wfms* w = (n_wfms*)b;
+    float* m = scratch_get(&w->sm, count);
+    cf32* z = (cf32*)scratch_get(&w->sc, 2 * count);
+    cf32* pf = (cf32*)scratch_get(&w->sp, 2 * count);
+    cf32* vco = (cf32*)scratch_get(&w->sv, 2 * count);
+    cf32* zd = (cf32*)scratch_get(&w->sd, 2 * count);
+    float* l = scratch_get(&w->sl, count);
+    float* r = scratch_get(&w->sr, count);
+    quad_process(&w->q, count, (const cf32*)in, m);
+    for (int i = 0; i < count; i++) { z[i].re = m[i]; z[i].im = 0.0f; }          /* RealToComplex (interleave with zeros) */
+    fir_process_cc(&w->pilot, count, z, pf);
+    pll_process(&w->pll, count, pf, vco);
+    delay_process(&w->lpr, count, m, m);
+    delay_process(&w->lmr, count, (const float*)z, (float*)zd);
+    for (int i = 0; i < count; i++) { vco[i].im = -vco[i].im; }                    /* math::Conjugate */
+    ovk_mul_32fc_32fc((ovk_cf32*)zd, (const ovk_cf32*)zd, (const ovk_cf32*)vco, (unsigned)count);
+    ovk_mul_32fc_32fc((ovk_cf32*)zd, (const ovk_cf32*)zd, (const ovk_cf32*)vco, (unsigned)count);
+    for (int i = 0; i < count; i++) {
+        float lmr = zd[i].re * 2.0f;                                             /* ComplexToReal, x2 */
+        l[i] = m[i] + lmr;
+        r[i] = m[i] - lmr;
+    }
+    if (w->lowPass) {
+        fir_process_r(&w->al, count, l, l);
+        fir_process_r(&w->ar, count, r, r);
+    }
+    float* o = (float*)out;
+    for (int i = 0; i < count; i++) { o[2 * i] = l[i]; o[2 * i + 1] = r[i]; }     /* LRToStereo */
+    return count;
+}
+static void n_wfms_reset(node* b) { (void)b; }   /* BroadcastFM::reset only resets demod / FIRs (not used by the tests) */
+static void n_wfms_destroy(node* b) {
+    n_wfms* w = (n_wfms*)b;
+    fir_free(&w->pilot); fir_free(&w->al); fir_free(&w->ar); free(w->lpr.buf); free(w->lmr.buf);
+    free(w->sm.p); free(w->sc.p); free(w->sp.p); free(w->sv.p); free(w->sd.p); free(w->sl.p); free(w->sr.p);
+    free(b);
+}
+static void* wfm_stereo_create(double dev, double sr, int lowPass) {
+    NODE_ALLOC(n_wfms);
+    n->base.process = n_wfms_proc; n->base.reset = n_wfms_reset; n->base.destroy = n_wfms_destroy;
+    quad_init(&n->q, dev, sr);
+    int np = orc_bandpass_c(18750.0, 19250.0, 3000.0, sr, 1, NULL, 0);
+    float* pt = (float*)malloc(sizeof(float) * 2 * (size_t)np);
+    orc_bandpass_c(18750.0, 19250.0, 3000.0, sr, 1, pt, np);
+    fir_init(&n->pilot, pt, 2 * np, 1, 2);          /* taps stored as 2*np floats; ntaps fixed up below */
+    n->pilot.ntaps = np;
+    free(pt);
+    pll_init(&n->pll, 25000.0 / sr, 0.0, hz_to_rads(19000.0, sr), hz_to_rads(18750.0, sr), hz_to_rads(19250.0, sr));
+    delay_init(&n->lpr, ((np - 1) / 2) + 1, 1);
+    delay_init(&n->lmr, ((np - 1) / 2) + 1, 2);
+    int nt;
+    float* t = lowpass_taps(15000.0, 4000.0, sr, 0, &nt);
+    fir_init(&n->al, t, nt, 1, 1);
+    fir_init(&n->ar, t, nt, 1, 1);
+    free(t);
+    n->lowPass = lowPass;
+    return n;
+}
 void* orc_wfm_create(double dev, double sr, int stereo, int lowPass) {
-    if (stereo) { return NULL; } /* stereo/RDS branch (broadcast_fm.h:147-190) is a "next" row, SURVEY 8f */
+    if (stereo) { return wfm_stereo_create(dev, sr, lowPass); }
     NODE_ALLOC(n_wfm);
     n->base.process = n_wfm_proc; n->base.reset = n_wfm_reset; n->base.destroy = n_wfm_destroy;
     quad_init(&n->q, dev, sr);
@@ -891,6 +1012,26 @@ void* orc_dcblock_c_create(double rate) {
     NODE_ALLOC(n_dc);
     n->base.process = n_dc_proc; n->base.reset = n_dc_reset; n->base.destroy = n_plain_destroy;
     n->rate = (float)rate;
+    return n;
+}
+
+/* ---- noise_reduction::PowerSquelch  (core/src/dsp/noise_reduction/power_squelch.h:33-50): mean amplitude of the chunk
+ *      (volk_32fc_magnitude_32f + volk_32f_accumulator_s32f, sequential fp32 sum) against the level in dB ---- */
+typedef struct { node base; float level; } n_sq;
+static int n_sq_proc(node* b, int count, const void* in, void* out) {
+    const cf32* x = (const cf32*)in;
+    float sum = 0.0f;
+    for (int i = 0; i < count; i++) { sum += sqrtf(x[i].re * x[i].re + x[i].im * x[i].im); }
+    sum /= (float)count;
+    if (10.0f * log10f(sum) >= ((n_sq*)b)->level) { memcpy(out, in, sizeof(cf32) * (size_t)count); }
+    else { memset(out, 0, sizeof(cf32) * (size_t)count); }
+    return count;
+}
+static void n_sq_reset(node* b) { (void)b; }
+void* orc_squelch_create(double level) {
+    NODE_ALLOC(n_sq);
+    n->base.process = n_sq_proc; n->base.reset = n_sq_reset; n->base.destroy = n_plain_destroy;
+    n->level = (float)level;
     return n;
 }
 

@@ -78,6 +78,7 @@ void* orc_am_create(int agcMode, double bandwidth, double agcAttack, double agcD
 void* orc_ssb_create(int mode, double bandwidth, double samplerate, double agcAttack, double agcDecay);
                                                                          /* SSB<stereo_t>; mode 0 USB 1 LSB 2 DSB */
 void* orc_dcblock_c_create(double rate);                                 /* correction::DCBlocker<complex_t> */
+void* orc_squelch_create(double level);                                   /* noise_reduction::PowerSquelch */
 void* orc_deemph_create(double tau, double samplerate);                  /* filter::Deemphasis<stereo_t> */
 /* returns output sample count (samples of the block's output type) */
 int   orc_process(void* h, int count, const void* in, void* out);

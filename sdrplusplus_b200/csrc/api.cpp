@@ -338,9 +338,11 @@ static int build_vfo_chain(b200_fe* fe, VfoSlot* v) {
     const b200_vfo_cfg& c = v->cfg;
     int rc = v->chain.add_rxvfo(fe->fs_eff, c.out_samplerate, c.bandwidth, c.offset);
     if (rc) { return rc; }
+    if (c.squelch_on && (rc = v->chain.add_squelch(c.squelch_level))) { return rc; }
     switch (c.demod) {
     case B200_DEMOD_RAW: break;
-    case B200_DEMOD_WFM: rc = v->chain.add_wfm(c.deviation, c.out_samplerate, c.low_pass != 0); break;
+    case B200_DEMOD_WFM: rc = v->chain.add_wfm(c.deviation, c.out_samplerate, c.low_pass != 0, false); break;
+    case B200_DEMOD_WFM_STEREO: rc = v->chain.add_wfm(c.deviation, c.out_samplerate, c.low_pass != 0, true); break;
     case B200_DEMOD_NFM: rc = v->chain.add_nfm(c.out_samplerate, c.bandwidth, c.low_pass != 0); break;
     case B200_DEMOD_AM: rc = v->chain.add_am(c.agc_mode, c.bandwidth, c.agc_attack, c.agc_decay, c.dc_block_rate, c.out_samplerate); break;
     case B200_DEMOD_USB: rc = v->chain.add_ssb(0, c.bandwidth, c.out_samplerate, c.agc_attack, c.agc_decay); break;
@@ -959,10 +961,9 @@ extern "C" b200_block* b200_quad_create(double dev, double sr) {
     return block_finish(b, b->chain.add_quad(dev, sr));
 }
 extern "C" b200_block* b200_wfm_create(double dev, double sr, int stereo, int lowPass) {
-    if (stereo) { set_error("stereo/RDS branch of BroadcastFM is not built yet (SURVEY 8f rank 3)"); return nullptr; }
     b200_block* b = block_new();
     if (!b) { return nullptr; }
-    return block_finish(b, b->chain.add_wfm(dev, sr, lowPass != 0));
+    return block_finish(b, b->chain.add_wfm(dev, sr, lowPass != 0, stereo != 0));
 }
 extern "C" b200_block* b200_nfm_create(double sr, double bw, int lowPass) {
     b200_block* b = block_new();
@@ -974,6 +975,11 @@ extern "C" b200_block* b200_am_create(int agcMode, double bw, double att, double
     b200_block* b = block_new();
     if (!b) { return nullptr; }
     return block_finish(b, b->chain.add_am(agcMode, bw, att, dec, dcr, sr));
+}
+extern "C" b200_block* b200_squelch_create(double level) {
+    b200_block* b = block_new();
+    if (!b) { return nullptr; }
+    return block_finish(b, b->chain.add_squelch(level));
 }
 extern "C" b200_block* b200_deemph_create(double tau, double sr) {
     if (tau <= 0 || sr <= 0) { set_error("bad deemphasis parameters"); return nullptr; }

@@ -69,6 +69,42 @@ std::vector<float> highpass_taps(double cutoff, double transWidth, double sample
     return taps;
 }
 
+// taps::bandPass<complex_t> (taps/band_pass.h:11-26) over windowedSinc<complex_t> (windowed_sinc.h:22-25): the window is
+// phasor(-offsetOmega * n) * nuttall(n, N) with offsetOmega and n narrowed to float (complex_t * double multiplies in
+// float), the sinc is narrowed to float before the complex multiply, and the final correction is a float multiply.
+// Returns interleaved (re, im) pairs.
+std::vector<float> bandpass_c_taps(double bandStart, double bandStop, double transWidth, double samplerate, bool odd) {
+    const float offsetOmega = (float)hz_to_rads((bandStart + bandStop) / 2.0, samplerate);
+    int count = estimate_tap_count(transWidth, samplerate);
+    if (odd && !(count % 2)) { count++; }
+    std::vector<float> taps(2 * (size_t)(count > 0 ? count : 0));
+    const double omega = hz_to_rads((bandStop - bandStart) / 2.0, samplerate);
+    const double half = (double)count / 2.0;
+    const double corr = 1.0 * omega / kPi;
+    for (int i = 0; i < count; i++) {
+        const double t = (double)i - half + 0.5;
+        const double n = t - half;
+        const float x = -offsetOmega * (float)n;
+        const float pr = cosf(x), pi = sinf(x);                    // math::phasor
+        const float wn = (float)nuttall(n, count);
+        const float wr = pr * wn, wi = pi * wn;
+        const float cr = (float)sinc(t * omega), ci = 0.0f;
+        const float re = (cr * wr) - (ci * wi), im = (ci * wr) + (cr * wi);
+        taps[2 * (size_t)i] = re * (float)corr;
+        taps[2 * (size_t)i + 1] = im * (float)corr;
+    }
+    return taps;
+}
+
+// loop::PhaseControlLoop<float>::criticallyDamped (phase_control_loop.h:27-32) with its float locals
+void pll_coefficients(double bandwidth, float& alpha, float& beta) {
+    const float bw = (float)bandwidth;
+    const float damp = (float)(std::sqrt(2.0) / 2.0);
+    const float den = (float)(1.0 + 2.0 * damp * bw + bw * bw);
+    alpha = (4 * damp * bw) / den;
+    beta = (4 * bw * bw) / den;
+}
+
 // iq_frontend.cpp:281-291
 std::vector<float> fft_window(int window, int nz) {
     std::vector<float> w(nz);

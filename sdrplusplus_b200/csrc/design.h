@@ -11,6 +11,8 @@ double hz_to_rads(double freq, double samplerate);                       // math
 int estimate_tap_count(double transWidth, double samplerate);             // taps::estimateTapCount
 std::vector<float> lowpass_taps(double cutoff, double transWidth, double samplerate, bool odd = false); // taps::lowPass
 std::vector<float> highpass_taps(double cutoff, double transWidth, double samplerate, bool odd = false);                 // taps::highPass
+std::vector<float> bandpass_c_taps(double bandStart, double bandStop, double transWidth, double samplerate, bool odd = false); // taps::bandPass<complex_t>, (re, im) pairs
+void pll_coefficients(double bandwidth, float& alpha, float& beta);      // PhaseControlLoop<float>::criticallyDamped
 std::vector<float> fft_window(int window, int nz);                       // IQFrontEnd::updateFFTPath window * (-1)^i
 void fft_frame_params(double samplerate, int size, double rate, int& nz, int& skip); // genReshapeParams
 

@@ -227,6 +227,28 @@ int FirRStage::configure(const std::vector<float>& t, bool stereo_) {
     return upload_pm(t, 1, 1);
 }
 
+// ------------------------------------------------------------------ StereoStage
+int StereoStage::configure(double samplerate) {
+    std::vector<float> t = bandpass_c_taps(18750.0, 19250.0, 3000.0, samplerate, true);     // broadcast_fm.h:44
+    ntaps = (int)(t.size() / 2);
+    hist = ntaps - 1;
+    delay = ((ntaps - 1) / 2) + 1;                                                           // broadcast_fm.h:48-49
+    pll_coefficients(25000.0 / samplerate, alpha, beta);                                     // broadcast_fm.h:47, pll.h:17-21
+    init_freq = (float)hz_to_rads(19000.0, samplerate);
+    min_freq = (float)hz_to_rads(18750.0, samplerate);
+    max_freq = (float)hz_to_rads(19250.0, samplerate);
+    int rc = taps.alloc(t.size() * sizeof(float));
+    if (rc) { return rc; }
+    B200_CK(cudaMemcpy(taps.p, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if ((rc = state.alloc(16))) { return rc; }
+    reset_state();
+    return 0;
+}
+void StereoStage::reset_state() {
+    const float st[2] = { 0.0f, init_freq };                                                 // PLL initPhase 0, initFreq 19 kHz
+    if (state.p) { cudaMemcpy(state.p, st, sizeof(st), cudaMemcpyHostToDevice); }
+}
+
 // ------------------------------------------------------------------ SeqStage
 static void agc_coefs(SeqJob& j, double setPoint, double attack, double decay, double maxGain, double maxOut) {
     // loop::AGC::init (agc.h:13-24): doubles narrowed to float members
@@ -295,6 +317,17 @@ int Chain::finalize(int max_in, bool dbl_first, const FuseCfg* fuse) {
         }
         else { s->cap_in = cap; }
         cap = s->max_out(cap);
+    }
+    {
+        int c2 = max_in;
+        for (auto& s : st) {
+            if (s->kind == K_STEREO) {
+                StereoStage* q = (StereoStage*)s.get();
+                int rc2;
+                if ((rc2 = q->p.alloc(((size_t)c2 + 8) * sizeof(float2), false)) || (rc2 = q->vco.alloc(((size_t)c2 + 8) * sizeof(float2), false))) { return rc2; }
+            }
+            c2 = s->max_out(c2);
+        }
     }
     out_es = st.back()->out_es;
     out_cap = cap;
@@ -592,9 +625,17 @@ int Chain::add_quad(double deviationHz, double samplerate) {
     st.push_back(std::move(q));
     return 0;
 }
-int Chain::add_wfm(double deviationHz, double samplerate, bool lowPass) {
+int Chain::add_wfm(double deviationHz, double samplerate, bool lowPass, bool stereo) {
     int rc = add_quad(deviationHz, samplerate);
     if (rc) { return rc; }
+    if (stereo) {
+        // pilot filter -> PLL -> L-R recovery -> (l, r); alFir / arFir are one real-tap FIR over the (l, r) pairs
+        auto sst = std::make_unique<StereoStage>();
+        if ((rc = sst->configure(samplerate))) { return rc; }
+        st.push_back(std::move(sst));
+        if (lowPass) { return add_fir_c(lowpass_taps(15000.0, 4000.0, samplerate), 1); }
+        return 0;
+    }
     if (lowPass) { return add_fir_r(lowpass_taps(15000.0, 4000.0, samplerate), true); }   // broadcast_fm.h:45
     st.push_back(std::make_unique<M2SStage>());
     return 0;
@@ -637,6 +678,14 @@ int Chain::add_af_chain(double afSR, double audioSR, bool highPass, double deemp
     return 0;
 }
 
+int Chain::add_squelch(double level) {
+    auto q = std::make_unique<SquelchStage>();
+    q->level = (float)level;
+    int rc = q->partial.alloc(SQ_MAXPARTS * sizeof(float));
+    if (rc) { return rc; }
+    st.push_back(std::move(q));
+    return 0;
+}
 int Chain::add_volume(double volume, bool muted) {
     const float v = powf((float)volume, 2);                                  // volume.h:14: _volume = powf(volume, 2)
     st.push_back(std::make_unique<ScaleStage>(st.empty() ? 2 : st.back()->out_es, muted ? 0.0f : v));
@@ -1103,6 +1152,26 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
         SeqParams sp; sp.njobs = 0;
         M2SParams mp; mp.njobs = 0; mp.max_n = 0;
         ScaleParams cp2; cp2.njobs = 0; cp2.max_n = 0;
+        StParams stp; stp.njobs = 0; stp.max_n = 0;
+        SqParams sqp; sqp.njobs = 0; sqp.max_n = 0;
+        auto sq_flush = [&]() -> int {
+            if (sqp.njobs == 0) { return 0; }
+            int nl = 0;
+            cudaError_t e = launch_squelch(sqp, ts, &nl);
+            if (e != cudaSuccess) { return cuda_fail(e, "launch_squelch"); }
+            launches += nl;
+            sqp.njobs = 0; sqp.max_n = 0;
+            return 0;
+        };
+        auto st_flush = [&]() -> int {
+            if (stp.njobs == 0) { return 0; }
+            int nl = 0;
+            cudaError_t e = launch_stereo(stp, ts, &nl);
+            if (e != cudaSuccess) { return cuda_fail(e, "launch_stereo"); }
+            launches += nl;
+            stp.njobs = 0; stp.max_n = 0;
+            return 0;
+        };
         for (Chain* c : chains) {
             if (lvl >= c->st.size()) { continue; }
             if (c->fp.active && lvl >= 1 && (int)lvl < c->fp.end) { continue; }     // done by the fused launch
@@ -1169,6 +1238,26 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
                 if (cp2.njobs == B200_BATCH) { rc = flush_batch(cp2, launch_scale, ts, launches); cp2.max_n = 0; }
                 break;
             }
+            case K_STEREO: {
+                StereoStage* f = (StereoStage*)s;
+                if (f->n_out <= 0) { break; }
+                StJob& j = stp.job[stp.njobs++];
+                j.in = f->base(); j.out = (float2*)f->out_ptr; j.taps = f->taps.as<float2>(); j.p = f->p.as<float2>(); j.vco = f->vco.as<float2>();
+                j.state = f->state.as<float>(); j.ntaps = f->ntaps; j.delay = f->delay; j.n = f->n_out;
+                j.alpha = f->alpha; j.beta = f->beta; j.min_freq = f->min_freq; j.max_freq = f->max_freq;
+                stp.max_n = std::max(stp.max_n, f->n_out);
+                if (stp.njobs == B200_BATCH) { rc = st_flush(); }
+                break;
+            }
+            case K_SQUELCH: {
+                SquelchStage* f = (SquelchStage*)s;
+                if (f->n_out <= 0) { break; }
+                SqJob& j = sqp.job[sqp.njobs++];
+                j.in = (const float2*)f->in_data(); j.out = (float2*)f->out_ptr; j.partial = f->partial.as<float>(); j.n = f->n_out; j.level = f->level;
+                sqp.max_n = std::max(sqp.max_n, f->n_out);
+                if (sqp.njobs == B200_BATCH) { rc = sq_flush(); }
+                break;
+            }
             case K_M2S: {
                 if (s->n_out <= 0) { break; }
                 M2SJob& j = mp.job[mp.njobs++];
@@ -1189,6 +1278,8 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
         if ((rc = flush_batch(sp, launch_seq, ts, launches))) { return rc; }
         if ((rc = flush_batch(mp, launch_m2s, ts, launches))) { return rc; }
         if ((rc = flush_batch(cp2, launch_scale, ts, launches))) { return rc; }
+        if ((rc = st_flush())) { return rc; }
+        if ((rc = sq_flush())) { return rc; }
     }
     // ---- history carry (the memmove at the end of every reference process()) ----
     CarryParams cp;

@@ -40,7 +40,7 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
-enum StageKind { K_XD, K_FIRC, K_POLY, K_QUAD, K_FIRR, K_SEQ, K_M2S, K_SCALE };
+enum StageKind { K_XD, K_FIRC, K_POLY, K_QUAD, K_FIRR, K_SEQ, K_M2S, K_SCALE, K_STEREO, K_SQUELCH };
 
 struct Stage {
     StageKind kind;
@@ -162,6 +162,27 @@ struct FusedPlan {
 };
 struct FuseCfg { bool on = false; int ob_max = 1280; int smem_limit = 110 * 1024; int threads = 256; int ob_force = 0; bool direct = true; int pre_reg = 8; };   // pre_reg: how many short decimating FIR stages may run in registers in front of the fused launch
 
+// stereo branch of BroadcastFM behind the discriminator (broadcast_fm.h:147-177): mono multiplex in, (l, r) out
+struct StereoStage : Stage {
+    int ntaps = 1, delay = 0;
+    float alpha = 0, beta = 0, min_freq = 0, max_freq = 0, init_freq = 0;
+    DevBuf taps, p, vco, state;
+    StereoStage() { kind = K_STEREO; in_es = 1; out_es = 2; }
+    int configure(double samplerate);
+    int plan(int n) override { n_in = n; n_out = n; return n; }
+    int max_out(int n) const override { return n; }
+    void reset_state() override;
+};
+
+// noise_reduction::PowerSquelch (power_squelch.h:33-50) between the VFO and the demodulator (radio IF chain)
+struct SquelchStage : Stage {
+    float level = -50.0f;
+    DevBuf partial;
+    SquelchStage() { kind = K_SQUELCH; in_es = 2; out_es = 2; }
+    int plan(int n) override { n_in = n; n_out = n; return n; }
+    int max_out(int n) const override { return n; }
+};
+
 struct ScaleStage : Stage {
     float gain = 1.0f;
     ScaleStage(int es, float g) { kind = K_SCALE; in_es = es; out_es = es; gain = g; }
@@ -195,13 +216,14 @@ struct Chain {
     int add_fir_c(const std::vector<float>& taps, int decim);
     int add_fir_r(const std::vector<float>& taps, bool stereo);
     int add_quad(double deviationHz, double samplerate);
-    int add_wfm(double deviationHz, double samplerate, bool lowPass);       // broadcast_fm.h:36-52 (mono)
+    int add_wfm(double deviationHz, double samplerate, bool lowPass, bool stereo = false);   // broadcast_fm.h:36-52,144-212
     int add_nfm(double samplerate, double bandwidth, bool lowPass);         // fm.h:24-40
     int add_am(int agcMode, double bandwidth, double attack, double decay, double dcRate, double samplerate); // am.h:28-45
     int add_ssb(int mode, double bandwidth, double samplerate, double attack, double decay); // ssb.h:22-35
     int add_deemph(double tau, double samplerate);                          // filter::Deemphasis<stereo_t> (deephasis.h:14-28)
     // radio AF chain: RationalResampler<stereo_t> -> [300 Hz high-pass FIR] -> [Deemphasis]  (radio_module.h:99-110,546-553)
     int add_af_chain(double afSamplerate, double audioSamplerate, bool highPass, double deemphTau);
+    int add_squelch(double level);                                          // noise_reduction::PowerSquelch (power_squelch.h:16-20)
     int add_volume(double volume, bool muted);                              // dsp::audio::Volume (volume.h:13-17,39-42)
 };
 

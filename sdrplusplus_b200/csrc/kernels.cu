@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(256) k_xd_tile(const __grid_constant__ XdParam
 #include "tails.cuh"
 #include "dfir_reg.cuh"
 #include "fused_tail.cuh"
+#include "stereo.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // retune edge: outputs whose tap window straddles the chunk start when the VFO offset changed at this

@@ -221,6 +221,26 @@ struct SeqJob {
 struct SeqParams { int njobs; SeqJob job[B200_BATCH]; };
 #define SEQ_STATE_FLOATS 8   // [0] carrier amp [1] audio amp [2] dc offset [3] rot re [4] rot im [5] deemph last l [6] last r
 
+// ---- stereo branch of BroadcastFM behind the discriminator (stereo.cuh) ----
+struct StJob {
+    const float* in;        // mono [hist | data], hist = ntaps - 1
+    float2* out;            // (l, r) before the audio low-pass
+    const float2* taps;     // pilot band-pass, complex
+    float2* p;              // scratch: pilot filter output, n
+    float2* vco;            // scratch: PLL output, n
+    float* state;           // [0] phase [1] freq
+    int ntaps, delay, n;
+    float alpha, beta, min_freq, max_freq;
+};
+struct StParams { int njobs; int max_n; StJob job[B200_BATCH]; };
+cudaError_t launch_stereo(const StParams& p, cudaStream_t s, int* nlaunch);
+
+// ---- noise_reduction::PowerSquelch at the VFO output (stereo.cuh) ----
+#define SQ_MAXPARTS 256
+struct SqJob { const float2* in; float2* out; float* partial; int n; float level; };
+struct SqParams { int njobs; int max_n; SqJob job[B200_BATCH]; };
+cudaError_t launch_squelch(const SqParams& p, cudaStream_t s, int* nlaunch);
+
 // ---- elementwise gain (dsp::audio::Volume, volume.h:39-42: volk_32f_s32f_multiply_32f) ----
 struct ScaleJob { const float* in; float* out; int n; float gain; };      // n floats
 struct ScaleParams { int njobs; int max_n; ScaleJob job[B200_BATCH]; };

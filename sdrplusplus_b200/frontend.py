@@ -31,9 +31,15 @@ class VfoConfig:
     af_volume_on: bool = False       # dsp::audio::Volume at the end: out = in * (muted ? 0 : volume^2)
     af_muted: bool = False
     af_volume: float = 1.0
+    squelch_on: bool = False         # noise_reduction::PowerSquelch in front of the demodulator (radio IF chain)
+    squelch_level: float = -50.0
 
     def with_volume(self, volume, muted=False):
         self.af_volume_on, self.af_volume, self.af_muted = True, volume, muted
+        return self
+
+    def with_squelch(self, level):
+        self.squelch_on, self.squelch_level = True, level
         return self
 
     def with_af(self, audio_sr=48000.0, high_pass=False, deemph_tau=50e-6):
@@ -44,6 +50,10 @@ class VfoConfig:
     def wfm(offset, bandwidth=150000.0):
         # decoder_modules/radio/src/demodulators/wfm.h:78,268-270: IF 250 kS/s, deviation = bandwidth/2
         return VfoConfig(offset, 250000.0, bandwidth, L.DEMOD_WFM, deviation=bandwidth / 2.0, low_pass=True)
+
+    @staticmethod
+    def wfm_stereo(offset, bandwidth=150000.0):
+        return VfoConfig(offset, 250000.0, bandwidth, L.DEMOD_WFM_STEREO, deviation=bandwidth / 2.0, low_pass=True)
 
     @staticmethod
     def nfm(offset, bandwidth=12500.0):
@@ -67,7 +77,8 @@ class VfoConfig:
     def to_c(self):
         return L.VfoCfg(self.offset, self.out_samplerate, self.bandwidth, self.demod, self.deviation, int(self.low_pass),
                         self.agc_mode, self.agc_attack, self.agc_decay, self.dc_block_rate, self.af_samplerate,
-                        int(self.af_high_pass), self.af_deemph_tau, int(self.af_volume_on), int(self.af_muted), float(self.af_volume))
+                        int(self.af_high_pass), self.af_deemph_tau, int(self.af_volume_on), int(self.af_muted), float(self.af_volume),
+                        int(self.squelch_on), float(self.squelch_level))
 
 
 _NP_FMT = {L.FMT_CF32: (np.complex64, 1), L.FMT_CS16: (np.int16, 2), L.FMT_CS8: (np.int8, 2)}
@@ -283,6 +294,10 @@ class Block:
     @staticmethod
     def deemph(tau, sr):
         return Block(L.load().b200_deemph_create(tau, sr), 2, 2)
+
+    @staticmethod
+    def squelch(level):
+        return Block(L.load().b200_squelch_create(level), 2, 2)
 
     def set_offset(self, *a):
         if len(a) == 2:

@@ -11,7 +11,7 @@ MAX_VFOS = 64
 FMT_CF32, FMT_CS16, FMT_CS8 = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 WIN_RECTANGULAR, WIN_BLACKMAN, WIN_NUTTALL = 0, 1, 2
-DEMOD_RAW, DEMOD_WFM, DEMOD_NFM, DEMOD_AM, DEMOD_USB, DEMOD_LSB, DEMOD_DSB = range(7)
+DEMOD_RAW, DEMOD_WFM, DEMOD_NFM, DEMOD_AM, DEMOD_USB, DEMOD_LSB, DEMOD_DSB, DEMOD_WFM_STEREO = range(8)
 AGC_CARRIER, AGC_AUDIO = 0, 1
 E = {0: "OK", -1: "EINVAL", -2: "ENODEV", -3: "ECUDA", -4: "ENOMEM", -5: "ECAP", -6: "ENOPLAN", -7: "ESTATE"}
 
@@ -27,7 +27,7 @@ class VfoCfg(C.Structure):
                 ("deviation", C.c_double), ("low_pass", C.c_int), ("agc_mode", C.c_int), ("agc_attack", C.c_double),
                 ("agc_decay", C.c_double), ("dc_block_rate", C.c_double), ("af_samplerate", C.c_double),
                 ("af_high_pass", C.c_int), ("af_deemph_tau", C.c_double), ("af_volume_on", C.c_int), ("af_muted", C.c_int),
-                ("af_volume", C.c_double)]
+                ("af_volume", C.c_double), ("squelch_on", C.c_int), ("squelch_level", C.c_double)]
 
 
 class Outputs(C.Structure):
@@ -100,6 +100,7 @@ SIGNATURES = {
     "b200_nfm_create": (_vp, [_d, _d, _i]),
     "b200_am_create": (_vp, [_i, _d, _d, _d, _d, _d]),
     "b200_ssb_create": (_vp, [_i, _d, _d, _d, _d]),
+    "b200_squelch_create": (_vp, [_d]),
     "b200_deemph_create": (_vp, [_d, _d]),
     "b200_block_process": (_i, [_vp, _i, _vp, _vp]),
     "b200_block_max_out": (_i, [_vp, _i]),

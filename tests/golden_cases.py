@@ -24,6 +24,18 @@ def digest(a):
     return np.array([a.size, float(np.sum(a * w)), float(np.sum(np.abs(a)))])
 
 
+def stereo_mpx_iq(n, fs, seed=5):
+    """FM carrier modulated with a stereo multiplex: L+R, 19 kHz pilot, L-R on the 38 kHz subcarrier (+ a little noise)."""
+    t = np.arange(n, dtype=np.float64) / fs
+    lpr = 0.4 * np.sin(2 * np.pi * 1000.0 * t) + 0.1 * np.sin(2 * np.pi * 3300.0 * t)
+    lmr = 0.3 * np.sin(2 * np.pi * 700.0 * t)
+    mpx = lpr + 0.1 * np.sin(2 * np.pi * 19000.0 * t) + lmr * np.sin(2 * np.pi * 38000.0 * t)
+    ph = 2 * np.pi * 75e3 * np.cumsum(mpx) / fs
+    rng = np.random.default_rng(seed)
+    x = 0.5 * np.exp(1j * ph) + 0.001 * (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n))
+    return x.astype(np.complex64)
+
+
 def run_cases(R):
     g = {}
     # ---- host-side design ----
@@ -74,6 +86,12 @@ def run_cases(R):
     g["usb_digest"] = digest(a)
     g["lsb_digest"] = digest(R.ssb(1, 2800.0, 24e3, 50 / 24e3, 5 / 24e3).process_chunks(v, 120))
     g["deemph_digest"] = digest(R.deemph(50e-6, 48e3).process_chunks(a, 480))
+    # stereo branch of BroadcastFM (pilot band-pass -> PLL -> L-R recovery) on a synthetic stereo multiplex; power squelch
+    ws = stereo_mpx_iq(100000, 250e3)
+    a = R.wfm(75e3, 250e3, True, True).process_chunks(ws.view(np.float32), 1250)
+    g["wfm_stereo_tail"] = a[-512:]
+    g["wfm_stereo_digest"] = digest(a)
+    g["squelch_digest"] = digest(R.squelch(-27.0).process_chunks((ws * np.linspace(0.02, 0.2, ws.size).astype(np.float32)).astype(np.complex64).view(np.float32), 1250))
     # radio AF chain behind WFM: 250 k -> 48 k stereo resampler, 300 Hz high-pass, 50 us deemphasis
     w = R.wfm(75e3, 250e3).process_chunks(vfo, 1250)
     af = R.resamp_stereo(250e3, 48e3).process_chunks(w, 1250)

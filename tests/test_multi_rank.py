@@ -116,9 +116,10 @@ def test_broadcast_and_vfo_group_sharding_gloo():
 
 # ---------------------------------------------------------------------------------------------- on the GPU
 def _gpu_worker(rank, world, port, outdir):
-    """config-4 sharding with the real kernels: rank 0 owns the stream and broadcasts every raw chunk, each rank runs
-    the CUDA front end for its VFO group.  With one GPU per rank the chunk is broadcast device-to-device over NCCL and
-    processed from device memory; when the ranks have to share cuda:0 (the single-GPU test box) the transport is gloo."""
+    """config-4 sharding with the real kernels: rank 0 owns the stream, every rank runs the CUDA front end for its VFO
+    group.  With one GPU per rank this is the product's sharded front end (b200_shard_*: the library broadcasts each raw
+    chunk over NCCL on its communication stream and processes it from device memory); when the ranks have to share
+    cuda:0 (the single-GPU test box) NCCL cannot run, the chunk travels over gloo and the plain front end processes it."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     nccl = torch.cuda.device_count() >= world
     dev = rank if nccl else 0
@@ -140,12 +141,16 @@ def _gpu_worker(rank, world, port, outdir):
     ids = {i: fe.add_vfo(cfgs[i]) for i in mine}
     outs = {i: [] for i in mine}
     lines = []
+    sh = None
+    if nccl:
+        # the product's own sharded path (b200_shard_*): rank 0 hands the chunk in, the library broadcasts it over NCCL
+        from sdrplusplus_b200.sharding import ShardedFrontEnd, make_unique_id
+        uid = [make_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        sh = ShardedFrontEnd(fe, rank, world, uid[0])
     for c in range(0, n, chunk):
-        seg = buf[2 * c: 2 * (c + chunk)].clone()
-        dist.broadcast(seg, src=0)
         if nccl:
             # device in, device out: the path a multi-GPU deployment runs
-            torch.cuda.synchronize()
             o = L.Outputs()
             keep = {}
             for i, vid in ids.items():
@@ -155,18 +160,26 @@ def _gpu_worker(rank, world, port, outdir):
             nl = max(1, fe.fft_max_lines(chunk))
             lt = torch.empty(nl * 65536, device="cuda", dtype=torch.float32)
             o.fft_out = lt.data_ptr(); o.fft_cap_lines = nl; o.out_mem = L.MEM_DEVICE
-            fe.process_ptr(seg.data_ptr(), chunk, L.FMT_CF32, L.MEM_DEVICE, o)
+            seg = buf[2 * c: 2 * (c + chunk)] if rank == 0 else None
+            torch.cuda.synchronize()
+            sh.submit_ptr(seg.data_ptr() if rank == 0 else 0, chunk, L.FMT_CF32, L.MEM_DEVICE, o)
+            sh.wait()
             for i, vid in ids.items():
                 y = keep[i][: 2 * o.vfo_count[vid]].cpu().numpy()
                 outs[i].append(y.view(np.complex64) if cfgs[i].demod == L.DEMOD_RAW else y.reshape(-1, 2))
             if o.fft_lines:
                 lines.append(lt[: o.fft_lines * 65536].cpu().numpy().reshape(-1, 65536))
         else:
+            seg = buf[2 * c: 2 * (c + chunk)].clone()
+            dist.broadcast(seg, src=0)
             o, ln = fe.process(seg.numpy().view(np.complex64))
             for i, vid in ids.items():
                 outs[i].append(o[vid])
             if ln.size:
                 lines.append(ln)
+    if sh is not None:
+        assert sh.bytes_broadcast() == 8 * n
+        sh.close()
     fe.close()
     np.savez(os.path.join(outdir, "rank%d.npz" % rank), lines=np.concatenate(lines) if lines else np.empty((0, 0), np.float32),
              transport=np.array([1 if nccl else 0]), **{"vfo%d" % i: np.concatenate(v) for i, v in outs.items()})

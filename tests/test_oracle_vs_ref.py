@@ -34,6 +34,8 @@ def test_blocks_bit_identical(oracle, ref_oracle, seed):
         (lambda o: o.am(0, 10e3, 2e-4, 2e-5, 4e-4, 250e3), 1250), (lambda o: o.ssb(0, 2800.0, 250e3, 2e-4, 2e-5), 1250),
         (lambda o: o.ssb(1, 2800.0, 250e3, 2e-4, 2e-5), 1250), (lambda o: o.ssb(2, 4600.0, 250e3, 2e-4, 2e-5), 1250),
         (lambda o: o.deemph(50e-6, 48e3), 480), (lambda o: o.resamp_stereo(250e3, 48e3), 1250),
+        (lambda o: o.wfm(75e3, 250e3, True, True), 1250), (lambda o: o.wfm(75e3, 250e3, True, False), 777),      # stereo branch: pilot PLL
+        (lambda o: o.squelch(-20.0), 1250), (lambda o: o.squelch(-60.0), 999),
     ]
     for f, ch in mk2:
         assert _same(f(R).process_chunks(y, ch), f(S).process_chunks(y, ch))
