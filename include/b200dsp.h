@@ -294,6 +294,19 @@ int       b200_fft_frame(b200_fft* f, const float* iq_nz, float* out_db);
 int       b200_fft_raw(b200_fft* f, const float* iq_nz, float* out_complex);    /* test hook: complex spectrum */
 void      b200_fft_destroy(b200_fft* f);
 
+/* BASELINE config 3 (not a reference block: SURVEY.md section 0 fact 9, section 8d): a 256-channel critically sampled polyphase
+ * filter-bank channelizer, `taps_per_branch` (127) taps per branch; prototype = the reference's
+ * taps::windowedSinc<float>(256 * 127, fs / 512, fs, window::nuttall) (core/src/dsp/taps/windowed_sinc.h:31-34).
+ * Channel k of output time m:  y_k[m] = sum_t h[t] x[n0 + t] e^{-j 2 pi k (n0 + t) / 256},  n0 = 256 m + 255 - (T - 1), T = 256 * 127
+ * (translate by -k fs/256, T-tap FIR, keep every 256th sample); the stream history is carried across calls.
+ * count: a multiple of 256; out[m * 256 + k]; returns the number of output times. */
+typedef struct b200_chan b200_chan;
+b200_chan* b200_chan_create(int channels, int taps_per_branch, int max_chunk);
+int        b200_chan_prototype(b200_chan* c, float* out, int cap);          /* the prototype taps (tests) */
+int        b200_chan_process(b200_chan* c, const void* iq, int count, int in_mem, void* out, int out_mem);
+long long  b200_chan_launch_count(b200_chan* c);
+void       b200_chan_destroy(b200_chan* c);
+
 /* pinned host memory for stream buffers (replaces buffer::alloc/volk_malloc, core/src/dsp/buffer/buffer.h:7-18) */
 void* b200_host_alloc(uint64_t bytes);
 void  b200_host_free(void* p);

@@ -1323,3 +1323,88 @@ extern "C" int b200_shard_wait(b200_shard* sh) {
     return b200_fe_wait(sh->fe);
 }
 extern "C" long long b200_shard_bytes_broadcast(b200_shard* sh) { return sh ? sh->bytes_broadcast : 0; }
+
+
+// ------------------------------------------------------------------ BASELINE config 3: polyphase filter-bank channelizer
+struct b200_chan {
+    int M = 256, P = 127, max_chunk = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf inbuf, u, y, h, tw;
+    std::vector<float> proto;
+    long long launches = 0;
+};
+extern "C" void b200_chan_destroy(b200_chan* c) {
+    if (!c) { return; }
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    delete c;
+}
+extern "C" b200_chan* b200_chan_create(int channels, int taps_per_branch, int max_chunk) {
+    if (ensure_device()) { return nullptr; }
+    if (channels != 256 || taps_per_branch < 1 || taps_per_branch > 255 || max_chunk < channels || (max_chunk % channels)) {
+        set_error("channelizer: 256 channels, 1..255 taps per branch, max_chunk a multiple of 256");
+        return nullptr;
+    }
+    b200_chan* c = new b200_chan;
+    c->M = channels; c->P = taps_per_branch; c->max_chunk = max_chunk;
+    const int M = c->M, P = c->P, T = M * P;
+    // prototype: taps::windowedSinc<float>(T, cutoff = fs / (2 M), fs, nuttall)  ->  omega = 2 pi / (2 M)
+    c->proto = windowed_sinc_taps(T, 3.14159265358979323846 / (double)M);
+    std::vector<float> hr((size_t)T);
+    for (int pI = 0; pI < P; pI++) {
+        for (int r = 0; r < M; r++) { hr[((size_t)(r >> 5) * P + pI) * 32 + (r & 31)] = c->proto[(size_t)pI * M + r]; }
+    }
+    std::vector<float2> tw((size_t)M);
+    for (int k = 0; k < M; k++) {
+        const double a = -2.0 * 3.14159265358979323846 * (double)k / (double)M;
+        tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    const size_t hist = (size_t)(P - 1) * M;
+    int rc = 0;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { cuda_fail(cudaGetLastError(), "cudaStreamCreate"); rc = B200_ECUDA; }
+    if (!rc) { rc = c->inbuf.alloc((hist + (size_t)max_chunk + 64) * sizeof(float2)); }
+    if (!rc) { rc = c->u.alloc((size_t)max_chunk * sizeof(float2), false); }
+    if (!rc) { rc = c->y.alloc((size_t)max_chunk * sizeof(float2), false); }
+    if (!rc) { rc = c->h.alloc(hr.size() * sizeof(float), false); }
+    if (!rc) { rc = c->tw.alloc(tw.size() * sizeof(float2), false); }
+    if (!rc && (cudaMemcpy(c->h.p, hr.data(), hr.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaMemcpy(c->tw.p, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaDeviceSynchronize() != cudaSuccess)) { cuda_fail(cudaGetLastError(), "channelizer tables"); rc = B200_ECUDA; }
+    if (rc) { b200_chan_destroy(c); return nullptr; }
+    return c;
+}
+extern "C" int b200_chan_prototype(b200_chan* c, float* out, int cap) {
+    if (!c) { set_error("null channelizer"); return B200_EINVAL; }
+    if (out) { memcpy(out, c->proto.data(), sizeof(float) * (size_t)std::min<int>((int)c->proto.size(), cap)); }
+    return (int)c->proto.size();
+}
+// count: complex input samples, a multiple of the channel count; out: [count / M][M] complex (channel k of output time m at
+// out[m * M + k]).  in_mem / out_mem: B200_MEM_*.  Returns the number of output times (count / M).
+extern "C" int b200_chan_process(b200_chan* c, const void* iq, int count, int in_mem, void* out, int out_mem) {
+    if (!c || (count > 0 && (!iq || !out))) { set_error("null argument"); return B200_EINVAL; }
+    if (count < 0 || count > c->max_chunk || (count % c->M)) { set_error("channelizer: count must be a multiple of %d, at most %d", c->M, c->max_chunk); return B200_ECAP; }
+    if (count == 0) { return 0; }
+    const int M = c->M, P = c->P, n_out = count / M;
+    const size_t hist = (size_t)(P - 1) * M;
+    cudaStream_t s = c->stream;
+    float2* data = c->inbuf.as<float2>() + hist;
+    B200_CK(cudaMemcpyAsync(data, iq, (size_t)count * sizeof(float2), in_mem == B200_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    ChanParams p;
+    p.in = c->inbuf.as<float2>(); p.u = c->u.as<float2>(); p.h = c->h.as<float>(); p.M = M; p.P = P; p.n_out = n_out;
+    float2* y = (out_mem == B200_MEM_DEVICE) ? (float2*)out : c->y.as<float2>();
+    int nl = 0;
+    cudaError_t e = launch_channelizer(p, y, c->tw.as<float2>(), s, &nl);
+    if (e != cudaSuccess) { return cuda_fail(e, "launch_channelizer"); }
+    // history for the next chunk: the last (P - 1) M samples of [hist | chunk] (memmove semantics: alias-safe kernel)
+    CarryParams cp;
+    cp.njobs = 1;
+    CarryJob& j = cp.job[0];
+    j.dst = c->inbuf.as<float>(); j.a = c->inbuf.as<float>(); j.b = data;
+    j.h = (int)hist; j.la = (int)hist; j.lb = count; j.esize = 2; j.bfmt = -1; j.scale = 0.0f;
+    e = launch_carry(cp, s);
+    if (e != cudaSuccess) { return cuda_fail(e, "launch_carry"); }
+    c->launches += nl + 1;
+    if (out_mem != B200_MEM_DEVICE) { B200_CK(cudaMemcpyAsync(out, c->y.p, (size_t)count * sizeof(float2), cudaMemcpyDeviceToHost, s)); }
+    B200_CK(cudaStreamSynchronize(s));
+    return n_out;
+}
+extern "C" long long b200_chan_launch_count(b200_chan* c) { return c ? c->launches : 0; }

@@ -41,8 +41,12 @@ int estimate_tap_count(double transWidth, double samplerate) { return (int)(3.8 
 std::vector<float> lowpass_taps(double cutoff, double transWidth, double samplerate, bool odd) {
     int count = estimate_tap_count(transWidth, samplerate);
     if (odd && !(count % 2)) { count++; }
+    return windowed_sinc_taps(count, hz_to_rads(cutoff, samplerate));
+}
+// taps::windowedSinc<float>(count, omega, window::nuttall) (taps/windowed_sinc.h:9-29; the (cutoff, samplerate) overload,
+// :31-34, passes omega = hzToRads(cutoff, samplerate))
+std::vector<float> windowed_sinc_taps(int count, double omega) {
     std::vector<float> taps(count > 0 ? count : 0);
-    const double omega = hz_to_rads(cutoff, samplerate);
     const double half = (double)count / 2.0;
     const double corr = 1.0 * omega / kPi;
     for (int i = 0; i < count; i++) {

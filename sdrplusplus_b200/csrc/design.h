@@ -10,6 +10,7 @@ namespace b200 {
 double hz_to_rads(double freq, double samplerate);                       // math::hzToRads (hz_to_rads.h:6-8)
 int estimate_tap_count(double transWidth, double samplerate);             // taps::estimateTapCount
 std::vector<float> lowpass_taps(double cutoff, double transWidth, double samplerate, bool odd = false); // taps::lowPass
+std::vector<float> windowed_sinc_taps(int count, double omega);          // taps::windowedSinc<float> with window::nuttall
 std::vector<float> highpass_taps(double cutoff, double transWidth, double samplerate, bool odd = false);                 // taps::highPass
 std::vector<float> bandpass_c_taps(double bandStart, double bandStop, double transWidth, double samplerate, bool odd = false); // taps::bandPass<complex_t>, (re, im) pairs
 void pll_coefficients(double bandwidth, float& alpha, float& beta);      // PhaseControlLoop<float>::criticallyDamped

@@ -261,6 +261,15 @@ struct CarryJob {
 #define CARRY_BATCH 64
 struct CarryParams { int njobs; CarryJob job[CARRY_BATCH]; };
 
+// ---- polyphase filter-bank channelizer, BASELINE config 3 (chanpfb.cuh) ----
+struct ChanParams {
+    const float2* in;        // [hist (P-1)*M | chunk]: sample (m + p) M + r of the window sits at in[(m + p) * M + r]
+    float2* u;               // [n_out][M] branch outputs
+    const float* h;          // taps re-ordered [M/32][P][32]: h[((r >> 5) * P + p) * 32 + (r & 31)] = h[p M + r]
+    int M, P, n_out;
+};
+cudaError_t launch_channelizer(const ChanParams& p, float2* y, const float2* tw, cudaStream_t s, int* nlaunch);
+
 // ---- FFT branch ----
 struct FftPlanDev {
     int N, logN;            // transform size

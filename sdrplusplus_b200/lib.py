@@ -110,6 +110,11 @@ SIGNATURES = {
     "b200_fft_frame": (_i, [_vp, _vp, _vp]),
     "b200_fft_raw": (_i, [_vp, _vp, _vp]),
     "b200_fft_destroy": (None, [_vp]),
+    "b200_chan_create": (_vp, [_i, _i, _i]),
+    "b200_chan_prototype": (_i, [_vp, _vp, _i]),
+    "b200_chan_process": (_i, [_vp, _vp, _i, _i, _vp, _i]),
+    "b200_chan_launch_count": (_ll, [_vp]),
+    "b200_chan_destroy": (None, [_vp]),
     "b200_host_alloc": (_vp, [C.c_uint64]),
     "b200_host_free": (None, [_vp]),
     "b200_pcm_packet_info": (_i, [_vp, _i, _ip, C.POINTER(C.c_float), _ip, _ip]),
