@@ -468,6 +468,7 @@ extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
         if (!strcmp(key, "ft_threads")) { fe->sch.fuse.threads = value; return 0; }
         if (!strcmp(key, "ft_direct")) { fe->sch.fuse.direct = value != 0; return 0; }
         if (!strcmp(key, "ft_prereg")) { fe->sch.fuse.pre_reg = value; return 0; }
+        if (!strcmp(key, "ft_regall")) { fe->sch.fuse.reg_all = value != 0; return 0; }
     }
     if (!strcmp(key, "fft")) { kernels_set_fft_variant(value); return 0; }
     if (!strcmp(key, "time_s1")) { fe->sch.time_s1 = value != 0; for (auto& t : fe->sch.timers) { t.used = 0; } return 0; }
@@ -1395,14 +1396,21 @@ extern "C" int b200_chan_process(b200_chan* c, const void* iq, int count, int in
     cudaError_t e = launch_channelizer(p, y, c->tw.as<float2>(), s, &nl);
     if (e != cudaSuccess) { return cuda_fail(e, "launch_channelizer"); }
     // history for the next chunk: the last (P - 1) M samples of [hist | chunk] (memmove semantics: alias-safe kernel)
-    CarryParams cp;
-    cp.njobs = 1;
-    CarryJob& j = cp.job[0];
-    j.dst = c->inbuf.as<float>(); j.a = c->inbuf.as<float>(); j.b = data;
-    j.h = (int)hist; j.la = (int)hist; j.lb = count; j.esize = 2; j.bfmt = -1; j.scale = 0.0f;
-    e = launch_carry(cp, s);
-    if (e != cudaSuccess) { return cuda_fail(e, "launch_carry"); }
-    c->launches += nl + 1;
+    if ((size_t)count >= hist) {
+        // the tail of the chunk does not overlap the history slot: a plain device copy
+        B200_CK(cudaMemcpyAsync(c->inbuf.p, c->inbuf.as<float2>() + count, hist * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+    }
+    else {
+        CarryParams cp;
+        cp.njobs = 1;
+        CarryJob& j = cp.job[0];
+        j.dst = c->inbuf.as<float>(); j.a = c->inbuf.as<float>(); j.b = data;
+        j.h = (int)hist; j.la = (int)hist; j.lb = count; j.esize = 2; j.bfmt = -1; j.scale = 0.0f;
+        e = launch_carry(cp, s);
+        if (e != cudaSuccess) { return cuda_fail(e, "launch_carry"); }
+        nl++;
+    }
+    c->launches += nl;
     if (out_mem != B200_MEM_DEVICE) { B200_CK(cudaMemcpyAsync(out, c->y.p, (size_t)count * sizeof(float2), cudaMemcpyDeviceToHost, s)); }
     B200_CK(cudaStreamSynchronize(s));
     return n_out;

@@ -194,6 +194,14 @@ int PolyStage::configure(int interp_, int decim_, const std::vector<float>& t) {
     int rc = bank.alloc(b.size() * sizeof(float));
     if (rc) { return rc; }
     B200_CK(cudaMemcpy(bank.p, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+    {
+        std::vector<float> kl(((size_t)tpp * interp + 3) & ~(size_t)3, 0.0f);
+        for (int ph = 0; ph < interp; ph++) {
+            for (int k = 0; k < tpp; k++) { kl[(size_t)k * interp + ph] = b[(size_t)ph * tpp + k]; }
+        }
+        if ((rc = bank_kl.alloc(kl.size() * sizeof(float)))) { return rc; }
+        B200_CK(cudaMemcpy(bank_kl.p, kl.data(), kl.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     return upload_pm(b, decim, interp);
 }
 int PolyStage::plan(int n) {
@@ -402,6 +410,25 @@ int Chain::plan_fused() {
     }
     const int nst = end - beg;
     if (nst < 2) { return 0; }
+    if (fcfg.reg_all && fcfg.pre_reg > 0) {
+        // every stage behind stage 1 has a register-window kernel of its own: no fused launch for this chain
+        bool all = true;
+        for (int i = 1; i < end && all; i++) {
+            const Stage* s = st[i].get();
+            switch (s->kind) {
+            case K_FIRC: {
+                const FirCStage* f = (const FirCStage*)s;
+                all = s->in_es == 2 && ((f->decim == 1 && f->ntaps <= 2000) || (f->decim > 1 && dfir_reg_supported(f->decim, f->ntaps)));
+                break;
+            }
+            case K_POLY: all = s->in_es == 2 && poly_reg_supported(((const PolyStage*)s)->interp, ((const PolyStage*)s)->decim) && ((const PolyStage*)s)->tpp <= 512; break;
+            case K_FIRR: all = ((const FirRStage*)s)->ntaps <= 2000; break;
+            case K_QUAD: case K_M2S: break;
+            default: all = false; break;
+            }
+        }
+        if (all) { return 0; }
+    }
     fp.beg = beg;
     FtStage d[FT_MAXST];
     for (int i = 0; i < nst; i++) { ft_describe(st[beg + i].get(), d[i]); }
@@ -1146,7 +1173,10 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
     // ---- remaining stages level by level: one launch per stage kind per level (batches of 16 VFOs) ----
     for (size_t lvl = 0; lvl < depth; lvl++) {
         FirParams fp; fp.njobs = 0; fp.max_out = 0;
+        FirParams fpr; fpr.njobs = 0; fpr.max_out = 0;              // decimation-1 filters with register windows
         PolyParams pp; pp.njobs = 0; pp.max_out = 0;
+        PolyParams ppr; ppr.njobs = 0; ppr.max_out = 0;             // polyphase resamplers with register windows: one (L, M) per batch
+        FirRParams rpr; rpr.njobs = 0; rpr.max_out = 0;
         QuadParams qp; qp.njobs = 0; qp.max_n = 0;
         FirRParams rp; rp.njobs = 0; rp.max_out = 0;
         SeqParams sp; sp.njobs = 0;
@@ -1183,6 +1213,14 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
                 FirCStage* f = (FirCStage*)s;
                 if (f->n_out <= 0) { break; }
                 if (dfr_ok(f)) { rc = dfr_push(f); break; }
+                if (fuse.pre_reg > 0 && f->decim == 1 && f->in_es == 2 && f->ntaps <= 2000 && f->chunk_offset == 0) {
+                    FirJob& jr = fpr.job[fpr.njobs++];
+                    jr.in = (const float2*)f->base(); jr.out = (float2*)f->out_ptr; jr.taps = f->taps.as<float>();
+                    jr.ntaps = f->ntaps; jr.decim = 1; jr.offset = 0; jr.n_out = f->n_out;
+                    fpr.max_out = std::max(fpr.max_out, f->n_out);
+                    if (fpr.njobs == B200_BATCH) { rc = flush_batch(fpr, launch_fir_reg, ts, launches); fpr.max_out = 0; }
+                    break;
+                }
                 FirJob& j = fp.job[fp.njobs++];
                 j.in = (const float2*)f->base(); j.out = (float2*)f->out_ptr; j.taps = f->taps.as<float>();
                 j.ntaps = f->ntaps; j.decim = f->decim; j.offset = f->chunk_offset; j.n_out = f->n_out;
@@ -1193,10 +1231,21 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
             case K_POLY: {
                 PolyStage* f = (PolyStage*)s;
                 if (f->n_out <= 0) { break; }
-                PolyJob& j = pp.job[pp.njobs++];
+                const bool regp = fuse.pre_reg > 0 && f->in_es == 2 && f->tpp <= 512 && poly_reg_supported(f->interp, f->decim);
+                if (regp && ppr.njobs > 0 && (ppr.job[0].interp != f->interp || ppr.job[0].decim != f->decim)) {
+                    rc = flush_batch(ppr, launch_poly_reg, ts, launches); ppr.max_out = 0;
+                    if (rc) { break; }
+                }
+                PolyJob& j = regp ? ppr.job[ppr.njobs++] : pp.job[pp.njobs++];
                 j.in = (const float2*)f->base(); j.out = (float2*)f->out_ptr; j.bank = f->bank.as<float>();
                 j.tpp = f->tpp; j.interp = f->interp; j.decim = f->decim; j.phase0 = f->chunk_phase; j.offset0 = f->chunk_offset;
                 j.n_out = f->n_out;
+                j.bank_kl = f->bank_kl.as<float>(); j.in_len = (long long)f->hist + f->n_in;
+                if (regp) {
+                    ppr.max_out = std::max(ppr.max_out, f->n_out);
+                    if (ppr.njobs == B200_BATCH) { rc = flush_batch(ppr, launch_poly_reg, ts, launches); ppr.max_out = 0; }
+                    break;
+                }
                 pp.max_out = std::max(pp.max_out, f->n_out);
                 if (pp.njobs == B200_BATCH) { rc = flush_batch(pp, launch_poly, ts, launches); pp.max_out = 0; }
                 break;
@@ -1214,6 +1263,14 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
             case K_FIRR: {
                 FirRStage* f = (FirRStage*)s;
                 if (f->n_out <= 0) { break; }
+                if (fuse.pre_reg > 0 && f->ntaps <= 2000) {
+                    FirRJob& jr = rpr.job[rpr.njobs++];
+                    jr.in = f->base(); jr.out = f->out_ptr; jr.taps = f->taps.as<float>();
+                    jr.ntaps = f->ntaps; jr.n_out = f->n_out; jr.stereo = f->stereo;
+                    rpr.max_out = std::max(rpr.max_out, f->n_out);
+                    if (rpr.njobs == B200_BATCH) { rc = flush_batch(rpr, launch_firr_reg, ts, launches); rpr.max_out = 0; }
+                    break;
+                }
                 FirRJob& j = rp.job[rp.njobs++];
                 j.in = f->base(); j.out = f->out_ptr; j.taps = f->taps.as<float>();
                 j.ntaps = f->ntaps; j.n_out = f->n_out; j.stereo = f->stereo;
@@ -1271,6 +1328,9 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
         }
         int rc;
         if ((rc = dfr_flush())) { return rc; }
+        if ((rc = flush_batch(fpr, launch_fir_reg, ts, launches))) { return rc; }
+        if ((rc = flush_batch(ppr, launch_poly_reg, ts, launches))) { return rc; }
+        if ((rc = flush_batch(rpr, launch_firr_reg, ts, launches))) { return rc; }
         if ((rc = flush_batch(fp, launch_fir_c, ts, launches))) { return rc; }
         if ((rc = flush_batch(pp, launch_poly, ts, launches))) { return rc; }
         if ((rc = flush_batch(qp, launch_quad, ts, launches))) { return rc; }

@@ -106,7 +106,7 @@ struct FirCStage : Stage {
 
 struct PolyStage : Stage {
     int interp = 1, decim = 1, tpp = 1, phase = 0, offset = 0, chunk_phase = 0, chunk_offset = 0;
-    DevBuf bank;
+    DevBuf bank, bank_kl;        // [interp][tpp] and [tpp][interp]
     PolyStage() { kind = K_POLY; }
     int configure(int interp_, int decim_, const std::vector<float>& taps);
     int plan(int n) override;
@@ -160,7 +160,7 @@ struct FusedPlan {
     size_t smem = 0;
     int buf[FT_MAXST], pitch[FT_MAXST], tap_off[FT_MAXST], qpitch[FT_MAXST];
 };
-struct FuseCfg { bool on = false; int ob_max = 1280; int smem_limit = 110 * 1024; int threads = 256; int ob_force = 0; bool direct = true; int pre_reg = 8; };   // pre_reg: how many short decimating FIR stages may run in registers in front of the fused launch
+struct FuseCfg { bool on = false; int ob_max = 1280; int smem_limit = 110 * 1024; int threads = 256; int ob_force = 0; bool direct = true; int pre_reg = 8; bool reg_all = true; };   // pre_reg: how many short decimating FIR stages may run in registers in front of the fused launch; reg_all: chains whose every stage has a register-window kernel are not fused at all
 
 // stereo branch of BroadcastFM behind the discriminator (broadcast_fm.h:147-177): mono multiplex in, (l, r) out
 struct StereoStage : Stage {

@@ -749,6 +749,7 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 #include "chanpfb.cuh"
+#include "tails_reg.cuh"
 
 template <int FMT, int RM, int QC>
 static cudaError_t launch_xd_tile_t(const XdParams& p, int MT, int JP, int QPC, int jmin, int ntiles, size_t smem,

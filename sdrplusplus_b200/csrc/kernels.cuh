@@ -83,8 +83,13 @@ struct PolyJob {
     float2* out;
     const float* bank;      // [interp][tpp]
     int tpp, interp, decim, phase0, offset0, n_out;
+    const float* bank_kl;   // the same bank as [tpp][interp] (k_poly_reg)
+    long long in_len;       // samples in `in` that may be read (history + this chunk's input)
 };
 struct PolyParams { int njobs; int max_out; PolyJob job[B200_BATCH]; };
+// register-window versions of the output-rate stages (tails_reg.cuh)
+bool poly_reg_supported(int interp, int decim);
+cudaError_t launch_poly_reg(const PolyParams& p, cudaStream_t s);           // every job: the same (interp, decim)
 
 // ---- FM discriminator (Quadrature::process, quadrature.h:39-46) ----
 struct QuadJob {
@@ -287,6 +292,8 @@ struct FftPlanDev {
 cudaError_t launch_xlate_decim(const XdParams& p, int fmt, int variant, cudaStream_t s, int* nlaunch);
 cudaError_t launch_xd_edge(const XdParams& p, int fmt, cudaStream_t s, int* nlaunch);
 cudaError_t launch_fir_c(const FirParams& p, cudaStream_t s);
+cudaError_t launch_fir_reg(const FirParams& p, cudaStream_t s);            // every job: decimation 1
+cudaError_t launch_firr_reg(const FirRParams& p, cudaStream_t s);
 cudaError_t launch_poly(const PolyParams& p, cudaStream_t s);
 cudaError_t launch_quad(const QuadParams& p, cudaStream_t s);
 cudaError_t launch_fir_r(const FirRParams& p, cudaStream_t s);
