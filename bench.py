@@ -354,6 +354,7 @@ def run_b200(args):
         fe.set_option("pair", args.pair)
         fe.set_option("s1", args.s1)
         fe.set_option("s1_mt", args.s1_mt)
+        fe.set_option("s1_stages", args.s1_stages)
         fe.set_option("tails", args.tails)
         for kv in [a for a in args.ft.split(",") if a]:
             fe.set_option(kv.split("=")[0], int(kv.split("=")[1]))
@@ -692,6 +693,7 @@ def main():
     ap.add_argument("--s1", type=int, default=8, help="stage-1 kernel variant (8 = filter-bank form fed by the TMA engine, 7 = filter bank on cp.async tiles, when the VFO plan allows it; else 6 = per-VFO complex taps)")
     ap.add_argument("--tails", type=int, default=2, help="2 = one fused tail launch per <= 16 VFOs (default), 1 = shared-memory tiled kernel per stage, 0 = one thread per output")
     ap.add_argument("--ft", default="", help="fused-tail tuning, e.g. ft_threads=256,ft_obmax=1024,ft_smem_kb=72")
+    ap.add_argument("--s1-stages", type=int, default=2, help="ring depth of the TMA stage 1 (2 = leaves shared memory for the kernels of the other streams, 3)")
     ap.add_argument("--s1-mt", type=int, default=0, help="force the stage-1 tile size (outputs per tile), 0 = automatic")
     ap.add_argument("--overlap", type=int, default=1, help="1 = tails of chunk k overlap stage 1 of chunk k+1 (default)")
     ap.add_argument("--pair", type=int, default=1, help="1 = VFOs at +f/-f share their stage-1 multiply-accumulates (default)")

@@ -164,7 +164,8 @@ struct b200_fe {
     double fs = 0;
     int max_chunk = 0;
     Scheduler sch;
-    cudaStream_t own_stream = nullptr, copy_stream = nullptr, fft_stream = nullptr, tail_stream = nullptr;
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr, fft_stream = nullptr, tail_stream = nullptr, join_stream = nullptr;
+    cudaEvent_t ev_tail_done[2] = { nullptr, nullptr };
     cudaEvent_t ev_fft_go = nullptr, ev_fft_done = nullptr, ev_lines_free = nullptr;
     bool overlap = true;         // tails of chunk k on their own stream, overlapping stage 1 of chunk k+1
     bool lines_busy = false;
@@ -226,12 +227,14 @@ extern "C" b200_fe* b200_fe_create(double samplerate, int max_chunk) {
               cudaStreamCreateWithFlags(&fe->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&fe->fft_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&fe->tail_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&fe->join_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&fe->ev_lines_free, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&fe->ev_fft_go, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&fe->ev_fft_done, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2 && ok; i++) {
         ok = cudaEventCreateWithFlags(&fe->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&fe->ev_compute[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&fe->ev_tail_done[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&fe->ev_out[i], cudaEventDisableTiming) == cudaSuccess;
     }
     if (!ok || fe->sch.init_raw()) {
@@ -257,10 +260,12 @@ extern "C" void b200_fe_destroy(b200_fe* fe) {
     for (int i = 0; i < 2; i++) {
         if (fe->ev_h2d[i]) { cudaEventDestroy(fe->ev_h2d[i]); }
         if (fe->ev_compute[i]) { cudaEventDestroy(fe->ev_compute[i]); }
+        if (fe->ev_tail_done[i]) { cudaEventDestroy(fe->ev_tail_done[i]); }
         if (fe->ev_out[i]) { cudaEventDestroy(fe->ev_out[i]); }
     }
     if (fe->ev_lines_free) { cudaEventDestroy(fe->ev_lines_free); }
     if (fe->tail_stream) { cudaStreamDestroy(fe->tail_stream); }
+    if (fe->join_stream) { cudaStreamDestroy(fe->join_stream); }
     for (int i = 0; i < 2; i++) {
         if (fe->sch.ev_stage1[i]) { cudaEventDestroy(fe->sch.ev_stage1[i]); }
         if (fe->sch.ev_tail[i]) { cudaEventDestroy(fe->sch.ev_tail[i]); }
@@ -458,6 +463,7 @@ extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
     if (!strcmp(key, "fft_async")) { fe->fft_async = value != 0; return 0; }
     if (!strcmp(key, "s1_mt")) { kernels_set_xd_tile(value); return 0; }
     if (!strcmp(key, "s1_cps")) { kernels_set_xd_cps(value); return 0; }
+    if (!strcmp(key, "s1_stages")) { kernels_set_xd_tma_stages(value); return 0; }
     if (!strcmp(key, "tails") || !strncmp(key, "ft_", 3)) {
         // 0: one thread per output; 1: shared-memory tiled kernels, one launch per stage; 2: one fused launch per <= 16 VFOs
         if (b200_fe_vfo_count(fe) > 0) { set_error("'%s' must be chosen before VFOs are added", key); return B200_ESTATE; }
@@ -721,14 +727,20 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
     // enqueued, so the two overlap on the device
     if ((rc = fe_fft_chunk(fe, dptr, in_fmt, count, &nlines))) { return rc; }
     fe->sch.in_scale = fe_ingest_scale(fe, in_fmt);
+    // host-side outputs leave through per-VFO device buffers that the copies of the previous chunk may still be reading
+    if (!direct && fe->nsub > 0) { B200_CK(cudaStreamWaitEvent(fe->sch.out_stream(), fe->ev_out[slot ^ 1], 0)); }
     if ((rc = fe->sch.run(chains, dptr, in_fmt, count, true))) { return rc; }
-    cudaStream_t os = fe->sch.out_stream();       // tail stream in overlapped mode, else the main stream
+    // join on a stream of its own: the VFO branch (tail stream) and the spectrum branch (its stream) of this chunk meet
+    // here, neither waits for the other -- the tail stream goes straight on to the next chunk
+    cudaStream_t os = fe->join_stream;
+    B200_CK(cudaEventRecord(fe->ev_tail_done[slot], fe->sch.out_stream()));
+    B200_CK(cudaStreamWaitEvent(os, fe->ev_tail_done[slot], 0));
     if (fe->fft_join_pending) {
         B200_CK(cudaStreamWaitEvent(os, fe->ev_fft_done, 0));
         fe->fft_join_pending = false;
     }
-    // the input chunk is no longer needed once stage 1, the raw carry (both before ev_s1 on the main stream, which
-    // `os` already waits on) and the spectrum branch are done
+    // the input chunk is no longer needed once stage 1, the raw carry (both in front of the tail on its stream) and the
+    // spectrum branch are done
     B200_CK(cudaEventRecord(fe->ev_compute[slot], os));
     fe->slot_used[slot] = true;
     // ---- outputs ----

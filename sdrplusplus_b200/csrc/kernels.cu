@@ -966,23 +966,29 @@ static PFN_tmap_encode tmap_encode_fn() {
     return fn;
 }
 int g_xd_tma_launches = 0;        // diagnostic: how many stage-1 launches took the TMA path
-template <int LOGD, int QC, int PS, int MT>
-static cudaError_t launch_xd_tma_t(const XdParams& p, const XtGeom& g, const CUtensorMap& tm, cudaStream_t s) {
+int g_xd_tma_stages = 2;          // ring depth of the TMA stage 1: 2 leaves a third of the SM's shared memory to the kernels of the other streams
+void kernels_set_xd_tma_stages(int n) { g_xd_tma_stages = (n == 3) ? 3 : 2; }
+template <int LOGD, int QC, int PS, int MT, int NST>
+static cudaError_t launch_xd_tma_n(const XdParams& p, const XtGeom& g, const CUtensorMap& tm, cudaStream_t s) {
     using Lay = XtLay<LOGD, QC, MT>;
-    const size_t smem = (size_t)XT_STAGES * Lay::STAGE + ((size_t)B200_BATCH * (PS + 16) + (size_t)Lay::NW * B200_BATCH * 4) * sizeof(float2) +
-                        2 * XT_STAGES * sizeof(unsigned long long) + 1024;
+    const size_t smem = (size_t)NST * Lay::STAGE + ((size_t)B200_BATCH * (PS + 16) + (size_t)Lay::NW * B200_BATCH * 4) * sizeof(float2) +
+                        2 * NST * sizeof(unsigned long long) + 1024;
     if ((int)smem > kernels_max_smem_optin()) { return cudaErrorInvalidValue; }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = set_smem(k_xd_tma<LOGD, QC, PS, MT>, smem);
+        cudaError_t e = set_smem(k_xd_tma<LOGD, QC, PS, MT, NST>, smem);
         if (e != cudaSuccess) { return e; }
         attr_set = true;
     }
     int grid = num_sms();
     if (grid > g.ntiles) { grid = g.ntiles; }
-    k_xd_tma<LOGD, QC, PS, MT><<<grid, (Lay::NW + 1) * 32, smem, s>>>(p, g, tm);
+    k_xd_tma<LOGD, QC, PS, MT, NST><<<grid, (Lay::NW + 1) * 32, smem, s>>>(p, g, tm);
     g_xd_tma_launches++;
     return cudaGetLastError();
+}
+template <int LOGD, int QC, int PS, int MT>
+static cudaError_t launch_xd_tma_t(const XdParams& p, const XtGeom& g, const CUtensorMap& tm, cudaStream_t s) {
+    return g_xd_tma_stages == 3 ? launch_xd_tma_n<LOGD, QC, PS, MT, 3>(p, g, tm, s) : launch_xd_tma_n<LOGD, QC, PS, MT, 2>(p, g, tm, s);
 }
 static bool try_xd_tma(const XdParams& p, cudaStream_t s, cudaError_t* err) {
     const int D = p.D, PS = p.pfb_ps;

@@ -333,4 +333,5 @@ int kernels_max_smem_optin();
 void kernels_set_tail_variant(int v);
 void kernels_set_fft_variant(int v);
 void kernels_set_xd_tile(int mt);     // 0 = automatic
+void kernels_set_xd_tma_stages(int n);   // ring depth of the TMA stage 1 (2 or 3)
 void kernels_set_xd_cps(int v);       // cap on stage-1 CTAs per SM, 0 = automatic

@@ -20,7 +20,7 @@
 #pragma once
 #include <cuda.h>
 
-#define XT_STAGES 3
+#define XT_STAGES NST        // ring depth, a template parameter of the kernel (2 or 3)
 #define XT_MAXTAPS 512
 
 struct XtGeom {
@@ -62,7 +62,7 @@ struct XtLay {
     static constexpr int NW = MT / 64;                                   // consumer warps
 };
 
-template <int LOGD, int QC, int PS, int MT>
+template <int LOGD, int QC, int PS, int MT, int NST>
 __global__ void __launch_bounds__((MT / 64 + 1) * 32, 1)
 k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, const __grid_constant__ CUtensorMap tm) {
     using Lay = XtLay<LOGD, QC, MT>;
