@@ -213,16 +213,17 @@ long long b200_fe_launch_count(b200_fe* fe);
 long long b200_fe_stat(b200_fe* fe, const char* key);
 /* Tuning / A-B switches (defaults are the fast paths; every variant is held to the same parity tests):
  *  "s1"      stage-1 kernel: 8 (default) filter-bank form fed by the TMA engine (cf32 chunks, VFO offsets on a common
- *            frequency grid, first decimation 32 or 64), else 7: the same form on cp.async tiles, else 6;
- *            6/5/4/3 per-VFO complex taps on cp.async tiles (4-warp x3 per SM / 4-warp / 16-warp / 8-warp CTAs);
- *            2, 1 single-buffered tiles; 0 one thread per output
- *  "pair"    1 = VFOs at +f / -f share their stage-1 sums (default)
- *  "tails"   2 = one fused launch for the stages after stage 1 (default), 1 = one tiled kernel per stage, 0 = plain;
- *            "ft_threads", "ft_obmax", "ft_ob", "ft_smem_kb", "ft_direct" tune the fused launch; "ft_prereg" 1 (default) = the
- *            short decimating FIR stages run with their window in registers (k_dfir_reg).  Before VFOs are added.
+ *            frequency grid, first decimation 32 or 64); 7 the same form on cp.async tiles; 6 per-VFO complex taps on
+ *            cp.async tiles, one tile buffer per CTA, three 4-warp CTAs per SM; 5 the same double-buffered, one CTA per SM;
+ *            0 one thread per output.  Each falls through to the next when a plan does not fit it.
+ *            "s1_stages" ring depth of the TMA kernel (2 default, 3); "pair" 1 = VFOs at +f / -f share their stage-1 sums
+ *  "tails"   2 (default): every stage behind stage 1 that has a register-window kernel runs in it (k_dfir_reg, k_poly_reg,
+ *            k_fir_reg, k_firr_reg; "ft_prereg" caps how many leading decimating FIRs may, "ft_regall" 0 keeps the others in
+ *            the fused launch k_tail_fused, tuned by "ft_threads", "ft_obmax", "ft_ob", "ft_smem_kb", "ft_direct");
+ *            1 = one tiled kernel per stage, 0 = one thread per output.  Before VFOs are added.
  *  "overlap" 1 = tails of chunk k overlap stage 1 of chunk k+1 on a second stream (default).  Before VFOs are added.
  *  "fft"     1 = register-resident four-step passes (default), 0 = shared-memory radix-8 passes; "fft_async" 1 = own stream
- *  "time_s1" 1 = bracket every stage-1 launch with CUDA events on the handle's stream (b200_fe_s1_stats) */
+ *  "time_s1" 1 = bracket the launch groups of every chunk with CUDA events (b200_fe_s1_stats / b200_fe_group_stats) */
 int b200_fe_set_option(b200_fe* fe, const char* key, int value);
 /* device time spent in the stage-1 (translate + first decimation) launches since the last call, and their count;
  * synchronises on the recorded events ("time_s1" must be on).  bench.py's roofline leg reads this. */

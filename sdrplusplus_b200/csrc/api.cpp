@@ -244,6 +244,7 @@ extern "C" b200_fe* b200_fe_create(double samplerate, int max_chunk) {
     }
     fe->sch.stream = fe->own_stream;
     fe->sch.fuse.on = true;
+    kernels_set_xd_tma_stages(2);          // process-wide tuning knobs start from their defaults with every new front end
     {
         int dev = 0, sms = 0;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) {

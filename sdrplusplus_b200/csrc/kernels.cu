@@ -101,118 +101,6 @@ __global__ void __launch_bounds__(128) k_xd_simple(const __grid_constant__ XdPar
     J.out[m] = cmulf(make_float2(ar, ai), ph);
 }
 
-// ------------------------------------------------------------------------------------------------
-// stage 1, tiled variant.  One CTA stages MT*D raw IQ samples ONCE in shared memory, de-interleaved by
-// decimation phase (X[r][j] = x(j*D + r)), and every VFO of the group convolves that tile with its own
-// complex taps: the IQ stream is read from HBM once for all VFOs.  Per lane: RM outputs (RM/2 aligned
-// pairs) x VR VFOs are register-blocked; the inner product uses packed f32x2 FMAs with the tap as the
-// scalar-broadcast operand:  A += g.re * x,  B += g.im * x,  y = (A.x - B.y, A.y + B.x).
-// ------------------------------------------------------------------------------------------------
-#define XD_VR 4
-template <int FMT, int RM, int QC>
-__global__ void __launch_bounds__(256) k_xd_tile(const __grid_constant__ XdParams p, int MT, int JP, int QPC, int jmin) {
-    extern __shared__ __align__(16) float2 smem[];
-    float2* X = smem;                         // [D][JP]
-    float2* G = smem + (size_t)p.D * JP;      // [njobs][QPC*D]
-    const int D = p.D;
-    const int tid = threadIdx.x;
-    const int nthr = blockDim.x;
-    const long long J0 = (long long)jmin + (long long)blockIdx.x * MT;
-
-    // ---- stage taps: G[v][k'] = gpad_v[(D-1-s_v) + k'] ----
-    const int gl = QPC * D;
-    for (int idx = tid; idx < p.njobs * gl; idx += nthr) {
-        int v = idx / gl, k = idx - v * gl;
-        const XdJob& Jv = p.job[v];
-        int a = Jv.offset - (Jv.T - 1);
-        int s = ((a % D) + D) % D;
-        G[idx] = __ldg(Jv.gpad + (D - 1 - s) + k);
-    }
-    // ---- stage the IQ tile, de-interleaved ----
-    const int ntile = D * (MT + QPC);
-    const long long ibase = J0 * D;
-    for (int idx = tid; idx < ntile; idx += nthr) {
-        int j = idx / D, r = idx - j * D;
-        X[r * JP + j] = load_x<FMT>(p, ibase + idx);
-    }
-    __syncthreads();
-
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
-    constexpr int NP = RM / 2;                // aligned output pairs per lane
-    const int nstrips = MT / (32 * RM);
-    const int ngroups = (p.njobs + XD_VR - 1) / XD_VR;
-    constexpr int WN = QC + 2;                // window samples per pair (even)
-
-    for (int task = warp; task < nstrips * ngroups; task += nwarps) {
-        const int strip = task % nstrips, grp = task / nstrips;
-        const int v0 = grp * XD_VR;
-        float2 A[NP][2][XD_VR], B[NP][2][XD_VR];
-#pragma unroll
-        for (int pi = 0; pi < NP; pi++)
-#pragma unroll
-            for (int o = 0; o < 2; o++)
-#pragma unroll
-                for (int v = 0; v < XD_VR; v++) { A[pi][o][v] = make_float2(0.f, 0.f); B[pi][o][v] = make_float2(0.f, 0.f); }
-
-        const int jl0 = strip * 32 * RM + 2 * lane;      // local j' of pair 0 (even); pair pi adds 64*pi
-        for (int r = 0; r < D; r++) {
-            const float2* row = X + r * JP;
-            for (int qc = 0; qc < QPC; qc += QC) {
-                float2 xs[NP][WN];
-#pragma unroll
-                for (int pi = 0; pi < NP; pi++) {
-                    const float4* src = reinterpret_cast<const float4*>(row + jl0 + 64 * pi + qc);
-#pragma unroll
-                    for (int u = 0; u < WN / 2; u++) {
-                        float4 t = src[u];
-                        xs[pi][2 * u] = make_float2(t.x, t.y);
-                        xs[pi][2 * u + 1] = make_float2(t.z, t.w);
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < QC; q++) {
-#pragma unroll
-                    for (int v = 0; v < XD_VR; v++) {
-                        // taps of VFOs beyond njobs read the zero-filled tail of G? no: clamp to a valid job
-                        int vv = (v0 + v < p.njobs) ? (v0 + v) : (p.njobs - 1);
-                        float2 g = G[vv * gl + (qc + q) * D + r];
-#pragma unroll
-                        for (int pi = 0; pi < NP; pi++)
-#pragma unroll
-                            for (int o = 0; o < 2; o++) {
-                                A[pi][o][v] = ffma2(make_float2(g.x, g.x), xs[pi][q + o], A[pi][o][v]);
-                                B[pi][o][v] = ffma2(make_float2(g.y, g.y), xs[pi][q + o], B[pi][o][v]);
-                            }
-                    }
-                }
-            }
-        }
-        // ---- epilogue: rotate by the closed-form phase at the window start and store ----
-#pragma unroll
-        for (int v = 0; v < XD_VR; v++) {
-            if (v0 + v >= p.njobs) { break; }
-            const XdJob& Jv = p.job[v0 + v];
-            const int a = Jv.offset - (Jv.T - 1);
-            const int s = ((a % D) + D) % D;
-            const int c = (a - s) / D;
-#pragma unroll
-            for (int pi = 0; pi < NP; pi++)
-#pragma unroll
-                for (int o = 0; o < 2; o++) {
-                    long long jj = J0 + jl0 + 64 * pi + o;
-                    long long m = jj - c;
-                    if (m >= 0 && m < Jv.n_out) {
-                        long long im = (long long)a + m * D;
-                        float2 acc = make_float2(A[pi][o][v].x - B[pi][o][v].y, A[pi][o][v].y + B[pi][o][v].x);
-                        float2 ph = phasor_u64(Jv.phase0 + Jv.w * (unsigned long long)im);
-                        Jv.out[m] = cmulf(acc, ph);
-                    }
-                }
-        }
-    }
-}
-
-
 #define FL_M_PI_REF 3.1415926535f   // math::normalizePhase (normalize_phase.h:6-10)
 #include "xd_pipe.cuh"
 #include "xd_pfb.cuh"
@@ -751,17 +639,6 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 #include "chanpfb.cuh"
 #include "tails_reg.cuh"
 
-template <int FMT, int RM, int QC>
-static cudaError_t launch_xd_tile_t(const XdParams& p, int MT, int JP, int QPC, int jmin, int ntiles, size_t smem,
-                                    cudaStream_t s) {
-    cudaError_t e = set_smem(k_xd_tile<FMT, RM, QC>, smem);
-    if (e != cudaSuccess) { return e; }
-    int ntasks = (MT / (32 * RM)) * ((p.njobs + XD_VR - 1) / XD_VR);
-    int nthr = 32 * (ntasks < 2 ? 2 : (ntasks > 8 ? 8 : ntasks));
-    k_xd_tile<FMT, RM, QC><<<ntiles, nthr, smem, s>>>(p, MT, JP, QPC, jmin);
-    return cudaGetLastError();
-}
-
 
 int g_xd_cps = 0;                 // cap on stage-1 CTAs per SM (0 = as many as fit): leaves room for the other streams
 void kernels_set_xd_cps(int v) { g_xd_cps = v; }
@@ -862,32 +739,13 @@ static bool try_xd_pipe(const XdParams& p, cudaStream_t s, cudaError_t* err, int
     g.MT = MT; g.QPC = QPC; g.org = org; g.logD = logD; g.jmin = jmin;
     g.ntiles = cdiv(jmax - jmin, MT);
     cudaError_t e;
-    if (nwarps == 4) {
-        switch (QC) {
-        case 4: e = launch_xd_pipe_t<FMT, 4, 128>(p, g, smem, s); break;
-        case 5: e = launch_xd_pipe_t<FMT, 5, 128>(p, g, smem, s); break;
-        case 6: e = launch_xd_pipe_t<FMT, 6, 128>(p, g, smem, s); break;
-        case 7: e = launch_xd_pipe_t<FMT, 7, 128>(p, g, smem, s); break;
-        default: e = launch_xd_pipe_t<FMT, 8, 128>(p, g, smem, s); break;
-        }
-    }
-    else if (nwarps == 16) {
-        switch (QC) {
-        case 4: e = launch_xd_pipe_t<FMT, 4, 512>(p, g, smem, s); break;
-        case 5: e = launch_xd_pipe_t<FMT, 5, 512>(p, g, smem, s); break;
-        case 6: e = launch_xd_pipe_t<FMT, 6, 512>(p, g, smem, s); break;
-        case 7: e = launch_xd_pipe_t<FMT, 7, 512>(p, g, smem, s); break;
-        default: e = launch_xd_pipe_t<FMT, 8, 512>(p, g, smem, s); break;
-        }
-    }
-    else {
-        switch (QC) {
-        case 4: e = launch_xd_pipe_t<FMT, 4, 256>(p, g, smem, s); break;
-        case 5: e = launch_xd_pipe_t<FMT, 5, 256>(p, g, smem, s); break;
-        case 6: e = launch_xd_pipe_t<FMT, 6, 256>(p, g, smem, s); break;
-        case 7: e = launch_xd_pipe_t<FMT, 7, 256>(p, g, smem, s); break;
-        default: e = launch_xd_pipe_t<FMT, 8, 256>(p, g, smem, s); break;
-        }
+    (void)nwarps;
+    switch (QC) {
+    case 4: e = launch_xd_pipe_t<FMT, 4, 128>(p, g, smem, s); break;
+    case 5: e = launch_xd_pipe_t<FMT, 5, 128>(p, g, smem, s); break;
+    case 6: e = launch_xd_pipe_t<FMT, 6, 128>(p, g, smem, s); break;
+    case 7: e = launch_xd_pipe_t<FMT, 7, 128>(p, g, smem, s); break;
+    default: e = launch_xd_pipe_t<FMT, 8, 128>(p, g, smem, s); break;
     }
     *err = e;
     return true;
@@ -1068,70 +926,16 @@ static cudaError_t launch_xd_fmt(const XdParams& p, int variant, cudaStream_t s,
         }
         variant = 6;
     }
-    if (variant >= 3) {
+    if (variant >= 1) {
+        // per-VFO complex taps on cp.async tiles, 4-warp CTAs: 5 = double-buffered, one CTA per SM; anything else = one tile
+        // buffer per CTA, three CTAs per SM (the retired 8- / 16-warp and single-buffer tile kernels map here)
         cudaError_t e = cudaSuccess;
-        if (try_xd_pipe<FMT>(p, s, &e, variant == 4 ? 16 : (variant >= 5 ? 4 : 8), variant == 6)) {
-            if (nlaunch) { (*nlaunch)++; }
-            return e;
-        }
-        variant = 1;     // shapes the pipelined kernel does not cover
-    }
-    // ---- tiled variant: needs padded taps of QPC*D entries; the host sized gpad for QC in {4,6,8} ----
-    if (variant >= 1 && D >= 2) {
-        int QP = p.QP;
-        // pick the unroll chunk that wastes the least padding (ties: larger chunk)
-        int best_qc = 6, best_pad = 1 << 30;
-        const int qcs[3] = { 8, 6, 4 };
-        for (int i = 0; i < 3; i++) {
-            int pad = ((QP + qcs[i] - 1) / qcs[i]) * qcs[i] - QP;
-            if (pad < best_pad) { best_pad = pad; best_qc = qcs[i]; }
-        }
-        const int QC = best_qc;
-        const int QPC = ((QP + QC - 1) / QC) * QC;
-        const int RM = (variant == 2) ? 2 : 4;
-        // tile range in block-index space
-        long long jmin = (1LL << 60), jmax = -(1LL << 60);
-        for (int v = 0; v < p.njobs; v++) {
-            if (p.job[v].n_out <= 0) { continue; }
-            int a = p.job[v].offset - (p.job[v].T - 1);
-            int sft = ((a % D) + D) % D;
-            long long c = (a - sft) / D;
-            if (c < jmin) { jmin = c; }
-            if (c + p.job[v].n_out > jmax) { jmax = c + p.job[v].n_out; }
-        }
-        if (jmin & 1) { jmin -= 1; }   // keep J0 even: LDS.128 alignment of the window loads
-        const int limit = kernels_max_smem_optin();
-        int MT = 0, JP = 0;
-        size_t smem = 0;
-        const int mts[4] = { 256, 128, 64, 32 * RM };
-        for (int i = 0; i < 4; i++) {
-            int mt = mts[i];
-            if (mt % (32 * RM)) { continue; }
-            int jp = mt + QPC + 2;
-            jp += (jp & 1);            // even pitch: rows stay 16-byte aligned (LDS.128 window loads)
-            if ((jp & 3) == 0) { jp += 2; }   // pitch = 2*odd: de-interleaving stores are at worst 2-way conflicted
-            size_t need = ((size_t)D * jp + (size_t)p.njobs * QPC * D) * sizeof(float2);
-            // aim for two CTAs per SM when possible
-            if (need * 2 <= (size_t)limit || (i == 3 && need <= (size_t)limit) || (need <= (size_t)limit && mt <= 64)) {
-                MT = mt; JP = jp; smem = need;
-                break;
-            }
-        }
-        if (MT) {
-            int ntiles = cdiv(jmax - jmin, MT);
-            cudaError_t e;
-#define XD_CASE(rm, qc) e = launch_xd_tile_t<FMT, rm, qc>(p, MT, JP, QPC, (int)jmin, ntiles, smem, s)
-            if (RM == 4) {
-                if (QC == 8) { XD_CASE(4, 8); } else if (QC == 6) { XD_CASE(4, 6); } else { XD_CASE(4, 4); }
-            }
-            else {
-                if (QC == 8) { XD_CASE(2, 8); } else if (QC == 6) { XD_CASE(2, 6); } else { XD_CASE(2, 4); }
-            }
-#undef XD_CASE
+        if (try_xd_pipe<FMT>(p, s, &e, 4, variant != 5)) {
             if (nlaunch) { (*nlaunch)++; }
             return e;
         }
     }
+    // shapes the tile kernels do not cover (pure translate, D = 1): one thread per output
     dim3 grid(cdiv(max_out, 128), p.njobs);
     k_xd_simple<FMT><<<grid, 128, 0, s>>>(p);
     if (nlaunch) { (*nlaunch)++; }
