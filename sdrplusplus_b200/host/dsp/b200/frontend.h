@@ -11,16 +11,20 @@ namespace dsp::b200 {
     class FrontEnd : public block {
     public:
         // acquire/release: the reference's FFT line callbacks (iq_frontend.h:23), unchanged
+        // decimRatio / dcBlocking: IQFrontEnd::init's arguments of the same name (iq_frontend.h:23); the decimation has to be
+        // known before the FFT branch and the VFOs are configured, which is why it is an init argument here too
         void init(stream<complex_t>* in, double samplerate, int fftSize, double fftRate, int fftWindow,
-                  float* (*acquireFFTBuffer)(void*), void (*releaseFFTBuffer)(void*), void* fftCtx) {
+                  float* (*acquireFFTBuffer)(void*), void (*releaseFFTBuffer)(void*), void* fftCtx,
+                  int decimRatio = 1, bool dcBlocking = false) {
             _in = in;
             acquire = acquireFFTBuffer; release = releaseFFTBuffer; ctx = fftCtx;
             fe = b200_fe_create(samplerate, in->bufferSize());
-            size = fftSize;
-            if (fe && fftSize) { b200_fe_set_fft(fe, fftSize, fftRate, fftWindow); }
-            lines = (float*)b200_host_alloc((uint64_t)(fe ? b200_fe_fft_max_lines(fe, in->bufferSize()) : 1) * fftSize * sizeof(float));
+            _samplerate = samplerate; _decim = decimRatio; _rate = fftRate; _window = fftWindow;
+            if (fe && decimRatio > 1) { b200_fe_set_decimation(fe, decimRatio); }
+            if (fe && dcBlocking) { b200_fe_set_dc_blocking(fe, 1); }
             registerInput(_in);
             inited = true;
+            setFFTSize(fftSize);
         }
         ~FrontEnd() override {
             if (inited) { stop(); }
@@ -41,7 +45,27 @@ namespace dsp::b200 {
             tempStart();
             return id;
         }
+        void removeVFO(int id) {
+            std::lock_guard<std::recursive_mutex> lk(ctrlMtx);
+            tempStop();
+            if (b200_fe_remove_vfo(fe, id) == 0 && id < (int)outs_.size() && outs_[id]) {
+                unregisterOutput(outs_[id]);
+                delete outs_[id];
+                outs_[id] = nullptr;
+            }
+            tempStart();
+        }
         void setVFOOffset(int id, double offset) { b200_fe_set_vfo_offset(fe, id, offset); }
+        void setVFOBandwidth(int id, double bandwidth) { b200_fe_set_vfo_bandwidth(fe, id, bandwidth); }
+        // IQFrontEnd::setDCBlocking / setInvertIQ (iq_frontend.cpp:117-123): take effect at the next chunk
+        void setDCBlocking(bool enabled) { b200_fe_set_dc_blocking(fe, enabled); }
+        void setInvertIQ(bool enabled) { b200_fe_set_invert_iq(fe, enabled); }
+        // IQFrontEnd::getEffectiveSamplerate (iq_frontend.cpp:214-216)
+        double getEffectiveSamplerate() const { return _samplerate / _decim; }
+        // IQFrontEnd::setFFTSize / setFFTRate / setFFTWindow (iq_frontend.cpp:185-201)
+        void setFFTSize(int fftSize) { size = fftSize; updateFFTPath(); }
+        void setFFTRate(double rate) { _rate = rate; updateFFTPath(); }
+        void setFFTWindow(int window) { _window = window; updateFFTPath(); }
         stream<stereo_t>* vfoOut(int id) { return outs_[id]; }
 
         int run() override {
@@ -70,6 +94,16 @@ namespace dsp::b200 {
             return count;
         }
     private:
+        void updateFFTPath() {
+            std::lock_guard<std::recursive_mutex> lk(ctrlMtx);
+            tempStop();
+            if (fe) { b200_fe_set_fft(fe, size, _rate, _window); }
+            b200_host_free(lines);
+            lines = (float*)b200_host_alloc((uint64_t)(fe && size ? b200_fe_fft_max_lines(fe, _in->bufferSize()) : 1) * (size ? size : 1) * sizeof(float));
+            tempStart();
+        }
+        double _samplerate = 0, _rate = 20.0;
+        int _decim = 1, _window = 2;
         stream<complex_t>* _in = nullptr;
         b200_fe* fe = nullptr;
         std::vector<stream<stereo_t>*> outs_;
