@@ -622,7 +622,7 @@ def run_b200(args):
     groups = [
         {"group": "stage 1", "kernels": s1_kernel, "avg_ms": s1_avg, "timed": s1_n, "bound": "hbm", "achieved": achieved, "peak": peak,
          "unit": "GB/s", "frac": (achieved / peak) if achieved else None},
-        {"group": "behind stage 1", "kernels": "k_dfir_reg x2, k_tail_fused, k_carry", "avg_ms": tail_avg, "timed": tail_n, "bound": "fp32 FMA issue",
+        {"group": "behind stage 1", "kernels": "k_dfir_reg x2, k_poly_reg, k_fir_reg, k_quad, k_firr_reg, k_carry (six dependent launches)", "avg_ms": tail_avg, "timed": tail_n, "bound": "fp32 FMA issue",
          "achieved": (tail_fma / (tail_avg * 1e-3) / 1e12) if tail_n else None, "peak": fma_peak / 1e12, "unit": "TFMA/s",
          "frac": (tail_fma / (tail_avg * 1e-3) / fma_peak) if tail_n else None, "useful_fma_per_chunk": tail_fma},
         {"group": "spectrum branch", "kernels": "k_fftr_p1, k_fftr_p2 (frames of a chunk batched)", "avg_ms": fft_avg, "timed": fft_n, "bound": "hbm / L2",

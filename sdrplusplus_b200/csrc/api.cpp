@@ -1,6 +1,8 @@
 // sdrplusplus_b200/csrc/api.cpp -- C ABI of libb200dsp.so (include/b200dsp.h) over engine.h.
 #include "../../include/b200dsp.h"
 #include "engine.h"
+#include <chrono>
+#include <map>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -187,6 +189,8 @@ struct b200_fe {
     cudaEvent_t ev_h2d[2] = { nullptr, nullptr }, ev_compute[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
     bool slot_used[2] = { false, false };
     unsigned long long nsub = 0, nwait = 0;
+    int host_direct = -1;                    // pinned host outputs written by the kernels themselves: -1 small chunks, 0 never, 1 always
+    long long host_ns[4] = { 0, 0, 0, 0 };   // host time of submit(): [0] checks + plans, [1] spectrum branch, [2] Scheduler::run, [3] join + outputs
     float scale16 = 1.0f / 32768.0f, scale8 = 1.0f / 128.0f;
     // IQFrontEnd pre-processing chain (iq_frontend.cpp:32-39): PowerDecimator -> DCBlocker -> Conjugate, off by default
     int decim = 1;               // setDecimation: everything behind it runs at fs_eff = fs / decim
@@ -449,6 +453,16 @@ extern "C" long long b200_fe_stat(b200_fe* fe, const char* key) {
     if (!strcmp(key, "launches")) { return fe->sch.launches; }
     if (!strcmp(key, "s1_tma_launches")) { return g_xd_tma_launches; }      // process-wide: stage-1 launches that took the TMA kernel
     if (!strcmp(key, "chunks")) { return (long long)fe->nsub; }
+    // host time spent inside b200_fe_submit since creation, by section (ns)
+    if (!strcmp(key, "host_ns_plan")) { return fe->host_ns[0]; }
+    if (!strcmp(key, "host_ns_fft")) { return fe->host_ns[1]; }
+    if (!strcmp(key, "host_ns_run")) { return fe->host_ns[2]; }
+    if (!strcmp(key, "host_ns_join")) { return fe->host_ns[3]; }
+    if (!strcmp(key, "graph_hits")) { return fe->sch.graph_hits; }
+    if (!strcmp(key, "graph_misses")) { return fe->sch.graph_misses; }
+    if (!strcmp(key, "graphs")) { return (long long)fe->sch.graphs.size(); }
+    if (!strcmp(key, "host_ns_stage1")) { return fe->sch.host_ns[0]; }
+    if (!strcmp(key, "host_ns_tail")) { return fe->sch.host_ns[1]; }
     return -1;
 }
 extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
@@ -478,6 +492,9 @@ extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
         if (!strcmp(key, "ft_regall")) { fe->sch.fuse.reg_all = value != 0; return 0; }
     }
     if (!strcmp(key, "fft")) { kernels_set_fft_variant(value); return 0; }
+    if (!strcmp(key, "host_direct")) { fe->host_direct = value; return 0; }
+    if (!strcmp(key, "graph")) { fe->sch.graph_tails = value; if (value == 0) { fe->sch.drop_graphs(); } return 0; }
+    if (!strcmp(key, "graph_max_count")) { fe->sch.graph_max_count = value; return 0; }
     if (!strcmp(key, "time_s1")) { fe->sch.time_s1 = value != 0; for (auto& t : fe->sch.timers) { t.used = 0; } return 0; }
     set_error("unknown option %s", key);
     return B200_EINVAL;
@@ -505,6 +522,22 @@ extern "C" int b200_fe_reset(b200_fe* fe) {
     fe->pos = 0;
     fe->fstart = 0;
     return rc;
+}
+
+// pinned buffers handed out by b200_host_alloc: under unified addressing the device can store into them directly, which is
+// how the audio of a small chunk leaves (no copy to enqueue).  Anything else goes through cudaMemcpyAsync.
+static std::mutex g_host_mtx;
+static std::map<uintptr_t, size_t> g_host_allocs;
+static bool host_buffer_is_ours(const void* p, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_host_mtx);
+    auto it = g_host_allocs.upper_bound((uintptr_t)p);
+    if (it == g_host_allocs.begin()) { return false; }
+    --it;
+    return (uintptr_t)p + bytes <= it->first + it->second;
+}
+
+static inline long long host_clock_ns() {
+    return (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 // apply RxVFO::setOffset / setBandwidth at the chunk boundary (rx_vfo.h:60-77)
@@ -622,6 +655,7 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
     if (in_fmt < 0 || in_fmt > 2) { set_error("bad input format"); return B200_EINVAL; }
     if (fe->nsub - fe->nwait >= 2) { set_error("two chunks already in flight: call b200_fe_wait"); return B200_ESTATE; }
     std::lock_guard<std::mutex> lck(fe->mtx);
+    const long long hp0 = host_clock_ns();
     apply_pending(fe);
     const int slot = (int)(fe->nsub & 1);
     cudaStream_t s = fe->sch.stream;
@@ -720,17 +754,27 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
     for (Chain* c : chains) { c->plan(count); }
     // device-resident outputs: the last stage of every chain (and the FFT epilogue) write straight into the caller's buffers
     const bool direct = (out->out_mem == B200_MEM_DEVICE);
-    for (size_t k = 0; k < chains.size(); k++) { chains[k]->out_override = direct ? (float*)out->vfo_out[ids[k]] : nullptr; }
+    // host outputs of a small chunk: the last kernel of a VFO stores straight into the caller's pinned buffer (a few KB over
+    // PCIe) when that buffer came from b200_host_alloc; large chunks keep the copy engine
+    const bool host_direct = !direct && fe->host_direct != 0 && (fe->host_direct > 0 || count <= fe->sch.graph_max_count);
+    std::vector<char> vdirect(chains.size(), direct ? 1 : 0);
+    for (size_t k = 0; k < chains.size(); k++) {
+        if (host_direct && host_buffer_is_ours(out->vfo_out[ids[k]], (size_t)out->vfo_cap[ids[k]] * chains[k]->out_es * sizeof(float))) { vdirect[k] = 1; }
+        chains[k]->out_override = vdirect[k] ? (float*)out->vfo_out[ids[k]] : nullptr;
+    }
     fe->lines_override = direct ? out->fft_out : nullptr;
     int nlines = 0;
     int rc;
     // fork the spectrum branch first; its join (a wait on the main stream) comes after the VFO branch has been
     // enqueued, so the two overlap on the device
+    const long long hp1 = host_clock_ns();
     if ((rc = fe_fft_chunk(fe, dptr, in_fmt, count, &nlines))) { return rc; }
+    const long long hp2 = host_clock_ns();
     fe->sch.in_scale = fe_ingest_scale(fe, in_fmt);
     // host-side outputs leave through per-VFO device buffers that the copies of the previous chunk may still be reading
     if (!direct && fe->nsub > 0) { B200_CK(cudaStreamWaitEvent(fe->sch.out_stream(), fe->ev_out[slot ^ 1], 0)); }
     if ((rc = fe->sch.run(chains, dptr, in_fmt, count, true))) { return rc; }
+    const long long hp3 = host_clock_ns();
     // join on a stream of its own: the VFO branch (tail stream) and the spectrum branch (its stream) of this chunk meet
     // here, neither waits for the other -- the tail stream goes straight on to the next chunk
     cudaStream_t os = fe->join_stream;
@@ -749,7 +793,7 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
     for (size_t k = 0; k < chains.size(); k++) {
         Chain* c = chains[k];
         out->vfo_count[ids[k]] = c->n_out;
-        if (c->n_out > 0 && !direct) {
+        if (c->n_out > 0 && !vdirect[k]) {
             B200_CK(cudaMemcpyAsync(out->vfo_out[ids[k]], c->out.p, (size_t)c->n_out * c->out_es * sizeof(float), kind, os));
         }
     }
@@ -762,6 +806,8 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
     B200_CK(cudaEventRecord(fe->ev_out[slot], os));
     trace_mark("outputs done", os);
     fe->nsub++;
+    const long long hp4 = host_clock_ns();
+    fe->host_ns[0] += hp1 - hp0; fe->host_ns[1] += hp2 - hp1; fe->host_ns[2] += hp3 - hp2; fe->host_ns[3] += hp4 - hp3;
     return 0;
 }
 
@@ -1081,10 +1127,20 @@ extern "C" void* b200_host_alloc(uint64_t bytes) {
     void* p = nullptr;
     cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 16);
     if (e != cudaSuccess) { cuda_fail(e, "cudaMallocHost"); return nullptr; }
+    {
+        std::lock_guard<std::mutex> lk(g_host_mtx);
+        g_host_allocs[(uintptr_t)p] = (size_t)(bytes ? bytes : 16);
+    }
     return p;
 }
 extern "C" void b200_host_free(void* p) {
-    if (p) { cudaFreeHost(p); }
+    if (p) {
+        {
+            std::lock_guard<std::mutex> lk(g_host_mtx);
+            g_host_allocs.erase((uintptr_t)p);
+        }
+        cudaFreeHost(p);
+    }
 }
 
 

@@ -1,5 +1,6 @@
 // sdrplusplus_b200/csrc/engine.cpp -- see engine.h
 #include "engine.h"
+#include <chrono>
 #include "../../include/b200dsp.h"
 #include <cmath>
 #include <cstdarg>
@@ -725,6 +726,7 @@ int Scheduler::init_raw() {
     return raw_hist.alloc((size_t)RAW_HIST * sizeof(float2));
 }
 Scheduler::~Scheduler() {
+    drop_graphs();
     for (Timer& t : timers) { for (cudaEvent_t e : t.ev) { cudaEventDestroy(e); } }
 }
 cudaEvent_t Scheduler::timer_begin(int group, cudaStream_t s) {
@@ -813,9 +815,79 @@ static int apply_pending_taps(FirCStage* f, cudaStream_t s) {
     return 0;
 }
 
+// ---- launch list of a chunk's tail section (engine.h: LaunchRec) ----
+static thread_local LaunchRec* g_rec = nullptr;      // set while Scheduler::run records instead of launching
+struct RecScope {
+    explicit RecScope(LaunchRec* r) { g_rec = r; }
+    ~RecScope() { g_rec = nullptr; }
+};
+static inline int rec_tag(const FirParams&) { return LaunchRec::T_FIR; }
+static inline int rec_tag(const PolyParams&) { return LaunchRec::T_POLY; }
+static inline int rec_tag(const FirRParams&) { return LaunchRec::T_FIRR; }
+static inline int rec_tag(const QuadParams&) { return LaunchRec::T_QUAD; }
+static inline int rec_tag(const SeqParams&) { return LaunchRec::T_SEQ; }
+static inline int rec_tag(const M2SParams&) { return LaunchRec::T_M2S; }
+static inline int rec_tag(const ScaleParams&) { return LaunchRec::T_SCALE; }
+static inline int rec_tag(const CarryParams&) { return LaunchRec::T_CARRY; }
+
+void LaunchRec::add(int tag, void* fn, const void* p, size_t size, int a, int b, size_t c) {
+    const size_t off = (bytes.size() + 15) & ~(size_t)15;
+    bytes.resize(off + size, 0);
+    memcpy(bytes.data() + off, p, size);
+    items.push_back(Item{ tag, fn, off, size, a, b, c });
+}
+unsigned long long LaunchRec::hash() const {
+    // 64-bit multiply-xorshift over the parameter bytes and the launch arguments
+    unsigned long long h = 0x9E3779B97F4A7C15ULL ^ (unsigned long long)items.size();
+    auto mix = [&](unsigned long long v) { h ^= v; h *= 0xD6E8FEB86659FD93ULL; h ^= h >> 32; };
+    for (const Item& it : items) {
+        mix((unsigned long long)it.tag); mix((unsigned long long)(uintptr_t)it.fn); mix((unsigned long long)it.size);
+        mix((unsigned long long)(unsigned)it.a | ((unsigned long long)(unsigned)it.b << 32)); mix((unsigned long long)it.c);
+    }
+    const size_t n8 = bytes.size() / 8;
+    const unsigned char* b = bytes.data();
+    for (size_t i = 0; i < n8; i++) { unsigned long long v; memcpy(&v, b + 8 * i, 8); mix(v); }
+    for (size_t i = n8 * 8; i < bytes.size(); i++) { mix(b[i]); }
+    return h;
+}
+int LaunchRec::replay(cudaStream_t s, long long* nlaunch) const {
+    for (const Item& it : items) {
+        const void* q = bytes.data() + it.off;
+        cudaError_t e = cudaSuccess;
+        int nl = 1;
+        switch (it.tag) {
+        case T_DFR: e = launch_dfir_reg(*(const DfrParams*)q, it.a, it.b, s); break;
+        case T_FIR: e = ((cudaError_t (*)(const FirParams&, cudaStream_t))it.fn)(*(const FirParams*)q, s); break;
+        case T_POLY: e = ((cudaError_t (*)(const PolyParams&, cudaStream_t))it.fn)(*(const PolyParams*)q, s); break;
+        case T_FIRR: e = ((cudaError_t (*)(const FirRParams&, cudaStream_t))it.fn)(*(const FirRParams*)q, s); break;
+        case T_QUAD: e = launch_quad(*(const QuadParams*)q, s); break;
+        case T_SEQ: e = launch_seq(*(const SeqParams*)q, s); break;
+        case T_M2S: e = launch_m2s(*(const M2SParams*)q, s); break;
+        case T_SCALE: e = launch_scale(*(const ScaleParams*)q, s); break;
+        case T_CARRY: e = launch_carry(*(const CarryParams*)q, s); break;
+        case T_STEREO: nl = 0; e = launch_stereo(*(const StParams*)q, s, &nl); break;
+        case T_SQUELCH: nl = 0; e = launch_squelch(*(const SqParams*)q, s, &nl); break;
+        case T_FUSED: e = launch_tail_fused(*(const FtParams*)q, it.a, it.b, it.c, s); break;
+        default: set_error("launch list: unknown tag %d", it.tag); return B200_EINVAL;
+        }
+        if (e != cudaSuccess) { return cuda_fail(e, "kernel launch (tail list)"); }
+        if (nlaunch) { *nlaunch += nl; }
+    }
+    return 0;
+}
+void Scheduler::drop_graphs() {
+    for (auto& kv : graphs) { if (kv.second.exec) { cudaGraphExecDestroy(kv.second.exec); } }
+    graphs.clear();
+}
+
 template <class P, class L>
 static int flush_batch(P& p, L launch, cudaStream_t s, long long& launches) {
     if (p.njobs == 0) { return 0; }
+    if (g_rec) {
+        g_rec->add(rec_tag(p), (void*)launch, &p, sizeof(P));
+        p.njobs = 0;
+        return 0;
+    }
     cudaError_t e = launch(p, s);
     if (e != cudaSuccess) { return cuda_fail(e, "kernel launch"); }
     launches++;
@@ -852,7 +924,59 @@ int Scheduler::apply_deferred(std::vector<Chain*>& chains) {
     return 0;
 }
 
+template <class P>
+static inline void zero_params(P& p, bool) { memset(&p, 0, sizeof(P)); }
+
+// the recorded launch list of this chunk: first sight -> plain launches; second sight -> capture into a graph; then replay
+int Scheduler::launch_recorded(cudaStream_t ts) {
+    if (rec.items.empty()) { return 0; }
+    const unsigned long long h = rec.hash();
+    auto it = graphs.find(h);
+    if (it != graphs.end() && it->second.key.size() == rec.bytes.size() && memcmp(it->second.key.data(), rec.bytes.data(), rec.bytes.size()) == 0) {
+        GraphEntry& g = it->second;
+        if (g.exec) {
+            B200_CK(cudaGraphLaunch(g.exec, ts));
+            launches += g.launches;
+            graph_hits++;
+            return 0;
+        }
+        // second sight: capture
+        if (cudaStreamBeginCapture(ts, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            long long nl = 0;
+            int rc = rec.replay(ts, &nl);
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamEndCapture(ts, &graph);
+            cudaGraphExec_t exec = nullptr;
+            if (rc == 0 && e == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                cudaGraphDestroy(graph);
+                g.exec = exec;
+                g.launches = nl;
+                B200_CK(cudaGraphLaunch(exec, ts));
+                launches += nl;
+                graph_misses++;
+                return 0;
+            }
+            if (graph) { cudaGraphDestroy(graph); }
+            cudaGetLastError();
+            graph_tails = 0;                       // capture is not possible here: plain launches from now on
+        }
+        return rec.replay(ts, &launches);
+    }
+    if (graphs.size() >= 256) { drop_graphs(); }
+    GraphEntry& g = graphs[h];
+    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }      // (hash collision with other bytes: start over)
+    g.key = rec.bytes;
+    g.launches = 0;
+    graph_misses++;
+    return rec.replay(ts, &launches);
+}
+
+static inline long long host_now_ns() {
+    return (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int count, bool carry_raw) {
+    const long long hp0 = host_now_ns();
     // ---- wiring ----
     const int parity = (int)(chunk_idx & 1);
     cudaStream_t ts = tail_stream ? tail_stream : stream;
@@ -1015,17 +1139,26 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
         B200_CK(cudaStreamWaitEvent(ts, ev_stage1[parity], 0));
     }
     trace_mark("tails start", ts);
+    const long long hp1 = host_now_ns();
+    host_ns[0] += hp1 - hp0;
     cudaEvent_t t_tail = timer_begin(1, ts);
+    // small chunks: record the launches of this section, replay a captured graph when the same list was seen before
+    const bool use_rec = graph_tails > 0 || (graph_tails < 0 && count <= graph_max_count);
+    if (use_rec) { rec.clear(); }
+    RecScope rec_scope(use_rec ? &rec : nullptr);
     // ---- short decimating FIRs with the window in registers (k_dfir_reg): one launch per level and plan stage ----
     DfrParams dfr;
-    dfr.njobs = 0; dfr.max_out = 0;
+    memset(&dfr, 0, sizeof(dfr));
     int dfr_D = 0, dfr_T = 0;
     const std::vector<float>* dfr_taps = nullptr;
     auto dfr_flush = [&]() -> int {
         if (dfr.njobs == 0) { return 0; }
-        cudaError_t e = launch_dfir_reg(dfr, dfr_D, dfr_T, ts);
-        if (e != cudaSuccess) { return cuda_fail(e, "launch_dfir_reg"); }
-        launches++;
+        if (g_rec) { g_rec->add(LaunchRec::T_DFR, nullptr, &dfr, sizeof(dfr), dfr_D, dfr_T); }
+        else {
+            cudaError_t e = launch_dfir_reg(dfr, dfr_D, dfr_T, ts);
+            if (e != cudaSuccess) { return cuda_fail(e, "launch_dfir_reg"); }
+            launches++;
+        }
         dfr.njobs = 0; dfr.max_out = 0;
         return 0;
     };
@@ -1104,7 +1237,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
                 ob = hi_ob;
             }
             FtParams fpar;
-            fpar.njobs = 0; fpar.pad = 0;
+            memset(&fpar, 0, sizeof(fpar));
             fpar.dbg = nullptr;
             static long long* g_ft_dbg = nullptr;
             static int g_ft_dbg_on = -1;
@@ -1127,9 +1260,12 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
             int max_slabs = 0;
             auto flush = [&]() -> int {
                 if (fpar.njobs == 0) { return 0; }
-                cudaError_t e = launch_tail_fused(fpar, max_slabs, threads, smem, ts);
-                if (e != cudaSuccess) { return cuda_fail(e, "launch_tail_fused"); }
-                launches++;
+                if (g_rec) { g_rec->add(LaunchRec::T_FUSED, nullptr, &fpar, sizeof(fpar), max_slabs, threads, smem); }
+                else {
+                    cudaError_t e = launch_tail_fused(fpar, max_slabs, threads, smem, ts);
+                    if (e != cudaSuccess) { return cuda_fail(e, "launch_tail_fused"); }
+                    launches++;
+                }
                 fpar.njobs = 0;
                 max_slabs = 0;
                 return 0;
@@ -1172,23 +1308,27 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
     }
     // ---- remaining stages level by level: one launch per stage kind per level (batches of 16 VFOs) ----
     for (size_t lvl = 0; lvl < depth; lvl++) {
-        FirParams fp; fp.njobs = 0; fp.max_out = 0;
-        FirParams fpr; fpr.njobs = 0; fpr.max_out = 0;              // decimation-1 filters with register windows
-        PolyParams pp; pp.njobs = 0; pp.max_out = 0;
-        PolyParams ppr; ppr.njobs = 0; ppr.max_out = 0;             // polyphase resamplers with register windows: one (L, M) per batch
-        FirRParams rpr; rpr.njobs = 0; rpr.max_out = 0;
-        QuadParams qp; qp.njobs = 0; qp.max_n = 0;
-        FirRParams rp; rp.njobs = 0; rp.max_out = 0;
-        SeqParams sp; sp.njobs = 0;
-        M2SParams mp; mp.njobs = 0; mp.max_n = 0;
-        ScaleParams cp2; cp2.njobs = 0; cp2.max_n = 0;
-        StParams stp; stp.njobs = 0; stp.max_n = 0;
-        SqParams sqp; sqp.njobs = 0; sqp.max_n = 0;
+        // zero-filled: the parameter blocks are hashed as a whole when the launch list is recorded
+        FirParams fp; zero_params(fp, use_rec);
+        FirParams fpr; zero_params(fpr, use_rec);                   // decimation-1 filters with register windows
+        PolyParams pp; zero_params(pp, use_rec);
+        PolyParams ppr; zero_params(ppr, use_rec);                  // polyphase resamplers with register windows: one (L, M) per batch
+        FirRParams rpr; zero_params(rpr, use_rec);
+        QuadParams qp; zero_params(qp, use_rec);
+        FirRParams rp; zero_params(rp, use_rec);
+        SeqParams sp; zero_params(sp, use_rec);
+        M2SParams mp; zero_params(mp, use_rec);
+        ScaleParams cp2; zero_params(cp2, use_rec);
+        StParams stp; zero_params(stp, use_rec);
+        SqParams sqp; zero_params(sqp, use_rec);
         auto sq_flush = [&]() -> int {
             if (sqp.njobs == 0) { return 0; }
             int nl = 0;
-            cudaError_t e = launch_squelch(sqp, ts, &nl);
-            if (e != cudaSuccess) { return cuda_fail(e, "launch_squelch"); }
+            if (g_rec) { g_rec->add(LaunchRec::T_SQUELCH, nullptr, &sqp, sizeof(sqp)); }
+            else {
+                cudaError_t e = launch_squelch(sqp, ts, &nl);
+                if (e != cudaSuccess) { return cuda_fail(e, "launch_squelch"); }
+            }
             launches += nl;
             sqp.njobs = 0; sqp.max_n = 0;
             return 0;
@@ -1196,8 +1336,11 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
         auto st_flush = [&]() -> int {
             if (stp.njobs == 0) { return 0; }
             int nl = 0;
-            cudaError_t e = launch_stereo(stp, ts, &nl);
-            if (e != cudaSuccess) { return cuda_fail(e, "launch_stereo"); }
+            if (g_rec) { g_rec->add(LaunchRec::T_STEREO, nullptr, &stp, sizeof(stp)); }
+            else {
+                cudaError_t e = launch_stereo(stp, ts, &nl);
+                if (e != cudaSuccess) { return cuda_fail(e, "launch_stereo"); }
+            }
             launches += nl;
             stp.njobs = 0; stp.max_n = 0;
             return 0;
@@ -1343,7 +1486,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
     }
     // ---- history carry (the memmove at the end of every reference process()) ----
     CarryParams cp;
-    cp.njobs = 0;
+    zero_params(cp, use_rec);
     auto push = [&](const CarryJob& j) -> int {
         cp.job[cp.njobs++] = j;
         if (cp.njobs == CARRY_BATCH) { return flush_batch(cp, launch_carry, ts, launches); }
@@ -1355,6 +1498,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
             if (s->kind == K_XD || s->hist <= 0 || s->fmid) { continue; }
             if (s->n_in <= 0 && !s->dbl) { continue; }      // a double-buffered stage always hands its history over
             CarryJob j;
+            memset(&j, 0, sizeof(j));
             j.dst = s->other_base(); j.a = s->base(); j.b = s->in_data();
             j.h = s->hist; j.la = s->hist; j.lb = s->n_in; j.esize = s->in_es; j.bfmt = -1; j.scale = 0.0f;
             int rc = push(j);
@@ -1363,9 +1507,15 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
     }
     int rcf = flush_batch(cp, launch_carry, ts, launches);
     if (rcf) { return rcf; }
+    if (use_rec) {
+        g_rec = nullptr;
+        int rcg = launch_recorded(ts);
+        if (rcg) { return rcg; }
+    }
     if (t_tail) { B200_CK(cudaEventRecord(t_tail, ts)); }
     trace_mark("tails+carry done", ts);
     if (tail_stream) { B200_CK(cudaEventRecord(ev_tail[parity], ts)); }
+    host_ns[1] += host_now_ns() - hp1;
     chunk_idx++;
     return 0;
 }

@@ -9,6 +9,7 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <unordered_map>
 #include "kernels.cuh"
 #include "design.h"
 
@@ -227,6 +228,21 @@ struct Chain {
     int add_volume(double volume, bool muted);                              // dsp::audio::Volume (volume.h:13-17,39-42)
 };
 
+// Launch list of everything behind stage 1 of one chunk (parameter blocks by value).  Small chunks are launch-bound: the
+// list is hashed, and a chunk whose list was seen before replays a captured CUDA graph (one cudaGraphLaunch instead of
+// seven to ten kernel launches).  Decimation offsets / resampler phases / buffer parities make the list periodic over a few
+// chunks for any fixed chunk size, so a handful of graphs covers a stream.
+struct LaunchRec {
+    enum Tag { T_DFR = 1, T_FIR, T_POLY, T_FIRR, T_QUAD, T_SEQ, T_M2S, T_SCALE, T_STEREO, T_SQUELCH, T_FUSED, T_CARRY };
+    struct Item { int tag; void* fn; size_t off, size; int a, b; size_t c; };
+    std::vector<Item> items;
+    std::vector<unsigned char> bytes;
+    void clear() { items.clear(); bytes.clear(); }
+    void add(int tag, void* fn, const void* p, size_t size, int a = 0, int b = 0, size_t c = 0);
+    unsigned long long hash() const;
+    int replay(cudaStream_t s, long long* nlaunch) const;     // the real launches, in order
+};
+
 // Runs a set of chains over one chunk: stage-1 launches grouped by decimation, then level by level one
 // launch per stage kind, then the history carry.
 struct Scheduler {
@@ -239,6 +255,16 @@ struct Scheduler {
     cudaStream_t out_stream() const { return tail_stream ? tail_stream : stream; }
     int enable_overlap(cudaStream_t tail);
     long long launches = 0;
+    // launch-list replay (LaunchRec): -1 = for chunks up to graph_max_count samples, 0 = never, 1 = always
+    int graph_tails = -1;
+    int graph_max_count = 1 << 22;
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; long long launches = 0; std::vector<unsigned char> key; };
+    std::unordered_map<unsigned long long, GraphEntry> graphs;
+    LaunchRec rec;
+    long long graph_hits = 0, graph_misses = 0;
+    void drop_graphs();
+    int launch_recorded(cudaStream_t ts);
+    long long host_ns[4] = { 0, 0, 0, 0 };   // host time of run(): [0] wiring + stage 1, [1] everything behind it (b200_fe_stat)
     int s1_variant = 8;          // 8: filter-bank stage 1 fed by the TMA engine (cf32 chunks), 7: cp.async filter bank, when the VFO plan allows it; else 6
     FuseCfg fuse;                // tails: one fused launch per <= 16 VFOs instead of one launch per stage kind
     int sm_count = 148;

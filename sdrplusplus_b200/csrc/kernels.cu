@@ -17,6 +17,8 @@
 //                             (iq_frontend.cpp:248-267)
 //   k_zoom_hold               doZoom + peak hold (waterfall.cpp:65-90, 935-939)
 #include "kernels.cuh"
+#include <unordered_map>
+#include <mutex>
 #include <math.h>
 #include <string.h>
 #include <algorithm>
@@ -629,9 +631,17 @@ int kernels_max_smem_optin() {
     return g_smem_optin;
 }
 
+// opt-in dynamic shared memory per kernel: grow-only and remembered, so the steady state costs no driver call per launch
 template <typename K>
 static cudaError_t set_smem(K kernel, size_t bytes) {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    static std::mutex mtx;
+    static std::unordered_map<const void*, size_t> have;
+    std::lock_guard<std::mutex> lk(mtx);
+    size_t& cur = have[(const void*)kernel];
+    if (bytes <= cur) { return cudaSuccess; }
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) { cur = bytes; }
+    return e;
 }
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -1042,20 +1052,27 @@ cudaError_t launch_quad(const QuadParams& p, cudaStream_t s) {
     return cudaGetLastError();
 }
 // resident CTAs of the fused tail per SM for a thread count and dynamic shared-memory size (registers included)
+// the opt-in shared-memory size of each k_tail_fused build only ever grows: the occupancy query and the launcher share it
+static size_t g_ft_attr[3] = { 0, 0, 0 };
+template <int NTV>
+static cudaError_t ft_ensure_smem(int slot, size_t smem_bytes) {
+    if (smem_bytes <= g_ft_attr[slot]) { return cudaSuccess; }
+    cudaError_t e = cudaFuncSetAttribute(k_tail_fused<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e == cudaSuccess) { g_ft_attr[slot] = smem_bytes; }
+    return e;
+}
 int tail_fused_ctas_per_sm(int threads, size_t smem_bytes) {
     int n = 0;
     cudaError_t e;
+    if ((int)smem_bytes > kernels_max_smem_optin()) { return 0; }
     if (threads == 512) {
-        cudaFuncSetAttribute(k_tail_fused<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_tail_fused<512>, 512, smem_bytes);
+        if ((e = ft_ensure_smem<512>(2, smem_bytes)) == cudaSuccess) { e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_tail_fused<512>, 512, smem_bytes); }
     }
     else if (threads == 256) {
-        cudaFuncSetAttribute(k_tail_fused<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_tail_fused<256>, 256, smem_bytes);
+        if ((e = ft_ensure_smem<256>(1, smem_bytes)) == cudaSuccess) { e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_tail_fused<256>, 256, smem_bytes); }
     }
     else {
-        cudaFuncSetAttribute(k_tail_fused<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_tail_fused<128>, 128, smem_bytes);
+        if ((e = ft_ensure_smem<128>(0, smem_bytes)) == cudaSuccess) { e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_tail_fused<128>, 128, smem_bytes); }
     }
     if (e != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
@@ -1064,14 +1081,10 @@ cudaError_t launch_tail_fused(const FtParams& p, int max_slabs, int threads, siz
     if (p.njobs <= 0 || max_slabs <= 0) { return cudaSuccess; }
     if ((int)smem_bytes > kernels_max_smem_optin()) { return cudaErrorInvalidValue; }
     dim3 grid(max_slabs, p.njobs);
-    static size_t attr[3] = { 0, 0, 0 };
 #define FT_LAUNCH(NTV, SLOT)                                                                                                   \
     do {                                                                                                                       \
-        if (smem_bytes > attr[SLOT]) {                                                                                         \
-            cudaError_t e = cudaFuncSetAttribute(k_tail_fused<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); \
-            if (e != cudaSuccess) { return e; }                                                                                \
-            attr[SLOT] = smem_bytes;                                                                                           \
-        }                                                                                                                      \
+        cudaError_t e = ft_ensure_smem<NTV>(SLOT, smem_bytes);                                                                 \
+        if (e != cudaSuccess) { return e; }                                                                                    \
         k_tail_fused<NTV><<<grid, NTV, smem_bytes, s>>>(p);                                                                    \
     } while (0)
     if (threads == 512) { FT_LAUNCH(512, 2); }
