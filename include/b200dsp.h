@@ -153,6 +153,14 @@ typedef struct {
      * below squelch_level dB is zeroed before it reaches the demodulator */
     int    squelch_on;
     double squelch_level;
+    /* the other two blocks of that IF chain, in the reference's order noise blanker -> squelch -> FM IF noise reduction:
+     * noise_reduction::NoiseBlanker (core/src/dsp/noise_reduction/noise_blanker.h:12-17,38-57) with the radio's rate
+     * 500 / out_samplerate (radio_module.h:526), and noise_reduction::FMIF (fm_if.h:20-24,44-77) with nr_bins bins
+     * (the radio's presets: 9, 15, 31, 32; radio_module.h:31-36; 2 ... 64 accepted) */
+    int    nb_on;
+    double nb_level;
+    int    nr_on;
+    int    nr_bins;
 } b200_vfo_cfg;
 
 typedef struct {
@@ -278,6 +286,9 @@ b200_block* b200_quad_create(double deviationHz, double samplerate);            
 b200_block* b200_wfm_create(double deviationHz, double samplerate, int stereo, int lowPass); /* demod::BroadcastFM (mono or stereo branch, broadcast_fm.h:144-212): complex -> stereo */
 b200_block* b200_nfm_create(double samplerate, double bandwidth, int lowPass);  /* demod::FM<stereo_t> */
 b200_block* b200_am_create(int agcMode, double bandwidth, double agcAttack, double agcDecay, double dcBlockRate, double samplerate); /* demod::AM<stereo_t> */
+b200_block* b200_noise_blanker_create(double rate, double level);                     /* noise_reduction::NoiseBlanker (noise_blanker.h:12-17): complex -> complex */
+int         b200_noise_blanker_set(b200_block* b, double rate, double level);         /* setRate / setLevel (noise_blanker.h:19-30): next chunk, the running amplitude is kept */
+b200_block* b200_fmif_create(int bins);                                              /* noise_reduction::FMIF (fm_if.h:20-24): complex -> complex */
 b200_block* b200_squelch_create(double level);                                       /* noise_reduction::PowerSquelch (power_squelch.h:33-50): complex -> complex */
 b200_block* b200_deemph_create(double tau, double samplerate);                       /* filter::Deemphasis<stereo_t> (deephasis.h:58-77): stereo -> stereo */
 b200_block* b200_ssb_create(int mode /*0 USB,1 LSB,2 DSB*/, double bandwidth, double samplerate, double agcAttack, double agcDecay); /* demod::SSB<stereo_t> */

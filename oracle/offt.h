@@ -32,8 +32,10 @@ typedef struct {
     offt_c* work; /* n scratch elements */
 } offt_plan;
 
+/* n a power of two: radix-4 / radix-2 Stockham passes.  Any other n (the 9 / 15 / 31-bin presets of the FM IF noise reduction,
+ * decoder_modules/radio/src/radio_module.h:31-36): the defining sum, out[k] = sum_j in[j] tw[(k j) mod n], j ascending. */
 static inline offt_plan* offt_create(int n) {
-    if (n < 1 || (n & (n - 1))) { return NULL; }
+    if (n < 1) { return NULL; }
     offt_plan* p = (offt_plan*)malloc(sizeof(offt_plan));
     p->n = n;
     p->tw = (offt_c*)malloc(sizeof(offt_c) * (size_t)n);
@@ -63,6 +65,20 @@ static inline offt_c offt_mul(offt_c a, offt_c b) {
 /* out may alias in.  Result in natural order. */
 static inline void offt_forward(const offt_plan* pl, const offt_c* in, offt_c* out) {
     const int N = pl->n;
+    if (N & (N - 1)) {
+        offt_c* y = pl->work;
+        for (int k = 0; k < N; k++) {
+            offt_c acc = { 0.0f, 0.0f };
+            for (int j = 0; j < N; j++) {
+                const offt_c pr = offt_mul(in[j], pl->tw[(int)(((long long)k * j) % N)]);
+                acc.re += pr.re;
+                acc.im += pr.im;
+            }
+            y[k] = acc;
+        }
+        memcpy(out, y, sizeof(offt_c) * (size_t)N);
+        return;
+    }
     if (in != out) { memcpy(out, in, sizeof(offt_c) * (size_t)N); }
     if (N == 1) { return; }
     offt_c* x = out;
@@ -110,6 +126,23 @@ static inline void offt_forward(const offt_plan* pl, const offt_c* in, offt_c* o
         offt_c* t = x; x = y; y = t;
     }
     if (x != out) { memcpy(out, x, sizeof(offt_c) * (size_t)N); }
+}
+
+/* Unnormalised inverse transform as the defining sum with conjugated twiddles, out[m] = sum_k in[k] conj(tw[(k m) mod n]),
+ * k ascending (any n; the one caller transforms a spectrum with a single non-zero bin, fm_if.h:62-66).  out must not alias in. */
+static inline void offt_backward(const offt_plan* pl, const offt_c* in, offt_c* out) {
+    const int N = pl->n;
+    for (int m = 0; m < N; m++) {
+        offt_c acc = { 0.0f, 0.0f };
+        for (int k = 0; k < N; k++) {
+            const offt_c w = pl->tw[(int)(((long long)k * m) % N)];
+            const offt_c cw = { w.re, -w.im };
+            const offt_c pr = offt_mul(in[k], cw);
+            acc.re += pr.re;
+            acc.im += pr.im;
+        }
+        out[m] = acc;
+    }
 }
 
 #ifdef __cplusplus

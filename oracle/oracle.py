@@ -116,6 +116,8 @@ class Oracle:
             "orc_ssb_create": (vp, [i, d, d, d, d]),
             "orc_dcblock_c_create": (vp, [d]),
             "orc_squelch_create": (vp, [d]),
+            "orc_nb_create": (vp, [d, d]),
+            "orc_fmif_create": (vp, [C.c_int]),
             "orc_deemph_create": (vp, [d, d]),
             "orc_process": (i, [vp, i, vp, vp]),
             "orc_reset": (None, [vp]),
@@ -250,6 +252,12 @@ class Oracle:
 
     def squelch(self, level):
         return Block(self.lib, self.lib.orc_squelch_create(level), 2, 2)
+
+    def noise_blanker(self, rate, level):
+        return Block(self.lib, self.lib.orc_nb_create(rate, level), 2, 2)
+
+    def fm_if(self, bins):
+        return Block(self.lib, self.lib.orc_fmif_create(bins), 2, 2)
 
     def deemph(self, tau, sr):
         return Block(self.lib, self.lib.orc_deemph_create(tau, sr), 2, 2)

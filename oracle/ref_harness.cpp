@@ -33,6 +33,8 @@
 #include <dsp/demod/ssb.h>
 #include <dsp/correction/dc_blocker.h>
 #include <dsp/noise_reduction/power_squelch.h>
+#include <dsp/noise_reduction/noise_blanker.h>
+#include <dsp/noise_reduction/fm_if.h>
 #include <dsp/compression/sample_stream_compressor.h>
 #include <dsp/compression/sample_stream_decompressor.h>
 #include <dsp/taps/low_pass.h>
@@ -175,6 +177,21 @@ namespace {
         noise_reduction::PowerSquelch b;
         SquelchNode(double level) { b.init(NULL, level); }
         int process(int count, const void* in, void* out) override { return b.process(count, (const complex_t*)in, (complex_t*)out); }
+    };
+
+    struct NbNode : Node {
+        noise_reduction::NoiseBlanker b;
+        Scratch<complex_t> s;
+        NbNode(double rate, double level) { b.init(NULL, rate, level); }
+        int process(int count, const void* in, void* out) override { return b.process(count, s.load(in, count), (complex_t*)out); }
+        void reset() override { b.reset(); }
+    };
+
+    struct FmIfNode : Node {
+        noise_reduction::FMIF b;
+        FmIfNode(int bins) { b.init(NULL, bins); }
+        int process(int count, const void* in, void* out) override { return b.process(count, (const complex_t*)in, (complex_t*)out); }
+        void reset() override { b.reset(); }
     };
 
     struct DeemphNode : Node {
@@ -333,6 +350,8 @@ void* orc_am_create(int agcMode, double bw, double att, double dec, double dcr, 
 void* orc_ssb_create(int mode, double bw, double sr, double att, double dec) { return new SsbNode(mode, bw, sr, att, dec); }
 void* orc_dcblock_c_create(double rate) { return new DcNode(rate); }
 void* orc_squelch_create(double level) { return new SquelchNode(level); }
+void* orc_nb_create(double rate, double level) { return new NbNode(rate, level); }
+void* orc_fmif_create(int bins) { return bins >= 2 ? new FmIfNode(bins) : nullptr; }
 void* orc_deemph_create(double tau, double sr) { return new DeemphNode(tau, sr); }
 
 int orc_process(void* h, int count, const void* in, void* out) { return ((Node*)h)->process(count, in, out); }

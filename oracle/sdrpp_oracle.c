@@ -1035,6 +1035,88 @@ void* orc_squelch_create(double level) {
     return n;
 }
 
+/* ---- noise_reduction::NoiseBlanker  (core/src/dsp/noise_reduction/noise_blanker.h:12-17,38-57): running mean amplitude
+ *      (amp starts at 1), samples more than `level` times above it are scaled back onto it ---- */
+typedef struct { node base; float rate, inv_rate, level, amp; } n_nb;
+static int n_nb_proc(node* b, int count, const void* in, void* out) {
+    n_nb* d = (n_nb*)b;
+    const cf32* x = (const cf32*)in;
+    cf32* y = (cf32*)out;
+    for (int i = 0; i < count; i++) {
+        float inAmp = sqrtf((x[i].re * x[i].re) + (x[i].im * x[i].im));      /* complex_t::amplitude (types.h:79-81) */
+        float gain = 1.0f;
+        if (inAmp != 0.0f) {
+            d->amp = (d->amp * d->inv_rate) + (inAmp * d->rate);
+            float excess = inAmp / d->amp;
+            if (excess > d->level) { gain = 1.0f / excess; }
+        }
+        y[i].re = x[i].re * gain;
+        y[i].im = x[i].im * gain;
+    }
+    return count;
+}
+static void n_nb_reset(node* b) { ((n_nb*)b)->amp = 1.0f; }
+void* orc_nb_create(double rate, double level) {
+    NODE_ALLOC(n_nb);
+    n->base.process = n_nb_proc; n->base.reset = n_nb_reset; n->base.destroy = n_plain_destroy;
+    n->rate = (float)rate;
+    n->inv_rate = 1.0f - n->rate;
+    n->level = (float)level;
+    n->amp = 1.0f;
+    return n;
+}
+
+/* ---- noise_reduction::FMIF  (core/src/dsp/noise_reduction/fm_if.h:44-77,95-123): per output sample a Nuttall-windowed
+ *      `bins`-point transform of the last `bins` samples, the strongest bin alone transformed back, element bins/2 kept ---- */
+typedef struct { node base; int bins; offt_plan* plan; cf32* buffer; size_t cap; float* win; offt_c* fin; offt_c* fout; offt_c* bin; offt_c* bout; float* ampbuf; } n_fmif;
+static int n_fmif_proc(node* b, int count, const void* in, void* out) {
+    n_fmif* d = (n_fmif*)b;
+    const int N = d->bins;
+    cf32* y = (cf32*)out;
+    if ((size_t)(N - 1 + count) > d->cap) {
+        d->cap = (size_t)(N - 1 + count) + 4096;
+        d->buffer = (cf32*)realloc(d->buffer, d->cap * sizeof(cf32));
+    }
+    memcpy(d->buffer + (N - 1), in, sizeof(cf32) * (size_t)count);
+    for (int i = 0; i < count; i++) {
+        ovk_mul_32fc_32f((ovk_cf32*)d->fin, (const ovk_cf32*)&d->buffer[i], d->win, (unsigned)N);
+        offt_forward(d->plan, d->fin, d->fout);
+        ovk_magnitude(d->ampbuf, (const ovk_cf32*)d->fout, (unsigned)N);
+        unsigned idx = ovk_index_max(d->ampbuf, (unsigned)N);
+        d->bin[idx] = d->fout[idx];
+        offt_backward(d->plan, d->bin, d->bout);
+        y[i].re = d->bout[N / 2].re;
+        y[i].im = d->bout[N / 2].im;
+        d->bin[idx].re = 0.0f; d->bin[idx].im = 0.0f;
+    }
+    memmove(d->buffer, d->buffer + count, sizeof(cf32) * (size_t)(N - 1));
+    return count;
+}
+static void n_fmif_reset(node* b) { n_fmif* d = (n_fmif*)b; memset(d->buffer, 0, sizeof(cf32) * (size_t)(d->bins - 1)); }
+static void n_fmif_destroy(node* b) {
+    n_fmif* d = (n_fmif*)b;
+    offt_destroy(d->plan);
+    free(d->buffer); free(d->win); free(d->fin); free(d->fout); free(d->bin); free(d->bout); free(d->ampbuf);
+    free(d);
+}
+void* orc_fmif_create(int bins) {
+    if (bins < 2) { return NULL; }
+    NODE_ALLOC(n_fmif);
+    n->base.process = n_fmif_proc; n->base.reset = n_fmif_reset; n->base.destroy = n_fmif_destroy;
+    n->bins = bins;
+    n->plan = offt_create(bins);
+    n->cap = (size_t)bins + 4096;
+    n->buffer = (cf32*)calloc(n->cap, sizeof(cf32));
+    n->win = (float*)malloc(sizeof(float) * (size_t)bins);
+    for (int i = 0; i < bins; i++) { n->win[i] = (float)win_nuttall(i, bins - 1); }       /* fm_if.h:116 */
+    n->fin = (offt_c*)calloc((size_t)bins, sizeof(offt_c));
+    n->fout = (offt_c*)calloc((size_t)bins, sizeof(offt_c));
+    n->bin = (offt_c*)calloc((size_t)bins, sizeof(offt_c));
+    n->bout = (offt_c*)calloc((size_t)bins, sizeof(offt_c));
+    n->ampbuf = (float*)calloc((size_t)bins, sizeof(float));
+    return n;
+}
+
 /* ---- filter::Deemphasis<stereo_t>  (core/src/dsp/filter/deephasis.h:14-28,58-77,91-94) ---- */
 typedef struct { node base; float alpha; float lastL, lastR; } n_de;
 static int n_de_proc(node* b, int count, const void* in, void* out) {

@@ -78,6 +78,8 @@ void* orc_am_create(int agcMode, double bandwidth, double agcAttack, double agcD
 void* orc_ssb_create(int mode, double bandwidth, double samplerate, double agcAttack, double agcDecay);
                                                                          /* SSB<stereo_t>; mode 0 USB 1 LSB 2 DSB */
 void* orc_dcblock_c_create(double rate);                                 /* correction::DCBlocker<complex_t> */
+void* orc_nb_create(double rate, double level);                            /* noise_reduction::NoiseBlanker */
+void* orc_fmif_create(int bins);                                           /* noise_reduction::FMIF */
 void* orc_squelch_create(double level);                                   /* noise_reduction::PowerSquelch */
 void* orc_deemph_create(double tau, double samplerate);                  /* filter::Deemphasis<stereo_t> */
 /* returns output sample count (samples of the block's output type) */

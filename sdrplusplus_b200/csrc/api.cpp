@@ -348,7 +348,10 @@ static int build_vfo_chain(b200_fe* fe, VfoSlot* v) {
     const b200_vfo_cfg& c = v->cfg;
     int rc = v->chain.add_rxvfo(fe->fs_eff, c.out_samplerate, c.bandwidth, c.offset);
     if (rc) { return rc; }
+    // radio IF chain (radio_module.h:94-96): noise blanker -> power squelch -> FM IF noise reduction
+    if (c.nb_on && (rc = v->chain.add_noise_blanker(500.0 / c.out_samplerate, c.nb_level))) { return rc; }
     if (c.squelch_on && (rc = v->chain.add_squelch(c.squelch_level))) { return rc; }
+    if (c.nr_on && (rc = v->chain.add_fmif(c.nr_bins))) { return rc; }
     switch (c.demod) {
     case B200_DEMOD_RAW: break;
     case B200_DEMOD_WFM: rc = v->chain.add_wfm(c.deviation, c.out_samplerate, c.low_pass != 0, false); break;
@@ -898,6 +901,8 @@ struct b200_block {
     double new_off_rad = 0, new_bw = 0;
     bool is_fir_c = false;
     std::vector<float> pend_taps;   // FIR::setTaps of a stand-alone complex-data filter
+    bool is_nb = false, pend_nb = false;
+    double new_nb_rate = 0, new_nb_level = 0;   // NoiseBlanker::setRate / setLevel: the running amplitude is kept
 };
 
 static b200_block* block_new() {
@@ -998,6 +1003,13 @@ extern "C" int b200_rxvfo_set_bandwidth(b200_block* b, double bw) {
 }
 // staged setter values -> stages; called by the worker at the top of process()
 static void block_apply_pending(b200_block* b) {
+    if (b->pend_nb) {
+        SeqStage* q = (SeqStage*)b->chain.st[0].get();
+        q->proto.nb_rate = (float)b->new_nb_rate;
+        q->proto.nb_inv_rate = 1.0f - q->proto.nb_rate;
+        q->proto.nb_level = (float)b->new_nb_level;
+        b->pend_nb = false;
+    }
     std::lock_guard<std::mutex> lck(b->mtx);
     if (b->pend_off) {
         ((XdStage*)b->chain.st[0].get())->set_offset_rad(b->new_off_rad);
@@ -1035,6 +1047,25 @@ extern "C" b200_block* b200_am_create(int agcMode, double bw, double att, double
     b200_block* b = block_new();
     if (!b) { return nullptr; }
     return block_finish(b, b->chain.add_am(agcMode, bw, att, dec, dcr, sr));
+}
+extern "C" b200_block* b200_noise_blanker_create(double rate, double level) {
+    b200_block* b = block_new();
+    if (!b) { return nullptr; }
+    b->is_nb = true;
+    b->new_nb_rate = rate; b->new_nb_level = level;
+    return block_finish(b, b->chain.add_noise_blanker(rate, level));
+}
+extern "C" int b200_noise_blanker_set(b200_block* b, double rate, double level) {
+    if (!b || !b->is_nb) { set_error("not a noise blanker block"); return B200_EINVAL; }
+    std::lock_guard<std::mutex> lck(b->mtx);
+    b->new_nb_rate = rate; b->new_nb_level = level;
+    b->pend_nb = true;
+    return 0;
+}
+extern "C" b200_block* b200_fmif_create(int bins) {
+    b200_block* b = block_new();
+    if (!b) { return nullptr; }
+    return block_finish(b, b->chain.add_fmif(bins));
 }
 extern "C" b200_block* b200_squelch_create(double level) {
     b200_block* b = block_new();

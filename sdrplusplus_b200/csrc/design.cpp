@@ -110,6 +110,20 @@ void pll_coefficients(double bandwidth, float& alpha, float& beta) {
 }
 
 // iq_frontend.cpp:281-291
+std::vector<float> fmif_window(int bins) {
+    std::vector<float> w((size_t)bins);
+    for (int i = 0; i < bins; i++) { w[i] = (float)nuttall(i, bins - 1); }
+    return w;
+}
+std::vector<float> dft_twiddles(int n) {
+    std::vector<float> t((size_t)2 * n);
+    for (int k = 0; k < n; k++) {
+        const double a = -2.0 * 3.14159265358979323846 * (double)k / (double)n;
+        t[2 * k] = (float)std::cos(a);
+        t[2 * k + 1] = (float)std::sin(a);
+    }
+    return t;
+}
 std::vector<float> fft_window(int window, int nz) {
     std::vector<float> w(nz);
     for (int i = 0; i < nz; i++) {

@@ -13,7 +13,9 @@ std::vector<float> lowpass_taps(double cutoff, double transWidth, double sampler
 std::vector<float> windowed_sinc_taps(int count, double omega);          // taps::windowedSinc<float> with window::nuttall
 std::vector<float> highpass_taps(double cutoff, double transWidth, double samplerate, bool odd = false);                 // taps::highPass
 std::vector<float> bandpass_c_taps(double bandStart, double bandStop, double transWidth, double samplerate, bool odd = false); // taps::bandPass<complex_t>, (re, im) pairs
-void pll_coefficients(double bandwidth, float& alpha, float& beta);      // PhaseControlLoop<float>::criticallyDamped
+void pll_coefficients(double bandwidth, float& alpha, float& beta);
+std::vector<float> fmif_window(int bins);                                // noise_reduction::FMIF::initBuffers: window::nuttall(i, bins - 1) (fm_if.h:116)
+std::vector<float> dft_twiddles(int n);                                  // exp(-2 pi i k / n) as (re, im) pairs, fp64 -> fp32      // PhaseControlLoop<float>::criticallyDamped
 std::vector<float> fft_window(int window, int nz);                       // IQFrontEnd::updateFFTPath window * (-1)^i
 void fft_frame_params(double samplerate, int size, double rate, int& nz, int& skip); // genReshapeParams
 

@@ -314,6 +314,33 @@ int SeqStage::configure_deemph(double tau, double samplerate) {
     return 0;
 }
 
+int SeqStage::configure_noise_blanker(double rate, double level) {
+    memset(&proto, 0, sizeof(proto));
+    proto.kind = 3;
+    proto.nb_rate = (float)rate;                        // noise_blanker.h:13-15: _rate, _invRate = 1.0f - _rate, _level are floats
+    proto.nb_inv_rate = 1.0f - proto.nb_rate;
+    proto.nb_level = (float)level;
+    in_es = 2;
+    out_es = 2;
+    memset(init_state, 0, sizeof(init_state));
+    init_state[7] = 1.0f;                               // amp = 1.0 (noise_blanker.h:74; reset() restores it)
+    int rc = state.alloc(sizeof(init_state));
+    if (rc) { return rc; }
+    B200_CK(cudaMemcpy(state.p, init_state, sizeof(init_state), cudaMemcpyHostToDevice));
+    return 0;
+}
+int FmIfStage::configure(int nbins) {
+    if (!fmif_supported(nbins)) { set_error("FM IF noise reduction: %d bins (supported: 2 ... %d)", nbins, 64); return B200_EINVAL; }
+    bins = nbins;
+    hist = bins - 1;
+    const std::vector<float> w = fmif_window(bins), t = dft_twiddles(bins);
+    int rc;
+    if ((rc = win.alloc(w.size() * sizeof(float), false)) || (rc = tw.alloc(t.size() * sizeof(float), false))) { return rc; }
+    B200_CK(cudaMemcpy(win.p, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    B200_CK(cudaMemcpy(tw.p, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
 // ------------------------------------------------------------------ Chain
 int Chain::finalize(int max_in, bool dbl_first, const FuseCfg* fuse) {
     if (st.empty()) { set_error("empty chain"); return B200_EINVAL; }
@@ -706,6 +733,20 @@ int Chain::add_af_chain(double afSR, double audioSR, bool highPass, double deemp
     return 0;
 }
 
+int Chain::add_noise_blanker(double rate, double level) {
+    auto s = std::make_unique<SeqStage>();
+    int rc = s->configure_noise_blanker(rate, level);
+    if (rc) { return rc; }
+    st.push_back(std::move(s));
+    return 0;
+}
+int Chain::add_fmif(int bins) {
+    auto s = std::make_unique<FmIfStage>();
+    int rc = s->configure(bins);
+    if (rc) { return rc; }
+    st.push_back(std::move(s));
+    return 0;
+}
 int Chain::add_squelch(double level) {
     auto q = std::make_unique<SquelchStage>();
     q->level = (float)level;
@@ -829,6 +870,7 @@ static inline int rec_tag(const SeqParams&) { return LaunchRec::T_SEQ; }
 static inline int rec_tag(const M2SParams&) { return LaunchRec::T_M2S; }
 static inline int rec_tag(const ScaleParams&) { return LaunchRec::T_SCALE; }
 static inline int rec_tag(const CarryParams&) { return LaunchRec::T_CARRY; }
+static inline int rec_tag(const FmIfParams&) { return LaunchRec::T_FMIF; }
 
 void LaunchRec::add(int tag, void* fn, const void* p, size_t size, int a, int b, size_t c) {
     const size_t off = (bytes.size() + 15) & ~(size_t)15;
@@ -865,6 +907,7 @@ int LaunchRec::replay(cudaStream_t s, long long* nlaunch) const {
         case T_M2S: e = launch_m2s(*(const M2SParams*)q, s); break;
         case T_SCALE: e = launch_scale(*(const ScaleParams*)q, s); break;
         case T_CARRY: e = launch_carry(*(const CarryParams*)q, s); break;
+        case T_FMIF: e = launch_fmif(*(const FmIfParams*)q, s); break;
         case T_STEREO: nl = 0; e = launch_stereo(*(const StParams*)q, s, &nl); break;
         case T_SQUELCH: nl = 0; e = launch_squelch(*(const SqParams*)q, s, &nl); break;
         case T_FUSED: e = launch_tail_fused(*(const FtParams*)q, it.a, it.b, it.c, s); break;
@@ -1321,6 +1364,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
         ScaleParams cp2; zero_params(cp2, use_rec);
         StParams stp; zero_params(stp, use_rec);
         SqParams sqp; zero_params(sqp, use_rec);
+        FmIfParams fmp; zero_params(fmp, use_rec);                  // one bin count per batch
         auto sq_flush = [&]() -> int {
             if (sqp.njobs == 0) { return 0; }
             int nl = 0;
@@ -1449,6 +1493,20 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
                 if (stp.njobs == B200_BATCH) { rc = st_flush(); }
                 break;
             }
+            case K_FMIF: {
+                FmIfStage* f = (FmIfStage*)s;
+                if (f->n_out <= 0) { break; }
+                if (fmp.njobs > 0 && fmp.job[0].bins != f->bins) {
+                    rc = flush_batch(fmp, launch_fmif, ts, launches); fmp.max_n = 0;
+                    if (rc) { break; }
+                }
+                FmIfJob& j = fmp.job[fmp.njobs++];
+                j.in = (const float2*)f->base(); j.out = (float2*)f->out_ptr; j.win = f->win.as<float>(); j.tw = f->tw.as<float2>();
+                j.n = f->n_out; j.bins = f->bins;
+                fmp.max_n = std::max(fmp.max_n, f->n_out);
+                if (fmp.njobs == B200_BATCH) { rc = flush_batch(fmp, launch_fmif, ts, launches); fmp.max_n = 0; }
+                break;
+            }
             case K_SQUELCH: {
                 SquelchStage* f = (SquelchStage*)s;
                 if (f->n_out <= 0) { break; }
@@ -1481,6 +1539,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
         if ((rc = flush_batch(sp, launch_seq, ts, launches))) { return rc; }
         if ((rc = flush_batch(mp, launch_m2s, ts, launches))) { return rc; }
         if ((rc = flush_batch(cp2, launch_scale, ts, launches))) { return rc; }
+        if ((rc = flush_batch(fmp, launch_fmif, ts, launches))) { return rc; }
         if ((rc = st_flush())) { return rc; }
         if ((rc = sq_flush())) { return rc; }
     }

@@ -41,7 +41,7 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
-enum StageKind { K_XD, K_FIRC, K_POLY, K_QUAD, K_FIRR, K_SEQ, K_M2S, K_SCALE, K_STEREO, K_SQUELCH };
+enum StageKind { K_XD, K_FIRC, K_POLY, K_QUAD, K_FIRR, K_SEQ, K_M2S, K_SCALE, K_STEREO, K_SQUELCH, K_FMIF };
 
 struct Stage {
     StageKind kind;
@@ -140,6 +140,7 @@ struct SeqStage : Stage {
     int configure_am(int agcMode, double attack, double decay, double dcRate);
     int configure_ssb(int mode, double bandwidth, double samplerate, double attack, double decay);
     int configure_deemph(double tau, double samplerate);
+    int configure_noise_blanker(double rate, double level);               // complex in, complex out
     int plan(int n) override { n_in = n; n_out = n; return n; }
     int max_out(int n) const override { return n; }
 };
@@ -184,6 +185,16 @@ struct SquelchStage : Stage {
     int max_out(int n) const override { return n; }
 };
 
+// noise_reduction::FMIF (fm_if.h:44-77): history = bins - 1 samples, one transform per output sample (ifnr.cuh)
+struct FmIfStage : Stage {
+    int bins = 32;
+    DevBuf win, tw;
+    FmIfStage() { kind = K_FMIF; in_es = 2; out_es = 2; }
+    int configure(int nbins);
+    int plan(int n) override { n_in = n; n_out = n; return n; }
+    int max_out(int n) const override { return n; }
+};
+
 struct ScaleStage : Stage {
     float gain = 1.0f;
     ScaleStage(int es, float g) { kind = K_SCALE; in_es = es; out_es = es; gain = g; }
@@ -224,6 +235,8 @@ struct Chain {
     int add_deemph(double tau, double samplerate);                          // filter::Deemphasis<stereo_t> (deephasis.h:14-28)
     // radio AF chain: RationalResampler<stereo_t> -> [300 Hz high-pass FIR] -> [Deemphasis]  (radio_module.h:99-110,546-553)
     int add_af_chain(double afSamplerate, double audioSamplerate, bool highPass, double deemphTau);
+    int add_noise_blanker(double rate, double level);                       // noise_reduction::NoiseBlanker (noise_blanker.h:12-17)
+    int add_fmif(int bins);                                                 // noise_reduction::FMIF (fm_if.h:20-24)
     int add_squelch(double level);                                          // noise_reduction::PowerSquelch (power_squelch.h:16-20)
     int add_volume(double volume, bool muted);                              // dsp::audio::Volume (volume.h:13-17,39-42)
 };
@@ -233,7 +246,7 @@ struct Chain {
 // seven to ten kernel launches).  Decimation offsets / resampler phases / buffer parities make the list periodic over a few
 // chunks for any fixed chunk size, so a handful of graphs covers a stream.
 struct LaunchRec {
-    enum Tag { T_DFR = 1, T_FIR, T_POLY, T_FIRR, T_QUAD, T_SEQ, T_M2S, T_SCALE, T_STEREO, T_SQUELCH, T_FUSED, T_CARRY };
+    enum Tag { T_DFR = 1, T_FIR, T_POLY, T_FIRR, T_QUAD, T_SEQ, T_M2S, T_SCALE, T_STEREO, T_SQUELCH, T_FUSED, T_CARRY, T_FMIF };
     struct Item { int tag; void* fn; size_t off, size; int a, b; size_t c; };
     std::vector<Item> items;
     std::vector<unsigned char> bytes;

@@ -266,6 +266,24 @@ __global__ void k_seq(const __grid_constant__ SeqParams p) {
         return;
     }
     if (threadIdx.x != 0) { return; }
+    if (J.kind == 3) {
+        // ---- NoiseBlanker: running mean amplitude, samples `level` times above it scaled back  (noise_blanker.h:38-57) ----
+        float amp = J.state[7];
+        float2* y = reinterpret_cast<float2*>(J.out);
+        for (int i = 0; i < n; i++) {
+            const float2 x = J.in[i];
+            const float inAmp = camp(x);
+            float gain = 1.0f;
+            if (inAmp != 0.0f) {
+                amp = __fadd_rn(__fmul_rn(amp, J.nb_inv_rate), __fmul_rn(inAmp, J.nb_rate));
+                const float excess = __fdiv_rn(inAmp, amp);
+                if (excess > J.nb_level) { gain = __fdiv_rn(1.0f, excess); }
+            }
+            y[i] = make_float2(__fmul_rn(x.x, gain), __fmul_rn(x.y, gain));
+        }
+        J.state[7] = amp;
+        return;
+    }
     AgcCoef c = { J.set_point, J.attack, J.inv_attack, J.decay, J.inv_decay, J.max_gain, J.max_out };
     float* st = J.state;
     if (J.kind == 0) {
@@ -647,6 +665,7 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 #include "chanpfb.cuh"
+#include "ifnr.cuh"
 #include "tails_reg.cuh"
 
 

@@ -216,15 +216,29 @@ struct SeqJob {
     float* out;             // n mono floats
     float* state;           // device state block (see kernels.cu: SEQ_STATE_*)
     int n;
-    int kind;               // 0 AM, 1 SSB, 2 stereo deemphasis (in/out are (l,r) pairs; threads 0/1 take one channel each)
+    int kind;               // 0 AM, 1 SSB, 2 stereo deemphasis (in/out are (l,r) pairs; threads 0/1 take one channel each),
+                            // 3 noise blanker (complex in, complex out)
     int agc_mode;           // AM: 0 carrier, 1 audio
     float set_point, attack, inv_attack, decay, inv_decay, max_gain, max_out; // loop::AGC (agc.h:13-24)
     float dc_rate;          // AM
     float delta_re, delta_im; // SSB second rotator phaseDelta (ssb.h:29, frequency_xlator.h:17)
     float alpha;            // deemphasis: dt / (tau + dt)  (deephasis.h:91-94)
+    float nb_rate, nb_inv_rate, nb_level;   // noise_reduction::NoiseBlanker (noise_blanker.h:12-17)
 };
 struct SeqParams { int njobs; SeqJob job[B200_BATCH]; };
-#define SEQ_STATE_FLOATS 8   // [0] carrier amp [1] audio amp [2] dc offset [3] rot re [4] rot im [5] deemph last l [6] last r
+#define SEQ_STATE_FLOATS 8   // [0] carrier amp [1] audio amp [2] dc offset [3] rot re [4] rot im [5] deemph last l [6] last r [7] blanker amp
+
+// ---- FM IF noise reduction (ifnr.cuh): noise_reduction::FMIF (fm_if.h:44-77) ----
+struct FmIfJob {
+    const float2* in;       // [hist | data], hist = bins - 1
+    float2* out;
+    const float* win;       // window::nuttall(i, bins - 1)
+    const float2* tw;       // exp(-2 pi i k / bins), k < bins
+    int n, bins;
+};
+struct FmIfParams { int njobs; int max_n; FmIfJob job[B200_BATCH]; };
+cudaError_t launch_fmif(const FmIfParams& p, cudaStream_t s);          // every job: the same bin count
+bool fmif_supported(int bins);
 
 // ---- stereo branch of BroadcastFM behind the discriminator (stereo.cuh) ----
 struct StJob {

@@ -33,6 +33,18 @@ class VfoConfig:
     af_volume: float = 1.0
     squelch_on: bool = False         # noise_reduction::PowerSquelch in front of the demodulator (radio IF chain)
     squelch_level: float = -50.0
+    nb_on: bool = False              # noise_reduction::NoiseBlanker in front of the squelch (rate 500 / out_samplerate)
+    nb_level: float = 10.0
+    nr_on: bool = False              # noise_reduction::FMIF behind the squelch
+    nr_bins: int = 32
+
+    def with_noise_blanker(self, level):
+        self.nb_on, self.nb_level = True, level
+        return self
+
+    def with_if_nr(self, bins=32):
+        self.nr_on, self.nr_bins = True, bins
+        return self
 
     def with_volume(self, volume, muted=False):
         self.af_volume_on, self.af_volume, self.af_muted = True, volume, muted
@@ -78,7 +90,8 @@ class VfoConfig:
         return L.VfoCfg(self.offset, self.out_samplerate, self.bandwidth, self.demod, self.deviation, int(self.low_pass),
                         self.agc_mode, self.agc_attack, self.agc_decay, self.dc_block_rate, self.af_samplerate,
                         int(self.af_high_pass), self.af_deemph_tau, int(self.af_volume_on), int(self.af_muted), float(self.af_volume),
-                        int(self.squelch_on), float(self.squelch_level))
+                        int(self.squelch_on), float(self.squelch_level), int(self.nb_on), float(self.nb_level),
+                        int(self.nr_on), int(self.nr_bins))
 
 
 _NP_FMT = {L.FMT_CF32: (np.complex64, 1), L.FMT_CS16: (np.int16, 2), L.FMT_CS8: (np.int8, 2)}
@@ -298,6 +311,14 @@ class Block:
     @staticmethod
     def squelch(level):
         return Block(L.load().b200_squelch_create(level), 2, 2)
+
+    @staticmethod
+    def noise_blanker(rate, level):
+        return Block(L.load().b200_noise_blanker_create(rate, level), 2, 2)
+
+    @staticmethod
+    def fm_if(bins):
+        return Block(L.load().b200_fmif_create(bins), 2, 2)
 
     def set_offset(self, *a):
         if len(a) == 2:

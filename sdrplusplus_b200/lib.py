@@ -27,7 +27,8 @@ class VfoCfg(C.Structure):
                 ("deviation", C.c_double), ("low_pass", C.c_int), ("agc_mode", C.c_int), ("agc_attack", C.c_double),
                 ("agc_decay", C.c_double), ("dc_block_rate", C.c_double), ("af_samplerate", C.c_double),
                 ("af_high_pass", C.c_int), ("af_deemph_tau", C.c_double), ("af_volume_on", C.c_int), ("af_muted", C.c_int),
-                ("af_volume", C.c_double), ("squelch_on", C.c_int), ("squelch_level", C.c_double)]
+                ("af_volume", C.c_double), ("squelch_on", C.c_int), ("squelch_level", C.c_double),
+                ("nb_on", C.c_int), ("nb_level", C.c_double), ("nr_on", C.c_int), ("nr_bins", C.c_int)]
 
 
 class Outputs(C.Structure):
@@ -101,6 +102,9 @@ SIGNATURES = {
     "b200_am_create": (_vp, [_i, _d, _d, _d, _d, _d]),
     "b200_ssb_create": (_vp, [_i, _d, _d, _d, _d]),
     "b200_squelch_create": (_vp, [_d]),
+    "b200_noise_blanker_create": (_vp, [_d, _d]),
+    "b200_fmif_create": (_vp, [_i]),
+    "b200_noise_blanker_set": (_i, [_vp, _d, _d]),
     "b200_deemph_create": (_vp, [_d, _d]),
     "b200_block_process": (_i, [_vp, _i, _vp, _vp]),
     "b200_block_max_out": (_i, [_vp, _i]),

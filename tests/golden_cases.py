@@ -92,6 +92,17 @@ def run_cases(R):
     g["wfm_stereo_tail"] = a[-512:]
     g["wfm_stereo_digest"] = digest(a)
     g["squelch_digest"] = digest(R.squelch(-27.0).process_chunks((ws * np.linspace(0.02, 0.2, ws.size).astype(np.float32)).astype(np.complex64).view(np.float32), 1250))
+    # IF chain of the radio module: noise blanker (impulses on top of the FM signal), FM IF noise reduction (32 and 15 bins)
+    imp = ws[:30000].copy()
+    imp[::997] *= np.float32(12.0)
+    a = R.noise_blanker(500.0 / 250e3, 3.0).process_chunks(imp.view(np.float32), 1250)
+    g["noise_blanker_tail"] = a[-256:]
+    g["noise_blanker_digest"] = digest(a)
+    wn = (ws[:30000] + noise_iq(30000, 9, 0.2)).astype(np.complex64)
+    a = R.fm_if(32).process_chunks(wn.view(np.float32), 1250)
+    g["fm_if32_tail"] = a[-256:]
+    g["fm_if32_digest"] = digest(a)
+    g["fm_if15_digest"] = digest(R.fm_if(15).process_chunks(wn.view(np.float32), 999))
     # radio AF chain behind WFM: 250 k -> 48 k stereo resampler, 300 Hz high-pass, 50 us deemphasis
     w = R.wfm(75e3, 250e3).process_chunks(vfo, 1250)
     af = R.resamp_stereo(250e3, 48e3).process_chunks(w, 1250)

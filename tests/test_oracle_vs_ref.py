@@ -36,6 +36,9 @@ def test_blocks_bit_identical(oracle, ref_oracle, seed):
         (lambda o: o.deemph(50e-6, 48e3), 480), (lambda o: o.resamp_stereo(250e3, 48e3), 1250),
         (lambda o: o.wfm(75e3, 250e3, True, True), 1250), (lambda o: o.wfm(75e3, 250e3, True, False), 777),      # stereo branch: pilot PLL
         (lambda o: o.squelch(-20.0), 1250), (lambda o: o.squelch(-60.0), 999),
+        # IF chain of the radio module (radio_module.h:90-96): noise blanker, FM IF noise reduction at its four presets
+        (lambda o: o.noise_blanker(500.0 / 24000.0, 2.0), 1250), (lambda o: o.noise_blanker(500.0 / 250e3, 1.2), 999),
+        (lambda o: o.fm_if(32), 1250), (lambda o: o.fm_if(9), 999), (lambda o: o.fm_if(15), 1250), (lambda o: o.fm_if(31), 640),
     ]
     for f, ch in mk2:
         assert _same(f(R).process_chunks(y, ch), f(S).process_chunks(y, ch))

@@ -99,10 +99,34 @@ def run(csz, nchunks, opts, timers, host=False):
     return r
 
 
+def h2d_probe():
+    """cudaMemcpyAsync of one chunk's worth of pinned int16 IQ, back to back: what the copy engine gives small transfers."""
+    out = {}
+    for nbytes in (2 << 20, 4 << 20, 8 << 20, 64 << 20):
+        h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        d.copy_(h, non_blocking=True); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            d.copy_(h, non_blocking=True)
+        e1.record(); torch.cuda.synchronize()
+        out[str(nbytes)] = {"us_per_copy": e0.elapsed_time(e1) * 1e3 / 50, "GB_per_s": 50 * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9}
+    return out
+
+
 def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "--one":           # one configuration, for ncu's launch list
+        L = lib.load()
+        assert L.b200_init(0) == 0
+        print(json.dumps(run(int(sys.argv[2]), 100, {"graph": 0}, False, False)))
+        return
+    from bench import bind_to_gpu_numa
+    numa = bind_to_gpu_numa(0)
     L = lib.load()
     assert L.b200_init(0) == 0
-    res = []
+    res = [{"numa": numa, "h2d_probe": h2d_probe()}]
+    print(json.dumps(res[0]), file=sys.stderr)
     for csz, n in ((500000, 800), (1000000, 600), (1 << 21, 300)):
         for host in (False, True):
             for opts in ({"graph": 0, "host_direct": 0}, {"graph": 0}, {}, {"ft_regall": 0}, {"ft_regall": 0, "ft_prereg": 0}):

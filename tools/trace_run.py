@@ -7,8 +7,8 @@ from sdrplusplus_b200 import lib
 import bench
 torch.cuda.set_device(0)
 L = lib.load(); lib.check(L.b200_init(0))
-chunk = 1 << 24
 opts = dict(a.split("=") for a in sys.argv[1:])
+chunk = int(opts.pop("chunk", 1 << 24))
 nofft = int(opts.pop("nofft", 0))
 host = int(opts.pop("host", 0))
 nsteps = int(opts.pop("steps", 8))
