@@ -345,7 +345,8 @@ def run_b200(args):
 
     chunk = args.chunk
     nbuf = 3
-    stream = torch.cuda.Stream()
+    # stage 1 runs on this stream: between the chain behind it (highest priority, csrc/api.cpp) and the spectrum branch (lowest)
+    stream = torch.cuda.Stream(priority=args.main_prio)
     with torch.cuda.stream(stream):
         offsets = OFFSETS if args.offsets == "sym" else [5e6, -7e6, 15e6, -17e6, 25e6, -27e6, 35e6, -37e6]
         fe = sb.FrontEnd(FS, chunk)
@@ -704,6 +705,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="diagnostic: only the int16 end-to-end leg")
     ap.add_argument("--c4", type=int, default=1, help="1 = also time BASELINE config 4 (one 1.024 GS/s stream, 64 VFOs sharded over the GPUs with an NCCL broadcast) and report it under 'c4'")
     ap.add_argument("--c3", type=int, default=1, help="1 = also time BASELINE config 3 (256-channel polyphase filter-bank channelizer) on rank 0 and report it under 'c3'")
+    ap.add_argument("--main-prio", type=int, default=-1, help="CUDA priority of the stream stage 1 runs on (0 = lowest; the library's own streams: B200_STREAM_PRIO)")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region (diagnostic)")
     args = ap.parse_args()
     if args.warmup < 3:

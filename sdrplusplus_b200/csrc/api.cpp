@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 
 using namespace b200;
@@ -189,6 +190,7 @@ struct b200_fe {
     cudaEvent_t ev_h2d[2] = { nullptr, nullptr }, ev_compute[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
     bool slot_used[2] = { false, false };
     unsigned long long nsub = 0, nwait = 0;
+    int fft_serial = 0;                      // 1: stage 1 of a chunk starts when the spectrum branch of that chunk is done
     int host_direct = -1;                    // pinned host outputs written by the kernels themselves: -1 small chunks, 0 never, 1 always
     long long host_ns[4] = { 0, 0, 0, 0 };   // host time of submit(): [0] checks + plans, [1] spectrum branch, [2] Scheduler::run, [3] join + outputs
     float scale16 = 1.0f / 32768.0f, scale8 = 1.0f / 128.0f;
@@ -227,10 +229,20 @@ extern "C" b200_fe* b200_fe_create(double samplerate, int max_chunk) {
     fe->fs_eff = samplerate;
     fe->max_chunk = max_chunk;
     fe->max_eff = max_chunk;
-    bool ok = cudaStreamCreateWithFlags(&fe->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+    // Stream priorities decide whose thread blocks the SMs take first when several kernels wait for room.  The chain behind
+    // stage 1 is a sequence of short dependent launches and sets the pace of a step: it goes first; the spectrum branch (a few
+    // frames per chunk, nobody waits for it before the outputs) goes last.  B200_STREAM_PRIO="tail,main,fft" (0 = lowest)
+    // overrides the order for experiments.
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);                     // lo: numerically largest = least urgent
+    int pt = 2, pm = 1, pf = 0;
+    if (const char* e = getenv("B200_STREAM_PRIO")) { sscanf(e, "%d,%d,%d", &pt, &pm, &pf); }
+    if (const char* e = getenv("B200_FFT_SERIAL")) { fe->fft_serial = atoi(e); }
+    auto prio = [&](int level) { int p = lo - level; return p < hi ? hi : p; };
+    bool ok = cudaStreamCreateWithPriority(&fe->own_stream, cudaStreamNonBlocking, prio(pm)) == cudaSuccess &&
               cudaStreamCreateWithFlags(&fe->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&fe->fft_stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&fe->tail_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&fe->fft_stream, cudaStreamNonBlocking, prio(pf)) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&fe->tail_stream, cudaStreamNonBlocking, prio(pt)) == cudaSuccess &&
               cudaStreamCreateWithFlags(&fe->join_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&fe->ev_lines_free, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&fe->ev_fft_go, cudaEventDisableTiming) == cudaSuccess &&
@@ -496,6 +508,7 @@ extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
     }
     if (!strcmp(key, "fft")) { kernels_set_fft_variant(value); return 0; }
     if (!strcmp(key, "host_direct")) { fe->host_direct = value; return 0; }
+    if (!strcmp(key, "fft_serial")) { fe->fft_serial = value; return 0; }
     if (!strcmp(key, "graph")) { fe->sch.graph_tails = value; if (value == 0) { fe->sch.drop_graphs(); } return 0; }
     if (!strcmp(key, "graph_max_count")) { fe->sch.graph_max_count = value; return 0; }
     if (!strcmp(key, "time_s1")) { fe->sch.time_s1 = value != 0; for (auto& t : fe->sch.timers) { t.used = 0; } return 0; }
@@ -647,6 +660,9 @@ static int fe_fft_chunk(b200_fe* fe, const void* dptr, int fmt, int count, int* 
         trace_mark("fft done", s);
         B200_CK(cudaEventRecord(fe->ev_fft_done, s));
         fe->fft_join_pending = true;     // joined by the caller after the VFO branch has been enqueued
+        // stage 1 of this chunk behind its spectrum branch: the two read the same chunk and, run side by side, slow each other
+        // down by more than running one after the other costs; the chain behind stage 1 (its own stream) fills the SMs beside them
+        if (fe->fft_serial && s != main_s) { B200_CK(cudaStreamWaitEvent(main_s, fe->ev_fft_done, 0)); }
     }
     fe->pos = end;
     return 0;
