@@ -238,6 +238,7 @@ extern "C" b200_fe* b200_fe_create(double samplerate, int max_chunk) {
     int pt = 2, pm = 1, pf = 0;
     if (const char* e = getenv("B200_STREAM_PRIO")) { sscanf(e, "%d,%d,%d", &pt, &pm, &pf); }
     if (const char* e = getenv("B200_FFT_SERIAL")) { fe->fft_serial = atoi(e); }
+    if (const char* e = getenv("B200_FFT_CTA")) { kernels_set_fft_cta(atoi(e)); }
     auto prio = [&](int level) { int p = lo - level; return p < hi ? hi : p; };
     bool ok = cudaStreamCreateWithPriority(&fe->own_stream, cudaStreamNonBlocking, prio(pm)) == cudaSuccess &&
               cudaStreamCreateWithFlags(&fe->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -494,6 +495,7 @@ extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
     if (!strcmp(key, "s1_mt")) { kernels_set_xd_tile(value); return 0; }
     if (!strcmp(key, "s1_cps")) { kernels_set_xd_cps(value); return 0; }
     if (!strcmp(key, "s1_stages")) { kernels_set_xd_tma_stages(value); return 0; }
+    if (!strcmp(key, "s1_ctas")) { kernels_set_xd_tma_ctas(value); return 0; }
     if (!strcmp(key, "tails") || !strncmp(key, "ft_", 3)) {
         // 0: one thread per output; 1: shared-memory tiled kernels, one launch per stage; 2: one fused launch per <= 16 VFOs
         if (b200_fe_vfo_count(fe) > 0) { set_error("'%s' must be chosen before VFOs are added", key); return B200_ESTATE; }
@@ -507,10 +509,12 @@ extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
         if (!strcmp(key, "ft_regall")) { fe->sch.fuse.reg_all = value != 0; return 0; }
     }
     if (!strcmp(key, "fft")) { kernels_set_fft_variant(value); return 0; }
+    if (!strcmp(key, "fft_cta")) { kernels_set_fft_cta(value); return 0; }
     if (!strcmp(key, "host_direct")) { fe->host_direct = value; return 0; }
     if (!strcmp(key, "fft_serial")) { fe->fft_serial = value; return 0; }
     if (!strcmp(key, "graph")) { fe->sch.graph_tails = value; if (value == 0) { fe->sch.drop_graphs(); } return 0; }
     if (!strcmp(key, "graph_max_count")) { fe->sch.graph_max_count = value; return 0; }
+    if (!strcmp(key, "tail_split")) { fe->sch.tail_split = value; fe->sch.drop_graphs(); return 0; }
     if (!strcmp(key, "time_s1")) { fe->sch.time_s1 = value != 0; for (auto& t : fe->sch.timers) { t.used = 0; } return 0; }
     set_error("unknown option %s", key);
     return B200_EINVAL;
@@ -775,7 +779,7 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
     const bool direct = (out->out_mem == B200_MEM_DEVICE);
     // host outputs of a small chunk: the last kernel of a VFO stores straight into the caller's pinned buffer (a few KB over
     // PCIe) when that buffer came from b200_host_alloc; large chunks keep the copy engine
-    const bool host_direct = !direct && fe->host_direct != 0 && (fe->host_direct > 0 || count <= fe->sch.graph_max_count);
+    const bool host_direct = !direct && fe->host_direct != 0 && (fe->host_direct > 0 || count <= (1 << 22));
     std::vector<char> vdirect(chains.size(), direct ? 1 : 0);
     for (size_t k = 0; k < chains.size(); k++) {
         if (host_direct && host_buffer_is_ours(out->vfo_out[ids[k]], (size_t)out->vfo_cap[ids[k]] * chains[k]->out_es * sizeof(float))) { vdirect[k] = 1; }

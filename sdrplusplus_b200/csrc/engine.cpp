@@ -768,6 +768,9 @@ int Scheduler::init_raw() {
 }
 Scheduler::~Scheduler() {
     drop_graphs();
+    if (tail_stream2) { cudaStreamSynchronize(tail_stream2); cudaStreamDestroy(tail_stream2); }
+    if (rec.ev_fork) { cudaEventDestroy(rec.ev_fork); }
+    if (rec.ev_join) { cudaEventDestroy(rec.ev_join); }
     for (Timer& t : timers) { for (cudaEvent_t e : t.ev) { cudaEventDestroy(e); } }
 }
 cudaEvent_t Scheduler::timer_begin(int group, cudaStream_t s) {
@@ -876,14 +879,14 @@ void LaunchRec::add(int tag, void* fn, const void* p, size_t size, int a, int b,
     const size_t off = (bytes.size() + 15) & ~(size_t)15;
     bytes.resize(off + size, 0);
     memcpy(bytes.data() + off, p, size);
-    items.push_back(Item{ tag, fn, off, size, a, b, c });
+    items.push_back(Item{ tag, fn, off, size, a, b, c, cur_branch });
 }
 unsigned long long LaunchRec::hash() const {
     // 64-bit multiply-xorshift over the parameter bytes and the launch arguments
     unsigned long long h = 0x9E3779B97F4A7C15ULL ^ (unsigned long long)items.size();
     auto mix = [&](unsigned long long v) { h ^= v; h *= 0xD6E8FEB86659FD93ULL; h ^= h >> 32; };
     for (const Item& it : items) {
-        mix((unsigned long long)it.tag); mix((unsigned long long)(uintptr_t)it.fn); mix((unsigned long long)it.size);
+        mix((unsigned long long)it.tag | ((unsigned long long)it.branch << 32)); mix((unsigned long long)(uintptr_t)it.fn); mix((unsigned long long)it.size);
         mix((unsigned long long)(unsigned)it.a | ((unsigned long long)(unsigned)it.b << 32)); mix((unsigned long long)it.c);
     }
     const size_t n8 = bytes.size() / 8;
@@ -892,8 +895,17 @@ unsigned long long LaunchRec::hash() const {
     for (size_t i = n8 * 8; i < bytes.size(); i++) { mix(b[i]); }
     return h;
 }
-int LaunchRec::replay(cudaStream_t s, long long* nlaunch) const {
+int LaunchRec::replay(cudaStream_t s0, long long* nlaunch) const {
+    // branch 1 (if any) forks from s0 before anything of this list runs and joins it at the end
+    bool two = false;
+    for (const Item& it : items) { two = two || it.branch != 0; }
+    if (two) {
+        if (!aux || !ev_fork || !ev_join) { set_error("launch list: no second stream"); return B200_ESTATE; }
+        B200_CK(cudaEventRecord(ev_fork, s0));
+        B200_CK(cudaStreamWaitEvent(aux, ev_fork, 0));
+    }
     for (const Item& it : items) {
+        cudaStream_t s = it.branch ? aux : s0;
         const void* q = bytes.data() + it.off;
         cudaError_t e = cudaSuccess;
         int nl = 1;
@@ -915,6 +927,10 @@ int LaunchRec::replay(cudaStream_t s, long long* nlaunch) const {
         }
         if (e != cudaSuccess) { return cuda_fail(e, "kernel launch (tail list)"); }
         if (nlaunch) { *nlaunch += nl; }
+    }
+    if (two) {
+        B200_CK(cudaEventRecord(ev_join, aux));
+        B200_CK(cudaStreamWaitEvent(s0, ev_join, 0));
     }
     return 0;
 }
@@ -940,6 +956,15 @@ static int flush_batch(P& p, L launch, cudaStream_t s, long long& launches) {
 
 int Scheduler::enable_overlap(cudaStream_t tail) {
     tail_stream = tail;
+    if (tail && !tail_stream2) {
+        int lo = 0, hi = 0, pr = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamGetPriority(tail, &pr) != cudaSuccess) { pr = hi; }
+        B200_CK(cudaStreamCreateWithPriority(&tail_stream2, cudaStreamNonBlocking, pr));
+        B200_CK(cudaEventCreateWithFlags(&rec.ev_fork, cudaEventDisableTiming));
+        B200_CK(cudaEventCreateWithFlags(&rec.ev_join, cudaEventDisableTiming));
+        rec.aux = tail_stream2;
+    }
     for (int i = 0; i < 2; i++) {
         if (!ev_stage1[i]) { B200_CK(cudaEventCreateWithFlags(&ev_stage1[i], cudaEventDisableTiming)); }
         if (!ev_tail[i]) { B200_CK(cudaEventCreateWithFlags(&ev_tail[i], cudaEventDisableTiming)); }
@@ -971,8 +996,9 @@ template <class P>
 static inline void zero_params(P& p, bool) { memset(&p, 0, sizeof(P)); }
 
 // the recorded launch list of this chunk: first sight -> plain launches; second sight -> capture into a graph; then replay
-int Scheduler::launch_recorded(cudaStream_t ts) {
+int Scheduler::launch_recorded(cudaStream_t ts, bool may_graph) {
     if (rec.items.empty()) { return 0; }
+    if (!may_graph) { return rec.replay(ts, &launches); }
     const unsigned long long h = rec.hash();
     auto it = graphs.find(h);
     if (it != graphs.end() && it->second.key.size() == rec.bytes.size() && memcmp(it->second.key.data(), rec.bytes.data(), rec.bytes.size()) == 0) {
@@ -1185,10 +1211,16 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
     const long long hp1 = host_now_ns();
     host_ns[0] += hp1 - hp0;
     cudaEvent_t t_tail = timer_begin(1, ts);
-    // small chunks: record the launches of this section, replay a captured graph when the same list was seen before
-    const bool use_rec = graph_tails > 0 || (graph_tails < 0 && count <= graph_max_count);
+    // The launches of this section are recorded, then replayed: as a captured CUDA graph when the same list was seen before
+    // (one cudaGraphLaunch instead of seven to ten launches), and in `tail_split` independent branches -- the chains of the
+    // first and of the second half of the VFOs on two streams -- because every kernel here is latency-bound at a fraction
+    // of the machine: two half-size chains side by side finish well before one full-size chain.
+    const int nsplit = (tail_split > 1 && tail_stream && tail_stream2 && chains.size() >= 4) ? 2 : 1;
+    const bool use_rec = nsplit > 1 || graph_tails > 0 || (graph_tails < 0 && count <= graph_max_count);
     if (use_rec) { rec.clear(); }
     RecScope rec_scope(use_rec ? &rec : nullptr);
+    std::vector<Chain*>& all_chains = chains;
+    auto tail_section = [&](std::vector<Chain*>& chains) -> int {
     // ---- short decimating FIRs with the window in registers (k_dfir_reg): one launch per level and plan stage ----
     DfrParams dfr;
     memset(&dfr, 0, sizeof(dfr));
@@ -1566,9 +1598,26 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
     }
     int rcf = flush_batch(cp, launch_carry, ts, launches);
     if (rcf) { return rcf; }
+    return 0;
+    };    // tail_section
+    if (nsplit == 1) {
+        rec.cur_branch = 0;
+        int rcs = tail_section(all_chains);
+        if (rcs) { return rcs; }
+    }
+    else {
+        const size_t half = (all_chains.size() + 1) / 2;
+        std::vector<Chain*> ga(all_chains.begin(), all_chains.begin() + half), gb(all_chains.begin() + half, all_chains.end());
+        rec.cur_branch = 0;
+        int rcs = tail_section(ga);
+        if (rcs) { return rcs; }
+        rec.cur_branch = 1;
+        if ((rcs = tail_section(gb))) { return rcs; }
+        rec.cur_branch = 0;
+    }
     if (use_rec) {
         g_rec = nullptr;
-        int rcg = launch_recorded(ts);
+        int rcg = launch_recorded(ts, graph_tails > 0 || (graph_tails < 0 && count <= graph_max_count));
         if (rcg) { return rcg; }
     }
     if (t_tail) { B200_CK(cudaEventRecord(t_tail, ts)); }

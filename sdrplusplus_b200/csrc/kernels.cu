@@ -639,6 +639,10 @@ __global__ void __launch_bounds__(256) k_zoom_hold(const float* __restrict__ lin
 static int g_smem_optin = -1;
 static int g_fft_variant = 1;     // 1: register-resident four-step passes where they apply; 0: shared-memory radix-8 passes
 void kernels_set_fft_variant(int v) { g_fft_variant = v; }
+int g_xd_tma_ctas = 0;            // persistent CTAs of the TMA stage 1 (0 = one per SM)
+void kernels_set_xd_tma_ctas(int v) { g_xd_tma_ctas = v; }
+static int g_fft_cta = 8;         // column / row transforms per CTA of the register-resident passes: 8 or 4
+void kernels_set_fft_cta(int v) { g_fft_cta = (v == 4) ? 4 : 8; }
 int kernels_max_smem_optin() {
     if (g_smem_optin < 0) {
         int dev = 0, v = 0;
@@ -867,7 +871,9 @@ static cudaError_t launch_xd_tma_n(const XdParams& p, const XtGeom& g, const CUt
         if (e != cudaSuccess) { return e; }
         attr_set = true;
     }
+    // one persistent CTA per SM, or fewer (kernels_set_xd_tma_ctas): the SMs left out are free for the kernels of the other streams
     int grid = num_sms();
+    if (g_xd_tma_ctas > 0 && g_xd_tma_ctas < grid) { grid = g_xd_tma_ctas; }
     if (grid > g.ntiles) { grid = g.ntiles; }
     k_xd_tma<LOGD, QC, PS, MT, NST><<<grid, (Lay::NW + 1) * 32, smem, s>>>(p, g, tm);
     g_xd_tma_launches++;
@@ -1171,32 +1177,36 @@ static cudaError_t launch_fft_fmt(const FftPlanDev& pl, const void* src, float2*
     // two passes
     if (g_fft_variant >= 1 && !out_raw && pl.tw_fine && pl.logN1 >= 8 && pl.logN1 <= 10 && pl.logN2 >= 8 && pl.logN2 <= 10) {
         // register-resident column / row transforms (fft_reg.cuh)
-        constexpr int CC = 8, RR = 8;
-#define FR_P1(RA, RB)                                                                                          \
+        // transforms per CTA: 8 (256 threads, 69 KB) or 4 (128 threads, 34 KB: at 128 registers a thread, a CTA of four still
+        // fits on an SM beside stage 1's persistent CTA AND a CTA of the chain behind it -- kernels_set_fft_cta)
+#define FR_P1(RA, RB, CC)                                                                                      \
         do {                                                                                                   \
             const size_t sm = (size_t)CC * FrGeom<RA, RB>::pitch * sizeof(float2);                             \
-            if (g_fft_variant >= 2) {                                                                          \
-                e = set_smem(k_fftr_p1<FMT, RA, RB, CC, 3>, sm);                                               \
-                if (e != cudaSuccess) { return e; }                                                            \
-                k_fftr_p1<FMT, RA, RB, CC, 3><<<dim3(pl.N2 / CC, nbatch), CC * FrGeom<RA, RB>::TP, sm, s>>>(pl, src, work, src_stride_bytes); \
-            }                                                                                                  \
-            else {                                                                                             \
-                e = set_smem(k_fftr_p1<FMT, RA, RB, CC, 2>, sm);                                               \
-                if (e != cudaSuccess) { return e; }                                                            \
-                k_fftr_p1<FMT, RA, RB, CC, 2><<<dim3(pl.N2 / CC, nbatch), CC * FrGeom<RA, RB>::TP, sm, s>>>(pl, src, work, src_stride_bytes); \
-            }                                                                                                  \
+            e = set_smem(k_fftr_p1<FMT, RA, RB, CC, 2>, sm);                                                   \
+            if (e != cudaSuccess) { return e; }                                                                \
+            k_fftr_p1<FMT, RA, RB, CC, 2><<<dim3(pl.N2 / CC, nbatch), CC * FrGeom<RA, RB>::TP, sm, s>>>(pl, src, work, src_stride_bytes); \
         } while (0)
-#define FR_P2(RA, RB)                                                                                          \
+#define FR_P2(RA, RB, RR)                                                                                      \
         do {                                                                                                   \
             const size_t sm = (size_t)RR * FrGeom<RA, RB>::pitch * sizeof(float2);                             \
             e = set_smem(k_fftr_p2<RA, RB, RR>, sm);                                                           \
             if (e != cudaSuccess) { return e; }                                                                \
             k_fftr_p2<RA, RB, RR><<<dim3(pl.N1 / RR, nbatch), RR * FrGeom<RA, RB>::TP, sm, s>>>(pl, work, out_db); \
         } while (0)
-        if (pl.logN1 == 10) { FR_P1(32, 32); } else if (pl.logN1 == 9) { FR_P1(16, 32); } else { FR_P1(16, 16); }
+        if (g_fft_cta == 4) {
+            if (pl.logN1 == 10) { FR_P1(32, 32, 4); } else if (pl.logN1 == 9) { FR_P1(16, 32, 4); } else { FR_P1(16, 16, 4); }
+        }
+        else {
+            if (pl.logN1 == 10) { FR_P1(32, 32, 8); } else if (pl.logN1 == 9) { FR_P1(16, 32, 8); } else { FR_P1(16, 16, 8); }
+        }
         e = cudaGetLastError();
         if (e != cudaSuccess) { return e; }
-        if (pl.logN2 == 10) { FR_P2(32, 32); } else if (pl.logN2 == 9) { FR_P2(16, 32); } else { FR_P2(16, 16); }
+        if (g_fft_cta == 4) {
+            if (pl.logN2 == 10) { FR_P2(32, 32, 4); } else if (pl.logN2 == 9) { FR_P2(16, 32, 4); } else { FR_P2(16, 16, 4); }
+        }
+        else {
+            if (pl.logN2 == 10) { FR_P2(32, 32, 8); } else if (pl.logN2 == 9) { FR_P2(16, 32, 8); } else { FR_P2(16, 16, 8); }
+        }
 #undef FR_P1
 #undef FR_P2
         if (nlaunch) { (*nlaunch) += 2; }

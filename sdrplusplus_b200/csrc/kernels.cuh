@@ -346,6 +346,8 @@ cudaError_t launch_zoom_hold_tbl(const float* line, const int* start, const int*
 int kernels_max_smem_optin();
 void kernels_set_tail_variant(int v);
 void kernels_set_fft_variant(int v);
+void kernels_set_xd_tma_ctas(int v);      // persistent CTAs of the TMA stage 1 (0 = one per SM)
+void kernels_set_fft_cta(int v);          // transforms per CTA of the register FFT passes (8 or 4)
 void kernels_set_xd_tile(int mt);     // 0 = automatic
 void kernels_set_xd_tma_stages(int n);   // ring depth of the TMA stage 1 (2 or 3)
 void kernels_set_xd_cps(int v);       // cap on stage-1 CTAs per SM, 0 = automatic

@@ -46,9 +46,16 @@ __device__ __forceinline__ void xt_mbar_arrive(unsigned bar) {
 __device__ __forceinline__ void xt_mbar_expect(unsigned bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void xt_tma_2d(unsigned dst, const CUtensorMap* tm, unsigned bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
-                 ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+// The raw chunk is read once and never again by this kernel: its lines are marked evict-first in L2, so that streaming 128 MiB
+// through does not push out what the kernels of the other streams come back for (stage outputs, FFT work buffers).
+__device__ __forceinline__ unsigned long long xt_policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void xt_tma_2d(unsigned dst, const CUtensorMap* tm, unsigned bar, int c0, int c1, unsigned long long pol) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;\n"
+                 ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(tm)), "r"(bar), "r"(c0), "r"(c1), "l"(pol) : "memory");
 }
 
 template <int LOGD, int QC, int MT>
@@ -109,6 +116,7 @@ k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, c
     if (warp == NW) {
         // ---------------- producer ----------------
         if (lane == 0) {
+            const unsigned long long pol = xt_policy_evict_first();
             int it = 0;
             for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, it++) {
                 const int st = it % XT_STAGES;
@@ -125,7 +133,7 @@ k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, c
                 for (int sg = 0; sg < NSEG; sg++) {
 #pragma unroll
                     for (int par = 0; par < 2; par++) {
-                        xt_tma_2d(dst + (unsigned)((sg * 2 + par) * REGION), &tm, full, par * 2 * D + sg * 32, row0);
+                        xt_tma_2d(dst + (unsigned)((sg * 2 + par) * REGION), &tm, full, par * 2 * D + sg * 32, row0, pol);
                     }
                 }
             }

@@ -17,10 +17,12 @@ EXE = os.path.join(ROOT, "build", "test_adapter")
 def test_adapter_headers_compile():
     """CPU-side: the adapter headers are self-contained C++17 and only need include/b200dsp.h."""
     host = os.path.join(ROOT, "sdrplusplus_b200", "host")
-    for h in ("dsp/stream.h", "dsp/block.h", "dsp/channel/rx_vfo.h", "dsp/demod/broadcast_fm.h", "dsp/b200/frontend.h"):
+    headers = sorted(os.path.relpath(os.path.join(d, f), host) for d, _, fs in os.walk(os.path.join(host, "dsp")) for f in fs if f.endswith(".h"))
+    assert len(headers) >= 33
+    for h in headers:                                   # every header of the mirrored tree, each on its own
         r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", host, "-x", "c++", os.path.join(host, h)],
                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-        assert r.returncode == 0, r.stdout
+        assert r.returncode == 0, (h, r.stdout)
 
 
 @pytest.mark.gpu

@@ -1,12 +1,12 @@
 #!/bin/bash
-# stream experiment: device-resident value of the bench workload under different stream priorities (tail,main,fft : main
-# stream priority of the bench) and with stage 1 serialised behind the spectrum branch
+# occupancy experiment: device-resident value of the bench workload with fewer persistent stage-1 CTAs (SMs left free for the
+# kernels of the other streams), tail split on / off
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-for cfg in "2,1,0:-1:0" "2,1,0:-1:1" "2,0,0:0:1" "0,0,0:0:1" "2,1,1:-1:1"; do
-    IFS=: read pr mp fs <<< "$cfg"
-    B200_FFT_SERIAL="$fs" B200_STREAM_PRIO="$pr" timeout 300 python bench.py --quick --steps 6 --warmup 3 --no-cpu --c3 0 --c4 0 --main-prio "$mp" > gpurun_out/prio_tmp.json 2> gpurun_out/prio_tmp.err
-    python - "$pr" "$mp" "$fs" <<'PY'
+for cfg in "0:1" "132:1" "120:1" "104:1" "120:2" "104:2" "88:2"; do
+    IFS=: read ctas sp <<< "$cfg"
+    timeout 300 python bench.py --quick --steps 8 --warmup 4 --no-cpu --c3 0 --c4 0 --ft tail_split=$sp,s1_ctas=$ctas > gpurun_out/prio_tmp.json 2> gpurun_out/prio_tmp.err
+    python - "$ctas" "$sp" <<'PY'
 import json,sys
 try:
     d=json.loads(open('gpurun_out/prio_tmp.json').read().strip().splitlines()[-1])
