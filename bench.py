@@ -573,6 +573,42 @@ def run_b200(args):
                     sweep[str(csz)] = {"value": csz * nchunks / (e0.elapsed_time(e1) * 1e-3) / 1e6, "unit": "MS/s", "chunks": nchunks,
                                        "us_per_chunk": e0.elapsed_time(e1) * 1e3 / nchunks}
                     fe3.close()
+                    # the same chunk size end to end: int16 IQ in pinned host memory -> H2D -> kernels -> audio and dB lines
+                    # in pinned host memory, four chunks in flight (the copy engine fed a few chunks ahead)
+                    fe4 = sb.FrontEnd(FS, csz)
+                    fe4.set_option("inflight", 4)
+                    fe4.set_fft(FFT_SIZE, FFT_RATE, lib.WIN_NUTTALL)
+                    ids4 = [fe4.add_vfo(sb.VfoConfig.wfm(o)) for o in offsets]
+                    o4, keep4 = [], []
+                    for _ in range(4):
+                        oo = lib.Outputs()
+                        for v in ids4:
+                            c4s = fe4.vfo_max_out(v, csz)
+                            t4 = Pinned(8 * c4s); keep4.append(t4); oo.vfo_out[v] = t4.data_ptr(); oo.vfo_cap[v] = c4s
+                        nl4 = max(1, fe4.fft_max_lines(csz))
+                        t4 = Pinned(4 * nl4 * FFT_SIZE); keep4.append(t4); oo.fft_out = t4.data_ptr(); oo.fft_cap_lines = nl4; oo.out_mem = lib.MEM_HOST
+                        o4.append(oo)
+                    hin = Pinned(64 << 20)
+                    hin.array(np.int16)[:] = (np.random.default_rng(7).standard_normal((64 << 20) // 2) * 3000).astype(np.int16)
+                    hslots = (64 << 20) // (4 * csz)
+
+                    def run4(n):
+                        infl = 0
+                        for i in range(n):
+                            fe4.submit_ptr(hin.data_ptr() + (i % hslots) * csz * 4, csz, lib.FMT_CS16, lib.MEM_HOST, o4[i % 4])
+                            infl += 1
+                            if infl == 4:
+                                fe4.wait(); infl -= 1
+                        while infl:
+                            fe4.wait(); infl -= 1
+                    run4(40)
+                    t0 = time.perf_counter(); run4(nchunks); wall4 = time.perf_counter() - t0
+                    sweep[str(csz)]["e2e_int16"] = {"value": csz * nchunks / wall4 / 1e6, "unit": "MS/s", "us_per_chunk": wall4 * 1e6 / nchunks,
+                                                    "inflight": 4, "timing": "wall clock around the pipelined submit/wait loop (H2D, kernels, outputs in pinned host memory)"}
+                    fe4.close()
+                    hin.free()
+                    for t4 in keep4:
+                        t4.free()
                 except Exception as ex:              # noqa: BLE001
                     sweep[str(csz)] = {"value": None, "error": repr(ex)}
         numa_all = [numa]
@@ -644,7 +680,7 @@ def run_b200(args):
                    "pipelining": "b200_fe_submit/wait, 2 chunks in flight", "s1_variant": args.s1, "tails_variant": args.tails,
                    "vfo_offsets_hz": offsets, "conjugate_pair_sharing": bool(args.pair) and args.offsets == "sym",
                    "tails_overlap_next_chunk": bool(args.overlap),
-                   "chunk_sweep": sweep, "chunk_sweep_note": "device-resident MS/s of the same graph at the reference's own chunk sizes (STREAM_BUFFER_SIZE caps a chunk at 1e6 samples, core/src/dsp/stream.h:9)"},
+                   "chunk_sweep": sweep, "chunk_sweep_note": "the same graph at the reference's own chunk sizes (STREAM_BUFFER_SIZE caps a chunk at 1e6 samples, core/src/dsp/stream.h:9): device-resident MS/s, and end to end from int16 IQ in pinned host memory"},
         "e2e": dict(e2e["cs16"], format="cs16", cf32=e2e["cf32"], cs8=e2e["cs8"], pcie_probe=probe, numa=numa, numa_per_rank=numa_all,
                     host_buffers="b200_host_alloc (cudaHostAlloc)"),
         "gpu_launches": int(launches),

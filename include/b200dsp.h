@@ -211,13 +211,16 @@ int b200_fe_reset(b200_fe* fe);
 int b200_fe_process(b200_fe* fe, const void* iq, int count, int in_fmt, int in_mem, b200_outputs* out);
 /* Pipelined pair: submit() enqueues chunk k (H2D on a side stream + kernels + D2H) and returns
  * immediately; wait() blocks until the OLDEST submitted chunk's outputs are complete and fills its
- * counts.  Up to 2 chunks in flight.  Values are identical to b200_fe_process; only timing changes. */
+ * counts.  Up to 2 chunks in flight (option "inflight": up to 4 -- each needs its own b200_outputs buffers).  Values are
+ * identical to b200_fe_process; only timing changes. */
 int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt, int in_mem, b200_outputs* out);
 int b200_fe_wait(b200_fe* fe);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 long long b200_fe_launch_count(b200_fe* fe);
 /* counters by name: "launches", "chunks", "s1_tma_launches" (stage-1 launches of this process that ran the TMA-fed
- * filter-bank kernel); -1 for an unknown key */
+ * filter-bank kernel), "graphs" / "graph_hits" / "graph_misses" (launch lists captured / replayed / launched plainly),
+ * "host_ns_plan" / "host_ns_fft" / "host_ns_run" / "host_ns_join" / "host_ns_stage1" / "host_ns_tail" (host time spent inside
+ * b200_fe_submit since creation, by section, in ns); -1 for an unknown key */
 long long b200_fe_stat(b200_fe* fe, const char* key);
 /* Tuning / A-B switches (defaults are the fast paths; every variant is held to the same parity tests):
  *  "s1"      stage-1 kernel: 8 (default) filter-bank form fed by the TMA engine (cf32 chunks, VFO offsets on a common
@@ -230,7 +233,15 @@ long long b200_fe_stat(b200_fe* fe, const char* key);
  *            the fused launch k_tail_fused, tuned by "ft_threads", "ft_obmax", "ft_ob", "ft_smem_kb", "ft_direct");
  *            1 = one tiled kernel per stage, 0 = one thread per output.  Before VFOs are added.
  *  "overlap" 1 = tails of chunk k overlap stage 1 of chunk k+1 on a second stream (default).  Before VFOs are added.
- *  "fft"     1 = register-resident four-step passes (default), 0 = shared-memory radix-8 passes; "fft_async" 1 = own stream
+ *  "fft"     1 = register-resident four-step passes (default), 0 = shared-memory radix-8 passes; "fft_async" 1 = own stream;
+ *            "fft_cta" 8 (default) or 4 transforms per CTA; "fft_serial" 1 = stage 1 of a chunk waits for its spectrum branch
+ *  "graph"   -1 (default) / 1: the launches behind stage 1 of a chunk are recorded; a chunk whose list was seen before
+ *            replays a captured CUDA graph (decimation offsets, resampler phases and buffer parities repeat after a few
+ *            chunks of any fixed size); 0 = plain launches.  "tail_split" 2 = two independent branches (halves of the VFOs)
+ *  "host_direct" -1 (default): VFO outputs in b200_host_alloc buffers are stored by the kernels themselves for chunks up to
+ *            4 Mi samples (no copy to enqueue), 1 always, 0 never (copy engine)
+ *  "inflight" chunks between b200_fe_submit and b200_fe_wait: 2 (default) ... 4
+ *  "s1_ctas" persistent CTAs of the TMA stage 1 (0 = one per SM)
  *  "time_s1" 1 = bracket the launch groups of every chunk with CUDA events (b200_fe_s1_stats / b200_fe_group_stats) */
 int b200_fe_set_option(b200_fe* fe, const char* key, int value);
 /* device time spent in the stage-1 (translate + first decimation) launches since the last call, and their count;

@@ -163,12 +163,16 @@ struct VfoSlot {
     double new_offset = 0, new_bw = 0;
 };
 
+// input slots / event sets of a front end: a chunk uses slot (index % FE_SLOTS); up to FE_SLOTS chunks may be between submit and
+// wait (default two, option "inflight": small chunks over PCIe want the copy engine fed a few chunks ahead)
+#define FE_SLOTS 4
+
 struct b200_fe {
     double fs = 0;
     int max_chunk = 0;
     Scheduler sch;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr, fft_stream = nullptr, tail_stream = nullptr, join_stream = nullptr;
-    cudaEvent_t ev_tail_done[2] = { nullptr, nullptr };
+    cudaEvent_t ev_tail_done[FE_SLOTS] = {};
     cudaEvent_t ev_fft_go = nullptr, ev_fft_done = nullptr, ev_lines_free = nullptr;
     bool overlap = true;         // tails of chunk k on their own stream, overlapping stage 1 of chunk k+1
     bool lines_busy = false;
@@ -177,7 +181,7 @@ struct b200_fe {
     bool fft_join_pending = false;
     std::vector<std::unique_ptr<VfoSlot>> vfos;
     std::mutex mtx;
-    DevBuf in_dev[2];
+    DevBuf in_dev[FE_SLOTS];
     // FFT branch
     bool fft_on = false;
     FftCore fft;
@@ -187,8 +191,9 @@ struct b200_fe {
     int max_lines = 0;
     unsigned long long pos = 0, fstart = 0;
     // pipelining
-    cudaEvent_t ev_h2d[2] = { nullptr, nullptr }, ev_compute[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
-    bool slot_used[2] = { false, false };
+    cudaEvent_t ev_h2d[FE_SLOTS] = {}, ev_compute[FE_SLOTS] = {}, ev_out[FE_SLOTS] = {};
+    bool slot_used[FE_SLOTS] = {};
+    int max_inflight = 2;                    // chunks between submit and wait (option "inflight", up to FE_SLOTS)
     unsigned long long nsub = 0, nwait = 0;
     int fft_serial = 0;                      // 1: stage 1 of a chunk starts when the spectrum branch of that chunk is done
     int host_direct = -1;                    // pinned host outputs written by the kernels themselves: -1 small chunks, 0 never, 1 always
@@ -200,7 +205,7 @@ struct b200_fe {
     bool dc_block = false, invert_iq = false;
     Chain pre;                   // the decimator (typed cf32 chain), built when decim > 1
     Scheduler sch_pre;
-    DevBuf pp[2];                // chunk after DC blocker / conjugate (one per chunk in flight)
+    DevBuf pp[FE_SLOTS];         // chunk after DC blocker / conjugate (one per chunk in flight)
     DevBuf dc_state, dc_segA, dc_segB;
     int max_eff = 0;             // largest chunk behind the decimator
 };
@@ -248,7 +253,7 @@ extern "C" b200_fe* b200_fe_create(double samplerate, int max_chunk) {
               cudaEventCreateWithFlags(&fe->ev_lines_free, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&fe->ev_fft_go, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&fe->ev_fft_done, cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 0; i < 2 && ok; i++) {
+    for (int i = 0; i < FE_SLOTS && ok; i++) {
         ok = cudaEventCreateWithFlags(&fe->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&fe->ev_compute[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&fe->ev_tail_done[i], cudaEventDisableTiming) == cudaSuccess &&
@@ -275,7 +280,7 @@ extern "C" b200_fe* b200_fe_create(double samplerate, int max_chunk) {
 extern "C" void b200_fe_destroy(b200_fe* fe) {
     if (!fe) { return; }
     cudaDeviceSynchronize();
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < FE_SLOTS; i++) {
         if (fe->ev_h2d[i]) { cudaEventDestroy(fe->ev_h2d[i]); }
         if (fe->ev_compute[i]) { cudaEventDestroy(fe->ev_compute[i]); }
         if (fe->ev_tail_done[i]) { cudaEventDestroy(fe->ev_tail_done[i]); }
@@ -511,6 +516,11 @@ extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
     if (!strcmp(key, "fft")) { kernels_set_fft_variant(value); return 0; }
     if (!strcmp(key, "fft_cta")) { kernels_set_fft_cta(value); return 0; }
     if (!strcmp(key, "host_direct")) { fe->host_direct = value; return 0; }
+    if (!strcmp(key, "inflight")) {
+        if (value < 1 || value > FE_SLOTS) { set_error("inflight: 1 ... %d", FE_SLOTS); return B200_EINVAL; }
+        fe->max_inflight = value;
+        return 0;
+    }
     if (!strcmp(key, "fft_serial")) { fe->fft_serial = value; return 0; }
     if (!strcmp(key, "graph")) { fe->sch.graph_tails = value; if (value == 0) { fe->sch.drop_graphs(); } return 0; }
     if (!strcmp(key, "graph_max_count")) { fe->sch.graph_max_count = value; return 0; }
@@ -676,11 +686,11 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
     if (!fe || !out || (count > 0 && !iq)) { set_error("null argument"); return B200_EINVAL; }
     if (count < 0 || count > fe->max_chunk) { set_error("count %d exceeds max_chunk %d", count, fe->max_chunk); return B200_ECAP; }
     if (in_fmt < 0 || in_fmt > 2) { set_error("bad input format"); return B200_EINVAL; }
-    if (fe->nsub - fe->nwait >= 2) { set_error("two chunks already in flight: call b200_fe_wait"); return B200_ESTATE; }
+    if (fe->nsub - fe->nwait >= (unsigned long long)fe->max_inflight) { set_error("%d chunks already in flight: call b200_fe_wait", fe->max_inflight); return B200_ESTATE; }
     std::lock_guard<std::mutex> lck(fe->mtx);
     const long long hp0 = host_clock_ns();
     apply_pending(fe);
-    const int slot = (int)(fe->nsub & 1);
+    const int slot = (int)(fe->nsub % FE_SLOTS);
     cudaStream_t s = fe->sch.stream;
     const size_t in_bytes = (size_t)count * bytes_per_sample(in_fmt);
     // ---- capacity checks against the exact counts, before anything is enqueued and before any state moves ----
@@ -795,7 +805,7 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
     const long long hp2 = host_clock_ns();
     fe->sch.in_scale = fe_ingest_scale(fe, in_fmt);
     // host-side outputs leave through per-VFO device buffers that the copies of the previous chunk may still be reading
-    if (!direct && fe->nsub > 0) { B200_CK(cudaStreamWaitEvent(fe->sch.out_stream(), fe->ev_out[slot ^ 1], 0)); }
+    if (!direct && fe->nsub > 0) { B200_CK(cudaStreamWaitEvent(fe->sch.out_stream(), fe->ev_out[(slot + FE_SLOTS - 1) % FE_SLOTS], 0)); }
     if ((rc = fe->sch.run(chains, dptr, in_fmt, count, true))) { return rc; }
     const long long hp3 = host_clock_ns();
     // join on a stream of its own: the VFO branch (tail stream) and the spectrum branch (its stream) of this chunk meet
@@ -837,7 +847,7 @@ extern "C" int b200_fe_submit(b200_fe* fe, const void* iq, int count, int in_fmt
 extern "C" int b200_fe_wait(b200_fe* fe) {
     if (!fe) { set_error("null fe"); return B200_EINVAL; }
     if (fe->nwait >= fe->nsub) { set_error("nothing in flight"); return B200_ESTATE; }
-    const int slot = (int)(fe->nwait & 1);
+    const int slot = (int)(fe->nwait % FE_SLOTS);
     B200_CK(cudaEventSynchronize(fe->ev_out[slot]));
     fe->nwait++;
     if (trace_on() && fe->nwait == fe->nsub && fe->nsub >= 8) { trace_dump("chunks in flight drained"); }
@@ -1344,8 +1354,8 @@ struct b200_shard {
     int rank = 0, world = 1;
     NcclComm comm = nullptr;
     cudaStream_t comm_stream = nullptr;
-    DevBuf buf[2];                       // the raw chunk on this rank (root: staged host input or the caller's device chunk)
-    cudaEvent_t ev_bcast[2] = { nullptr, nullptr }, ev_src[2] = { nullptr, nullptr };
+    DevBuf buf[FE_SLOTS];                // the raw chunk on this rank (root: staged host input or the caller's device chunk)
+    cudaEvent_t ev_bcast[FE_SLOTS] = {}, ev_src[FE_SLOTS] = {};
     unsigned long long nsub = 0;
     long long bytes_broadcast = 0;
 };
@@ -1364,7 +1374,7 @@ extern "C" void b200_shard_destroy(b200_shard* sh) {
     if (!sh) { return; }
     cudaDeviceSynchronize();
     if (sh->comm) { nccl().CommDestroy(sh->comm); }
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < FE_SLOTS; i++) {
         if (sh->ev_bcast[i]) { cudaEventDestroy(sh->ev_bcast[i]); }
         if (sh->ev_src[i]) { cudaEventDestroy(sh->ev_src[i]); }
     }
@@ -1378,7 +1388,7 @@ extern "C" b200_shard* b200_shard_create(b200_fe* fe, int rank, int world, const
     b200_shard* sh = new b200_shard;
     sh->fe = fe; sh->rank = rank; sh->world = world;
     bool ok = cudaStreamCreateWithFlags(&sh->comm_stream, cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; i < 2 && ok; i++) {
+    for (int i = 0; i < FE_SLOTS && ok; i++) {
         ok = cudaEventCreateWithFlags(&sh->ev_bcast[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&sh->ev_src[i], cudaEventDisableTiming) == cudaSuccess;
     }
@@ -1404,7 +1414,7 @@ extern "C" int b200_shard_submit(b200_shard* sh, const void* iq, int count, int 
         if (!rc1) { sh->nsub++; }
         return rc1;
     }
-    const int slot = (int)(fe->nsub & 1);                   // the front end's own input slot of this chunk
+    const int slot = (int)(fe->nsub % FE_SLOTS);            // the front end's own input slot of this chunk
     const size_t bytes = (size_t)count * bytes_per_sample(in_fmt);
     cudaStream_t cs = sh->comm_stream, ms = fe->sch.stream;
     if (sh->buf[slot].bytes < bytes) {

@@ -16,7 +16,7 @@ FS, FFT_SIZE, FFT_RATE = 100e6, 1 << 20, 20.0
 OFFS = [-35e6, -25e6, -15e6, -5e6, 5e6, 15e6, 25e6, 35e6]
 
 
-def run(csz, nchunks, opts, timers, host=False):
+def run(csz, nchunks, opts, timers, host=False, depth=2):
     import ctypes as C
     import numpy as np
     L = lib.load()
@@ -24,10 +24,11 @@ def run(csz, nchunks, opts, timers, host=False):
     fe = sb.FrontEnd(FS, csz)
     for k, v in opts.items():
         fe.set_option(k, v)
+    fe.set_option("inflight", depth)
     fe.set_fft(FFT_SIZE, FFT_RATE, lib.WIN_NUTTALL)
     ids = [fe.add_vfo(sb.VfoConfig.wfm(o)) for o in OFFS]
     outs, keep = [], []
-    for _ in range(2):
+    for _ in range(depth):
         oo = lib.Outputs()
         nl = max(1, fe.fft_max_lines(csz))
         if host:
@@ -60,11 +61,11 @@ def run(csz, nchunks, opts, timers, host=False):
         infl, hs, hw = 0, 0.0, 0.0
         for i in range(n):
             t0 = time.perf_counter()
-            fe.submit_ptr(base + (i % nslots) * step, csz, fmt, mem, outs[i % 2])
+            fe.submit_ptr(base + (i % nslots) * step, csz, fmt, mem, outs[i % depth])
             t1 = time.perf_counter()
             hs += t1 - t0
             infl += 1
-            if infl == 2:
+            if infl == depth:
                 fe.wait(); infl -= 1
                 hw += time.perf_counter() - t1
         while infl:
@@ -80,7 +81,7 @@ def run(csz, nchunks, opts, timers, host=False):
     e0.record(); hs, hw = loop(nchunks); e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / nchunks
-    r = {"chunk": csz, "opts": opts, "mem": "host int16" if host else "device cf32", "graph_hits": fe.stat("graph_hits"), "graphs": fe.stat("graphs"), "us_per_chunk": us, "GS_per_s": csz / us / 1e3, "launches_per_chunk": (fe.launch_count() - l0) / nchunks,
+    r = {"chunk": csz, "opts": opts, "inflight": depth, "mem": "host int16" if host else "device cf32", "graph_hits": fe.stat("graph_hits"), "graphs": fe.stat("graphs"), "us_per_chunk": us, "GS_per_s": csz / us / 1e3, "launches_per_chunk": (fe.launch_count() - l0) / nchunks,
          "host_submit_us": hs * 1e6 / nchunks, "host_wait_us": hw * 1e6 / nchunks,
          "host_sections_us": {k[8:]: (fe.stat(k) - h0[k]) / 1e3 / nchunks for k in keys}}
     if timers:
@@ -129,10 +130,10 @@ def main():
     print(json.dumps(res[0]), file=sys.stderr)
     for csz, n in ((500000, 800), (1000000, 600), (1 << 21, 300)):
         for host in (False, True):
-            for opts in ({"graph": 0, "host_direct": 0}, {"graph": 0}, {}, {"ft_regall": 0}, {"ft_regall": 0, "ft_prereg": 0}):
-                for timers in (False, True) if not opts and not host else (False,):
+            for opts, depth in (({"graph": 0, "host_direct": 0}, 2), ({}, 2), ({}, 3), ({}, 4)):
+                for timers in (False,):
                     try:
-                        res.append(dict(run(csz, n, opts, timers, host), timers=timers))
+                        res.append(dict(run(csz, n, opts, timers, host, depth), timers=timers))
                     except Exception as ex:      # noqa: BLE001
                         res.append({"chunk": csz, "opts": opts, "error": repr(ex)})
                     print(json.dumps(res[-1]), file=sys.stderr)
