@@ -348,7 +348,9 @@ int b200_pcm_packet_info(const void* packet, int bytes, int* fmt, float* scale, 
 int b200_fe_set_ingest_scale(b200_fe* fe, int fmt, float scale);
 /* IQ export: dsp::compression::SampleStreamCompressor::process (sample_stream_compressor.h:30-66): finds the
  * maximum VALUE of the 2*count floats (volk_32f_index_max_32u), writes header + payload scaled by 32768/max
- * (int16) or 128/max (int8), rounded like rintf and saturated; B200_FMT_CF32 copies.  Returns the packet size. */
+ * (int16) or 128/max (int8), rounded like rintf and saturated; B200_FMT_CF32 copies.  Returns the packet size.
+ * Runs on a stream of the calling thread with grow-only scratch buffers (no allocation, no device-wide synchronisation per
+ * packet); with device buffers, work the caller queued on other streams than the default one must be finished. */
 int b200_pcm_compress(const float* iq, int count, int pcm_fmt, void* packet, int cap_bytes, int mem);
 /* Recorder sample types: wav::Writer::write (core/src/utils/wav.cpp:150-183): uint8 = x*127 + 128 (truncated),
  * int16 = rint(x*32767) saturated, int32 = rint(x*2147483647) saturated (the device saturates at INT_MAX where the

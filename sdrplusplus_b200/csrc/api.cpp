@@ -1265,46 +1265,69 @@ extern "C" int b200_export_convert(const float* in, long long n, int sample_type
 }
 
 // SampleStreamCompressor::process (sample_stream_compressor.h:30-66): 8-byte header + PCM payload
+// per-thread scratch of the packet builder: grow-only device buffers and a stream of its own, so that building a packet neither
+// allocates nor synchronises the device (the compressor adapter calls this once per chunk from its worker thread)
+namespace {
+struct PcmScratch {
+    DevBuf in, out, mx;
+    cudaStream_t stream = nullptr;
+    ~PcmScratch() { if (stream) { cudaStreamDestroy(stream); } }
+    int ensure(DevBuf& b, size_t bytes) {
+        if (b.bytes >= bytes) { return 0; }
+        return b.alloc(bytes + bytes / 4 + 64, false);
+    }
+};
+}
 extern "C" int b200_pcm_compress(const float* iq, int count, int pcm_fmt, void* packet, int cap_bytes, int mem) {
     if (!iq || !packet || count < 0) { set_error("null argument"); return B200_EINVAL; }
+    if (ensure_device()) { return B200_ENODEV; }
     const int bps = pcm_fmt == B200_FMT_CF32 ? 8 : (pcm_fmt == B200_FMT_CS16 ? 4 : (pcm_fmt == B200_FMT_CS8 ? 2 : 0));
     if (!bps) { set_error("bad pcm format %d", pcm_fmt); return B200_EINVAL; }
-    const int bytes = 8 + count * bps;
+    const long long bytes64 = 8 + (long long)count * bps;
+    if (bytes64 > 2147483647LL) { set_error("packet of %d samples does not fit an int byte count", count); return B200_ECAP; }
+    const int bytes = (int)bytes64;
     if (cap_bytes < bytes) { set_error("packet buffer too small"); return B200_ECAP; }
     const unsigned short sampleType = pcm_fmt == B200_FMT_CF32 ? 2 : (pcm_fmt == B200_FMT_CS16 ? 1 : 0);
     const bool dev = mem == B200_MEM_DEVICE;
-    DevBuf di, dout, dmax;
+    static thread_local PcmScratch sc;
+    if (!sc.stream && cudaStreamCreateWithFlags(&sc.stream, cudaStreamNonBlocking) != cudaSuccess) { return cuda_fail(cudaGetLastError(), "cudaStreamCreate"); }
+    cudaStream_t st = sc.stream;
     int rc;
     const float* src = iq;
+    // device buffers: whatever the caller queued on the default stream is finished first (work on other streams is the
+    // caller's to synchronise, as for any device pointer handed to the library)
+    if (dev) { B200_CK(cudaStreamSynchronize(nullptr)); }
     if (!dev) {
-        if ((rc = di.alloc((size_t)count * 8 + 16, false))) { return rc; }
-        B200_CK(cudaMemcpy(di.p, iq, (size_t)count * 8, cudaMemcpyHostToDevice));
-        src = di.as<float>();
+        if ((rc = sc.ensure(sc.in, (size_t)count * 8 + 16))) { return rc; }
+        B200_CK(cudaMemcpyAsync(sc.in.p, iq, (size_t)count * 8, cudaMemcpyHostToDevice, st));
+        src = sc.in.as<float>();
+        if ((rc = sc.ensure(sc.out, (size_t)bytes + 16))) { return rc; }
     }
     unsigned char hdr[8] = { 0 };
     memcpy(hdr + 2, &sampleType, 2);
     unsigned char* dst = (unsigned char*)packet;
-    if ((rc = dout.alloc((size_t)bytes + 16, false))) { return rc; }
-    unsigned char* dpk = dev ? dst : dout.as<unsigned char>();
+    unsigned char* dpk = dev ? dst : sc.out.as<unsigned char>();
     if (pcm_fmt == B200_FMT_CF32) {
-        B200_CK(cudaMemcpy(dpk + 8, src, (size_t)count * 8, cudaMemcpyDeviceToDevice));
+        B200_CK(cudaMemcpyAsync(dpk + 8, src, (size_t)count * 8, cudaMemcpyDeviceToDevice, st));
     }
     else {
-        if ((rc = dmax.alloc(16, true))) { return rc; }
+        if ((rc = sc.ensure(sc.mx, 16))) { return rc; }
         float maxVal = 0.0f;
         if (count > 0) {
-            cudaError_t e = launch_index_max(src, (long long)count * 2, dmax.as<float>(), nullptr);
+            B200_CK(cudaMemsetAsync(sc.mx.p, 0, 16, st));
+            cudaError_t e = launch_index_max(src, (long long)count * 2, sc.mx.as<float>(), st);
             if (e != cudaSuccess) { return cuda_fail(e, "launch_index_max"); }
-            B200_CK(cudaMemcpy(&maxVal, dmax.p, sizeof(float), cudaMemcpyDeviceToHost));
+            B200_CK(cudaMemcpyAsync(&maxVal, sc.mx.p, sizeof(float), cudaMemcpyDeviceToHost, st));
+            B200_CK(cudaStreamSynchronize(st));            // the scale of the packet depends on it
         }
         memcpy(hdr + 4, &maxVal, 4);
         const float scalar = (pcm_fmt == B200_FMT_CS16 ? 32768.0f : 128.0f) / maxVal;
-        cudaError_t e = launch_export(src, (long long)count * 2, pcm_fmt == B200_FMT_CS16 ? EXP_I16 : EXP_I8, scalar, dpk + 8, nullptr);
+        cudaError_t e = launch_export(src, (long long)count * 2, pcm_fmt == B200_FMT_CS16 ? EXP_I16 : EXP_I8, scalar, dpk + 8, st);
         if (e != cudaSuccess) { return cuda_fail(e, "launch_export"); }
     }
-    B200_CK(cudaMemcpy(dpk, hdr, 8, cudaMemcpyHostToDevice));
-    if (!dev) { B200_CK(cudaMemcpy(dst, dpk, (size_t)bytes, cudaMemcpyDeviceToHost)); }
-    else { B200_CK(cudaStreamSynchronize(nullptr)); }
+    B200_CK(cudaMemcpyAsync(dpk, hdr, 8, cudaMemcpyHostToDevice, st));
+    if (!dev) { B200_CK(cudaMemcpyAsync(dst, dpk, (size_t)bytes, cudaMemcpyDeviceToHost, st)); }
+    B200_CK(cudaStreamSynchronize(st));
     return bytes;
 }
 
