@@ -64,6 +64,9 @@ extern "C" {
 #define B200_DEMOD_USB  4    /* demod::SSB<stereo_t> Mode::USB           -- ssb.h:77-92             */
 #define B200_DEMOD_LSB  5
 #define B200_DEMOD_DSB  6
+#define B200_DEMOD_WFM_RDS    8  /* the RDS branch of demod::BroadcastFM instead of audio: discriminator -> RealToComplex -> FrequencyXlator(-57 kHz) ->
+                                  * RationalResampler to 5 kS/s (broadcast_fm.h:52-53,165-170,196-202); output = complex_t at 5 kS/s, what
+                                  * decoder_modules/radio/src/rds_demod.h consumes */
 #define B200_DEMOD_WFM_STEREO 7  /* demod::BroadcastFM stereo branch: pilot filter + PLL + L-R recovery -- broadcast_fm.h:147-190 */
 
 #define B200_AGC_CARRIER 0   /* demod::AM::AGCMode (am.h:14-17) */
@@ -295,6 +298,7 @@ int         b200_rxvfo_set_offset(b200_block* b, double offset);
 int         b200_rxvfo_set_bandwidth(b200_block* b, double bandwidth);
 b200_block* b200_quad_create(double deviationHz, double samplerate);            /* demod::Quadrature (quadrature.h:39-46): complex -> float */
 b200_block* b200_wfm_create(double deviationHz, double samplerate, int stereo, int lowPass); /* demod::BroadcastFM (mono or stereo branch, broadcast_fm.h:144-212): complex -> stereo */
+b200_block* b200_wfm_rds_create(double deviationHz, double samplerate);             /* its RDS branch (rdsOut, broadcast_fm.h:165-170,196-202): complex IF -> complex at 5 kS/s */
 b200_block* b200_nfm_create(double samplerate, double bandwidth, int lowPass);  /* demod::FM<stereo_t> */
 b200_block* b200_am_create(int agcMode, double bandwidth, double agcAttack, double agcDecay, double dcBlockRate, double samplerate); /* demod::AM<stereo_t> */
 b200_block* b200_noise_blanker_create(double rate, double level);                     /* noise_reduction::NoiseBlanker (noise_blanker.h:12-17): complex -> complex */

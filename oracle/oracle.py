@@ -111,6 +111,7 @@ class Oracle:
             "orc_rxvfo_set_bandwidth": (None, [vp, d]),
             "orc_quad_create": (vp, [d, d]),
             "orc_wfm_create": (vp, [d, d, i, i]),
+            "orc_wfm_rds_create": (vp, [d, d]),
             "orc_nfm_create": (vp, [d, d, i]),
             "orc_am_create": (vp, [i, d, d, d, d, d]),
             "orc_ssb_create": (vp, [i, d, d, d, d]),
@@ -249,6 +250,10 @@ class Oracle:
 
     def dcblock_c(self, rate):
         return Block(self.lib, self.lib.orc_dcblock_c_create(rate), 2, 2)
+
+    def wfm_rds(self, dev, sr):
+        """BroadcastFM's RDS side output: complex in at sr, complex out at 5 kS/s."""
+        return Block(self.lib, self.lib.orc_wfm_rds_create(dev, sr), 2, 2)
 
     def squelch(self, level):
         return Block(self.lib, self.lib.orc_squelch_create(level), 2, 2)

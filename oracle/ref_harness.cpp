@@ -137,6 +137,21 @@ namespace {
         void reset() override { b.reset(); }
     };
 
+    // the RDS side output of BroadcastFM (rdsOut = true): the audio is computed too and dropped
+    struct WfmRdsNode : Node {
+        demod::BroadcastFM b;
+        Scratch<complex_t> s;
+        std::vector<stereo_t> audio;
+        WfmRdsNode(double dev, double sr, bool stereo) { b.init(NULL, dev, sr, stereo, true, true); }
+        int process(int count, const void* in, void* out) override {
+            if ((int)audio.size() < count) { audio.resize((size_t)count); }
+            int rdsCount = 0;
+            b.process(count, s.load(in, count), audio.data(), rdsCount, (complex_t*)out);
+            return rdsCount;
+        }
+        void reset() override { b.reset(); }
+    };
+
     struct NfmNode : Node {
         demod::FM<stereo_t> b;
         Scratch<complex_t> s;
@@ -342,6 +357,8 @@ void orc_rxvfo_set_offset(void* h, double off) { ((RxVfoNode*)h)->b.setOffset(of
 void orc_rxvfo_set_bandwidth(void* h, double bw) { ((RxVfoNode*)h)->b.setBandwidth(bw); }
 void* orc_quad_create(double dev, double sr) { return new QuadNode(dev, sr); }
 void* orc_wfm_create(double dev, double sr, int stereo, int lp) { return new WfmNode(dev, sr, stereo != 0, lp != 0); }
+void* orc_wfm_rds_create(double dev, double sr) { return new WfmRdsNode(dev, sr, false); }
+void* orc_wfm_rds_stereo_create(double dev, double sr) { return new WfmRdsNode(dev, sr, true); }
 void* orc_nfm_create(double sr, double bw, int lp) { return new NfmNode(sr, bw, lp != 0); }
 void* orc_am_create(int agcMode, double bw, double att, double dec, double dcr, double sr) {
     if (agcMode != 0 && agcMode != 1) { return NULL; }

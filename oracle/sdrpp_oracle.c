@@ -791,6 +791,22 @@ static int n_wfm_proc(node* b, int count, const void* in, void* out) {
 }
 static void n_wfm_reset(node* b) { n_wfm* w = (n_wfm*)b; w->q.phase = 0.0f; fir_reset(&w->al); }
 static void n_wfm_destroy(node* b) { n_wfm* w = (n_wfm*)b; fir_free(&w->al); free(w->s.p); free(b); }
+/* ---- demod::BroadcastFM, RDS side output  (core/src/dsp/demod/broadcast_fm.h:52-53,165-170,196-202): discriminator ->
+ *      RealToComplex -> FrequencyXlator(-57 kHz) -> RationalResampler to 5 kS/s; the same three blocks in the mono and in
+ *      the stereo branch ---- */
+typedef struct { node base; fmquad_t q; xlator_t x; rresamp_t r; scratch_t s; cf32* c; size_t cap; } n_wfmrds;
+static int n_wfmrds_proc(node* b, int count, const void* in, void* out) {
+    n_wfmrds* w = (n_wfmrds*)b;
+    float* m = scratch_get(&w->s, count);
+    if ((size_t)count > w->cap) { w->cap = (size_t)count + 1024; w->c = (cf32*)realloc(w->c, w->cap * sizeof(cf32)); }
+    quad_process(&w->q, count, (const cf32*)in, m);
+    for (int i = 0; i < count; i++) { w->c[i].re = m[i]; w->c[i].im = 0.0f; }       /* convert::RealToComplex (real_to_complex.h) */
+    xl_process(&w->x, count, w->c, w->c);
+    return rr_process(&w->r, count, w->c, (cf32*)out);
+}
+static void n_wfmrds_reset(node* b) { (void)b; }
+static void n_wfmrds_destroy(node* b) { n_wfmrds* w = (n_wfmrds*)b; rr_free(&w->r); free(w->s.p); free(w->c); free(b); }
+
 /* ---- demod::BroadcastFM stereo branch  (core/src/dsp/demod/broadcast_fm.h:36-66,147-190): RealToComplex -> pilot band-pass
  *      (FIR<complex_t,complex_t>, taps::bandPass<complex_t>(18750,19250,3000,fs,odd)) -> loop::PLL (pll.h:64-70 over
  *      PhaseControlLoop, phase_control_loop.h:27-32,58-85) -> Delay x2 -> conj, two complex multiplies -> real part * 2 ->
@@ -910,6 +926,14 @@ static void* wfm_stereo_create(double dev, double sr, int lowPass) {
     fir_init(&n->ar, t, nt, 1, 1);
     free(t);
     n->lowPass = lowPass;
+    return n;
+}
+void* orc_wfm_rds_create(double dev, double sr) {
+    NODE_ALLOC(n_wfmrds);
+    n->base.process = n_wfmrds_proc; n->base.reset = n_wfmrds_reset; n->base.destroy = n_wfmrds_destroy;
+    quad_init(&n->q, dev, sr);
+    xl_init(&n->x, hz_to_rads(-57000.0, sr));
+    if (rr_init(&n->r, sr, 5000.0)) { free(n); return NULL; }
     return n;
 }
 void* orc_wfm_create(double dev, double sr, int stereo, int lowPass) {

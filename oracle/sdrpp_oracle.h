@@ -72,6 +72,7 @@ void  orc_rxvfo_set_offset(void* h, double offset);
 void  orc_rxvfo_set_bandwidth(void* h, double bw);
 void* orc_quad_create(double deviationHz, double samplerate);            /* demod::Quadrature: cf32 -> f32 */
 void* orc_wfm_create(double deviationHz, double samplerate, int stereo, int lowPass); /* BroadcastFM: cf32 -> stereo */
+void* orc_wfm_rds_create(double deviationHz, double samplerate);                    /* BroadcastFM's rdsOut: cf32 -> cf32 at 5 kS/s */
 void* orc_nfm_create(double samplerate, double bandwidth, int lowPass);  /* FM<stereo_t>: cf32 -> stereo */
 void* orc_am_create(int agcMode, double bandwidth, double agcAttack, double agcDecay, double dcBlockRate,
                     double samplerate);                                  /* AM<stereo_t>; agcMode 0 CARRIER 1 AUDIO 2 NONE */

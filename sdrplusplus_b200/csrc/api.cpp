@@ -374,6 +374,7 @@ static int build_vfo_chain(b200_fe* fe, VfoSlot* v) {
     case B200_DEMOD_RAW: break;
     case B200_DEMOD_WFM: rc = v->chain.add_wfm(c.deviation, c.out_samplerate, c.low_pass != 0, false); break;
     case B200_DEMOD_WFM_STEREO: rc = v->chain.add_wfm(c.deviation, c.out_samplerate, c.low_pass != 0, true); break;
+    case B200_DEMOD_WFM_RDS: rc = v->chain.add_wfm_rds(c.deviation, c.out_samplerate); break;
     case B200_DEMOD_NFM: rc = v->chain.add_nfm(c.out_samplerate, c.bandwidth, c.low_pass != 0); break;
     case B200_DEMOD_AM: rc = v->chain.add_am(c.agc_mode, c.bandwidth, c.agc_attack, c.agc_decay, c.dc_block_rate, c.out_samplerate); break;
     case B200_DEMOD_USB: rc = v->chain.add_ssb(0, c.bandwidth, c.out_samplerate, c.agc_attack, c.agc_decay); break;
@@ -382,10 +383,11 @@ static int build_vfo_chain(b200_fe* fe, VfoSlot* v) {
     default: set_error("unknown demodulator %d", c.demod); return B200_EINVAL;
     }
     if (rc) { return rc; }
-    if (c.af_samplerate > 0 && c.demod != B200_DEMOD_RAW) {
+    const bool audio = c.demod != B200_DEMOD_RAW && c.demod != B200_DEMOD_WFM_RDS;     // the AF chain and the volume follow audio only
+    if (c.af_samplerate > 0 && audio) {
         if ((rc = v->chain.add_af_chain(c.out_samplerate, c.af_samplerate, c.af_high_pass != 0, c.af_deemph_tau))) { return rc; }
     }
-    if (c.af_volume_on && c.demod != B200_DEMOD_RAW) {
+    if (c.af_volume_on && audio) {
         if ((rc = v->chain.add_volume(c.af_volume, c.af_muted != 0))) { return rc; }
     }
     const bool ov = fe->sch.tail_stream != nullptr;
@@ -1066,6 +1068,11 @@ extern "C" b200_block* b200_wfm_create(double dev, double sr, int stereo, int lo
     b200_block* b = block_new();
     if (!b) { return nullptr; }
     return block_finish(b, b->chain.add_wfm(dev, sr, lowPass != 0, stereo != 0));
+}
+extern "C" b200_block* b200_wfm_rds_create(double dev, double sr) {
+    b200_block* b = block_new();
+    if (!b) { return nullptr; }
+    return block_finish(b, b->chain.add_wfm_rds(dev, sr));
 }
 extern "C" b200_block* b200_nfm_create(double sr, double bw, int lowPass) {
     b200_block* b = block_new();

@@ -133,6 +133,14 @@ void XdStage::set_offset_rad(double rad) {
     taps_dirty = true;
 }
 
+void RxlStage::set_offset_rad(double rad) {
+    long double turns = effective_omega(rad) / kTwoPiL;
+    long double scaled = turns * 18446744073709551616.0L;
+    if (scaled >= 9223372036854775807.0L) { scaled = 9223372036854775807.0L; }
+    if (scaled <= -9223372036854775807.0L) { scaled = -9223372036854775807.0L; }
+    w = (unsigned long long)(long long)llroundl(scaled);
+}
+
 int XdStage::upload_taps(cudaStream_t s) {
     if (!gpad.p || gpad.bytes < (size_t)gpad_len * sizeof(float2)) {
         int rc = gpad.alloc((size_t)gpad_len * sizeof(float2));
@@ -695,6 +703,14 @@ int Chain::add_wfm(double deviationHz, double samplerate, bool lowPass, bool ste
     st.push_back(std::make_unique<M2SStage>());
     return 0;
 }
+int Chain::add_wfm_rds(double deviationHz, double samplerate) {
+    int rc = add_quad(deviationHz, samplerate);
+    if (rc) { return rc; }
+    auto x = std::make_unique<RxlStage>();
+    x->set_offset_rad(hz_to_rads(-57000.0, samplerate));                 // xlator.init(NULL, -57000.0, samplerate)
+    st.push_back(std::move(x));
+    return add_resampler(samplerate, 5000.0);                              // rdsResamp.init(NULL, samplerate, 5000.0)
+}
 int Chain::add_nfm(double samplerate, double bandwidth, bool lowPass) {
     int rc = add_quad(bandwidth / 2.0, samplerate);                                         // fm.h:28
     if (rc) { return rc; }
@@ -874,6 +890,7 @@ static inline int rec_tag(const M2SParams&) { return LaunchRec::T_M2S; }
 static inline int rec_tag(const ScaleParams&) { return LaunchRec::T_SCALE; }
 static inline int rec_tag(const CarryParams&) { return LaunchRec::T_CARRY; }
 static inline int rec_tag(const FmIfParams&) { return LaunchRec::T_FMIF; }
+static inline int rec_tag(const RxlParams&) { return LaunchRec::T_RXL; }
 
 void LaunchRec::add(int tag, void* fn, const void* p, size_t size, int a, int b, size_t c) {
     const size_t off = (bytes.size() + 15) & ~(size_t)15;
@@ -920,6 +937,7 @@ int LaunchRec::replay(cudaStream_t s0, long long* nlaunch) const {
         case T_SCALE: e = launch_scale(*(const ScaleParams*)q, s); break;
         case T_CARRY: e = launch_carry(*(const CarryParams*)q, s); break;
         case T_FMIF: e = launch_fmif(*(const FmIfParams*)q, s); break;
+        case T_RXL: e = launch_rxl(*(const RxlParams*)q, s); break;
         case T_STEREO: nl = 0; e = launch_stereo(*(const StParams*)q, s, &nl); break;
         case T_SQUELCH: nl = 0; e = launch_squelch(*(const SqParams*)q, s, &nl); break;
         case T_FUSED: e = launch_tail_fused(*(const FtParams*)q, it.a, it.b, it.c, s); break;
@@ -1397,6 +1415,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
         StParams stp; zero_params(stp, use_rec);
         SqParams sqp; zero_params(sqp, use_rec);
         FmIfParams fmp; zero_params(fmp, use_rec);                  // one bin count per batch
+        RxlParams xlp; zero_params(xlp, use_rec);
         auto sq_flush = [&]() -> int {
             if (sqp.njobs == 0) { return 0; }
             int nl = 0;
@@ -1525,6 +1544,15 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
                 if (stp.njobs == B200_BATCH) { rc = st_flush(); }
                 break;
             }
+            case K_RXL: {
+                RxlStage* f = (RxlStage*)s;
+                if (f->n_out <= 0) { break; }
+                RxlJob& j = xlp.job[xlp.njobs++];
+                j.in = f->in_data(); j.out = (float2*)f->out_ptr; j.n = f->n_out; j.phase0 = f->chunk_phase0; j.w = f->w;
+                xlp.max_n = std::max(xlp.max_n, f->n_out);
+                if (xlp.njobs == B200_BATCH) { rc = flush_batch(xlp, launch_rxl, ts, launches); xlp.max_n = 0; }
+                break;
+            }
             case K_FMIF: {
                 FmIfStage* f = (FmIfStage*)s;
                 if (f->n_out <= 0) { break; }
@@ -1572,6 +1600,7 @@ int Scheduler::run(std::vector<Chain*>& chains, const void* raw, int fmt, int co
         if ((rc = flush_batch(mp, launch_m2s, ts, launches))) { return rc; }
         if ((rc = flush_batch(cp2, launch_scale, ts, launches))) { return rc; }
         if ((rc = flush_batch(fmp, launch_fmif, ts, launches))) { return rc; }
+        if ((rc = flush_batch(xlp, launch_rxl, ts, launches))) { return rc; }
         if ((rc = st_flush())) { return rc; }
         if ((rc = sq_flush())) { return rc; }
     }

@@ -41,7 +41,7 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
-enum StageKind { K_XD, K_FIRC, K_POLY, K_QUAD, K_FIRR, K_SEQ, K_M2S, K_SCALE, K_STEREO, K_SQUELCH, K_FMIF };
+enum StageKind { K_XD, K_FIRC, K_POLY, K_QUAD, K_FIRR, K_SEQ, K_M2S, K_SCALE, K_STEREO, K_SQUELCH, K_FMIF, K_RXL };
 
 struct Stage {
     StageKind kind;
@@ -185,6 +185,17 @@ struct SquelchStage : Stage {
     int max_out(int n) const override { return n; }
 };
 
+// RealToComplex + FrequencyXlator in one pass (the RDS branch of BroadcastFM, broadcast_fm.h:165-170): real in, complex out,
+// closed-form phase like stage 1 (the angle of the reference's fp32-rounded phaseDelta, exact u64 accumulation)
+struct RxlStage : Stage {
+    unsigned long long w = 0, phase = 0, chunk_phase0 = 0;
+    RxlStage() { kind = K_RXL; in_es = 1; out_es = 2; }
+    void set_offset_rad(double rad);
+    int plan(int n) override { n_in = n; n_out = n; chunk_phase0 = phase; phase += w * (unsigned long long)(long long)n; return n; }
+    int max_out(int n) const override { return n; }
+    void reset_state() override { phase = 0; }
+};
+
 // noise_reduction::FMIF (fm_if.h:44-77): history = bins - 1 samples, one transform per output sample (ifnr.cuh)
 struct FmIfStage : Stage {
     int bins = 32;
@@ -235,6 +246,7 @@ struct Chain {
     int add_deemph(double tau, double samplerate);                          // filter::Deemphasis<stereo_t> (deephasis.h:14-28)
     // radio AF chain: RationalResampler<stereo_t> -> [300 Hz high-pass FIR] -> [Deemphasis]  (radio_module.h:99-110,546-553)
     int add_af_chain(double afSamplerate, double audioSamplerate, bool highPass, double deemphTau);
+    int add_wfm_rds(double deviationHz, double samplerate);                 // BroadcastFM's RDS branch: discriminator -> -57 kHz -> 5 kS/s (broadcast_fm.h:52-53,165-170)
     int add_noise_blanker(double rate, double level);                       // noise_reduction::NoiseBlanker (noise_blanker.h:12-17)
     int add_fmif(int bins);                                                 // noise_reduction::FMIF (fm_if.h:20-24)
     int add_squelch(double level);                                          // noise_reduction::PowerSquelch (power_squelch.h:16-20)
@@ -246,7 +258,7 @@ struct Chain {
 // seven to ten kernel launches).  Decimation offsets / resampler phases / buffer parities make the list periodic over a few
 // chunks for any fixed chunk size, so a handful of graphs covers a stream.
 struct LaunchRec {
-    enum Tag { T_DFR = 1, T_FIR, T_POLY, T_FIRR, T_QUAD, T_SEQ, T_M2S, T_SCALE, T_STEREO, T_SQUELCH, T_FUSED, T_CARRY, T_FMIF };
+    enum Tag { T_DFR = 1, T_FIR, T_POLY, T_FIRR, T_QUAD, T_SEQ, T_M2S, T_SCALE, T_STEREO, T_SQUELCH, T_FUSED, T_CARRY, T_FMIF, T_RXL };
     struct Item { int tag; void* fn; size_t off, size; int a, b; size_t c; int branch; };
     int cur_branch = 0;              // items added now belong to this branch (0: the stream of the list, 1: `aux`, forked and joined)
     cudaStream_t aux = nullptr;

@@ -228,6 +228,15 @@ __global__ void __launch_bounds__(256) k_m2s(const __grid_constant__ M2SParams p
     reinterpret_cast<float2*>(J.out)[i] = make_float2(v, v);
 }
 
+__global__ void __launch_bounds__(256) k_rxl(const __grid_constant__ RxlParams p) {
+    const RxlJob& J = p.job[blockIdx.y];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= J.n) { return; }
+    const float v = __ldg(J.in + i);
+    const float2 ph = phasor_u64(J.phase0 + J.w * (unsigned long long)i);
+    J.out[i] = make_float2(v * ph.x, v * ph.y);
+}
+
 // ------------------------------------------------------------------------------------------------
 // sequential audio-rate tails: one thread per VFO.  Arithmetic is written with explicit _rn intrinsics
 // (no FMA contraction) because the AGC is branchy: the decisions must follow the reference's rounding.
@@ -1147,6 +1156,12 @@ cudaError_t launch_m2s(const M2SParams& p, cudaStream_t s) {
     if (p.max_n <= 0 || p.njobs <= 0) { return cudaSuccess; }
     dim3 grid(cdiv(p.max_n, 256), p.njobs);
     k_m2s<<<grid, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_rxl(const RxlParams& p, cudaStream_t s) {
+    if (p.max_n <= 0 || p.njobs <= 0) { return cudaSuccess; }
+    dim3 grid(cdiv(p.max_n, 256), p.njobs);
+    k_rxl<<<grid, 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 cudaError_t launch_scale(const ScaleParams& p, cudaStream_t s) {

@@ -268,6 +268,12 @@ struct ScaleParams { int njobs; int max_n; ScaleJob job[B200_BATCH]; };
 struct M2SJob { const float* in; float* out; int n; };
 struct M2SParams { int njobs; int max_n; M2SJob job[B200_BATCH]; };
 
+// ---- real -> complex + frequency translation in one pass (RealToComplex + FrequencyXlator of the RDS branch,
+//      broadcast_fm.h:165-170,196-202): out[i] = in[i] * e^{j 2 pi (phase0 + i w) / 2^64}, exact u64 phase ----
+struct RxlJob { const float* in; float2* out; int n; int pad; unsigned long long phase0, w; };
+struct RxlParams { int njobs; int max_n; RxlJob job[B200_BATCH]; };
+cudaError_t launch_rxl(const RxlParams& p, cudaStream_t s);
+
 // ---- end-of-chunk history carry: dst[0..h) = last h elements of concat(a[0..la), b[0..lb)) ----
 // dst may alias a (memmove semantics of fir.h:80 / decimating_fir.h:65 / polyphase_resampler.h:96).
 struct CarryJob {

@@ -68,6 +68,11 @@ class VfoConfig:
         return VfoConfig(offset, 250000.0, bandwidth, L.DEMOD_WFM_STEREO, deviation=bandwidth / 2.0, low_pass=True)
 
     @staticmethod
+    def wfm_rds(offset, bandwidth=150000.0):
+        # the RDS branch of BroadcastFM: complex baseband of the 57 kHz subcarrier at 5 kS/s (rds_demod.h's input)
+        return VfoConfig(offset, 250000.0, bandwidth, L.DEMOD_WFM_RDS, deviation=bandwidth / 2.0)
+
+    @staticmethod
     def nfm(offset, bandwidth=12500.0):
         return VfoConfig(offset, 50000.0, bandwidth, L.DEMOD_NFM, low_pass=True)          # nfm.h:29,56-58
 
@@ -221,7 +226,7 @@ class FrontEnd:
         for vid, cfg in self.vfos.items():
             n = o.vfo_count[vid]
             y = bufs[vid][: 2 * n].copy()
-            outs[vid] = y.view(np.complex64) if cfg.demod == L.DEMOD_RAW else y.reshape(-1, 2)
+            outs[vid] = y.view(np.complex64) if cfg.demod in (L.DEMOD_RAW, L.DEMOD_WFM_RDS) else y.reshape(-1, 2)
         lines = fft[: o.fft_lines].copy() if fft is not None else np.empty((0, 0), np.float32)
         return outs, lines
 
@@ -291,6 +296,10 @@ class Block:
     @staticmethod
     def wfm(dev, sr, stereo=False, lowpass=True):
         return Block(L.load().b200_wfm_create(dev, sr, int(stereo), int(lowpass)), 2, 2)
+
+    @staticmethod
+    def wfm_rds(dev, sr):
+        return Block(L.load().b200_wfm_rds_create(dev, sr), 2, 2)
 
     @staticmethod
     def nfm(sr, bw, lowpass=True):

@@ -2,8 +2,9 @@
 // samplerate, stereo, lowPass, rdsOut) / setDeviation / setSamplerate / setStereo / setLowPass / setRDSOut / reset /
 // process(count, in, out, rdsOutCount, rdsout) / run / rdsOut, core/src/dsp/demod/broadcast_fm.h:20-240), forwarding to
 // libb200dsp (b200_wfm_*): discriminator, 19 kHz pilot filter + PLL + L-R recovery (stereo), audio low-pass.
-// The RDS side output is the discriminator output as complex samples (broadcast_fm.h:156-160: rtoc of the demodulated
-// signal); it is produced on request from the same pass.
+// The RDS side output is the reference's: the demodulated multiplex as complex samples, translated by -57 kHz and resampled
+// to 5 kS/s (broadcast_fm.h:52-53,165-170,196-202) -- the stream decoder_modules/radio/src/rds_demod.h reads; it comes from
+// its own GPU pass over the same chunk (b200_wfm_rds_create).
 #pragma once
 #include <vector>
 #include "../processor.h"
@@ -23,7 +24,7 @@ namespace dsp::demod {
             registerOutput(&this->rdsOut);
             base_type::init(in);
         }
-        bool ok() const { return blk.ok() && (!_rds || quad.ok()); }
+        bool ok() const { return blk.ok() && (!_rds || rds.ok()); }
         void setDeviation(double deviation) { _dev = deviation; rebuild(); }
         void setSamplerate(double samplerate) { _sr = samplerate; rebuild(); }
         void setStereo(bool stereo) { _stereo = stereo; rebuild(); }
@@ -33,16 +34,14 @@ namespace dsp::demod {
             std::lock_guard<std::recursive_mutex> lk(ctrlMtx);
             tempStop();
             blk.reset();
-            quad.reset();
+            rds.reset();
             tempStart();
         }
         // the reference's signature: rdsOutCount / rdsout receive the RDS branch (0 samples while it is off)
         inline int process(int count, complex_t* in, stereo_t* out_, int& rdsOutCount, complex_t* rdsout = nullptr) {
             rdsOutCount = 0;
-            if (_rds && rdsout && quad.ok()) {
-                if ((int)mono.size() < count) { mono.resize((size_t)count); }
-                const int n = quad.process(count, in, mono.data());
-                for (int i = 0; i < n; i++) { rdsout[i].re = mono[(size_t)i]; rdsout[i].im = 0.0f; }
+            if (_rds && rdsout && rds.ok()) {
+                const int n = rds.process(count, in, rdsout);
                 rdsOutCount = n > 0 ? n : 0;
             }
             return blk.process(count, in, out_);
@@ -67,7 +66,7 @@ namespace dsp::demod {
     private:
         void make() {
             blk.adopt(b200_wfm_create(_dev, _sr, _stereo ? 1 : 0, _lowPass ? 1 : 0));
-            quad.adopt(_rds ? b200_quad_create(_dev, _sr) : nullptr);
+            rds.adopt(_rds ? b200_wfm_rds_create(_dev, _sr) : nullptr);
         }
         void rebuild() {
             std::lock_guard<std::recursive_mutex> lk(ctrlMtx);
@@ -77,7 +76,6 @@ namespace dsp::demod {
         }
         double _dev = 75000.0, _sr = 250000.0;
         bool _stereo = false, _lowPass = true, _rds = false;
-        std::vector<float> mono;
-        b200::Handle blk, quad;
+        b200::Handle blk, rds;
     };
 }

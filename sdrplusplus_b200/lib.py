@@ -11,7 +11,7 @@ MAX_VFOS = 64
 FMT_CF32, FMT_CS16, FMT_CS8 = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 WIN_RECTANGULAR, WIN_BLACKMAN, WIN_NUTTALL = 0, 1, 2
-DEMOD_RAW, DEMOD_WFM, DEMOD_NFM, DEMOD_AM, DEMOD_USB, DEMOD_LSB, DEMOD_DSB, DEMOD_WFM_STEREO = range(8)
+DEMOD_RAW, DEMOD_WFM, DEMOD_NFM, DEMOD_AM, DEMOD_USB, DEMOD_LSB, DEMOD_DSB, DEMOD_WFM_STEREO, DEMOD_WFM_RDS = range(9)
 AGC_CARRIER, AGC_AUDIO = 0, 1
 E = {0: "OK", -1: "EINVAL", -2: "ENODEV", -3: "ECUDA", -4: "ENOMEM", -5: "ECAP", -6: "ENOPLAN", -7: "ESTATE"}
 
@@ -104,6 +104,7 @@ SIGNATURES = {
     "b200_squelch_create": (_vp, [_d]),
     "b200_noise_blanker_create": (_vp, [_d, _d]),
     "b200_fmif_create": (_vp, [_i]),
+    "b200_wfm_rds_create": (_vp, [_d, _d]),
     "b200_noise_blanker_set": (_i, [_vp, _d, _d]),
     "b200_deemph_create": (_vp, [_d, _d]),
     "b200_block_process": (_i, [_vp, _i, _vp, _vp]),

@@ -92,6 +92,10 @@ def run_cases(R):
     g["wfm_stereo_tail"] = a[-512:]
     g["wfm_stereo_digest"] = digest(a)
     g["squelch_digest"] = digest(R.squelch(-27.0).process_chunks((ws * np.linspace(0.02, 0.2, ws.size).astype(np.float32)).astype(np.complex64).view(np.float32), 1250))
+    # RDS side output of BroadcastFM: discriminator -> -57 kHz -> 5 kS/s
+    a = R.wfm_rds(75e3, 250e3).process_chunks(ws.view(np.float32), 1250)
+    g["wfm_rds_tail"] = a[-256:]
+    g["wfm_rds_digest"] = digest(a)
     # IF chain of the radio module: noise blanker (impulses on top of the FM signal), FM IF noise reduction (32 and 15 bins)
     imp = ws[:30000].copy()
     imp[::997] *= np.float32(12.0)

@@ -99,3 +99,59 @@ def test_if_chain_in_front_end(sb, oracle, report):
                                        "wfm_nr32_rel_rms": e_w, "wfm_samples_behind_a_tied_bin": b_w}
     assert e_n < TOL and e_w < TOL, (e_n, e_w)
     assert b_n <= 800 and b_w <= 600, (b_n, b_w)
+
+
+def _rds_iq(n, fs, seed):
+    """FM carrier whose multiplex carries a 19 kHz pilot and a BPSK-like 57 kHz subcarrier (what the RDS branch pulls out)"""
+    t = np.arange(n) / fs
+    rng = np.random.default_rng(seed)
+    bits = np.repeat(rng.integers(0, 2, n // 200 + 1) * 2 - 1, 200)[:n].astype(np.float64)       # 1187.5 baud-ish
+    mpx = 0.4 * np.sin(2 * np.pi * 1000 * t) + 0.1 * np.sin(2 * np.pi * 19000 * t) + 0.05 * bits * np.sin(2 * np.pi * 57000 * t)
+    ph = 2 * np.pi * 75000.0 * np.cumsum(mpx) / fs
+    return (0.5 * np.exp(1j * ph)).astype(np.complex64) + noise_iq(n, seed, 0.002)
+
+
+@pytest.mark.parametrize("chunk", [1250, 7001])
+def test_wfm_rds_branch_block(sb, oracle, report, chunk):
+    """BroadcastFM's rdsOut (broadcast_fm.h:165-170): discriminator -> RealToComplex -> FrequencyXlator(-57 kHz) -> 5 kS/s.
+    The reference translates with its fp32 phase recurrence; the GPU uses the closed form: gated against
+    the oracle's exact-phase mode, the distance of the faithful oracle from it is the reported floor."""
+    fs, n = 250e3, 200000
+    x = _rds_iq(n, fs, 5).view(np.float32)
+    y = sb.Block.wfm_rds(75e3, fs).process_chunks(x, chunk).view(np.complex64)
+    yf = oracle.wfm_rds(75e3, fs).process_chunks(x, chunk).view(np.complex64)
+    oracle.set_rotator_mode(1)
+    try:
+        ye = oracle.wfm_rds(75e3, fs).process_chunks(x, chunk).view(np.complex64)
+    finally:
+        oracle.set_rotator_mode(0)
+    assert y.shape == ye.shape == yf.shape and abs(y.size - n // 50) <= 1
+    e, floor, e_f = rel_rms(y[100:], ye[100:]), rel_rms(yf[100:], ye[100:]), rel_rms(y[100:], yf[100:])
+    report["wfm_rds_block_chunk%d" % chunk] = {"rel_rms_vs_exact_phase": e, "reference_recurrence_vs_exact_phase": floor, "rel_rms_vs_faithful": e_f}
+    assert e < TOL, e
+    assert e_f < floor + TOL, (e_f, floor)
+    # the subcarrier really arrives at baseband: most of the output power sits within +-2.4 kHz (the whole 5 kS/s band) and
+    # the signal is far above the noise floor of the translated multiplex
+    assert np.std(y[100:]) > 1e-3
+
+
+def test_wfm_rds_vfo_in_front_end(sb, oracle, report):
+    """the same branch as a VFO of the fused front end (B200_DEMOD_WFM_RDS) next to the audio VFO of the same station"""
+    FS, n, chunk = 2.0e6, 800000, 40000
+    base = _rds_iq(n // 8, 250e3, 6)
+    up = np.repeat(base, 8)[:n]
+    t = np.arange(n) / FS
+    x = (up * np.exp(2j * np.pi * 250e3 * t)).astype(np.complex64) + noise_iq(n, 8, 0.002)
+    fe = sb.FrontEnd(FS, chunk)
+    va, vr = fe.add_vfo(sb.VfoConfig.wfm(250e3)), fe.add_vfo(sb.VfoConfig.wfm_rds(250e3))
+    outs, _ = fe.process_chunks(x, chunk)
+    oracle.set_rotator_mode(1)
+    try:
+        v, d = oracle.rxvfo(FS, 250e3, 150e3, 250e3), oracle.wfm_rds(75e3, 250e3)
+        ye = np.concatenate([d.process(v.process(x[i:i + chunk].view(np.float32))).view(np.complex64) for i in range(0, n, chunk)])
+    finally:
+        oracle.set_rotator_mode(0)
+    assert outs[vr].shape == ye.shape and outs[va].shape[0] == n // 8
+    e = rel_rms(outs[vr][100:], ye[100:])
+    report["wfm_rds_vfo_in_front_end"] = {"rel_rms_vs_exact_phase": e}
+    assert e < TOL, e

@@ -101,3 +101,64 @@ def test_audio_stored_straight_into_pinned_host_buffers(sb):
             L.b200_host_free(C.c_void_p(o.vfo_out[v]))
     for a, b in zip(res[0], res[1]):
         assert a.size > 0 and a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_four_chunks_in_flight_same_bits(sb):
+    """option "inflight" 4: submit runs up to four chunks ahead of wait (each with its own pinned input and output buffers);
+    the stream that comes out is the one the synchronous call produces, bit for bit."""
+    from sdrplusplus_b200 import lib
+    L = lib.load()
+    L.b200_host_alloc.restype = C.c_void_p
+    chunk, nch, depth = 50000, 30, 4
+    x = _signal(chunk * nch)
+    # reference run: one chunk at a time
+    fe = sb.FrontEnd(FS, chunk)
+    fe.set_fft(65536, 400.0, 2)
+    ids = [fe.add_vfo(sb.VfoConfig.wfm(o)) for o in OFFS]
+    ref, ref_lines = fe.process_chunks(x, chunk)
+    fe.close()
+    fe = sb.FrontEnd(FS, chunk)
+    fe.set_option("inflight", depth)
+    fe.set_fft(65536, 400.0, 2)
+    ids2 = [fe.add_vfo(sb.VfoConfig.wfm(o)) for o in OFFS]
+    assert ids2 == ids
+    nl = max(1, fe.fft_max_lines(chunk))
+    hin = [L.b200_host_alloc(chunk * 8) for _ in range(depth)]
+    outs = []
+    for _ in range(depth):
+        o = lib.Outputs()
+        for v in ids:
+            cap = fe.vfo_max_out(v, chunk)
+            o.vfo_out[v] = L.b200_host_alloc(8 * cap); o.vfo_cap[v] = cap
+        o.fft_out = L.b200_host_alloc(4 * nl * 65536); o.fft_cap_lines = nl; o.out_mem = lib.MEM_HOST
+        outs.append(o)
+    acc, lines = {v: [] for v in ids}, []
+
+    def collect(k):
+        o = outs[k % depth]
+        for v in ids:
+            acc[v].append(np.ctypeslib.as_array((C.c_float * (2 * o.vfo_count[v])).from_address(o.vfo_out[v])).copy())
+        if o.fft_lines:
+            lines.append(np.ctypeslib.as_array((C.c_float * (o.fft_lines * 65536)).from_address(o.fft_out)).copy().reshape(-1, 65536))
+    done = 0
+    for c in range(nch):
+        C.memmove(hin[c % depth], x[c * chunk:(c + 1) * chunk].ctypes.data, chunk * 8)
+        fe.submit_ptr(hin[c % depth], chunk, lib.FMT_CF32, lib.MEM_HOST, outs[c % depth])
+        if c - done + 1 == depth:
+            fe.wait(); collect(done); done += 1
+    while done < nch:
+        fe.wait(); collect(done); done += 1
+    with pytest.raises(lib.B200Error):
+        fe.wait()                                                    # nothing left in flight
+    fe.close()
+    for v in ids:
+        y = np.concatenate(acc[v]).reshape(-1, 2)
+        assert y.shape == ref[v].shape and np.array_equal(y.view(np.uint32), ref[v].view(np.uint32))
+    got = np.concatenate(lines) if lines else np.empty((0, 65536), np.float32)
+    assert got.shape == ref_lines.shape and np.array_equal(got.view(np.uint32), ref_lines.view(np.uint32))
+    for p in hin:
+        L.b200_host_free(C.c_void_p(p))
+    for o in outs:
+        for v in ids:
+            L.b200_host_free(C.c_void_p(o.vfo_out[v]))
+        L.b200_host_free(C.c_void_p(o.fft_out))

@@ -28,6 +28,15 @@ def test_blocks_bit_identical(oracle, ref_oracle, seed):
     for f, ch in mk:
         assert _same(f(R).process_chunks(x, ch), f(S).process_chunks(x, ch))
     y = R.rxvfo(FS, 250e3, 150e3, 300e3).process_chunks(x, 12000)
+    # RDS side output of BroadcastFM (rdsOut): the restatement against the reference's mono branch, and the reference's stereo
+    # branch against its mono branch (the same three blocks behind the same discriminator)
+    rds_ref = R.wfm_rds(75e3, 250e3).process_chunks(y, 1250)
+    assert abs(rds_ref.size // 2 - (y.size // 2) // 50) <= 1 and _same(rds_ref, S.wfm_rds(75e3, 250e3).process_chunks(y, 1250))
+    import ctypes as C
+    from oracle.oracle import Block
+    R.lib.orc_wfm_rds_stereo_create.restype = C.c_void_p
+    R.lib.orc_wfm_rds_stereo_create.argtypes = [C.c_double, C.c_double]
+    assert _same(Block(R.lib, R.lib.orc_wfm_rds_stereo_create(75e3, 250e3), 2, 2).process_chunks(y, 1250), rds_ref)
     mk2 = [
         (lambda o: o.quad(75e3, 250e3), 1250), (lambda o: o.wfm(75e3, 250e3), 1250), (lambda o: o.wfm(75e3, 250e3, False, False), 999),
         (lambda o: o.nfm(250e3, 12500.0, True), 1250), (lambda o: o.am(1, 10e3, 2e-4, 2e-5, 4e-4, 250e3), 1250),
