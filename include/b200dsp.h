@@ -313,6 +313,23 @@ int  b200_block_max_out(b200_block* b, int count);
 int  b200_block_reset(b200_block* b);
 void b200_block_destroy(b200_block* b);
 
+/* RDSDemod, the symbol-rate half of the RDS path (decoder_modules/radio/src/rds_demod.h:20-73): FastAGC -> Costas loop ->
+ * complex band-pass -> second Costas loop at the symbol frequency -> real part -> Mueller & Mueller clock recovery (128 x 8
+ * polyphase interpolator) -> slicer -> differential decoder.  Input: the complex 5 kS/s stream BroadcastFM's rdsOut carries
+ * (b200_wfm_rds_create, or a front-end VFO in B200_DEMOD_WFM_RDS mode); `in` may be a host or a device pointer.  Per recovered
+ * symbol one soft value (RDSDemod::soft) and one decoded bit (RDSDemod::out), written to HOST buffers of at least
+ * b200_rds_demod_max_out(count) entries; returns the number of symbols of this call (it depends on the recovered clock, which
+ * is why this block is not a front-end stage: every other count is known on the host before the launch).
+ * The three feedback loops run on one thread of the device in the reference's fp32 statement order; the band-pass in parallel. */
+typedef struct b200_rds_demod b200_rds_demod;
+b200_rds_demod* b200_rds_demod_create(void);
+int        b200_rds_demod_process(b200_rds_demod* r, int count, const void* in_iq, float* soft, uint8_t* hard);
+int        b200_rds_demod_max_out(int count);
+int        b200_rds_demod_reset(b200_rds_demod* r);                        /* RDSDemod::reset (rds_demod.h:52-62) */
+long long  b200_rds_demod_launch_count(b200_rds_demod* r);
+int        b200_rds_demod_taps(float* bandpass_iq, int cap_taps, float* bank_128x8);   /* test hook: tap count; the two designed tap sets */
+void       b200_rds_demod_destroy(b200_rds_demod* r);
+
 /* Stand-alone spectrum handler == IQFrontEnd::handler on one already-framed block of nz samples:
  * window*(-1)^n -> FFT -> 10log10(|X/N|^2)  (iq_frontend.cpp:248-267).  Host in, host out. */
 typedef struct b200_fft b200_fft;

@@ -76,6 +76,44 @@ class Block:
             pass
 
 
+class RdsDemod:
+    def __init__(self, lib):
+        self._lib, self._h = lib, lib.orc_rdsdemod_create()
+        if not self._h:
+            raise RuntimeError("oracle block creation failed")
+
+    def process(self, x):
+        x = np.ascontiguousarray(x, np.complex64).reshape(-1)
+        soft = np.empty(x.size + 16, np.float32)
+        hard = np.empty(x.size + 16, np.uint8)
+        n = self._lib.orc_rdsdemod_process(self._h, int(x.size), x.ctypes.data_as(C.c_void_p), soft.ctypes.data_as(C.c_void_p),
+                                           hard.ctypes.data_as(C.c_void_p))
+        if n < 0:
+            raise RuntimeError("oracle process failed")
+        return soft[:n].copy(), hard[:n].copy()
+
+    def process_chunks(self, x, chunk):
+        x = np.ascontiguousarray(x, np.complex64).reshape(-1)
+        parts = [self.process(x[i:i + chunk]) for i in range(0, x.size, chunk)]
+        if not parts:
+            return np.empty(0, np.float32), np.empty(0, np.uint8)
+        return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+
+    def reset(self):
+        self._lib.orc_rdsdemod_reset(self._h)
+
+    def close(self):
+        if self._h:
+            self._lib.orc_rdsdemod_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Oracle:
     def __init__(self, kind="restatement"):
         path = _PATHS[kind]
@@ -120,6 +158,11 @@ class Oracle:
             "orc_nb_create": (vp, [d, d]),
             "orc_fmif_create": (vp, [C.c_int]),
             "orc_deemph_create": (vp, [d, d]),
+            "orc_rdsdemod_create": (vp, []),
+            "orc_rdsdemod_process": (i, [vp, i, vp, vp, vp]),
+            "orc_rdsdemod_reset": (None, [vp]),
+            "orc_rdsdemod_free": (None, [vp]),
+            "orc_rdsdemod_taps": (i, [vp, i, vp]),
             "orc_process": (i, [vp, i, vp, vp]),
             "orc_reset": (None, [vp]),
             "orc_free": (None, [vp]),
@@ -266,6 +309,16 @@ class Oracle:
 
     def deemph(self, tau, sr):
         return Block(self.lib, self.lib.orc_deemph_create(tau, sr), 2, 2)
+
+    def rds_demod(self):
+        """RDSDemod (decoder_modules/radio/src/rds_demod.h): complex at 5 kS/s in -> (soft float32, hard uint8) per symbol."""
+        return RdsDemod(self.lib)
+
+    def rds_demod_taps(self):
+        bp = np.empty(2 * 1024, np.float32)
+        bank = np.empty(128 * 8, np.float32)
+        n = self.lib.orc_rdsdemod_taps(bp.ctypes.data_as(C.c_void_p), 1024, bank.ctypes.data_as(C.c_void_p))
+        return bp[: 2 * n].view(np.complex64).copy(), bank.reshape(128, 8)
 
     # ---- spectrum branch ----
     def fft_params(self, sr, size, rate):

@@ -44,6 +44,19 @@
 #include <dsp/window/nuttall.h>
 #include <dsp/window/blackman.h>
 #include <fftw3.h>
+// RDSDemod keeps its blocks private and MM its work buffer protected; the harness needs the latter to give the buffer the
+// defined start (zeros) the reference leaves to the allocator (mm.h:36-37).  Standard and dsp headers above are already
+// included (include guards), so the two keywords are only redefined for rds_demod.h and clock_recovery/mm.h.
+#include <dsp/loop/fast_agc.h>
+#include <dsp/loop/costas.h>
+#include <dsp/convert/complex_to_real.h>
+#include <dsp/digital/binary_slicer.h>
+#include <dsp/digital/differential_decoder.h>
+#define private public
+#define protected public
+#include <rds_demod.h>
+#undef private
+#undef protected
 
 #include "sdrpp_oracle.h"
 
@@ -370,6 +383,44 @@ void* orc_squelch_create(double level) { return new SquelchNode(level); }
 void* orc_nb_create(double rate, double level) { return new NbNode(rate, level); }
 void* orc_fmif_create(int bins) { return bins >= 2 ? new FmIfNode(bins) : nullptr; }
 void* orc_deemph_create(double tau, double sr) { return new DeemphNode(tau, sr); }
+
+// RDSDemod (decoder_modules/radio/src/rds_demod.h): the reference's own class, driven through its process()
+struct RdsDemodBox {
+    RDSDemod d;
+    RdsDemodBox() {
+        d.init(NULL, false);
+        // recov.out.free() has been called by init; the work buffer is what needs a defined content
+        memset(d.recov.buffer, 0, sizeof(float) * (size_t)(STREAM_BUFFER_SIZE + d.recov._interpTapCount));
+    }
+};
+void* orc_rdsdemod_create(void) { return new RdsDemodBox(); }
+int orc_rdsdemod_process(void* h, int count, const float* in_iq, float* soft, uint8_t* hard) {
+    RdsDemodBox* b = (RdsDemodBox*)h;
+    std::vector<complex_t> in((size_t)count + 1);
+    memcpy(in.data(), in_iq, sizeof(complex_t) * (size_t)count);
+    std::vector<float> so((size_t)count + 16);
+    std::vector<uint8_t> ha((size_t)count + 16);
+    int n = b->d.process(count, in.data(), so.data(), ha.data());
+    memcpy(soft, so.data(), sizeof(float) * (size_t)n);
+    memcpy(hard, ha.data(), (size_t)n);
+    return n;
+}
+void orc_rdsdemod_reset(void* h) {
+    RdsDemodBox* b = (RdsDemodBox*)h;
+    b->d.reset();          // RDSDemod::reset (rds_demod.h:52-62); the blocks are not running, tempStop / tempStart do nothing
+}
+void orc_rdsdemod_free(void* h) { delete (RdsDemodBox*)h; }
+int orc_rdsdemod_taps(float* bandpass, int cap_bp, float* bank) {
+    RdsDemodBox b;
+    int nt = b.d.taps.size;
+    if (bandpass) { memcpy(bandpass, b.d.taps.taps, sizeof(complex_t) * (size_t)(nt < cap_bp ? nt : cap_bp)); }
+    if (bank) {
+        for (int p = 0; p < b.d.recov.interpBank.phaseCount; p++) {
+            memcpy(bank + (size_t)p * b.d.recov.interpBank.tapsPerPhase, b.d.recov.interpBank.phases[p], sizeof(float) * (size_t)b.d.recov.interpBank.tapsPerPhase);
+        }
+    }
+    return nt;
+}
 
 int orc_process(void* h, int count, const void* in, void* out) { return ((Node*)h)->process(count, in, out); }
 void orc_reset(void* h) { ((Node*)h)->reset(); }

@@ -1168,6 +1168,170 @@ void* orc_deemph_create(double tau, double sr) {
     return n;
 }
 
+/* ---- RDSDemod, the symbol-rate half of the RDS path  (decoder_modules/radio/src/rds_demod.h:20-73) behind BroadcastFM's rdsOut:
+ *      loop::FastAGC<complex_t>(1.0, 1e6, 0.1)            fast_agc.h:61-80
+ *   -> loop::Costas<2>(0.005)                             costas.h:18-24,28-33 over PhaseControlLoop (phase_control_loop.h:58-85)
+ *   -> filter::FIR<complex_t,complex_t>, taps::bandPass<complex_t>(0, 2375, 100, 5000)     fir.h:74-76, band_pass.h:11-26
+ *   -> loop::Costas<2>(0.01, phase 0, freq f = hzToRads(2375/2, 5000), limits f -/+ 10 %)
+ *   -> convert::ComplexToReal -> clock_recovery::MM<float>(5000/(2375/2), 1e-6, 0.01, 0.01)   mm.h:94-147 (128 x 8 interpolator bank)
+ *   -> digital::BinarySlicer -> digital::DifferentialDecoder(2)
+ *      Two outputs per recovered symbol: the soft value (MM output) and the differentially decoded bit.
+ *      MM's work buffer is not cleared by the reference (mm.h:36-37: buffer::alloc without clear); its first 7 samples are zero here,
+ *      which is what a fresh allocation of that size holds, and the reference build used for pinning clears it too. ---- */
+typedef struct { float alpha, beta, phase, freq, minFreq, maxFreq; } pcl_t;
+static void pcl_advance(pcl_t* p, float err, int clampPhase, float minPhase, float maxPhase) {
+    p->freq += p->beta * err;                                            /* PhaseControlLoop::advance */
+    if (p->freq > p->maxFreq) { p->freq = p->maxFreq; }
+    else if (p->freq < p->minFreq) { p->freq = p->minFreq; }
+    p->phase += p->freq + (p->alpha * err);
+    if (clampPhase) {
+        const float phaseDelta = maxPhase - minPhase;
+        while (p->phase > maxPhase) { p->phase -= phaseDelta; }
+        while (p->phase < minPhase) { p->phase += phaseDelta; }
+    }
+}
+static void costas2_process(pcl_t* p, int count, const cf32* in, cf32* out) {
+    for (int i = 0; i < count; i++) {
+        const float x = -p->phase;
+        const cf32 ph = { cosf(x), sinf(x) };                            /* math::phasor(-pcl.phase) */
+        cf32 v;
+        v.re = (in[i].re * ph.re) - (in[i].im * ph.im);                  /* complex_t * complex_t (types.h:23-25) */
+        v.im = (in[i].im * ph.re) + (in[i].re * ph.im);
+        out[i] = v;
+        float err = v.re * v.im;                                         /* errorFunction, ORDER == 2 */
+        if (err < -1.0f) { err = -1.0f; }                                /* std::clamp<float>(err, -1, 1) */
+        if (err > 1.0f) { err = 1.0f; }
+        pcl_advance(p, err, 1, -FL_M_PI, FL_M_PI);
+    }
+}
+static void pcl_from_pll(pcl_t* c, const pll_t* p) {
+    c->alpha = p->alpha; c->beta = p->beta; c->phase = p->phase; c->freq = p->freq; c->minFreq = p->minFreq; c->maxFreq = p->maxFreq;
+}
+#define RDS_INTERP_PHASES 128
+#define RDS_INTERP_TAPS 8
+typedef struct {
+    float gain, setPoint, maxGain, rate, initGain;       /* FastAGC */
+    pcl_t c1, c2, c1_init, c2_init;                        /* the two Costas loops */
+    fir_t bp;                                              /* complex taps (ntaps complex, stored as 2*ntaps floats) */
+    pcl_t mm; float mm_omega;                              /* MM's PhaseControlLoop<float, false> */
+    float bank[RDS_INTERP_PHASES][RDS_INTERP_TAPS];
+    float* mmbuf;                                          /* STREAM_BUFFER_SIZE + taps */
+    int mm_offset; float lastOut;
+    uint8_t diff_last;
+    cf32 *a, *b; size_t cap;
+} rdsdemod_t;
+void* orc_rdsdemod_create(void) {
+    rdsdemod_t* r = (rdsdemod_t*)calloc(1, sizeof(rdsdemod_t));
+    if (!r) { return NULL; }
+    r->setPoint = (float)1.0; r->maxGain = (float)1e6; r->rate = (float)0.1; r->initGain = (float)1.0; r->gain = r->initGain;
+    pll_t t;
+    pll_init(&t, 0.005f, 0.0, 0.0, -FL_M_PI, FL_M_PI);                 /* costas.init(NULL, 0.005f) */
+    pcl_from_pll(&r->c1, &t); r->c1_init = r->c1;
+    int nt = orc_bandpass_c(0.0, 2375.0, 100.0, 5000.0, 0, NULL, 0);
+    float* bt = (float*)malloc(sizeof(float) * 2 * (size_t)nt);
+    orc_bandpass_c(0.0, 2375.0, 100.0, 5000.0, 0, bt, nt);
+    fir_init(&r->bp, bt, 2 * nt, 1, 2);
+    r->bp.ntaps = nt;
+    free(bt);
+    const double baudfreq = hz_to_rads(2375.0 / 2.0, 5000.0);
+    pll_init(&t, 0.01, 0.0, baudfreq, baudfreq - (baudfreq * 0.1), baudfreq + (baudfreq * 0.1));
+    pcl_from_pll(&r->c2, &t); r->c2_init = r->c2;
+    /* recov.init(NULL, omega, omegaGain 1e-6, muGain 0.01, omegaRelLimit 0.01): pcl.init(muGain, omegaGain, 0, 0, 1, omega, omega(1-l), omega(1+l)) */
+    const double omega = 5000.0 / (2375.0 / 2.0), lim = 0.01;
+    r->mm.alpha = (float)0.01; r->mm.beta = (float)1e-6; r->mm.phase = 0.0f; r->mm.freq = (float)omega;
+    r->mm.minFreq = (float)(omega * (1.0 - lim)); r->mm.maxFreq = (float)(omega * (1.0 + lim));
+    r->mm_omega = (float)omega;
+    /* generateInterpTaps (mm.h:168-173): windowedSinc<float>(128*8, hzToRads(0.5/128, 1.0), nuttall, norm = 128), phase-reversed bank */
+    {
+        const int count = RDS_INTERP_PHASES * RDS_INTERP_TAPS;
+        const double om = hz_to_rads(0.5 / (double)RDS_INTERP_PHASES, 1.0);
+        const double half = (double)count / 2.0;
+        const double corr = (double)RDS_INTERP_PHASES * om / DB_M_PI;
+        for (int i = 0; i < count; i++) {
+            double tt = (double)i - half + 0.5;
+            float tap = (float)(sinc_d(tt * om) * win_nuttall(tt - half, count) * corr);
+            r->bank[(RDS_INTERP_PHASES - 1) - (i % RDS_INTERP_PHASES)][i / RDS_INTERP_PHASES] = tap;
+        }
+    }
+    r->mmbuf = (float*)calloc((size_t)STREAM_BUFFER_SIZE + RDS_INTERP_TAPS, sizeof(float));
+    return r;
+}
+void orc_rdsdemod_free(void* h) {
+    rdsdemod_t* r = (rdsdemod_t*)h;
+    if (!r) { return; }
+    fir_free(&r->bp); free(r->mmbuf); free(r->a); free(r->b); free(r);
+}
+void orc_rdsdemod_reset(void* h) {                                       /* RDSDemod::reset (rds_demod.h:52-62) */
+    rdsdemod_t* r = (rdsdemod_t*)h;
+    r->gain = r->initGain;
+    r->c1.phase = r->c1_init.phase; r->c1.freq = r->c1_init.freq;
+    memset(r->bp.buffer, 0, sizeof(cf32) * (size_t)(r->bp.ntaps - 1));
+    r->c2.phase = r->c2_init.phase; r->c2.freq = r->c2_init.freq;
+    r->mm_offset = 0; r->mm.phase = 0.0f; r->mm.freq = r->mm_omega; r->lastOut = 0.0f;     /* MM::reset keeps the work buffer */
+    r->diff_last = 0;
+}
+int orc_rdsdemod_taps(float* bandpass, int cap_bp, float* bank) {        /* test hook: the two tap sets */
+    int nt = orc_bandpass_c(0.0, 2375.0, 100.0, 5000.0, 0, bandpass, cap_bp);
+    if (bank) {
+        rdsdemod_t* r = (rdsdemod_t*)orc_rdsdemod_create();
+        memcpy(bank, r->bank, sizeof(r->bank));
+        orc_rdsdemod_free(r);
+    }
+    return nt;
+}
+int orc_rdsdemod_process(void* h, int count, const float* in_iq, float* soft, uint8_t* hard) {
+    rdsdemod_t* r = (rdsdemod_t*)h;
+    const cf32* in = (const cf32*)in_iq;
+    if (count < 0 || count > STREAM_BUFFER_SIZE) { return -1; }
+    if ((size_t)count > r->cap) {
+        r->cap = (size_t)count + 1024;
+        r->a = (cf32*)realloc(r->a, r->cap * sizeof(cf32));
+        r->b = (cf32*)realloc(r->b, r->cap * sizeof(cf32));
+    }
+    /* FastAGC<complex_t>::process (fast_agc.h:61-80) */
+    for (int i = 0; i < count; i++) {
+        r->a[i].re = in[i].re * r->gain;
+        r->a[i].im = in[i].im * r->gain;
+        float amp = camp(r->a[i]);
+        r->gain += (r->setPoint - amp) * r->rate;
+        if (r->gain > r->maxGain) { r->gain = r->maxGain; }
+    }
+    costas2_process(&r->c1, count, r->a, r->b);
+    fir_process_cc(&r->bp, count, r->b, r->b);
+    costas2_process(&r->c2, count, r->b, r->a);
+    /* ComplexToReal, then MM<float>::process (mm.h:94-147) in place */
+    float* buf = r->mmbuf;
+    for (int i = 0; i < count; i++) { buf[RDS_INTERP_TAPS - 1 + i] = r->a[i].re; }
+    int outCount = 0;
+    while (r->mm_offset < count) {
+        float fph = floorf(r->mm.phase * (float)RDS_INTERP_PHASES);
+        int phase = (int)fph;                                            /* std::clamp<int>(floorf(..), 0, phaseCount - 1) */
+        if (phase < 0) { phase = 0; }
+        if (phase > RDS_INTERP_PHASES - 1) { phase = RDS_INTERP_PHASES - 1; }
+        float outVal;
+        ovk_dot_32f(&outVal, &buf[r->mm_offset], r->bank[phase], RDS_INTERP_TAPS);
+        soft[outCount++] = outVal;
+        float sl = (r->lastOut > 0.0) ? 1.0 : -1.0, so = (outVal > 0.0) ? 1.0 : -1.0;    /* math::step<float> (step.h:15) */
+        float error = (sl * outVal) - (r->lastOut * so);
+        r->lastOut = outVal;
+        if (error > 1.0f) { error = 1.0f; }
+        if (error < -1.0f) { error = -1.0f; }
+        pcl_advance(&r->mm, error, 0, 0.0f, 1.0f);
+        float delta = floorf(r->mm.phase);
+        r->mm_offset += delta;                                           /* int += float: converted through float */
+        r->mm.phase -= delta;
+    }
+    r->mm_offset -= count;
+    memmove(buf, &buf[count], (RDS_INTERP_TAPS - 1) * sizeof(float));
+    /* BinarySlicer (binary_slicer.h:14-19), DifferentialDecoder(2) (differential_decoder.h:39-44) */
+    for (int i = 0; i < outCount; i++) {
+        uint8_t bit = soft[i] > 0.0f;
+        hard[i] = (uint8_t)((bit - r->diff_last + 2) % 2);
+        r->diff_last = bit;
+    }
+    return outCount;
+}
+
 int orc_process(void* h, int count, const void* in, void* out) { return ((node*)h)->process((node*)h, count, in, out); }
 void orc_reset(void* h) { ((node*)h)->reset((node*)h); }
 void orc_free(void* h) { if (h) { ((node*)h)->destroy((node*)h); } }

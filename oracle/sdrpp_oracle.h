@@ -88,6 +88,14 @@ int   orc_process(void* h, int count, const void* in, void* out);
 void  orc_reset(void* h);
 void  orc_free(void* h);
 
+/* RDSDemod (decoder_modules/radio/src/rds_demod.h:64-73): cf32 at 5 kS/s -> one soft value and one differentially decoded
+ * bit per recovered symbol; returns the symbol count of this call */
+void* orc_rdsdemod_create(void);
+int   orc_rdsdemod_process(void* h, int count, const float* in_iq, float* soft, uint8_t* hard);
+void  orc_rdsdemod_reset(void* h);
+void  orc_rdsdemod_free(void* h);
+int   orc_rdsdemod_taps(float* bandpass, int cap_bp, float* bank);      /* test hook: band-pass taps (count returned), 128 x 8 interpolator bank */
+
 /* ---- spectrum branch (IQFrontEnd::handler / updateFFTPath, iq_frontend.cpp:248-309) ---- */
 void  orc_fft_params(double samplerate, int size, double rate, int* skip, int* nz); /* genReshapeParams */
 void  orc_window_buf(int window, int nz, float* out);                    /* window(i,nz) * (-1)^i as float */

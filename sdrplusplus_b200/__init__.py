@@ -5,7 +5,7 @@ ctypes binding the tests and bench.py use, plus the host-side mirrors of the ref
 block interfaces.  There is no CPU fallback: every compute call fails loudly without a CUDA device.
 """
 from .lib import load, B200Error  # noqa: F401
-from .frontend import FrontEnd, VfoConfig, Block, SpectrumHandler  # noqa: F401
+from .frontend import FrontEnd, VfoConfig, Block, SpectrumHandler, RdsDemod  # noqa: F401
 from . import lib as _lib  # noqa: F401
 
-__all__ = ["load", "B200Error", "FrontEnd", "VfoConfig", "Block", "SpectrumHandler"]
+__all__ = ["load", "B200Error", "FrontEnd", "VfoConfig", "Block", "SpectrumHandler", "RdsDemod"]

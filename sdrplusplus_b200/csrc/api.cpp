@@ -1157,6 +1157,134 @@ extern "C" int b200_block_reset(b200_block* b) {
     return b->sch.reset_raw();
 }
 
+// ------------------------------------------------------------------ RDSDemod (decoder_modules/radio/src/rds_demod.h)
+// Not a Chain stage: the clock recovery's output count depends on the data, so it cannot be mirrored on the host like the
+// counts of every other block; the count comes back with the symbols (one small copy + one synchronisation per call at 5 kS/s).
+struct b200_rds_demod {
+    cudaStream_t stream = nullptr;
+    DevBuf in, soft, hard, state, taps, bank;
+    RdsState init;               // what reset() restores
+    RdsJob proto;
+    int max_chunk = 1000000;     // STREAM_BUFFER_SIZE (core/src/dsp/stream.h:9)
+    int out_cap = 0;
+    RdsState* hstate = nullptr;  // pinned: the state block (with the symbol count) after a launch
+    float* hsoft = nullptr;      // pinned staging of the symbols
+    unsigned char* hhard = nullptr;
+    long long launches = 0;
+};
+extern "C" int b200_rds_demod_max_out(int count) {
+    if (count < 0) { return 0; }
+    // the recovered clock stays within 1 % of 5000 / 1187.5 samples per symbol (MM's omegaRelLimit, rds_demod.h:32)
+    const double omega_min = (5000.0 / (2375.0 / 2.0)) * (1.0 - 0.01);
+    return (int)((double)count / omega_min) + 2;
+}
+extern "C" void b200_rds_demod_destroy(b200_rds_demod* r) {
+    if (!r) { return; }
+    if (r->stream) { cudaStreamSynchronize(r->stream); cudaStreamDestroy(r->stream); }
+    if (r->hstate) { cudaFreeHost(r->hstate); }
+    if (r->hsoft) { cudaFreeHost(r->hsoft); }
+    if (r->hhard) { cudaFreeHost(r->hhard); }
+    delete r;
+}
+extern "C" b200_rds_demod* b200_rds_demod_create(void) {
+    if (ensure_device()) { return nullptr; }
+    b200_rds_demod* r = new b200_rds_demod;
+    int rc = 0;
+    if (cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "cudaStreamCreate"); r->stream = nullptr; }
+    // init() of rds_demod.h:20-41
+    const std::vector<float> bp = bandpass_c_taps(0.0, 2375.0, 100.0, 5000.0, false);      // (re, im) pairs
+    const std::vector<float> bank = mm_interp_bank(RDS_MM_PHASES, RDS_MM_TAPS);
+    const int nt = (int)bp.size() / 2;
+    if (!rc && (nt < 2 || nt > RDS_MAXTAPS)) { set_error("RDS band-pass of %d taps", nt); rc = B200_EINVAL; }
+    r->out_cap = b200_rds_demod_max_out(r->max_chunk);
+    if (!rc) { rc = r->in.alloc((size_t)r->max_chunk * sizeof(float2), false); }
+    if (!rc) { rc = r->soft.alloc((size_t)r->out_cap * sizeof(float), false); }
+    if (!rc) { rc = r->hard.alloc((size_t)r->out_cap, false); }
+    if (!rc) { rc = r->state.alloc(sizeof(RdsState), false); }
+    if (!rc) { rc = r->taps.alloc(bp.size() * sizeof(float), false); }
+    if (!rc) { rc = r->bank.alloc(bank.size() * sizeof(float), false); }
+    if (!rc && cudaMallocHost((void**)&r->hstate, sizeof(RdsState)) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "cudaMallocHost"); }
+    if (!rc && cudaMallocHost((void**)&r->hsoft, (size_t)r->out_cap * sizeof(float)) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "cudaMallocHost"); }
+    if (!rc && cudaMallocHost((void**)&r->hhard, (size_t)r->out_cap) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "cudaMallocHost"); }
+    if (rc) { b200_rds_demod_destroy(r); return nullptr; }
+    RdsJob& J = r->proto;
+    memset(&J, 0, sizeof(J));
+    J.ntaps = nt;
+    J.set_point = (float)1.0; J.max_gain = (float)1e6; J.rate = (float)0.1;               // agc.init(NULL, 1.0, 1e6, 0.1)
+    pll_coefficients(0.005f, J.c1_alpha, J.c1_beta);                                       // costas.init(NULL, 0.005f)
+    J.c1_min = -3.1415926535f; J.c1_max = 3.1415926535f;                                   // FL_M_PI (math/constants.h:4)
+    const double baud = hz_to_rads(2375.0 / 2.0, 5000.0);
+    pll_coefficients(0.01, J.c2_alpha, J.c2_beta);                                         // costas2.init(NULL, 0.01, 0, f, f - 10 %, f + 10 %)
+    J.c2_min = (float)(baud - (baud * 0.1)); J.c2_max = (float)(baud + (baud * 0.1));
+    const double omega = 5000.0 / (2375.0 / 2.0);                                          // recov.init(NULL, omega, 1e-6, 0.01, 0.01)
+    J.mm_alpha = (float)0.01; J.mm_beta = (float)1e-6;
+    J.mm_min = (float)(omega * (1.0 - 0.01)); J.mm_max = (float)(omega * (1.0 + 0.01));
+    memset(&r->init, 0, sizeof(r->init));
+    r->init.gain = (float)1.0;
+    r->init.c2_freq = (float)baud;
+    r->init.mm_freq = (float)omega;
+    cudaError_t e = cudaMemcpyAsync(r->taps.p, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream);
+    if (e == cudaSuccess) { e = cudaMemcpyAsync(r->bank.p, bank.data(), bank.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream); }
+    if (e == cudaSuccess) { e = cudaMemcpyAsync(r->state.p, &r->init, sizeof(RdsState), cudaMemcpyHostToDevice, r->stream); }
+    if (e == cudaSuccess) { e = cudaStreamSynchronize(r->stream); }
+    if (e != cudaSuccess) { cuda_fail(e, "RDS demodulator tables"); b200_rds_demod_destroy(r); return nullptr; }
+    return r;
+}
+extern "C" int b200_rds_demod_process(b200_rds_demod* r, int count, const void* in, float* soft, uint8_t* hard) {
+    if (!r || (count > 0 && (!in || !soft || !hard))) { set_error("null argument"); return B200_EINVAL; }
+    if (count < 0 || count > r->max_chunk) { set_error("count %d exceeds the block's chunk limit %d", count, r->max_chunk); return B200_ECAP; }
+    if (count == 0) { return 0; }
+    cudaStream_t s = r->stream;
+    B200_CK(cudaMemcpyAsync(r->in.p, in, (size_t)count * sizeof(float2), cudaMemcpyDefault, s));      // host or device memory
+    RdsParams p;
+    memset(&p, 0, sizeof(p));
+    p.njobs = 1;
+    p.job[0] = r->proto;
+    RdsJob& J = p.job[0];
+    J.in = r->in.as<float2>(); J.soft = r->soft.as<float>(); J.hard = r->hard.as<unsigned char>();
+    J.state = r->state.as<RdsState>(); J.taps = r->taps.as<float2>(); J.bank = r->bank.as<float>();
+    J.n = count; J.out_cap = r->out_cap;
+    cudaError_t e = launch_rds_demod(p, s);
+    if (e != cudaSuccess) { return cuda_fail(e, "launch_rds_demod"); }
+    r->launches++;
+    const int bound = std::min(r->out_cap, b200_rds_demod_max_out(count));
+    B200_CK(cudaMemcpyAsync(r->hstate, r->state.p, sizeof(RdsState), cudaMemcpyDeviceToHost, s));
+    B200_CK(cudaMemcpyAsync(r->hsoft, r->soft.p, (size_t)bound * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B200_CK(cudaMemcpyAsync(r->hhard, r->hard.p, (size_t)bound, cudaMemcpyDeviceToHost, s));
+    B200_CK(cudaStreamSynchronize(s));
+    const int n = r->hstate->out_count;
+    if (n < 0 || n > bound) { set_error("RDS clock recovery produced %d symbols from %d samples (bound %d)", n, count, bound); return B200_ECAP; }
+    memcpy(soft, r->hsoft, (size_t)n * sizeof(float));
+    memcpy(hard, r->hhard, (size_t)n);
+    return n;
+}
+extern "C" int b200_rds_demod_reset(b200_rds_demod* r) {
+    if (!r) { set_error("null block"); return B200_EINVAL; }
+    // RDSDemod::reset (rds_demod.h:52-62): gain, loop phases / frequencies, band-pass delay line, MM offset / phase / lastOut,
+    // decoder memory.  MM::reset (mm.h:83-92) leaves its work-buffer tail alone: so does this.
+    B200_CK(cudaStreamSynchronize(r->stream));
+    B200_CK(cudaMemcpyAsync(r->hstate, r->state.p, sizeof(RdsState), cudaMemcpyDeviceToHost, r->stream));
+    B200_CK(cudaStreamSynchronize(r->stream));
+    RdsState st = r->init;
+    memcpy(st.m_hist, r->hstate->m_hist, sizeof(st.m_hist));
+    *r->hstate = st;
+    B200_CK(cudaMemcpyAsync(r->state.p, r->hstate, sizeof(RdsState), cudaMemcpyHostToDevice, r->stream));
+    B200_CK(cudaStreamSynchronize(r->stream));
+    return 0;
+}
+extern "C" long long b200_rds_demod_launch_count(b200_rds_demod* r) { return r ? r->launches : 0; }
+/* test hooks: the two tap sets of the block as the host designs them */
+extern "C" int b200_rds_demod_taps(float* bandpass, int cap_bp, float* bank) {
+    const std::vector<float> bp = bandpass_c_taps(0.0, 2375.0, 100.0, 5000.0, false);
+    const int nt = (int)bp.size() / 2;
+    if (bandpass) { memcpy(bandpass, bp.data(), sizeof(float) * 2 * (size_t)std::min(nt, cap_bp)); }
+    if (bank) {
+        const std::vector<float> b = mm_interp_bank(RDS_MM_PHASES, RDS_MM_TAPS);
+        memcpy(bank, b.data(), b.size() * sizeof(float));
+    }
+    return nt;
+}
+
 // ------------------------------------------------------------------ stand-alone spectrum handler
 struct b200_fft {
     FftCore core;

@@ -109,6 +109,20 @@ void pll_coefficients(double bandwidth, float& alpha, float& beta) {
     beta = (4 * bw * bw) / den;
 }
 
+// clock_recovery::MM::generateInterpTaps (mm.h:168-173)
+std::vector<float> mm_interp_bank(int phases, int taps) {
+    const int count = phases * taps;
+    const double omega = hz_to_rads(0.5 / (double)phases, 1.0);
+    const double half = (double)count / 2.0;
+    const double corr = (double)phases * omega / kPi;
+    std::vector<float> bank((size_t)count, 0.0f);
+    for (int i = 0; i < count; i++) {
+        const double t = (double)i - half + 0.5;
+        bank[(size_t)((phases - 1) - (i % phases)) * taps + (i / phases)] = (float)(sinc(t * omega) * nuttall(t - half, count) * corr);
+    }
+    return bank;
+}
+
 // iq_frontend.cpp:281-291
 std::vector<float> fmif_window(int bins) {
     std::vector<float> w((size_t)bins);

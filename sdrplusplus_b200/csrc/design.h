@@ -14,6 +14,9 @@ std::vector<float> windowed_sinc_taps(int count, double omega);          // taps
 std::vector<float> highpass_taps(double cutoff, double transWidth, double samplerate, bool odd = false);                 // taps::highPass
 std::vector<float> bandpass_c_taps(double bandStart, double bandStop, double transWidth, double samplerate, bool odd = false); // taps::bandPass<complex_t>, (re, im) pairs
 void pll_coefficients(double bandwidth, float& alpha, float& beta);
+// clock_recovery::MM::generateInterpTaps (mm.h:168-173): windowedSinc<float>(phases * taps, hzToRads(0.5 / phases, 1), nuttall,
+// norm = phases) laid out by buildPolyphaseBank (polyphase_bank.h:15-48) as [phases][taps]
+std::vector<float> mm_interp_bank(int phases, int taps);
 std::vector<float> fmif_window(int bins);                                // noise_reduction::FMIF::initBuffers: window::nuttall(i, bins - 1) (fm_if.h:116)
 std::vector<float> dft_twiddles(int n);                                  // exp(-2 pi i k / n) as (re, im) pairs, fp64 -> fp32      // PhaseControlLoop<float>::criticallyDamped
 std::vector<float> fft_window(int window, int nz);                       // IQFrontEnd::updateFFTPath window * (-1)^i

@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(128) k_xd_simple(const __grid_constant__ XdPar
 #include "dfir_reg.cuh"
 #include "fused_tail.cuh"
 #include "stereo.cuh"
+#include "rds.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // retune edge: outputs whose tap window straddles the chunk start when the VFO offset changed at this

@@ -254,6 +254,37 @@ struct StJob {
 struct StParams { int njobs; int max_n; StJob job[B200_BATCH]; };
 cudaError_t launch_stereo(const StParams& p, cudaStream_t s, int* nlaunch);
 
+// ---- RDSDemod, the symbol-rate half of the RDS path (rds.cuh; decoder_modules/radio/src/rds_demod.h:64-73) ----
+#define RDS_MAXTAPS 256
+#define RDS_MM_PHASES 128
+#define RDS_MM_TAPS 8
+struct RdsState {
+    float gain;                         // FastAGC::_gain
+    float c1_phase, c1_freq;            // first Costas loop
+    float c2_phase, c2_freq;            // second Costas loop
+    float mm_phase, mm_freq, last_out;  // MM: pcl.phase (mu), pcl.freq (omega), lastOut
+    int offset, diff_last;              // MM::offset, DifferentialDecoder::last
+    int out_count;                      // symbols of the last launch
+    int pad;
+    float2 c1_hist[RDS_MAXTAPS];        // band-pass delay line (ntaps - 1 used)
+    float m_hist[RDS_MM_TAPS];          // MM work-buffer tail (7 used)
+};
+struct RdsJob {
+    const float2* in;       // n complex samples at 5 kS/s
+    float* soft;            // out_cap
+    unsigned char* hard;    // out_cap
+    RdsState* state;
+    const float2* taps;     // band-pass, complex
+    const float* bank;      // [RDS_MM_PHASES][RDS_MM_TAPS]
+    int n, ntaps, out_cap, pad;
+    float set_point, max_gain, rate;
+    float c1_alpha, c1_beta, c1_min, c1_max;
+    float c2_alpha, c2_beta, c2_min, c2_max;
+    float mm_alpha, mm_beta, mm_min, mm_max;
+};
+struct RdsParams { int njobs; int pad; RdsJob job[B200_BATCH]; };
+cudaError_t launch_rds_demod(const RdsParams& p, cudaStream_t s);
+
 // ---- noise_reduction::PowerSquelch at the VFO output (stereo.cuh) ----
 #define SQ_MAXPARTS 256
 struct SqJob { const float2* in; float2* out; float* partial; int n; float level; };

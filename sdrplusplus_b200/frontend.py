@@ -367,6 +367,50 @@ class Block:
             pass
 
 
+class RdsDemod:
+    """RDSDemod (decoder_modules/radio/src/rds_demod.h): complex at 5 kS/s in -> (soft float32, decoded bits uint8) per symbol."""
+
+    def __init__(self):
+        self._l = L.load()
+        self._h = L.check_ptr(self._l.b200_rds_demod_create())
+
+    def process(self, x):
+        """x: complex64 numpy array, or a CUDA tensor of interleaved float32 (re, im) pairs (read in place)."""
+        if hasattr(x, "data_ptr"):
+            count, ptr = x.numel() // 2, x.data_ptr()
+        else:
+            x = np.ascontiguousarray(x, np.complex64).reshape(-1)
+            count, ptr = x.size, x.ctypes.data
+        cap = max(1, self._l.b200_rds_demod_max_out(count))
+        soft, hard = np.empty(cap, np.float32), np.empty(cap, np.uint8)
+        n = L.check(self._l.b200_rds_demod_process(self._h, count, ptr, soft.ctypes.data, hard.ctypes.data))
+        return soft[:n].copy(), hard[:n].copy()
+
+    def process_chunks(self, x, chunk):
+        x = np.ascontiguousarray(x, np.complex64).reshape(-1)
+        parts = [self.process(x[i:i + chunk]) for i in range(0, x.size, chunk)]
+        if not parts:
+            return np.empty(0, np.float32), np.empty(0, np.uint8)
+        return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+
+    def reset(self):
+        L.check(self._l.b200_rds_demod_reset(self._h))
+
+    def launch_count(self):
+        return self._l.b200_rds_demod_launch_count(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._l.b200_rds_demod_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class SpectrumHandler:
     def __init__(self, size, nz, window=L.WIN_NUTTALL):
         self._l = L.load()

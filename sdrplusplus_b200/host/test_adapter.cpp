@@ -10,6 +10,7 @@
 #include "dsp/channel/rx_vfo.h"
 #include "dsp/demod/broadcast_fm.h"
 #include "dsp/b200/frontend.h"
+#include "radio/rds_demod.h"
 #include "dsp/compression/sample_stream_compressor.h"   // compiled here; exercised through the C ABI in tests/test_gpu_parity.py
 
 static std::vector<float> g_line(65536);
@@ -61,6 +62,50 @@ int main(int argc, char** argv) {
         fwrite(audio.data(), sizeof(dsp::stereo_t), audio.size(), o);
         fclose(o);
         printf("%zu %d\n", audio.size(), g_lines);
+        return 0;
+    }
+    if (argc > 3 && !strcmp(argv[3], "rds")) {
+        // the radio module's RDS wiring (demodulators/wfm.h:78-81): BroadcastFM(rdsOut = true) -> RDSDemod; input at the 250 kS/s IF
+        const int ifchunk = 12500;
+        dsp::stream<dsp::complex_t> ifin(ifchunk);
+        dsp::demod::BroadcastFM wfm(&ifin, 75000.0, 250000.0, false, true, true);
+        RDSDemod rds(&wfm.rdsOut, true);
+        if (!wfm.ok() || !rds.ok()) { fprintf(stderr, "%s\n", b200_last_error()); return 3; }
+        rds.start();
+        wfm.start();
+        const size_t nch = iq.size() / ifchunk;
+        std::thread w([&] {
+            for (size_t i = 0; i < nch; i++) {
+                memcpy(ifin.writeBuf, &iq[i * ifchunk], ifchunk * sizeof(dsp::complex_t));
+                if (!ifin.swap(ifchunk)) { return; }
+            }
+        });
+        std::thread audio([&] {                       // the audio output has to be drained like the radio's sink does
+            for (size_t c = 0; c < nch; c++) {
+                if (wfm.out.read() < 0) { return; }
+                wfm.out.flush();
+            }
+        });
+        std::vector<uint8_t> bits;
+        std::vector<float> softs;
+        for (size_t c = 0; c < nch; c++) {            // one RDS chunk (250 samples at 5 kS/s) per IF chunk
+            int n = rds.out.read();
+            if (n < 0) { break; }
+            bits.insert(bits.end(), rds.out.readBuf, rds.out.readBuf + n);
+            rds.out.flush();
+            int m = rds.soft.read();
+            if (m < 0) { break; }
+            softs.insert(softs.end(), rds.soft.readBuf, rds.soft.readBuf + m);
+            rds.soft.flush();
+        }
+        w.join();
+        audio.join();
+        wfm.stop();
+        rds.stop();
+        FILE* o = fopen(argv[2], "wb");
+        fwrite(bits.data(), 1, bits.size(), o);
+        fclose(o);
+        printf("%zu %zu\n", bits.size(), softs.size());
         return 0;
     }
     dsp::channel::RxVFO vfo(&input, fs, 250000.0, 150000.0, 300000.0);

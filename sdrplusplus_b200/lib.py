@@ -111,6 +111,13 @@ SIGNATURES = {
     "b200_block_max_out": (_i, [_vp, _i]),
     "b200_block_reset": (_i, [_vp]),
     "b200_block_destroy": (None, [_vp]),
+    "b200_rds_demod_create": (_vp, []),
+    "b200_rds_demod_process": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "b200_rds_demod_max_out": (_i, [_i]),
+    "b200_rds_demod_reset": (_i, [_vp]),
+    "b200_rds_demod_launch_count": (_ll, [_vp]),
+    "b200_rds_demod_taps": (_i, [_vp, _i, _vp]),
+    "b200_rds_demod_destroy": (None, [_vp]),
     "b200_fft_create": (_vp, [_i, _i, _i]),
     "b200_fft_frame": (_i, [_vp, _vp, _vp]),
     "b200_fft_raw": (_i, [_vp, _vp, _vp]),

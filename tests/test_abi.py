@@ -117,3 +117,17 @@ def test_pcm_packet_header_parsing_matches_reference_decompressor(oracle):
     bad[2] = 9
     with pytest.raises(L.B200Error):
         frontend.pcm_packet_info(bad)
+
+
+def test_rds_demod_tap_sets_bit_exact(oracle):
+    """RDSDemod's two designed tap sets (band-pass of rds_demod.h:29, MM's 128 x 8 interpolator bank of mm.h:168-173) as the
+    library's host side designs them, against the oracle (itself pinned to the reference build)."""
+    L = lib.load()
+    bp = np.zeros(2 * 256, np.float32)
+    bank = np.zeros(128 * 8, np.float32)
+    n = L.b200_rds_demod_taps(bp.ctypes.data, 256, bank.ctypes.data)
+    obp, obank = oracle.rds_demod_taps()
+    assert n == obp.size == 190
+    assert np.array_equal(bp[: 2 * n].view(np.uint32), obp.view(np.float32).view(np.uint32))
+    assert np.array_equal(bank.view(np.uint32), obank.reshape(-1).view(np.uint32))
+    assert L.b200_rds_demod_max_out(0) == 2 and L.b200_rds_demod_max_out(5000) >= 1188 + 12

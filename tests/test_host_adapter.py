@@ -19,6 +19,7 @@ def test_adapter_headers_compile():
     host = os.path.join(ROOT, "sdrplusplus_b200", "host")
     headers = sorted(os.path.relpath(os.path.join(d, f), host) for d, _, fs in os.walk(os.path.join(host, "dsp")) for f in fs if f.endswith(".h"))
     assert len(headers) >= 33
+    headers.append(os.path.join("radio", "rds_demod.h"))      # the radio module's RDSDemod (decoder_modules/radio/src/rds_demod.h)
     for h in headers:                                   # every header of the mirrored tree, each on its own
         r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", host, "-x", "c++", os.path.join(host, h)],
                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -44,3 +45,31 @@ def test_adapter_graph_matches_oracle(oracle, tmp_path, mode):
     assert rel_rms(got[4000:], ref[4000:]) < 1e-5
     if mode == "fused":
         assert int(r.stdout.split()[1]) == 2          # two 65536-pt lines completed in 240000 samples at 20 fps
+
+
+@pytest.mark.gpu
+def test_adapter_rds_wiring_decodes_bits(oracle, tmp_path):
+    """The radio module's RDS wiring on the adapter classes (demodulators/wfm.h:78-81): BroadcastFM(rdsOut) -> RDSDemod as
+    worker-thread blocks; the decoded bits are the oracle chain's and the transmitted ones."""
+    from util import rds_mpx_iq
+    if not os.path.exists(EXE):
+        pytest.skip("build/test_adapter missing: run python __graft_entry__.py")
+    x, bits = rds_mpx_iq(1500, 3)
+    x = x[: (x.size // 12500) * 12500]
+    src, dst = tmp_path / "if.f32", tmp_path / "bits.u8"
+    x.tofile(src)
+    r = subprocess.run([EXE, str(src), str(dst), "rds"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout
+    got = np.fromfile(dst, np.uint8)
+    nb, ns = (int(v) for v in r.stdout.split()[:2])
+    assert nb == ns == got.size
+    oracle.set_rotator_mode(1)
+    try:
+        y = oracle.wfm_rds(75e3, 250e3).process_chunks(x.view(np.float32), 12500).view(np.complex64)
+    finally:
+        oracle.set_rotator_mode(0)
+    _, ho = oracle.rds_demod().process_chunks(y, 250)
+    assert abs(got.size - ho.size) <= 1
+    n = min(got.size, ho.size)
+    assert np.count_nonzero(got[300:n] != ho[300:n]) <= 2          # a symbol on the threshold may differ (tests/test_gpu_rds.py)
+    assert max(np.mean(got[300:1300] == bits[k: k + 1000]) for k in range(200, 400)) > 0.995

@@ -60,3 +60,47 @@ def to_i16(x):
     """complex64 in [-1,1) -> interleaved int16 IQ (file_source format)."""
     v = np.clip(np.round(x.view(np.float32) * 32768.0), -32768, 32767).astype(np.int16)
     return v
+
+
+def rds_baseband(nbits, seed, fs=5000.0, amp=0.02, cfo_hz=1.5, phase0=0.7, noise_amp=0.002):
+    """An RDS-like complex baseband at `fs` (what BroadcastFM's rdsOut carries): random bits, differentially encoded, biphase
+    symbols at 1187.5 Bd (two half-symbols of opposite sign) with raised-cosine edges, a small residual carrier offset and
+    phase, uniform noise.  Returns (complex64 samples, the bits)."""
+    rng = np.random.default_rng(seed)
+    bits = rng.integers(0, 2, nbits)
+    enc = np.cumsum(bits) % 2                                   # differential encoding
+    chips = np.repeat(2.0 * enc - 1.0, 2) * np.tile([1.0, -1.0], nbits)
+    chip_rate = 2375.0
+    n = int(nbits * 2 * fs / chip_rate)
+    t = np.arange(n, dtype=np.float64) / fs
+    k = t * chip_rate
+    idx = np.minimum(k.astype(np.int64), chips.size - 1)
+    frac = k - idx
+    nxt = chips[np.minimum(idx + 1, chips.size - 1)]
+    # raised-cosine transition over the last 40 % of a chip
+    w = np.clip((frac - 0.6) / 0.4, 0.0, 1.0)
+    base = chips[idx] + (nxt - chips[idx]) * 0.5 * (1.0 - np.cos(np.pi * w))
+    x = amp * base * np.exp(1j * (2 * np.pi * cfo_hz * t + phase0))
+    x = x + (rng.uniform(-noise_amp, noise_amp, n) + 1j * rng.uniform(-noise_amp, noise_amp, n))
+    return x.astype(np.complex64), bits
+
+
+def rds_mpx_iq(nbits, seed, fs=250e3):
+    """FM carrier at `fs` whose multiplex carries programme audio, the 19 kHz pilot and a biphase RDS subcarrier at 57 kHz
+    (1187.5 Bd, differentially encoded).  Returns (complex64 IQ, bits)."""
+    rng = np.random.default_rng(seed)
+    bits = rng.integers(0, 2, nbits)
+    enc = np.cumsum(bits) % 2
+    chips = np.repeat(2.0 * enc - 1.0, 2) * np.tile([1.0, -1.0], nbits)
+    n = int(nbits * fs / 1187.5)
+    t = np.arange(n, dtype=np.float64) / fs
+    k = t * 2375.0
+    idx = np.minimum(k.astype(np.int64), chips.size - 1)
+    frac = k - idx
+    nxt = chips[np.minimum(idx + 1, chips.size - 1)]
+    w = np.clip((frac - 0.5) / 0.5, 0.0, 1.0)
+    base = chips[idx] + (nxt - chips[idx]) * 0.5 * (1.0 - np.cos(np.pi * w))
+    mpx = 0.4 * np.sin(2 * np.pi * 1000 * t) + 0.1 * np.sin(2 * np.pi * 19000 * t) + 0.06 * base * np.sin(2 * np.pi * 57000 * t + 0.4)
+    ph = 2 * np.pi * 75000.0 * np.cumsum(mpx) / fs
+    x = 0.5 * np.exp(1j * ph) + 0.001 * (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n))
+    return x.astype(np.complex64), bits
