@@ -1243,11 +1243,11 @@ extern "C" int b200_rds_demod_process(b200_rds_demod* r, int count, const void* 
     RdsJob& J = p.job[0];
     J.in = r->in.as<float2>(); J.soft = r->soft.as<float>(); J.hard = r->hard.as<unsigned char>();
     J.state = r->state.as<RdsState>(); J.taps = r->taps.as<float2>(); J.bank = r->bank.as<float>();
-    J.n = count; J.out_cap = r->out_cap;
+    const int bound = std::min(r->out_cap, b200_rds_demod_max_out(count));
+    J.n = count; J.out_cap = bound;
     cudaError_t e = launch_rds_demod(p, s);
     if (e != cudaSuccess) { return cuda_fail(e, "launch_rds_demod"); }
     r->launches++;
-    const int bound = std::min(r->out_cap, b200_rds_demod_max_out(count));
     B200_CK(cudaMemcpyAsync(r->hstate, r->state.p, sizeof(RdsState), cudaMemcpyDeviceToHost, s));
     B200_CK(cudaMemcpyAsync(r->hsoft, r->soft.p, (size_t)bound * sizeof(float), cudaMemcpyDeviceToHost, s));
     B200_CK(cudaMemcpyAsync(r->hhard, r->hard.p, (size_t)bound, cudaMemcpyDeviceToHost, s));

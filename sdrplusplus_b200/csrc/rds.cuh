@@ -109,7 +109,9 @@ __global__ void __launch_bounds__(RDS_THREADS) k_rds_demod(const __grid_constant
                 mb[RDS_MM_TAPS - 1 + i] = rds_costas(fb[i], p2, f2, J.c2_alpha, J.c2_beta, J.c2_min, J.c2_max).x;     // ComplexToReal
             }
             // MM<float>::process on this tile (count = tn)
-            while (offset < tn) {
+            // (a non-finite input would stall the reference's loop for good; here the symbol capacity ends it and the host
+            // reports the overflow)
+            while (offset < tn && nout <= J.out_cap) {
                 int ph = (int)floorf(__fmul_rn(mph, (float)RDS_MM_PHASES));
                 ph = ph < 0 ? 0 : (ph > RDS_MM_PHASES - 1 ? RDS_MM_PHASES - 1 : ph);
                 float acc = 0.f;
