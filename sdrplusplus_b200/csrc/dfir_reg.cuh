@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(DFR_THREADS) k_dfir_reg(const __grid_constant_
     using G = DfrGeom<D, T, R>;
     extern __shared__ __align__(16) float4 dfr_sm[];
     const FirJob& J = p.job[blockIdx.y];
+    pdl_trigger();
     const int mt = blockIdx.x * DFR_THREADS * R;              // first output of this CTA
     if (mt >= J.n_out) { return; }
     const long long first = (long long)J.offset + (long long)mt * D;
@@ -43,10 +44,11 @@ __global__ void __launch_bounds__(DFR_THREADS) k_dfir_reg(const __grid_constant_
         // every load of the tile in flight at once (the fill is one round trip to L2 / HBM, not NPT / 128 of them)
         constexpr int NIT = (G::NPT + DFR_THREADS - 1) / DFR_THREADS;
         float4 t[NIT];
+        pdl_wait();
 #pragma unroll
         for (int u = 0; u < NIT; u++) {
             const int i = threadIdx.x + u * DFR_THREADS;
-            t[u] = (i < G::NPT && i < need) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            t[u] = (i < G::NPT && i < need) ? __ldcg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < NIT; u++) {
@@ -93,8 +95,7 @@ __global__ void __launch_bounds__(DFR_THREADS) k_dfir_reg(const __grid_constant_
 template <int D, int T, int R>
 static cudaError_t launch_dfir_reg_t(const DfrParams& p, cudaStream_t s) {
     dim3 grid((unsigned)((p.max_out + DFR_THREADS * R - 1) / (DFR_THREADS * R)), (unsigned)p.njobs);
-    k_dfir_reg<D, T, R><<<grid, DFR_THREADS, DfrGeom<D, T, R>::SMEM, s>>>(p);
-    return cudaGetLastError();
+    return launch_chain(k_dfir_reg<D, T, R>, grid, dim3(DFR_THREADS), DfrGeom<D, T, R>::SMEM, s, p);
 }
 // true when (D, T) is one of the plan stages the kernel is built for
 bool dfir_reg_supported(int D, int T) {

@@ -80,6 +80,42 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     return *reinterpret_cast<float2*>(&rd);
 }
 
+// ---- programmatic dependent launch (PDL) for the chain of small dependent kernels behind stage 1 ----
+// A chain kernel lets its successor be scheduled as soon as all of its own CTAs are running (pdl_trigger), and touches the
+// stage buffers only after its predecessor has completed and its writes are visible (pdl_wait): the successor's launch
+// latency, CTA scheduling and table loads (taps, banks: written at configure time) hide under the predecessor.  Both are
+// no-ops in a kernel launched without the attribute.  Data a predecessor wrote is read with ld.global.cg (L2) after the
+// wait, never with the non-coherent path: the CTA was resident before those lines were written.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#define PDL_DEFAULT 2
+static int g_pdl = -1;                               // 0 off, 1 always, 2 small grids only; -1: read B200_PDL once (else PDL_DEFAULT)
+int kernels_pdl() {
+    if (g_pdl < 0) { const char* e = getenv("B200_PDL"); g_pdl = e ? atoi(e) : PDL_DEFAULT; if (g_pdl < 0 || g_pdl > 2) { g_pdl = PDL_DEFAULT; } }
+    return g_pdl;
+}
+void kernels_set_pdl(int mode) { g_pdl = (mode >= 0 && mode <= 2) ? mode : PDL_DEFAULT; }
+static int num_sms();
+// <<<>>> with the programmatic-serialization attribute (captured into graphs as programmatic edges).  Mode 2, the default,
+// gives it to launches of at most two CTAs per SM: with the small grids of the reference's own chunk sizes (<= 1e6 samples)
+// the early-resident successor costs nothing and the chain of seven dependent launches shortens by a third (500 k-sample
+// chunks: 19.9 -> 21.6 GS/s); with the grids of a 16 Mi-sample chunk the successor's waiting CTAs take shared memory and
+// registers from the spectrum branch on the other stream, which is what bounds the step there (156 -> 139 GS/s when forced).
+template <class P>
+static cudaError_t launch_chain(void (*k)(const P), dim3 grid, dim3 block, size_t smem, cudaStream_t s, const P& p) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    const int mode = kernels_pdl();
+    if (mode == 1 || (mode == 2 && (long long)grid.x * grid.y * grid.z <= 2LL * num_sms())) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, k, p);
+}
+
 // ------------------------------------------------------------------------------------------------
 // stage 1, plain variant: one thread per (output, VFO); reads IQ through L1/L2.  Kept as the in-library
 // cross-check of the tiled kernel (option "s1" = 0) and as the fallback for shapes the tile does not cover.
@@ -186,11 +222,13 @@ __global__ void __launch_bounds__(256) k_poly(const __grid_constant__ PolyParams
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_quad(const __grid_constant__ QuadParams p) {
     const QuadJob& J = p.job[blockIdx.y];
+    pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= J.n) { return; }
+    pdl_wait();
     // J.in[0] is the last sample of the previous chunk (zero at start: atan2f(0,0) = 0 = Quadrature's initial phase)
-    float2 c = __ldg(J.in + i + 1);
-    float2 q = __ldg(J.in + i);
+    float2 c = __ldcg(J.in + i + 1);
+    float2 q = __ldcg(J.in + i);
     float cur = atan2f(c.y, c.x);
     float prev = atan2f(q.y, q.x);
     float diff = __fsub_rn(cur, prev);
@@ -397,6 +435,8 @@ __device__ __forceinline__ float carry_elem(const CarryJob& J, long long s, int 
 }
 __global__ void __launch_bounds__(256) k_carry(const __grid_constant__ CarryParams p) {
     const CarryJob& J = p.job[blockIdx.x];
+    pdl_trigger();
+    pdl_wait();
     const long long L = (long long)J.la + J.lb;
     const int hf = J.h * J.esize;                 // floats to produce
     for (int base = 0; base < hf; base += blockDim.x) {
@@ -1083,8 +1123,7 @@ cudaError_t launch_poly(const PolyParams& p, cudaStream_t s) {
 cudaError_t launch_quad(const QuadParams& p, cudaStream_t s) {
     if (p.max_n <= 0 || p.njobs <= 0) { return cudaSuccess; }
     dim3 grid(cdiv(p.max_n, 256), p.njobs);
-    k_quad<<<grid, 256, 0, s>>>(p);
-    return cudaGetLastError();
+    return launch_chain(k_quad, grid, dim3(256), 0, s, p);
 }
 // resident CTAs of the fused tail per SM for a thread count and dynamic shared-memory size (registers included)
 // the opt-in shared-memory size of each k_tail_fused build only ever grows: the occupancy query and the launcher share it
@@ -1173,8 +1212,7 @@ cudaError_t launch_scale(const ScaleParams& p, cudaStream_t s) {
 }
 cudaError_t launch_carry(const CarryParams& p, cudaStream_t s) {
     if (p.njobs <= 0) { return cudaSuccess; }
-    k_carry<<<p.njobs, 256, 0, s>>>(p);
-    return cudaGetLastError();
+    return launch_chain(k_carry, dim3((unsigned)p.njobs), dim3(256), 0, s, p);
 }
 
 template <int FMT>

@@ -285,6 +285,10 @@ struct RdsJob {
 struct RdsParams { int njobs; int pad; RdsJob job[B200_BATCH]; };
 cudaError_t launch_rds_demod(const RdsParams& p, cudaStream_t s);
 
+// programmatic dependent launch for the chain kernels behind stage 1 (kernels.cu: launch_chain); env B200_PDL, option "pdl"
+int kernels_pdl();
+void kernels_set_pdl(int on);
+
 // ---- noise_reduction::PowerSquelch at the VFO output (stereo.cuh) ----
 #define SQ_MAXPARTS 256
 struct SqJob { const float2* in; float2* out; float* partial; int n; float level; };

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(TR_THREADS) k_poly_reg(const __grid_constant__
     using G = PolyGeom<L, M>;
     extern __shared__ __align__(16) float2 tr_sm[];
     const PolyJob& J = p.job[blockIdx.y];
+    pdl_trigger();
     const int tpp = J.tpp;
     // periods are aligned to the outputs whose phase is 0: m_a = first such output index (0 <= m_a < L)
     int m_a = 0;
@@ -55,9 +56,10 @@ __global__ void __launch_bounds__(TR_THREADS) k_poly_reg(const __grid_constant__
         // 8-byte elements at an arbitrary (possibly odd) start: plain coalesced loads; indices before the buffer (period 0 of
         // a chunk can start in front of the oldest history sample: those outputs are never stored) read as zero
         const long long lim = J.in_len;
+        pdl_wait();
         for (int j = threadIdx.x; j < nx + G::W; j += TR_THREADS) {
             const long long s = b0 + j;
-            X[j] = (j < nx && s >= 0 && s < lim) ? __ldg(J.in + s) : make_float2(0.0f, 0.0f);
+            X[j] = (j < nx && s >= 0 && s < lim) ? __ldcg(J.in + s) : make_float2(0.0f, 0.0f);
         }
     }
     __syncthreads();
@@ -131,8 +133,7 @@ static cudaError_t launch_poly_reg_t(const PolyParams& p, int max_tpp, cudaStrea
     if (e != cudaSuccess) { return e; }
     const int periods = (p.max_out + L - 1) / L + 1;
     dim3 grid((unsigned)((periods + PR_PER - 1) / PR_PER), (unsigned)p.njobs);
-    k_poly_reg<L, M><<<grid, TR_THREADS, smem, s>>>(p);
-    return cudaGetLastError();
+    return launch_chain(k_poly_reg<L, M>, grid, dim3(TR_THREADS), smem, s, p);
 }
 bool poly_reg_supported(int L, int M) {
     return (L == 16 && M == 25) || (L == 5 && M == 6) || (L == 2 && M == 3) || (L == 4 && M == 5) || (L == 2 && M == 5);
@@ -179,6 +180,7 @@ __device__ __forceinline__ void frg_block(float2 (&acc)[FRG_R], const float2 (&l
 __global__ void __launch_bounds__(TR_THREADS) k_fir_reg(const __grid_constant__ FirParams p) {
     extern __shared__ __align__(16) float2 tr_sm[];
     const FirJob& J = p.job[blockIdx.y];
+    pdl_trigger();
     const int mt = blockIdx.x * TS_TILE;
     if (mt >= J.n_out) { return; }
     const int T = J.ntaps;
@@ -197,8 +199,9 @@ __global__ void __launch_bounds__(TR_THREADS) k_fir_reg(const __grid_constant__ 
         const int nout = min(TS_TILE, J.n_out - mt);
         const int need = (nout + T - 1 + sh + 1) / 2;                 // pairs that hold data an output needs
         const float4* __restrict__ src = reinterpret_cast<const float4*>(J.in + (first - sh));
+        pdl_wait();
         for (int i = threadIdx.x; i < npairs; i += TR_THREADS) {
-            X4[(i >> 2) * 5 + (i & 3)] = (i < need) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            X4[(i >> 2) * 5 + (i & 3)] = (i < need) ? __ldcg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     __syncthreads();
@@ -252,8 +255,7 @@ cudaError_t launch_fir_reg(const FirParams& p, cudaStream_t s) {
     cudaError_t e = set_smem(k_fir_reg, smem);
     if (e != cudaSuccess) { return e; }
     dim3 grid((unsigned)((p.max_out + TS_TILE - 1) / TS_TILE), (unsigned)p.njobs);
-    k_fir_reg<<<grid, TR_THREADS, smem, s>>>(p);
-    return cudaGetLastError();
+    return launch_chain(k_fir_reg, grid, dim3(TR_THREADS), smem, s, p);
 }
 
 // ------------------------------------------------------------------------------------------------ real FIR (+ mono -> stereo)
@@ -284,6 +286,7 @@ __device__ __forceinline__ void frr_block(float2 (&acc)[8], const float2 (&elo)[
 __global__ void __launch_bounds__(TR_THREADS) k_firr_reg(const __grid_constant__ FirRParams p) {
     extern __shared__ __align__(16) float2 tr_sm[];
     const FirRJob& J = p.job[blockIdx.y];
+    pdl_trigger();
     const int mt = blockIdx.x * TS_TILE;
     if (mt >= J.n_out) { return; }
     const int T = J.ntaps;
@@ -301,8 +304,9 @@ __global__ void __launch_bounds__(TR_THREADS) k_firr_reg(const __grid_constant__
         const float* __restrict__ src = J.in + mt;                    // 4-byte elements, any alignment: scalar loads
         float* Ef = reinterpret_cast<float*>(E4);
         float* Of = reinterpret_cast<float*>(O4);
+        pdl_wait();
         for (int n = threadIdx.x; n < 2 * npairs; n += TR_THREADS) {
-            const float v = (n < need) ? __ldg(src + n) : 0.0f;
+            const float v = (n < need) ? __ldcg(src + n) : 0.0f;
             // pair q lives in group q >> 2 (12 floats per group), slot q & 3
             const int qe = n >> 1;
             Ef[(qe >> 2) * 12 + (qe & 3) * 2 + (n & 1)] = v;
@@ -365,6 +369,5 @@ cudaError_t launch_firr_reg(const FirRParams& p, cudaStream_t s) {
     cudaError_t e = set_smem(k_firr_reg, smem);
     if (e != cudaSuccess) { return e; }
     dim3 grid((unsigned)((p.max_out + TS_TILE - 1) / TS_TILE), (unsigned)p.njobs);
-    k_firr_reg<<<grid, TR_THREADS, smem, s>>>(p);
-    return cudaGetLastError();
+    return launch_chain(k_firr_reg, grid, dim3(TR_THREADS), smem, s, p);
 }
