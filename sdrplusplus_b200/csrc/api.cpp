@@ -267,6 +267,7 @@ extern "C" b200_fe* b200_fe_create(double samplerate, int max_chunk) {
     fe->sch.stream = fe->own_stream;
     fe->sch.fuse.on = true;
     kernels_set_xd_tma_stages(2);          // process-wide tuning knobs start from their defaults with every new front end
+    kernels_set_xd_tma_diag(0);
     {
         int dev = 0, sms = 0;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) {
@@ -502,6 +503,8 @@ extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
     if (!strcmp(key, "s1_mt")) { kernels_set_xd_tile(value); return 0; }
     if (!strcmp(key, "s1_cps")) { kernels_set_xd_cps(value); return 0; }
     if (!strcmp(key, "s1_stages")) { kernels_set_xd_tma_stages(value); return 0; }
+    if (!strcmp(key, "s1_seg")) { kernels_set_xd_tma_seg(value); return 0; }
+    if (!strcmp(key, "s1_diag")) { kernels_set_xd_tma_diag(value); return 0; }                   // measurement only: outputs are garbage
     if (!strcmp(key, "s1_ctas")) { kernels_set_xd_tma_ctas(value); return 0; }
     if (!strcmp(key, "tails") || !strncmp(key, "ft_", 3)) {
         // 0: one thread per output; 1: shared-memory tiled kernels, one launch per stage; 2: one fused launch per <= 16 VFOs

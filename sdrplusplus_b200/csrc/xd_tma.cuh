@@ -31,7 +31,8 @@ struct XtGeom {
     int s;                    // leading zero taps
     int cj;                   // window of output m starts in block cj + m
     int rows_tma;             // super-rows the tensor map covers (all inside the chunk)
-    int pad;
+    int diag;                 // measurement only (option "s1_diag"): 1 = tiles are loaded but not filtered (what the TMA ring alone
+                              // sustains), 2 = tiles are filtered but never loaded (what the consumer warps alone sustain); results are garbage
 };
 
 __device__ __forceinline__ void xt_mbar_init(unsigned bar, int count) {
@@ -69,11 +70,53 @@ struct XtLay {
     static constexpr int NW = MT / 64;                                   // consumer warps
 };
 
-template <int LOGD, int QC, int PS, int MT, int NST>
+// decimation-phase pairs [RP0, RP1) of a tile -- they all lie in ONE 128-byte segment (8 pairs per segment), whose two parity
+// regions start at sb -- into the 2 x PS class sums of a lane.  Every index is a compile-time constant: taps from the constant
+// bank, accumulators in registers.
+template <int LOGD, int QC, int PS, int REGION, int RP0, int RP1, int NQH>
+__device__ __forceinline__ void xt_accumulate(float2 (&S)[2][PS], const XtGeom& g, unsigned sb, const unsigned (&aoff)[NQH]) {
+    constexpr int D = 1 << LOGD;
+    static_assert((RP0 >> 3) == ((RP1 - 1) >> 3), "one segment per call");
+#pragma unroll
+    for (int rp = RP0; rp < RP1; rp++) {
+#pragma unroll
+        for (int q = 0; q <= QC; q++) {
+            const unsigned addr = sb + (unsigned)((q & 1) * REGION) + (aoff[q >> 1] ^ (unsigned)((rp & 7) << 4));
+            float4 x;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(addr));
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int r = 2 * rp + e;
+                const float2 xe = e ? make_float2(x.z, x.w) : make_float2(x.x, x.y);
+                if (q < QC) {
+                    const float t = g.g[q * D + r];
+                    S[0][(q * D + r) % PS] = ffma2(make_float2(t, t), xe, S[0][(q * D + r) % PS]);
+                }
+                if (q >= 1) {
+                    const float t = g.g[(q - 1) * D + r];
+                    S[1][((q - 1) * D + r) % PS] = ffma2(make_float2(t, t), xe, S[1][((q - 1) * D + r) % PS]);
+                }
+            }
+        }
+    }
+}
+
+// SPS = segments per ring slot.  SPS = NSEG: a slot is a whole tile (NSEG * 2 boxes), the consumers wait once per tile and
+// hand the tile back when all of it is filtered -- with a ring of two, ONE tile is in flight per SM while the other is being
+// consumed, and the time per tile is the memory latency plus the tile's transfer at the SM's share of the HBM bandwidth
+// (0.8 + 1.6 us for 69 KB at 6.5 TB/s / 148; measured 2.5 us).  SPS = 1: a slot is one 128-byte segment of the tile (its two
+// parity boxes); the filter loop walks the decimation phases segment by segment, so a segment goes back to the TMA engine as
+// soon as its eight phase pairs are done and the ring (NST * NSEG slots, the same shared memory) keeps all but one segment in
+// flight.
+template <int LOGD, int QC, int PS, int MT, int NST, int SPS>
 __global__ void __launch_bounds__((MT / 64 + 1) * 32, 1)
 k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, const __grid_constant__ CUtensorMap tm) {
     using Lay = XtLay<LOGD, QC, MT>;
     constexpr int D = Lay::D, NSEG = Lay::NSEG, NR = Lay::NR, REGION = Lay::REGION, STAGE = Lay::STAGE, NW = Lay::NW;
+    static_assert(SPS == 1 || SPS == NSEG, "a slot is one segment or the whole tile");
+    constexpr int STEPS = NSEG / SPS;                                    // slots a tile takes
+    constexpr int NSLOT = NST * STEPS;                                   // ring depth in slots
+    constexpr int SLOT = SPS * 2 * REGION;                               // bytes per slot
     extern __shared__ __align__(1024) unsigned char xt_smem[];
     // the dynamic window is 1024-byte aligned by the launch (checked on the host side: static shared memory is tiny)
     const unsigned sbase = ((unsigned)__cvta_generic_to_shared(xt_smem) + 1023u) & ~1023u;
@@ -82,14 +125,14 @@ k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, c
     float2* TL = C + (size_t)B200_BATCH * PS;                            // [njobs][16]  e^{j w_v D j}
     float2* PHW = TL + (size_t)B200_BATCH * 16;                          // [NW][njobs][4] per warp and tile: coarse phase
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(PHW + (size_t)NW * B200_BATCH * 4);
-    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);     // full[s] = bar0 + 8 s, empty[s] = bar0 + 8 (XT_STAGES + s)
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);     // full[s] = bar0 + 8 s, empty[s] = bar0 + 8 (NSLOT + s)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) {
-        for (int s = 0; s < XT_STAGES; s++) {
+        for (int s = 0; s < NSLOT; s++) {
             xt_mbar_init(bar0 + 8 * s, 1);
-            xt_mbar_init(bar0 + 8 * (XT_STAGES + s), NW);
+            xt_mbar_init(bar0 + 8 * (NSLOT + s), NW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -115,25 +158,29 @@ k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, c
 
     if (warp == NW) {
         // ---------------- producer ----------------
-        if (lane == 0) {
+        if (lane == 0 && !(g.diag & 2)) {
             const unsigned long long pol = xt_policy_evict_first();
-            int it = 0;
-            for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, it++) {
-                const int st = it % XT_STAGES;
-                const unsigned ph = (unsigned)((it / XT_STAGES) & 1);
-                xt_mbar_wait(bar0 + 8 * (XT_STAGES + st), ph ^ 1u);
+            int it = 0;                                                  // slot steps issued so far
+            for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
                 const long long J0 = g.jmin + (long long)tile * MT;
-                const unsigned full = bar0 + 8 * st;
+                const int row0 = (int)(J0 >> 1);
                 // every tile comes in through the TMA engine; rows outside the tensor (negative: stream history in front of
                 // the chunk; past its last full super-row: the ragged end) arrive zero-filled and are patched by the consumers
-                xt_mbar_expect(full, (unsigned)STAGE);
-                const unsigned dst = sbase + (unsigned)(st * STAGE);
-                const int row0 = (int)(J0 >> 1);
 #pragma unroll
-                for (int sg = 0; sg < NSEG; sg++) {
+                for (int step = 0; step < STEPS; step++, it++) {
+                    const int sl = it % NSLOT;
+                    const unsigned ph = (unsigned)((it / NSLOT) & 1);
+                    xt_mbar_wait(bar0 + 8 * (NSLOT + sl), ph ^ 1u);
+                    const unsigned full = bar0 + 8 * sl;
+                    xt_mbar_expect(full, (unsigned)SLOT);
+                    const unsigned dst = sbase + (unsigned)(sl * SLOT);
 #pragma unroll
-                    for (int par = 0; par < 2; par++) {
-                        xt_tma_2d(dst + (unsigned)((sg * 2 + par) * REGION), &tm, full, par * 2 * D + sg * 32, row0, pol);
+                    for (int s2 = 0; s2 < SPS; s2++) {
+                        const int sg = step * SPS + s2;
+#pragma unroll
+                        for (int par = 0; par < 2; par++) {
+                            xt_tma_2d(dst + (unsigned)((s2 * 2 + par) * REGION), &tm, full, par * 2 * D + sg * 32, row0, pol);
+                        }
                     }
                 }
             }
@@ -150,10 +197,8 @@ k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, c
         const unsigned row = (unsigned)((jl >> 1) + qh);
         aoff[qh] = row * 128u + ((row & 7u) << 4);
     }
-    int it = 0;
-    for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, it++) {
-        const int st = it % XT_STAGES;
-        const unsigned ph = (unsigned)((it / XT_STAGES) & 1);
+    int it = 0;                                     // slot steps consumed so far (the producer's sequence)
+    for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
         const long long J0 = g.jmin + (long long)tile * MT;
         // coarse phase table of this warp's 64 outputs: entry (job, i) = phase at output jl0 + 16 i, drift-centred
         {
@@ -168,65 +213,73 @@ k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, c
                 PHW[(warp * B200_BATCH + vv) * 4 + i] = phasor_u64(Jv.phase0 + Jv.w * (unsigned long long)im0 + (unsigned long long)corr);
             }
         }
-        xt_mbar_wait(bar0 + 8 * st, ph);
-        const unsigned sb = sbase + (unsigned)(st * STAGE);
-        if (!tile_fast(J0)) {
-            // patch what the tensor map does not cover: samples before the chunk (from the carried raw history) and the
-            // samples of the last, partial super-row.  A few hundred at most, once or twice per launch.
-            const long long ibase = J0 * D + g.org;
-            unsigned char* stg = gbase + st * STAGE;
-            constexpr int NSAMP = (MT + QC + 1) * D;
-            const long long tensor_end = (long long)g.org + (long long)g.rows_tma * (2 * D);
-            // the tensor's row 0 starts at sample g.org: everything of this tile in front of it was zero-filled -- stream
-            // history (index < 0) AND the first g.org samples of the chunk
-            const long long front = (long long)g.org - ibase;
-            const int head = (int)(front > 0 ? (front < NSAMP ? front : NSAMP) : 0);
-            long long t0 = tensor_end - ibase, t1 = (long long)p.count - ibase;
-            if (t0 < head) { t0 = head; }
-            if (t1 > NSAMP) { t1 = NSAMP; }
-            auto patch = [&](int idx) {
-                const float2 v = load_x<FMT_CF32>(p, ibase + idx);
-                const int j = idx >> LOGD, r = idx & (D - 1), row = j >> 1;
-                const int off = ((r >> 4) * 2 + (j & 1)) * REGION + row * 128 + ((((r >> 1) & 7) ^ (row & 7)) << 4) + (r & 1) * 8;
-                *reinterpret_cast<float2*>(stg + off) = v;
-            };
-            for (int idx = tid; idx < head; idx += NW * 32) { patch(idx); }
-            for (long long idx = t0 + tid; idx < t1; idx += NW * 32) { patch((int)idx); }
-            asm volatile("bar.sync 1, %0;\n" ::"n"(NW * 32) : "memory");
-        }
+        const bool fast = tile_fast(J0);
 
-        // ---- accumulate: D/2 phase pairs x (QC+1) window blocks, 2 outputs x PS classes per lane ----
+        // ---- accumulate: D/2 phase pairs x (QC+1) window blocks, 2 outputs x PS classes per lane, slot by slot ----
         float2 S[2][PS];
 #pragma unroll
         for (int o = 0; o < 2; o++)
 #pragma unroll
             for (int a = 0; a < PS; a++) { S[o][a] = make_float2(0.f, 0.f); }
-#pragma unroll
-        for (int rp = 0; rp < D / 2; rp++) {
-#pragma unroll
-            for (int q = 0; q <= QC; q++) {
-                const unsigned addr = sb + (unsigned)(((rp >> 3) * 2 + (q & 1)) * REGION) + (aoff[q >> 1] ^ (unsigned)((rp & 7) << 4));
-                float4 x;
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(addr));
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const int r = 2 * rp + e;
-                    const float2 xe = e ? make_float2(x.z, x.w) : make_float2(x.x, x.y);
-                    if (q < QC) {
-                        const float t = g.g[q * D + r];
-                        S[0][(q * D + r) % PS] = ffma2(make_float2(t, t), xe, S[0][(q * D + r) % PS]);
-                    }
-                    if (q >= 1) {
-                        const float t = g.g[(q - 1) * D + r];
-                        S[1][((q - 1) * D + r) % PS] = ffma2(make_float2(t, t), xe, S[1][((q - 1) * D + r) % PS]);
-                    }
+        auto slot_step = [&](auto stepc) {
+            constexpr int STEP = decltype(stepc)::value;
+            const int sl = it % NSLOT;
+            const unsigned ph = (unsigned)((it / NSLOT) & 1);
+            it++;
+            if (!(g.diag & 2)) { xt_mbar_wait(bar0 + 8 * sl, ph); }
+            const unsigned sb = sbase + (unsigned)(sl * SLOT);
+            if (!fast && !g.diag) {
+                // patch what the tensor map does not cover: samples before the chunk (from the carried raw history) and the
+                // samples of the last, partial super-row -- those of this slot's segments.  A few hundred at most, once or
+                // twice per launch.
+                const long long ibase = J0 * D + g.org;
+                unsigned char* stg = gbase + sl * SLOT;
+                constexpr int NSAMP = (MT + QC + 1) * D;
+                const long long tensor_end = (long long)g.org + (long long)g.rows_tma * (2 * D);
+                // the tensor's row 0 starts at sample g.org: everything of this tile in front of it was zero-filled -- stream
+                // history (index < 0) AND the first g.org samples of the chunk
+                const long long front = (long long)g.org - ibase;
+                const int head = (int)(front > 0 ? (front < NSAMP ? front : NSAMP) : 0);
+                long long t0 = tensor_end - ibase, t1 = (long long)p.count - ibase;
+                if (t0 < head) { t0 = head; }
+                if (t1 > NSAMP) { t1 = NSAMP; }
+                auto patch = [&](int idx) {
+                    const int j = idx >> LOGD, r = idx & (D - 1), row = j >> 1;
+                    const int s2 = (r >> 4) - STEP * SPS;                // segment of the sample, relative to this slot
+                    if (s2 < 0 || s2 >= SPS) { return; }
+                    const float2 v = load_x<FMT_CF32>(p, ibase + idx);
+                    const int off = (s2 * 2 + (j & 1)) * REGION + row * 128 + ((((r >> 1) & 7) ^ (row & 7)) << 4) + (r & 1) * 8;
+                    *reinterpret_cast<float2*>(stg + off) = v;
+                };
+                for (int idx = tid; idx < head; idx += NW * 32) { patch(idx); }
+                for (long long idx = t0 + tid; idx < t1; idx += NW * 32) { patch((int)idx); }
+                asm volatile("bar.sync 1, %0;\n" ::"n"(NW * 32) : "memory");
+            }
+            if (g.diag & 1) { }
+            else if constexpr (SPS == 1) {
+                xt_accumulate<LOGD, QC, PS, REGION, 8 * STEP, 8 * STEP + 8, NQH>(S, g, sb, aoff);
+            }
+            else {
+                xt_accumulate<LOGD, QC, PS, REGION, 0, 8, NQH>(S, g, sb, aoff);
+                xt_accumulate<LOGD, QC, PS, REGION, 8, 16, NQH>(S, g, sb + 2 * REGION, aoff);
+                if constexpr (NSEG == 4) {
+                    xt_accumulate<LOGD, QC, PS, REGION, 16, 24, NQH>(S, g, sb + 4 * REGION, aoff);
+                    xt_accumulate<LOGD, QC, PS, REGION, 24, 32, NQH>(S, g, sb + 6 * REGION, aoff);
                 }
             }
+            // the slot is consumed: hand it back to the producer
+            __syncwarp();
+            if (lane == 0 && !(g.diag & 2)) { xt_mbar_arrive(bar0 + 8 * (NSLOT + sl)); }
+        };
+        slot_step(std::integral_constant<int, 0>{});
+        if constexpr (STEPS >= 2) { slot_step(std::integral_constant<int, 1>{}); }
+        if constexpr (STEPS == 4) {
+            slot_step(std::integral_constant<int, 2>{});
+            slot_step(std::integral_constant<int, 3>{});
         }
-        // the stage is consumed: hand it back to the producer before the (register-only) combination
-        __syncwarp();
-        if (lane == 0) { xt_mbar_arrive(bar0 + 8 * (XT_STAGES + st)); }
+        static_assert(STEPS == 1 || STEPS == 2 || STEPS == 4, "D = 32 or 64");
 
+        if (g.diag & 1) { continue; }
         // ---- combine per slot (a VFO, or a +f / -f pair sharing A = sum cos*S and B = sum sin*S), rotate, store ----
         const long long m0 = J0 + jl - (long long)g.cj;
         const int nout = p.job[0].n_out;                       // every job of a filter-bank launch has the same length
