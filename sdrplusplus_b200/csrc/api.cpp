@@ -503,8 +503,6 @@ extern "C" int b200_fe_set_option(b200_fe* fe, const char* key, int value) {
     if (!strcmp(key, "s1_mt")) { kernels_set_xd_tile(value); return 0; }
     if (!strcmp(key, "s1_cps")) { kernels_set_xd_cps(value); return 0; }
     if (!strcmp(key, "s1_stages")) { kernels_set_xd_tma_stages(value); return 0; }
-    if (!strcmp(key, "s1_seg")) { kernels_set_xd_tma_seg(value); return 0; }
-    if (!strcmp(key, "s1_split")) { kernels_set_xd_tma_split(value); return 0; }
     if (!strcmp(key, "s1_diag")) { kernels_set_xd_tma_diag(value); return 0; }                   // measurement only: outputs are garbage
     if (!strcmp(key, "s1_ctas")) { kernels_set_xd_tma_ctas(value); return 0; }
     if (!strcmp(key, "tails") || !strncmp(key, "ft_", 3)) {

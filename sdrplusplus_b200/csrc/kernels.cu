@@ -911,28 +911,15 @@ int g_xd_tma_stages = 2;          // ring depth of the TMA stage 1: 2 leaves a t
 void kernels_set_xd_tma_stages(int n) { g_xd_tma_stages = (n == 3) ? 3 : 2; }
 static int g_xd_tma_diag = 0;     // XtGeom::diag (measurement only)
 void kernels_set_xd_tma_diag(int v) { g_xd_tma_diag = v & 3; }
-static int g_xd_tma_seg = -1;     // ring slots of the TMA stage 1: 1 = one 128-byte segment of a tile per slot, 0 = a whole tile (default); -1: B200_S1_SEG once
-void kernels_set_xd_tma_seg(int v) { g_xd_tma_seg = v ? 1 : 0; }
-static int xd_tma_seg() {
-    if (g_xd_tma_seg < 0) { const char* e = getenv("B200_S1_SEG"); g_xd_tma_seg = (e ? atoi(e) : 0) ? 1 : 0; }
-    return g_xd_tma_seg;
-}
-static int g_xd_tma_split = -1;   // 1 = filter warps and combine warps (k_xd_tma SPLIT); -1: B200_S1_SPLIT once, else XT_SPLIT_DEFAULT
-#define XT_SPLIT_DEFAULT 0
-void kernels_set_xd_tma_split(int v) { g_xd_tma_split = v ? 1 : 0; }
-static int xd_tma_split() {
-    if (g_xd_tma_split < 0) { const char* e = getenv("B200_S1_SPLIT"); g_xd_tma_split = (e ? atoi(e) : XT_SPLIT_DEFAULT) ? 1 : 0; }
-    return g_xd_tma_split;
-}
-template <int LOGD, int QC, int PS, int MT, int NST, int SPS, int SPLIT>
+template <int LOGD, int QC, int PS, int MT, int NST>
 static cudaError_t launch_xd_tma_n(const XdParams& p, const XtGeom& g, const CUtensorMap& tm, cudaStream_t s) {
     using Lay = XtLay<LOGD, QC, MT>;
     const size_t smem = (size_t)NST * Lay::STAGE + ((size_t)B200_BATCH * (PS + 16) + (size_t)Lay::NW * B200_BATCH * 4) * sizeof(float2) +
-                        (2 * NST * Lay::NSEG + 2 * Lay::NW) * sizeof(unsigned long long) + 1024;
+                        2 * NST * sizeof(unsigned long long) + 1024;
     if ((int)smem > kernels_max_smem_optin()) { return cudaErrorInvalidValue; }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = set_smem(k_xd_tma<LOGD, QC, PS, MT, NST, SPS, SPLIT>, smem);
+        cudaError_t e = set_smem(k_xd_tma<LOGD, QC, PS, MT, NST>, smem);
         if (e != cudaSuccess) { return e; }
         attr_set = true;
     }
@@ -940,20 +927,13 @@ static cudaError_t launch_xd_tma_n(const XdParams& p, const XtGeom& g, const CUt
     int grid = num_sms();
     if (g_xd_tma_ctas > 0 && g_xd_tma_ctas < grid) { grid = g_xd_tma_ctas; }
     if (grid > g.ntiles) { grid = g.ntiles; }
-    k_xd_tma<LOGD, QC, PS, MT, NST, SPS, SPLIT><<<grid, ((SPLIT ? 2 : 1) * Lay::NW + 1) * 32, smem, s>>>(p, g, tm);
+    k_xd_tma<LOGD, QC, PS, MT, NST><<<grid, (Lay::NW + 1) * 32, smem, s>>>(p, g, tm);
     g_xd_tma_launches++;
     return cudaGetLastError();
 }
 template <int LOGD, int QC, int PS, int MT>
 static cudaError_t launch_xd_tma_t(const XdParams& p, const XtGeom& g, const CUtensorMap& tm, cudaStream_t s) {
-    constexpr int NSEG = XtLay<LOGD, QC, MT>::NSEG;
-    if (xd_tma_split()) {
-        return g_xd_tma_stages == 3 ? launch_xd_tma_n<LOGD, QC, PS, MT, 3, NSEG, 1>(p, g, tm, s) : launch_xd_tma_n<LOGD, QC, PS, MT, 2, NSEG, 1>(p, g, tm, s);
-    }
-    if (xd_tma_seg()) {
-        return g_xd_tma_stages == 3 ? launch_xd_tma_n<LOGD, QC, PS, MT, 3, 1, 0>(p, g, tm, s) : launch_xd_tma_n<LOGD, QC, PS, MT, 2, 1, 0>(p, g, tm, s);
-    }
-    return g_xd_tma_stages == 3 ? launch_xd_tma_n<LOGD, QC, PS, MT, 3, NSEG, 0>(p, g, tm, s) : launch_xd_tma_n<LOGD, QC, PS, MT, 2, NSEG, 0>(p, g, tm, s);
+    return g_xd_tma_stages == 3 ? launch_xd_tma_n<LOGD, QC, PS, MT, 3>(p, g, tm, s) : launch_xd_tma_n<LOGD, QC, PS, MT, 2>(p, g, tm, s);
 }
 static bool try_xd_tma(const XdParams& p, cudaStream_t s, cudaError_t* err) {
     const int D = p.D, PS = p.pfb_ps;

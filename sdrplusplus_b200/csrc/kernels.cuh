@@ -390,8 +390,6 @@ void kernels_set_fft_variant(int v);
 void kernels_set_xd_tma_ctas(int v);      // persistent CTAs of the TMA stage 1 (0 = one per SM)
 void kernels_set_fft_cta(int v);          // transforms per CTA of the register FFT passes (8 or 4)
 void kernels_set_xd_tile(int mt);     // 0 = automatic
-void kernels_set_xd_tma_seg(int v);       // ring slots of the TMA stage 1: 1 = a 128-byte segment of a tile, 0 = a whole tile (default)
-void kernels_set_xd_tma_split(int v);     // 1 = filter warps + combine warps in the TMA stage 1
 void kernels_set_xd_tma_diag(int v);      // measurement only: 1 = load the tiles, do not filter; 2 = filter, do not load
 void kernels_set_xd_tma_stages(int n);   // ring depth of the TMA stage 1 (2 or 3)
 void kernels_set_xd_cps(int v);       // cap on stage-1 CTAs per SM, 0 = automatic

@@ -101,36 +101,21 @@ __device__ __forceinline__ void xt_accumulate(float2 (&S)[2][PS], const XtGeom& 
     }
 }
 
-// SPS = segments per ring slot.  SPS = NSEG (default): a slot is a whole tile (NSEG * 2 boxes), the consumers wait once per
-// tile and hand the tile back when all of it is filtered.  SPS = 1: a slot is one 128-byte segment of the tile (its two parity
-// boxes); the filter loop walks the decimation phases segment by segment, so a segment goes back to the TMA engine as soon as
-// its eight phase pairs are done and the ring (NST * NSEG slots, the same shared memory) keeps all but one segment in flight.
-// Measured (profiles/r02_s1_bounds.json): no gain (37.4 against 36.2 us) -- the ring is not what bounds the kernel: with the
-// filter switched off the loads alone run at 26 us per chunk (0.89 of the measured copy bandwidth) at either slot size and
-// either depth, with the loads switched off the consumers alone need 34 us.
-//
-// SPLIT (needs SPS = NSEG): the two halves of a consumer's work go to different warps.  Warps 0 .. NW-1 only FILTER: wait for
-// the tile, accumulate the 2 x PS class sums of their lanes, park them in the rows of the tile no other warp reads (a warp's
-// 64 outputs own rows 32 w + NQH .. 32 w + 31 of every region) and signal their partner.  Warps NW .. 2 NW - 1 only COMBINE:
-// take the sums, hand the tile back to the producer, then do the per-VFO combination, rotation and stores of the tile while
-// the filter warp is already on the next one.  Measured on the bench workload (tools/s1_bounds.py): the TMA ring alone
-// sustains 26 us per 16 Mi-sample chunk, filter + combination on one warp per scheduler need 34 us whatever the data does --
-// splitting them gives every scheduler two warps with independent instruction streams and no block-wide barrier.
-template <int LOGD, int QC, int PS, int MT, int NST, int SPS, int SPLIT>
-__global__ void __launch_bounds__(((SPLIT ? 2 : 1) * (MT / 64) + 1) * 32, 1)
+// What bounds it (profiles/r02_s1_bounds.json, option "s1_diag"): with the filter switched off the TMA ring alone moves a
+// 16 Mi-sample chunk in 26 us (0.89 of the measured copy bandwidth) at ring depth 2 or 3; with the loads switched off the
+// consumer warps alone need 34 us; the kernel takes 36 us.  Three restructurings of the consumer side were built, validated
+// on the whole GPU suite and measured, and none moved that number (the code is in the history):
+// two groups of warps sharing a tile with an exchange of partial sums (40 us), ring slots of one 128-byte segment so that a
+// segment goes back to the TMA engine after eight phase pairs (37 us), filter warps handing their class sums to combine warps
+// through the tile's private rows (36 us, twice the warps per scheduler).
+template <int LOGD, int QC, int PS, int MT, int NST>
+__global__ void __launch_bounds__((MT / 64 + 1) * 32, 1)
 k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, const __grid_constant__ CUtensorMap tm) {
     using Lay = XtLay<LOGD, QC, MT>;
     constexpr int D = Lay::D, NSEG = Lay::NSEG, NR = Lay::NR, REGION = Lay::REGION, STAGE = Lay::STAGE, NW = Lay::NW;
-    static_assert(SPS == 1 || SPS == NSEG, "a slot is one segment or the whole tile");
-    static_assert(!SPLIT || SPS == NSEG, "split consumers take whole tiles");
     constexpr int NQH = (QC >> 1) + 1;
-    constexpr int NCW = (SPLIT ? 2 : 1) * NW;                            // warps on the consumer side; the producer is warp NCW
-    constexpr int TW0 = SPLIT ? NW : 0;                                  // first of the NW warps that build and use the phase tables
-    constexpr int SCAP = (32 - NQH) / 2;                                 // class sums (256 B each per warp) that fit a warp's private rows of one region
-    static_assert(!SPLIT || 2 * PS <= 2 * SCAP, "the class sums of a warp fit its private rows of two regions");
-    constexpr int STEPS = NSEG / SPS;                                    // slots a tile takes
-    constexpr int NSLOT = NST * STEPS;                                   // ring depth in slots
-    constexpr int SLOT = SPS * 2 * REGION;                               // bytes per slot
+    constexpr int NSLOT = NST;                                           // ring depth: a slot is a whole tile (NSEG * 2 boxes)
+    constexpr int SLOT = STAGE;
     extern __shared__ __align__(1024) unsigned char xt_smem[];
     // the dynamic window is 1024-byte aligned by the launch (checked on the host side: static shared memory is tiny)
     const unsigned sbase = ((unsigned)__cvta_generic_to_shared(xt_smem) + 1023u) & ~1023u;
@@ -140,7 +125,6 @@ k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, c
     float2* PHW = TL + (size_t)B200_BATCH * 16;                          // [NW][njobs][4] per warp and tile: coarse phase
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(PHW + (size_t)NW * B200_BATCH * 4);
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);     // full[s] = bar0 + 8 s, empty[s] = bar0 + 8 (NSLOT + s)
-    const unsigned sbar0 = bar0 + 8 * 2 * NSLOT;                         // SPLIT: sums ready [w] = sbar0 + 8 w, sums taken [w] = sbar0 + 8 (NW + w)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -149,18 +133,11 @@ k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, c
             xt_mbar_init(bar0 + 8 * s, 1);
             xt_mbar_init(bar0 + 8 * (NSLOT + s), NW);
         }
-        if (SPLIT) {
-            for (int w = 0; w < NW; w++) {
-                xt_mbar_init(sbar0 + 8 * w, 32);                         // every lane of the filter warp arrives behind its own stores
-                xt_mbar_init(sbar0 + 8 * (NW + w), 1);
-            }
-        }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
     // the producer starts the first tiles right away; the consumers build their tables under those loads
-    if (warp >= TW0 && warp < TW0 + NW) {
-        const int tid = (int)threadIdx.x - TW0 * 32;
+    if (warp < NW) {
         for (int idx = tid; idx < p.njobs * PS; idx += NW * 32) {
             const int v = idx / PS, b = idx - v * PS;
             int a = (b - g.s) % PS;
@@ -178,7 +155,7 @@ k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, c
     // the chunk, the ragged end) get their missing samples patched in by the consumer warps after the TMA boxes landed
     auto tile_fast = [&](long long J0) { return J0 >= 0 && (J0 >> 1) + Lay::NEED <= (long long)g.rows_tma; };
 
-    if (warp == NCW) {
+    if (warp == NW) {
         // ---------------- producer ----------------
         if (lane == 0 && !(g.diag & 2)) {
             const unsigned long long pol = xt_policy_evict_first();
@@ -188,21 +165,18 @@ k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, c
                 const int row0 = (int)(J0 >> 1);
                 // every tile comes in through the TMA engine; rows outside the tensor (negative: stream history in front of
                 // the chunk; past its last full super-row: the ragged end) arrive zero-filled and are patched by the consumers
+                const int sl = it % NSLOT;
+                const unsigned ph = (unsigned)((it / NSLOT) & 1);
+                it++;
+                xt_mbar_wait(bar0 + 8 * (NSLOT + sl), ph ^ 1u);
+                const unsigned full = bar0 + 8 * sl;
+                xt_mbar_expect(full, (unsigned)SLOT);
+                const unsigned dst = sbase + (unsigned)(sl * SLOT);
 #pragma unroll
-                for (int step = 0; step < STEPS; step++, it++) {
-                    const int sl = it % NSLOT;
-                    const unsigned ph = (unsigned)((it / NSLOT) & 1);
-                    xt_mbar_wait(bar0 + 8 * (NSLOT + sl), ph ^ 1u);
-                    const unsigned full = bar0 + 8 * sl;
-                    xt_mbar_expect(full, (unsigned)SLOT);
-                    const unsigned dst = sbase + (unsigned)(sl * SLOT);
+                for (int sg = 0; sg < NSEG; sg++) {
 #pragma unroll
-                    for (int s2 = 0; s2 < SPS; s2++) {
-                        const int sg = step * SPS + s2;
-#pragma unroll
-                        for (int par = 0; par < 2; par++) {
-                            xt_tma_2d(dst + (unsigned)((s2 * 2 + par) * REGION), &tm, full, par * 2 * D + sg * 32, row0, pol);
-                        }
+                    for (int par = 0; par < 2; par++) {
+                        xt_tma_2d(dst + (unsigned)((sg * 2 + par) * REGION), &tm, full, par * 2 * D + sg * 32, row0, pol);
                     }
                 }
             }
@@ -211,34 +185,27 @@ k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, c
     }
 
     // ---------------- consumers ----------------
-    const int wl = (SPLIT && warp >= NW) ? warp - NW : warp;     // which 64 outputs of a tile
-    const bool filters = !SPLIT || warp < NW, combines = !SPLIT || warp >= NW;
-    const int jl = wl * 64 + 2 * lane;              // first of this lane's two adjacent outputs (even)
+    const int jl = warp * 64 + 2 * lane;            // first of this lane's two adjacent outputs (even)
     unsigned aoff[NQH];
 #pragma unroll
     for (int qh = 0; qh < NQH; qh++) {
         const unsigned row = (unsigned)((jl >> 1) + qh);
         aoff[qh] = row * 128u + ((row & 7u) << 4);
     }
-    // SPLIT: where class sum idx of this lane is parked inside tile buffer `sb` (rows only this warp's lanes read)
-    auto park = [&](unsigned sb, int idx) {
-        return sb + (unsigned)((idx < SCAP ? 0 : REGION) + (32 * wl + NQH) * 128 + ((idx < SCAP ? idx : idx - SCAP) * 32 + lane) * 8);
-    };
-    int tix = 0;                                    // tiles this CTA has taken so far
-    int it = 0;                                     // slot steps consumed so far (the producer's sequence)
-    for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, tix++) {
+    int it = 0;                                     // tiles consumed so far (the producer's sequence)
+    for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
         const long long J0 = g.jmin + (long long)tile * MT;
         // coarse phase table of this warp's 64 outputs: entry (job, i) = phase at output jl0 + 16 i, drift-centred
-        if (combines) {
+        {
             for (int e = lane; e < p.njobs * 4; e += 32) {
                 const int vv = e >> 2, i = e & 3;
                 const XdJob& Jv = p.job[vv];
                 const int a0 = Jv.offset - (Jv.T - 1);
-                const long long im0 = (long long)a0 + (J0 + wl * 64 + i * 16 - (long long)g.cj) * D;
+                const long long im0 = (long long)a0 + (J0 + warp * 64 + i * 16 - (long long)g.cj) * D;
                 unsigned long long dr = Jv.w * (unsigned long long)PS;
                 if (p.pfb_sigma < 0) { dr -= 0x8000000000000000ULL; }
                 const long long corr = (long long)dr * (long long)(Jv.T / (2 * PS));
-                PHW[(wl * B200_BATCH + vv) * 4 + i] = phasor_u64(Jv.phase0 + Jv.w * (unsigned long long)im0 + (unsigned long long)corr);
+                PHW[(warp * B200_BATCH + vv) * 4 + i] = phasor_u64(Jv.phase0 + Jv.w * (unsigned long long)im0 + (unsigned long long)corr);
             }
         }
         const bool fast = tile_fast(J0);
@@ -249,96 +216,47 @@ k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, c
         for (int o = 0; o < 2; o++)
 #pragma unroll
             for (int a = 0; a < PS; a++) { S[o][a] = make_float2(0.f, 0.f); }
-        auto slot_step = [&](auto stepc) {
-            constexpr int STEP = decltype(stepc)::value;
-            const int sl = it % NSLOT;
-            const unsigned ph = (unsigned)((it / NSLOT) & 1);
-            it++;
-            if (!(g.diag & 2)) { xt_mbar_wait(bar0 + 8 * sl, ph); }
-            const unsigned sb = sbase + (unsigned)(sl * SLOT);
-            if (!fast && !g.diag) {
-                // patch what the tensor map does not cover: samples before the chunk (from the carried raw history) and the
-                // samples of the last, partial super-row -- those of this slot's segments.  A few hundred at most, once or
-                // twice per launch.
-                const long long ibase = J0 * D + g.org;
-                unsigned char* stg = gbase + sl * SLOT;
-                constexpr int NSAMP = (MT + QC + 1) * D;
-                const long long tensor_end = (long long)g.org + (long long)g.rows_tma * (2 * D);
-                // the tensor's row 0 starts at sample g.org: everything of this tile in front of it was zero-filled -- stream
-                // history (index < 0) AND the first g.org samples of the chunk
-                const long long front = (long long)g.org - ibase;
-                const int head = (int)(front > 0 ? (front < NSAMP ? front : NSAMP) : 0);
-                long long t0 = tensor_end - ibase, t1 = (long long)p.count - ibase;
-                if (t0 < head) { t0 = head; }
-                if (t1 > NSAMP) { t1 = NSAMP; }
-                auto patch = [&](int idx) {
-                    const int j = idx >> LOGD, r = idx & (D - 1), row = j >> 1;
-                    const int s2 = (r >> 4) - STEP * SPS;                // segment of the sample, relative to this slot
-                    if (s2 < 0 || s2 >= SPS) { return; }
-                    const float2 v = load_x<FMT_CF32>(p, ibase + idx);
-                    const int off = (s2 * 2 + (j & 1)) * REGION + row * 128 + ((((r >> 1) & 7) ^ (row & 7)) << 4) + (r & 1) * 8;
-                    *reinterpret_cast<float2*>(stg + off) = v;
-                };
-                for (int idx = tid; idx < head; idx += NW * 32) { patch(idx); }
-                for (long long idx = t0 + tid; idx < t1; idx += NW * 32) { patch((int)idx); }
-                asm volatile("bar.sync 2, %0;\n" ::"n"(NW * 32) : "memory");      // the filter warps (id 1: the table builders)
-            }
-            if (g.diag & 1) { }
-            else if constexpr (SPS == 1) {
-                xt_accumulate<LOGD, QC, PS, REGION, 8 * STEP, 8 * STEP + 8, NQH>(S, g, sb, aoff);
-            }
-            else {
-                xt_accumulate<LOGD, QC, PS, REGION, 0, 8, NQH>(S, g, sb, aoff);
-                xt_accumulate<LOGD, QC, PS, REGION, 8, 16, NQH>(S, g, sb + 2 * REGION, aoff);
-                if constexpr (NSEG == 4) {
-                    xt_accumulate<LOGD, QC, PS, REGION, 16, 24, NQH>(S, g, sb + 4 * REGION, aoff);
-                    xt_accumulate<LOGD, QC, PS, REGION, 24, 32, NQH>(S, g, sb + 6 * REGION, aoff);
-                }
-            }
-            // the slot is consumed: hand it back to the producer
-            __syncwarp();
-            if (!SPLIT && lane == 0 && !(g.diag & 2)) { xt_mbar_arrive(bar0 + 8 * (NSLOT + sl)); }
-        };
-        if (filters) {
-            slot_step(std::integral_constant<int, 0>{});
-            if constexpr (STEPS >= 2) { slot_step(std::integral_constant<int, 1>{}); }
-            if constexpr (STEPS == 4) {
-                slot_step(std::integral_constant<int, 2>{});
-                slot_step(std::integral_constant<int, 3>{});
+        const int sl = it % NSLOT;
+        const unsigned ph = (unsigned)((it / NSLOT) & 1);
+        it++;
+        if (!(g.diag & 2)) { xt_mbar_wait(bar0 + 8 * sl, ph); }
+        const unsigned sb = sbase + (unsigned)(sl * SLOT);
+        if (!fast && !g.diag) {
+            // patch what the tensor map does not cover: samples before the chunk (from the carried raw history) and the
+            // samples of the last, partial super-row.  A few hundred at most, once or twice per launch.
+            const long long ibase = J0 * D + g.org;
+            unsigned char* stg = gbase + sl * SLOT;
+            constexpr int NSAMP = (MT + QC + 1) * D;
+            const long long tensor_end = (long long)g.org + (long long)g.rows_tma * (2 * D);
+            // the tensor's row 0 starts at sample g.org: everything of this tile in front of it was zero-filled -- stream
+            // history (index < 0) AND the first g.org samples of the chunk
+            const long long front = (long long)g.org - ibase;
+            const int head = (int)(front > 0 ? (front < NSAMP ? front : NSAMP) : 0);
+            long long t0 = tensor_end - ibase, t1 = (long long)p.count - ibase;
+            if (t0 < head) { t0 = head; }
+            if (t1 > NSAMP) { t1 = NSAMP; }
+            auto patch = [&](int idx) {
+                const float2 v = load_x<FMT_CF32>(p, ibase + idx);
+                const int j = idx >> LOGD, r = idx & (D - 1), row = j >> 1;
+                const int off = ((r >> 4) * 2 + (j & 1)) * REGION + row * 128 + ((((r >> 1) & 7) ^ (row & 7)) << 4) + (r & 1) * 8;
+                *reinterpret_cast<float2*>(stg + off) = v;
+            };
+            for (int idx = tid; idx < head; idx += NW * 32) { patch(idx); }
+            for (long long idx = t0 + tid; idx < t1; idx += NW * 32) { patch((int)idx); }
+            asm volatile("bar.sync 1, %0;\n" ::"n"(NW * 32) : "memory");
+        }
+        if (!(g.diag & 1)) {
+            xt_accumulate<LOGD, QC, PS, REGION, 0, 8, NQH>(S, g, sb, aoff);
+            xt_accumulate<LOGD, QC, PS, REGION, 8, 16, NQH>(S, g, sb + 2 * REGION, aoff);
+            if constexpr (NSEG == 4) {
+                xt_accumulate<LOGD, QC, PS, REGION, 16, 24, NQH>(S, g, sb + 4 * REGION, aoff);
+                xt_accumulate<LOGD, QC, PS, REGION, 24, 32, NQH>(S, g, sb + 6 * REGION, aoff);
             }
         }
-        static_assert(STEPS == 1 || STEPS == 2 || STEPS == 4, "D = 32 or 64");
-        if constexpr (SPLIT) {
-            const unsigned sb = sbase + (unsigned)((tix % NST) * STAGE);            // SPS = NSEG: slot = tile buffer, one step per tile
-            const unsigned par = (unsigned)(tix & 1);
-            if (filters) {
-                // the partner has taken the sums of the previous tile (so it is at most one phase behind on `ready`)
-                if (tix > 0) { xt_mbar_wait(sbar0 + 8 * (NW + wl), par ^ 1u); }
-#pragma unroll
-                for (int o = 0; o < 2; o++)
-#pragma unroll
-                    for (int a = 0; a < PS; a++) {
-                        asm volatile("st.shared.v2.f32 [%0], {%1, %2};\n" ::"r"(park(sb, o * PS + a)), "f"(S[o][a].x), "f"(S[o][a].y) : "memory");
-                    }
-                xt_mbar_arrive(sbar0 + 8 * wl);                                     // every lane, behind its own stores
-                continue;
-            }
-            xt_mbar_wait(sbar0 + 8 * wl, par);
-#pragma unroll
-            for (int o = 0; o < 2; o++)
-#pragma unroll
-                for (int a = 0; a < PS; a++) {
-                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(S[o][a].x), "=f"(S[o][a].y) : "r"(park(sb, o * PS + a)) : "memory");
-                }
-            // the tile buffer goes back to the TMA engine (generic-proxy accesses of this buffer are over), the filter warp may
-            // signal the next sums
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-                if (!(g.diag & 2)) { xt_mbar_arrive(bar0 + 8 * (NSLOT + (tix % NST))); }
-                xt_mbar_arrive(sbar0 + 8 * (NW + wl));
-            }
-        }
+        static_assert(NSEG == 2 || NSEG == 4, "D = 32 or 64");
+        // the tile is consumed: hand it back to the producer before the (register-only) combination
+        __syncwarp();
+        if (lane == 0 && !(g.diag & 2)) { xt_mbar_arrive(bar0 + 8 * (NSLOT + sl)); }
 
         if (g.diag & 1) { continue; }
         // ---- combine per slot (a VFO, or a +f / -f pair sharing A = sum cos*S and B = sum sin*S), rotate, store ----
@@ -359,14 +277,14 @@ k_xd_tma(const __grid_constant__ XdParams p, const __grid_constant__ XtGeom g, c
                 B1 = ffma2(make_float2(c.y, c.y), S[1][a], B1);
             }
             {
-                const float2 pc = PHW[(wl * B200_BATCH + ja) * 4 + ih];
+                const float2 pc = PHW[(warp * B200_BATCH + ja) * 4 + ih];
                 const float2 p0 = cmulf(pc, TL[ja * 16 + il]), p1 = cmulf(pc, TL[ja * 16 + il + 1]);
                 float2* out = p.job[ja].out + m0;
                 if (ok0) { out[0] = cmulf(make_float2(A0.x - B0.y, A0.y + B0.x), p0); }
                 if (ok1) { out[1] = cmulf(make_float2(A1.x - B1.y, A1.y + B1.x), p1); }
             }
             if (jb >= 0) {
-                const float2 pc = PHW[(wl * B200_BATCH + jb) * 4 + ih];
+                const float2 pc = PHW[(warp * B200_BATCH + jb) * 4 + ih];
                 const float2 p0 = cmulf(pc, TL[jb * 16 + il]), p1 = cmulf(pc, TL[jb * 16 + il + 1]);
                 float2* out = p.job[jb].out + m0;
                 if (ok0) { out[0] = cmulf(make_float2(A0.x + B0.y, A0.y - B0.x), p0); }      // conjugate coefficients

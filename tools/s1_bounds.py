@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """What bounds stage 1 (k_xd_tma) on the bench workload: the kernel alone (nothing else on the GPU), then with its two halves
 switched off in turn -- tiles loaded by the TMA ring but not filtered (what the loads alone sustain), tiles filtered but never
-loaded (what the four consumer warps per SM alone sustain) -- for both ring layouts and ring depths.  CUDA-event time per launch.
+loaded (what the four consumer warps per SM alone sustain) -- at both ring depths.  CUDA-event time per launch.
     python tools/s1_bounds.py > gpurun_out/s1_bounds.json"""
 import json
 import os
@@ -46,13 +46,11 @@ def main():
     chunk = 1 << 24
     algo = 9.0 * chunk
     res = []
-    for seg in (0, 1):
-        for stages in (2, 3):
-            for diag, what in ((0, "whole kernel"), (1, "tiles loaded, not filtered"), (2, "tiles filtered, not loaded")):
-                us = run(chunk, {"s1_seg": seg, "s1_stages": stages, "s1_diag": diag})
-                res.append({"ring_slot": "segment" if seg else "tile", "stages": stages, "mode": what, "us_per_launch": us,
-                            "GBps_algorithmic": algo / us / 1e3})
-                print(json.dumps(res[-1]), file=sys.stderr)
+    for stages in (2, 3):
+        for diag, what in ((0, "whole kernel"), (1, "tiles loaded, not filtered"), (2, "tiles filtered, not loaded")):
+            us = run(chunk, {"s1_stages": stages, "s1_diag": diag})
+            res.append({"ring_slot": "tile", "stages": stages, "mode": what, "us_per_launch": us, "GBps_algorithmic": algo / us / 1e3})
+            print(json.dumps(res[-1]), file=sys.stderr)
     print(json.dumps(res, indent=1))
 
 
