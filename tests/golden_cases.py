@@ -3,7 +3,7 @@ restatement) over seeded inputs and returns {name: array}.  tools/make_golden.py
 and commits the result; tests/test_oracle.py runs it on the restatement and demands bit-identical arrays."""
 import numpy as np
 
-from util import noise_iq, fm_carrier, am_carrier, ssb_tone
+from util import noise_iq, fm_carrier, am_carrier, ssb_tone, rds_baseband, rds_mpx_iq
 
 FS = 2.4e6
 
@@ -96,6 +96,21 @@ def run_cases(R):
     a = R.wfm_rds(75e3, 250e3).process_chunks(ws.view(np.float32), 1250)
     g["wfm_rds_tail"] = a[-256:]
     g["wfm_rds_digest"] = digest(a)
+    # RDSDemod of the radio module (rds_demod.h): AGC, two Costas loops, band-pass, M&M clock recovery, slicer, differential
+    # decoder -- on a synthetic 5 kS/s RDS baseband and behind the rdsOut branch of an FM carrier with a 57 kHz subcarrier
+    xr, _ = rds_baseband(1500, 31)
+    soft, hard = R.rds_demod().process_chunks(xr, 839)
+    g["rds_demod_soft_tail"] = soft[-256:]
+    g["rds_demod_soft_digest"] = digest(soft)
+    g["rds_demod_bits"] = np.packbits(hard)
+    xm, _ = rds_mpx_iq(400, 7)
+    rds_if = R.wfm_rds(75e3, 250e3).process_chunks(xm.view(np.float32), 12500).view(np.complex64)
+    soft, hard = R.rds_demod().process_chunks(rds_if, 250)
+    g["rds_chain_soft_digest"] = digest(soft)
+    g["rds_chain_bits"] = np.packbits(hard)
+    bp, bank = R.rds_demod_taps()
+    g["rds_bandpass_taps"] = bp.view(np.float32).copy()
+    g["rds_interp_bank_digest"] = digest(bank)
     # IF chain of the radio module: noise blanker (impulses on top of the FM signal), FM IF noise reduction (32 and 15 bins)
     imp = ws[:30000].copy()
     imp[::997] *= np.float32(12.0)
