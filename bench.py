@@ -680,6 +680,7 @@ def run_b200(args):
                    "pipelining": "b200_fe_submit/wait, 2 chunks in flight", "s1_variant": args.s1, "tails_variant": args.tails,
                    "vfo_offsets_hz": offsets, "conjugate_pair_sharing": bool(args.pair) and args.offsets == "sym",
                    "tails_overlap_next_chunk": bool(args.overlap),
+                   "chain_launch": "chain behind stage 1 replayed as a CUDA graph; programmatic dependent launch (B200_PDL=%s) for launches of at most 2 CTAs per SM" % os.environ.get("B200_PDL", "2"),
                    "chunk_sweep": sweep, "chunk_sweep_note": "the same graph at the reference's own chunk sizes (STREAM_BUFFER_SIZE caps a chunk at 1e6 samples, core/src/dsp/stream.h:9): device-resident MS/s, and end to end from int16 IQ in pinned host memory"},
         "e2e": dict(e2e["cs16"], format="cs16", cf32=e2e["cf32"], cs8=e2e["cs8"], pcie_probe=probe, numa=numa, numa_per_rank=numa_all,
                     host_buffers="b200_host_alloc (cudaHostAlloc)"),
