@@ -245,6 +245,13 @@ long long b200_fe_stat(b200_fe* fe, const char* key);
  *            4 Mi samples (no copy to enqueue), 1 always, 0 never (copy engine)
  *  "inflight" chunks between b200_fe_submit and b200_fe_wait: 2 (default) ... 4
  *  "s1_ctas" persistent CTAs of the TMA stage 1 (0 = one per SM)
+ *  "pdl"     programmatic dependent launch for the chain kernels behind stage 1 (a successor is scheduled and loads its tables
+ *            under its predecessor, and touches the stage buffers behind griddepcontrol.wait): 2 (default) launches of at most
+ *            two CTAs per SM -- the small grids of chunks up to about 1e6 samples --, 1 every launch, 0 never.  Process-wide;
+ *            also the environment variable B200_PDL
+ *  "s1_diag" measurement only (outputs are garbage): 1 = the TMA stage 1 loads its tiles but does not filter them, 2 = it
+ *            filters whatever its tile buffers hold and loads nothing -- what the ring alone and the consumer warps alone
+ *            sustain (tools/s1_bounds.py); reset to 0 by every b200_fe_create
  *  "time_s1" 1 = bracket the launch groups of every chunk with CUDA events (b200_fe_s1_stats / b200_fe_group_stats) */
 int b200_fe_set_option(b200_fe* fe, const char* key, int value);
 /* device time spent in the stage-1 (translate + first decimation) launches since the last call, and their count;
