@@ -131,3 +131,39 @@ def test_rds_demod_tap_sets_bit_exact(oracle):
     assert np.array_equal(bp[: 2 * n].view(np.uint32), obp.view(np.float32).view(np.uint32))
     assert np.array_equal(bank.view(np.uint32), obank.reshape(-1).view(np.uint32))
     assert L.b200_rds_demod_max_out(0) == 2 and L.b200_rds_demod_max_out(5000) >= 1188 + 12
+
+
+def test_shipped_library_carries_the_blackwell_paths():
+    """cuobjdump census of libb200dsp.so: sm_100a only; stage 1 is fed by the TMA engine under mbarriers (UTMALDG, SYNCS) and
+    filters with packed FMAs whose taps come from the constant bank; the chain kernels behind it carry the programmatic
+    dependent launch pair (PREEXIT = griddepcontrol.launch_dependents, ACQBULK = griddepcontrol.wait)."""
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    try:
+        elf = subprocess.run([exe, "-lelf", lib.LIB_PATH], capture_output=True, text=True, timeout=120)
+        sass = subprocess.run([exe, "-sass", lib.LIB_PATH], capture_output=True, text=True, timeout=600)
+    except (OSError, subprocess.TimeoutExpired):
+        pytest.skip("cuobjdump not available")
+    if elf.returncode != 0 or sass.returncode != 0:
+        pytest.skip("cuobjdump cannot read the library here")
+    archs = set(l.split(".")[-2] for l in elf.stdout.splitlines() if ".cubin" in l)
+    assert archs == {"sm_100a"}, archs
+    fun, census = None, {}
+    for line in sass.stdout.splitlines():
+        if "Function :" in line:
+            fun = line.split("Function :")[1].strip()
+            census[fun] = {"UTMALDG": 0, "SYNCS": 0, "FFMA2": 0, "PREEXIT": 0, "ACQBULK": 0}
+        elif fun:
+            for k in census[fun]:
+                if k in line:
+                    census[fun][k] += 1
+    s1 = [c for f, c in census.items() if "k_xd_tma" in f]
+    assert len(s1) >= 8                                         # D = 32 / 64, PS = 8 / 10, ring of 2 / 3
+    for c in s1:
+        assert c["UTMALDG"] >= 4 and c["SYNCS"] >= 6 and c["FFMA2"] >= 200, c
+    for name in ("k_dfir_reg", "k_poly_reg", "k_fir_reg", "k_firr_reg", "k_quad", "k_carry"):
+        ks = [c for f, c in census.items() if name in f]
+        assert ks, name
+        for c in ks:
+            assert c["PREEXIT"] >= 1 and c["ACQBULK"] >= 1, (name, c)
