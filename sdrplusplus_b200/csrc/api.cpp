@@ -1174,6 +1174,7 @@ struct b200_rds_demod {
     float* hsoft = nullptr;      // pinned staging of the symbols
     unsigned char* hhard = nullptr;
     long long launches = 0;
+    std::mutex mtx;              // process() and reset() may come from different threads (worker / control), like the other blocks
 };
 extern "C" int b200_rds_demod_max_out(int count) {
     if (count < 0) { return 0; }
@@ -1237,6 +1238,7 @@ extern "C" int b200_rds_demod_process(b200_rds_demod* r, int count, const void* 
     if (!r || (count > 0 && (!in || !soft || !hard))) { set_error("null argument"); return B200_EINVAL; }
     if (count < 0 || count > r->max_chunk) { set_error("count %d exceeds the block's chunk limit %d", count, r->max_chunk); return B200_ECAP; }
     if (count == 0) { return 0; }
+    std::lock_guard<std::mutex> lk(r->mtx);
     cudaStream_t s = r->stream;
     B200_CK(cudaMemcpyAsync(r->in.p, in, (size_t)count * sizeof(float2), cudaMemcpyDefault, s));      // host or device memory
     RdsParams p;
@@ -1265,6 +1267,7 @@ extern "C" int b200_rds_demod_reset(b200_rds_demod* r) {
     if (!r) { set_error("null block"); return B200_EINVAL; }
     // RDSDemod::reset (rds_demod.h:52-62): gain, loop phases / frequencies, band-pass delay line, MM offset / phase / lastOut,
     // decoder memory.  MM::reset (mm.h:83-92) leaves its work-buffer tail alone: so does this.
+    std::lock_guard<std::mutex> lk(r->mtx);
     B200_CK(cudaStreamSynchronize(r->stream));
     B200_CK(cudaMemcpyAsync(r->hstate, r->state.p, sizeof(RdsState), cudaMemcpyDeviceToHost, r->stream));
     B200_CK(cudaStreamSynchronize(r->stream));
