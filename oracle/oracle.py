@@ -320,6 +320,23 @@ class Oracle:
         n = self.lib.orc_rdsdemod_taps(bp.ctypes.data_as(C.c_void_p), 1024, bank.ctypes.data_as(C.c_void_p))
         return bp[: 2 * n].view(np.complex64).copy(), bank.reshape(128, 8)
 
+    def rds_group_decode(self, bits):
+        """reference build only: the radio module's RDS group decoder (rds.cpp) on a bit stream -> (PI code or None, PS name or None)"""
+        L = self.lib
+        L.orc_rdsdec_create.restype = C.c_void_p
+        L.orc_rdsdec_process.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_rdsdec_pi.argtypes = [C.c_void_p]
+        L.orc_rdsdec_ps.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.orc_rdsdec_free.argtypes = [C.c_void_p]
+        b = np.ascontiguousarray(bits, np.uint8)
+        h = L.orc_rdsdec_create()
+        L.orc_rdsdec_process(h, b.ctypes.data_as(C.c_void_p), int(b.size))
+        pi = L.orc_rdsdec_pi(h)
+        buf = C.create_string_buffer(64)
+        n = L.orc_rdsdec_ps(h, buf, 64)
+        L.orc_rdsdec_free(h)
+        return (pi if pi >= 0 else None), (buf.value.decode("latin-1") if n >= 0 else None)
+
     # ---- spectrum branch ----
     def fft_params(self, sr, size, rate):
         skip, nz = C.c_int(), C.c_int()

@@ -57,6 +57,11 @@
 #include <rds_demod.h>
 #undef private
 #undef protected
+// the radio module's RDS group decoder (block synchronisation, error correction, group parsing on the bit stream): CPU logic
+// of the reference, outside the restated path -- compiled from where it lies so that tests can show the bits the demodulator
+// delivers are the ones the reference's own decoder understands
+#include <rds.h>
+#include <rds.cpp>
 
 #include "sdrpp_oracle.h"
 
@@ -410,6 +415,23 @@ void orc_rdsdemod_reset(void* h) {
     b->d.reset();          // RDSDemod::reset (rds_demod.h:52-62); the blocks are not running, tempStop / tempStart do nothing
 }
 void orc_rdsdemod_free(void* h) { delete (RdsDemodBox*)h; }
+// rds::Decoder (decoder_modules/radio/src/rds.h:214-240): bits in, programme identification and service name out
+void* orc_rdsdec_create(void) { return new rds::Decoder(); }
+void orc_rdsdec_process(void* h, const uint8_t* bits, int count) {
+    std::vector<uint8_t> b(bits, bits + count);
+    ((rds::Decoder*)h)->process(b.data(), count);
+}
+int orc_rdsdec_pi(void* h) { rds::Decoder* d = (rds::Decoder*)h; return d->piCodeValid() ? (int)d->getPICode() : -1; }
+int orc_rdsdec_ps(void* h, char* out, int cap) {
+    rds::Decoder* d = (rds::Decoder*)h;
+    if (!d->PSNameValid()) { return -1; }
+    std::string s = d->getPSName(false);
+    int n = (int)s.size() < cap - 1 ? (int)s.size() : cap - 1;
+    memcpy(out, s.data(), (size_t)n);
+    out[n] = 0;
+    return n;
+}
+void orc_rdsdec_free(void* h) { delete (rds::Decoder*)h; }
 int orc_rdsdemod_taps(float* bandpass, int cap_bp, float* bank) {
     RdsDemodBox b;
     int nt = b.d.taps.size;

@@ -4,6 +4,7 @@
 #pragma once
 #include <map>
 #include <string>
+#include <type_traits>
 
 class ConfNode {
 public:
@@ -15,10 +16,10 @@ public:
     ConfNode& operator=(double v) { num = v; return *this; }
     ConfNode& operator=(int v) { num = v; return *this; }
     ConfNode& operator=(const std::string& v) { str = v; return *this; }
-    operator bool() const { return num != 0.0; }
-    operator float() const { return (float)num; }
-    operator double() const { return num; }
-    operator int() const { return (int)num; }
+    // numbers convert to any arithmetic type but the character types (so that `std::string s = node` has one reading)
+    template <class T, class = typename std::enable_if<std::is_arithmetic<T>::value && !std::is_same<T, char>::value &&
+                                                         !std::is_same<T, signed char>::value && !std::is_same<T, unsigned char>::value>::type>
+    operator T() const { return (T)(std::is_same<T, bool>::value ? (num != 0.0) : num); }
     operator std::string() const { return str; }
 private:
     std::map<std::string, ConfNode> kids;

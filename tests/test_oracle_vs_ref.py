@@ -128,3 +128,17 @@ def test_rds_demod_bit_identical(oracle, ref_oracle):
     tail = hard[600:]
     best = max(np.mean(tail[: 2000] == bits[d: d + 2000]) for d in range(560, 640))
     assert best > 0.99, best
+
+
+def test_rds_bits_are_what_the_reference_group_decoder_reads(oracle, ref_oracle):
+    """An RDS subcarrier carrying four type-0A groups (PI 0xB200, PS name 'B200 DSP', checkwords per IEC 62106) on an FM
+    carrier -> rdsOut branch -> RDSDemod (restatement, and the reference's own class) -> the reference's OWN group decoder
+    (decoder_modules/radio/src/rds.cpp, compiled from where it lies) finds the PI code and the name."""
+    from util import rds_mpx_iq, rds_group_bits
+    bits = rds_group_bits(0xB200, "B200 DSP", 6)
+    assert ref_oracle.rds_group_decode(bits) == (0xB200, "B200 DSP")               # the generator builds valid blocks
+    x, _ = rds_mpx_iq(0, 3, bits=bits)
+    for O in (oracle, ref_oracle):
+        y = O.wfm_rds(75e3, 250e3).process_chunks(x.view(np.float32), 12500).view(np.complex64)
+        _, hard = O.rds_demod().process_chunks(y, 250)
+        assert ref_oracle.rds_group_decode(hard) == (0xB200, "B200 DSP")

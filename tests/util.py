@@ -85,11 +85,42 @@ def rds_baseband(nbits, seed, fs=5000.0, amp=0.02, cfo_hz=1.5, phase0=0.7, noise
     return x.astype(np.complex64), bits
 
 
-def rds_mpx_iq(nbits, seed, fs=250e3):
+def rds_checkword(info16, offset):
+    """the 10-bit checkword of an RDS block: remainder of info(x) x^10 by g(x) = x^10 + x^8 + x^7 + x^5 + x^4 + x^3 + 1,
+    plus the block's offset word (IEC 62106; the syndromes the decoders look for follow from it)"""
+    reg = info16 << 10
+    for i in range(25, 9, -1):
+        if reg & (1 << i):
+            reg ^= 0x5B9 << (i - 10)
+    return (reg & 0x3FF) ^ offset
+
+
+def rds_group_bits(pi, ps_name, repeats):
+    """bit stream of `repeats` cycles of the four type-0A groups that carry the 8-character programme service name"""
+    OFF = {"A": 0x0FC, "B": 0x198, "C": 0x168, "D": 0x1B4}
+    ps = (ps_name + " " * 8)[:8]
+    bits = []
+    for _ in range(repeats):
+        for seg in range(4):
+            blocks = [("A", pi),
+                      ("B", (0 << 12) | (0 << 11) | (0 << 10) | (10 << 5) | (0 << 4) | (1 << 3) | (0 << 2) | seg),   # group 0A, PTY 10, music
+                      ("C", 0xE0CD),                                                                                # AF: "1 AF follows", 107.9 MHz
+                      ("D", (ord(ps[2 * seg]) << 8) | ord(ps[2 * seg + 1]))]
+            for name, info in blocks:
+                word = (info << 10) | rds_checkword(info, OFF[name])
+                bits.extend((word >> k) & 1 for k in range(25, -1, -1))
+    return np.array(bits, np.int64)
+
+
+def rds_mpx_iq(nbits, seed, fs=250e3, bits=None):
     """FM carrier at `fs` whose multiplex carries programme audio, the 19 kHz pilot and a biphase RDS subcarrier at 57 kHz
     (1187.5 Bd, differentially encoded).  Returns (complex64 IQ, bits)."""
     rng = np.random.default_rng(seed)
-    bits = rng.integers(0, 2, nbits)
+    if bits is None:
+        bits = rng.integers(0, 2, nbits)
+    else:
+        bits = np.asarray(bits, np.int64)
+        nbits = bits.size
     enc = np.cumsum(bits) % 2
     chips = np.repeat(2.0 * enc - 1.0, 2) * np.tile([1.0, -1.0], nbits)
     n = int(nbits * fs / 1187.5)
