@@ -3,8 +3,8 @@ unchanged, against the adapter headers in sdrplusplus_b200/host/dsp (same class 
 on a GPU they produce the oracle's audio.
 
 The wrapper headers are read where they lie under /root/reference through a symlink farm in build/ (nothing is copied into
-the repository); `demod.h` there is the reference's file minus the two includes that pull in the RDS decoder and the CW
-demodulator (symbol-rate CPU blocks, out of scope: SURVEY.md section 2.1).  The GPU box has no /root/reference: it runs the
+the repository); `demod.h` there is the reference's file minus the CW demodulator (not on the path) and, for the six plain
+wrappers, minus wfm.h -- which is built separately with the RDS chain behind it (build_radio_wfm).  The GPU box has no /root/reference: it runs the
 binary built here (build/ travels with the snapshot like the library does)."""
 import os
 import subprocess
@@ -108,7 +108,8 @@ def test_adapter_headers_cover_the_hot_path_blocks():
                 "channel/rx_vfo.h", "channel/frequency_xlator.h", "multirate/rational_resampler.h", "multirate/power_decimator.h",
                 "filter/fir.h", "filter/deephasis.h", "taps/tap.h", "taps/low_pass.h", "taps/high_pass.h",
                 "demod/quadrature.h", "demod/fm.h", "demod/am.h", "demod/ssb.h", "demod/broadcast_fm.h",
-                "convert/mono_to_stereo.h", "convert/complex_to_stereo.h", "compression/sample_stream_compressor.h", "b200/frontend.h"]:
+                "convert/mono_to_stereo.h", "convert/complex_to_stereo.h", "compression/sample_stream_compressor.h", "b200/frontend.h",
+                "sink/handler_sink.h", "buffer/reshaper.h", "noise_reduction/noise_blanker.h", "noise_reduction/fm_if.h", "noise_reduction/power_squelch.h"]:
         assert os.path.exists(os.path.join(host, rel)), rel
 
 
