@@ -73,3 +73,30 @@ def test_adapter_rds_wiring_decodes_bits(oracle, tmp_path):
     n = min(got.size, ho.size)
     assert np.count_nonzero(got[300:n] != ho[300:n]) <= 2          # a symbol on the threshold may differ (tests/test_gpu_rds.py)
     assert max(np.mean(got[300:1300] == bits[k: k + 1000]) for k in range(200, 400)) > 0.995
+
+
+@pytest.mark.parametrize("keep,skip,total,chunk", [(8, -5, 100, 7), (4, 3, 200, 5), (4096, 39 - 4096, 9000, 250), (16, 0, 160, 16)])
+def test_reshaper_and_handler_glue_blocks_on_cpu(keep, skip, total, chunk):
+    """dsp::buffer::Reshaper + dsp::sink::Handler (host/dsp/buffer/reshaper.h, host/dsp/sink/handler_sink.h) as worker-thread
+    blocks, against the framing rule of core/src/dsp/buffer/reshaper.h:100-126: blocks of `keep` samples; skip > 0 drops samples
+    between blocks, skip < 0 repeats the last -skip samples of a block at the head of the next (zeros before the first)."""
+    exe = os.path.join(ROOT, "build", "test_glue")
+    if not os.path.exists(exe):
+        pytest.skip("build/test_glue missing: run python __graft_entry__.py")
+    r = subprocess.run([exe, str(keep), str(skip), str(total), str(chunk)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout
+    got = [np.array(l.split(), np.float64) for l in r.stdout.strip().splitlines()]
+    x = np.arange(1, total + 1, dtype=np.float64)
+    carry = min(-skip, keep) if skip < 0 else 0
+    fresh = keep - carry
+    if fresh < 1:
+        fresh, carry = 1, keep - 1
+    want, pos, prev = [], 0, np.zeros(keep)
+    while pos + fresh <= total:
+        blk = np.concatenate([prev[fresh:], x[pos: pos + fresh]]) if carry else x[pos: pos + fresh]
+        want.append(blk)
+        prev = blk
+        pos += fresh + max(skip, 0)
+    assert len(got) == len(want), (len(got), len(want))
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
